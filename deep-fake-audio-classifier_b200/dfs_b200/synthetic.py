@@ -1,0 +1,157 @@
+"""Seeded synthetic weights, features and labels for the scoring path.
+
+The reference ships no trained weights, no features and no labels, so
+every parity test and the benchmark run on *random-init weights of the named
+architecture* and synthetic ``[N, 321, 180]`` LFCC-like maps (BASELINE.json north_star).
+
+Everything here is pure numpy on a PCG64 stream so the same (seed) gives the same
+arrays in the build container and on the GPU box.  State-dict key names and tensor
+shapes follow the reference exactly:
+
+* CNN2D  – /root/reference/src/model.py:14-31   (conv.{0,5,10}, BN conv.{1,6,11}, classifier)
+* CNN1D  – /root/reference/src/model_cnn1d.py:14-35 (conv.{0,4,8}, BN conv.{1,5,9}, classifier)
+* CAE    – /root/reference/src/model_cae.py:32-81 (encoder.{0,4,8,12}, BN encoder.{1,5,9,13},
+           decoder.{0,3,6,9}, BN decoder.{1,4,7})
+
+BatchNorm running stats / affine are randomised (gamma~U(.5,1.5), beta,mu~N(0,.1),
+var~U(.5,1.5)): the default init makes BN an identity and would hide folding bugs
+(SURVEY.md §7.1 step 1).
+"""
+from __future__ import annotations
+
+import hashlib
+from collections import OrderedDict
+
+import numpy as np
+
+T_FRAMES = 321
+N_FEATS = 180
+FEATURE_STD = 3.2  # real data: std 3.19 (results/archive/20260206_final_prep/model_prediction_report.md:28)
+
+
+def _rng(seed: int) -> np.random.Generator:
+    return np.random.Generator(np.random.PCG64(seed))
+
+
+def _uniform_fan_in(rng, shape, fan_in):
+    bound = 1.0 / np.sqrt(float(fan_in))
+    return rng.uniform(-bound, bound, size=shape).astype(np.float32)
+
+
+def _bn(rng, sd, prefix, c):
+    sd[prefix + ".weight"] = rng.uniform(0.5, 1.5, size=c).astype(np.float32)
+    sd[prefix + ".bias"] = (0.1 * rng.standard_normal(c)).astype(np.float32)
+    sd[prefix + ".running_mean"] = (0.1 * rng.standard_normal(c)).astype(np.float32)
+    sd[prefix + ".running_var"] = rng.uniform(0.5, 1.5, size=c).astype(np.float32)
+    sd[prefix + ".num_batches_tracked"] = np.array(100, dtype=np.int64)
+
+
+def cnn2d_state(seed: int = 0, in_features: int = N_FEATS, base_channels: int = 32,
+                logit_scale: float = 1.0) -> "OrderedDict[str, np.ndarray]":
+    """Random-init CNN2D state dict. ``logit_scale`` rescales the classifier weights
+    ("trained-like" regime of SURVEY.md §7.2 #5: logits spanning +-20 instead of +-0.01)."""
+    rng = _rng(1000 + seed)
+    bc = base_channels
+    sd = OrderedDict()
+    chans = [(1, bc), (bc, 2 * bc), (2 * bc, 4 * bc)]
+    for (ci, co), conv_i, bn_i in zip(chans, (0, 5, 10), (1, 6, 11)):
+        sd[f"conv.{conv_i}.weight"] = _uniform_fan_in(rng, (co, ci, 3, 3), ci * 9)
+        sd[f"conv.{conv_i}.bias"] = _uniform_fan_in(rng, (co,), ci * 9)
+        _bn(rng, sd, f"conv.{bn_i}", co)
+    fan = 4 * bc * in_features
+    sd["classifier.weight"] = _uniform_fan_in(rng, (1, fan), fan) * np.float32(logit_scale)
+    sd["classifier.bias"] = _uniform_fan_in(rng, (1,), fan)
+    return sd
+
+
+def cnn1d_state(seed: int = 0, in_features: int = N_FEATS, base_channels: int = 32,
+                logit_scale: float = 1.0) -> "OrderedDict[str, np.ndarray]":
+    rng = _rng(2000 + seed)
+    bc = base_channels
+    sd = OrderedDict()
+    chans = [(in_features, bc), (bc, 2 * bc), (2 * bc, 4 * bc)]
+    for (ci, co), conv_i, bn_i in zip(chans, (0, 4, 8), (1, 5, 9)):
+        sd[f"conv.{conv_i}.weight"] = _uniform_fan_in(rng, (co, ci, 3), ci * 3)
+        sd[f"conv.{conv_i}.bias"] = _uniform_fan_in(rng, (co,), ci * 3)
+        _bn(rng, sd, f"conv.{bn_i}", co)
+    sd["classifier.weight"] = _uniform_fan_in(rng, (1, 4 * bc), 4 * bc) * np.float32(logit_scale)
+    sd["classifier.bias"] = _uniform_fan_in(rng, (1,), 4 * bc)
+    return sd
+
+
+def cae_state(seed: int = 0, base_channels: int = 32) -> "OrderedDict[str, np.ndarray]":
+    rng = _rng(3000 + seed)
+    bc = base_channels
+    sd = OrderedDict()
+    enc = [(1, bc), (bc, 2 * bc), (2 * bc, 4 * bc), (4 * bc, 8 * bc)]
+    for (ci, co), conv_i, bn_i in zip(enc, (0, 4, 8, 12), (1, 5, 9, 13)):
+        sd[f"encoder.{conv_i}.weight"] = _uniform_fan_in(rng, (co, ci, 3, 3), ci * 9)
+        sd[f"encoder.{conv_i}.bias"] = _uniform_fan_in(rng, (co,), ci * 9)
+        _bn(rng, sd, f"encoder.{bn_i}", co)
+    dec = [(8 * bc, 4 * bc), (4 * bc, 2 * bc), (2 * bc, bc), (bc, 1)]
+    for (ci, co), conv_i, bn_i in zip(dec, (0, 3, 6, 9), (1, 4, 7, None)):
+        # ConvTranspose2d weight is (Cin, Cout, 2, 2); torch's fan_in for it is Cout*kh*kw
+        sd[f"decoder.{conv_i}.weight"] = _uniform_fan_in(rng, (ci, co, 2, 2), co * 4)
+        sd[f"decoder.{conv_i}.bias"] = _uniform_fan_in(rng, (co,), co * 4)
+        if bn_i is not None:
+            _bn(rng, sd, f"decoder.{bn_i}", co)
+    return sd
+
+
+def normalizer_stats(seed: int = 1, n_feats: int = N_FEATS):
+    """mean180 ~ N(0, .1), std180 ~ U(2, 4) -> z-scored input ~ N(0,1)."""
+    rng = _rng(4000 + seed)
+    mean = (0.1 * rng.standard_normal(n_feats)).astype(np.float32)
+    std = rng.uniform(2.0, 4.0, size=n_feats).astype(np.float32)
+    return mean, std
+
+
+def features(n: int, seed: int = 1234, start: int = 0) -> np.ndarray:
+    """``[n, 321, 180]`` fp32 ~ N(0, 3.2^2); utterance ``i`` depends only on (seed, start+i)."""
+    out = np.empty((n, T_FRAMES, N_FEATS), dtype=np.float32)
+    for i in range(n):
+        rng = np.random.Generator(np.random.PCG64([seed, start + i]))
+        out[i] = (FEATURE_STD * rng.standard_normal((T_FRAMES, N_FEATS), dtype=np.float32))
+    return out
+
+
+def labels(n: int, seed: int = 42, p_bonafide: float = 0.4) -> np.ndarray:
+    return (_rng(5000 + seed).random(n) < p_bonafide).astype(np.uint8)
+
+
+def tie_free_scores(n: int, seed: int = 0, k: float = 6.0):
+    """Distinct fp32 scores + labels with an EER strictly between 0 and 0.5.
+
+    Scores are distinct fp32 *bit patterns* in a positive range ([0.25, 0.75) when n fits,
+    else [2^-20, 1)), assigned through a seeded affine bijection ``rank = (a*i + b) mod n``
+    (gcd(a, n) = 1), so no two scores tie -- drawing ``rand()`` would collide massively at
+    100 M.  Labels are Bernoulli(sigmoid(k * (rank/n - 0.5))).
+    """
+    import math
+    rng = _rng(6000 + seed)
+    lo, hi = (int(np.float32(v).view(np.uint32)) for v in (0.25, 0.75))
+    if n > hi - lo:
+        lo, hi = (int(np.float32(v).view(np.uint32)) for v in (2.0 ** -20, 1.0))
+    if n > hi - lo:
+        raise ValueError("n too large for distinct positive fp32 scores")
+    step = (hi - lo) // max(n, 1)
+    a = int(rng.integers(n // 3 + 1, max(n // 2, n // 3 + 2))) | 1
+    while math.gcd(a, max(n, 1)) != 1:
+        a += 2
+    b = int(rng.integers(0, max(n, 1)))
+    idx = np.arange(n, dtype=np.uint64)
+    ranks = (idx * np.uint64(a) + np.uint64(b)) % np.uint64(max(n, 1))   # a*n < 2^64 for n < 2^32
+    scores = (np.uint64(lo) + ranks * np.uint64(step)).astype(np.uint32).view(np.float32)
+    p = 1.0 / (1.0 + np.exp(-k * (ranks.astype(np.float64) / max(n, 1) - 0.5)))
+    lab = (rng.random(n) < p).astype(np.uint8)
+    return scores, lab
+
+
+def state_digest(sd) -> str:
+    """sha256 over the arrays of a state dict / list of arrays (goldens pin the factory)."""
+    h = hashlib.sha256()
+    items = sd.items() if hasattr(sd, "items") else enumerate(sd)
+    for k, v in items:
+        h.update(str(k).encode())
+        h.update(np.ascontiguousarray(v).tobytes())
+    return h.hexdigest()
