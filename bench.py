@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- utterances/sec of the scoring hot path (BASELINE.json metric, config[1]):
+2D-CNN batch scoring of ~1M synthetic [321x180] utterances, bf16 operands / fp32 accumulation,
+sharded over N GPUs (one process per GPU) with one NCCL all-gather of the scores per step and the
+EER of the gathered scores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass over the rank's resident pool of P utterances (default 16,640 = 3.85 GB of fp32
+features, far larger than the 126 MB L2) through conv1 -> conv2 -> conv3 -> head (+ all-gather at
+N > 1) + the EER of the step's scores.  K = 60 steps ~ 1.0 M utterances per GPU.
+Rank 0 prints ONE JSON line (keys: see the driver contract in DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "deep-fake-audio-classifier_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+FLOP_PER_UTT = {"cnn2d": 3_218_376_960, "cae": 1_792_021_760, "cnn1d": 30_816_256}
+CONV3_FLOP_PER_UTT = 2 * 1_061_683_200
+CONV2_FLOP_PER_UTT = 2 * 530_841_600
+BYTES_PER_UTT = 321 * 180 * 4
+METRIC = "utterances/sec scoring [321x180] LFCC maps (2D-CNN) + EER"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pool", type=int, default=16640, help="utterances resident per GPU and scored per step")
+    ap.add_argument("--chunk", type=int, default=0, help="utterances per internal pass (0 = library default 208)")
+    ap.add_argument("--e2e-pool", type=int, default=4160, help="utterances in pinned host memory for the e2e leg")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops_burst=p["bf16_tflops"], tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm_gbs=p["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+
+
+def cpu_reference_rate(torch, feats_cpu, sd, seconds, all_threads=True):
+    """Times the oracle's restatement of the predict.py loop (bs 32, no_grad, all host threads) on a bounded sample."""
+    from oracle import models_torch as ot
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores if all_threads else 1)
+    ot.reference_loop_supervised(ot.cnn2d_forward, sd, feats_cpu[:8])          # warm the oneDNN primitives
+    t0 = time.perf_counter()
+    probe = ot.reference_loop_supervised(ot.cnn2d_forward, sd, feats_cpu[:32])
+    rate = 32 / (time.perf_counter() - t0)
+    n = int(min(feats_cpu.shape[0], max(32, (rate * seconds) // 32 * 32)))
+    t0 = time.perf_counter()
+    scores = ot.reference_loop_supervised(ot.cnn2d_forward, sd, feats_cpu[:n])
+    dt = time.perf_counter() - t0
+    del probe
+    return n / dt, n, cores, scores
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port of the predict.py loop,
+    /root/reference is pure Python and is not installable as a package) on the box's host cores; rank 0 only."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+
+    from dfs_b200 import synthetic as syn
+    from oracle import eer as oeer
+    from oracle import models_torch as ot
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = syn.cnn2d_state(0)
+    pool = torch.from_numpy(syn.features(256, seed=1234))
+    ot.reference_loop_supervised(ot.cnn2d_forward, sd, pool[:8])
+    t0 = time.perf_counter()
+    ot.reference_loop_supervised(ot.cnn2d_forward, sd, pool[:32])
+    rate = 32 / (time.perf_counter() - t0)
+    per_step = int(max(32, min(256, (rate * 120.0 / (args.steps + args.warmup)) // 32 * 32)))
+    lab = syn.labels(per_step)
+    for _ in range(args.warmup):
+        ot.reference_loop_supervised(ot.cnn2d_forward, sd, pool[:per_step])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s = ot.reference_loop_supervised(ot.cnn2d_forward, sd, pool[:per_step])
+        oeer.calculate_eer(s, lab)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "2D-CNN scoring + EER, reference CPU path (predict.py loop, bs 32)", "utterances_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "utterances/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} utterances/step x {args.steps} steps, torch CPU fp32, {cores} threads"},
+        "e2e": {"value": value, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import dfs_b200 as D
+    from dfs_b200 import synthetic as syn
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the scoring path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    P = args.pool
+    sd = syn.cnn2d_state(0)
+    scorer = D.Cnn2dScorer(sd, device=local, max_chunk=args.chunk)
+    # rank r owns global utterances [r*P, (r+1)*P): generated on the device from (seed, global index)
+    pool = D.fill_features(P, first_utt=rank * P, seed=1234, device=local)
+    labels_global = torch.from_numpy(syn.labels(P * world)).to(dev)
+    scores = torch.empty(P, dtype=torch.float32, device=dev)
+    gathered = torch.empty(P * world, dtype=torch.float32, device=dev) if world > 1 else scores
+
+    def step():
+        s = scorer.score(pool, apply_sigmoid=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, s)
+            g = gathered
+        else:
+            g = s
+        return D.eer_details(g, labels_global), s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res, s_last = step()
+    # per-kernel event pairs: one profiled warm-up step sizes the event pool; inside the timed region the
+    # pairs are read back right after each step's EER (which has already synchronised the stream)
+    scorer.set_option("profile", 1)
+    step()
+    scorer.profile(4)
+    kms, kcnt = [0.0] * 4, [0] * 4
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = D._native.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        res, s_last = step()
+        a, b = scorer.profile(4)
+        kms = [x + y for x, y in zip(kms, a)]
+        kcnt = [x + y for x, y in zip(kcnt, b)]
+    ev1.record()
+    barrier()
+    launches = D._native.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    scorer.set_option("profile", 0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = P * world * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: the same metric through the public host-buffer call (pinned host -> H2D -> kernels -> D2H) ----
+    Pe = args.e2e_pool
+    host_pool = torch.empty((Pe, 321, 180), dtype=torch.float32, pin_memory=True)
+    host_pool.copy_(pool[:Pe])
+    scorer.score_host(host_pool, 1)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_scores = scorer.score_host(host_pool, 1)
+        D.eer_details(e2e_scores, labels_global[:Pe])
+    torch.cuda.synchronize()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = Pe * world * args.e2e_steps / float(e2e_dt.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    chunk = args.chunk or 208
+    conv3_ms = kms[2] / max(kcnt[2], 1)
+    utt_per_launch = P / max(kcnt[2] / args.steps, 1)
+    achieved = CONV3_FLOP_PER_UTT * utt_per_launch / (conv3_ms * 1e-3) / 1e12 if conv3_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel<64,128> (CNN2D conv3, 66% of the FLOPs)", "achieved": achieved,
+                "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": None,
+                "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)",
+                "flops_per_launch": CONV3_FLOP_PER_UTT * utt_per_launch, "avg_launch_ms": conv3_ms,
+                "kernel_ms_share": {k: v / max(sum(kms), 1e-9) for k, v in zip(("conv1", "conv2", "conv3", "head"), kms)},
+                "conv2_tflops": CONV2_FLOP_PER_UTT * utt_per_launch / (kms[1] / max(kcnt[1], 1) * 1e-3) / 1e12 if kms[1] > 0 else None,
+                "whole_path_tflops": value / world * FLOP_PER_UTT["cnn2d"] / 1e12,
+                "whole_path_frac_of_sustained_peak": value / world * FLOP_PER_UTT["cnn2d"] / 1e12 / pk["tflops_sustained"]}
+
+    out = {"metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+           "data": "synthetic",
+           "config": {"workload": "BASELINE configs[1]: 2D-CNN (src/model.py) batch scoring, bf16 operands / fp32 accumulate, + EER per step",
+                      "utterances_per_step_per_gpu": P, "total_utterances": P * world * args.steps, "chunk": chunk,
+                      "l2": "inputs larger than L2 (pool %.2f GB per GPU, cycled)" % (P * BYTES_PER_UTT / 1e9),
+                      "weights": "random-init CNN2D, seeded (dfs_b200.synthetic.cnn2d_state(0)); no checkpoints ship with the reference",
+                      "parallelism": f"dp{world} (utterance shards, one NCCL all-gather of scores per step)" if world > 1 else "dp1"},
+           "eer": {"value": res["eer"], "threshold": res["threshold"], "n": P * world},
+           "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+           "e2e": {"value": e2e_value, "unit": "utterances/s", "h2d_bytes_per_step": Pe * BYTES_PER_UTT, "d2h_bytes_per_step": Pe * 4,
+                   "utterances_per_step_per_gpu": Pe, "steps": args.e2e_steps,
+                   "note": "dfs_score_host: pinned host features -> double-buffered H2D -> kernels -> D2H scores, + EER"}}
+
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu = 2048
+        feats_cpu = pool[:n_cpu].cpu()
+        rate, n_used, cores, ref_scores = cpu_reference_rate(torch, feats_cpu, sd, args.cpu_seconds)
+        dev_scores = s_last[:n_used].cpu().numpy()
+        rel = float(np.max(np.abs(dev_scores - ref_scores) / np.abs(ref_scores)))
+        from oracle import eer as oeer
+        lab = labels_global[:n_used].cpu().numpy()
+        out["cpu_baseline"] = {"value": rate, "unit": "utterances/s", "cores": cores, "kind": "port",
+                               "sample": f"first {n_used} utterances of the pool, oracle port of the predict.py loop (bs 32, torch CPU fp32)"}
+        out["parity"] = {"max_rel_err_scores_vs_cpu_reference": rel, "n": n_used, "tolerance": 1e-3,
+                         "eer_cpu": oeer.calculate_eer(ref_scores, lab)[0], "eer_gpu": D.calculate_eer(dev_scores, lab)[0]}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,537 @@
+// api.cu -- the C ABI of include/dfs_b200.h: model handles (BN folding, weight re-packing,
+// workspaces), the chunked scoring loops and the host-buffer pipeline.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "layout.cuh"
+
+using namespace dfs;
+
+// ------------------------------------------------------------------------------------------
+// error string + launch counter
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void dfs_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void dfs_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" const char* dfs_last_error(void) { return g_err; }
+extern "C" int dfs_version(void) { return 100; }
+extern "C" int64_t dfs_launch_count(void) { return (int64_t)g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// model handle
+// ------------------------------------------------------------------------------------------
+enum { KIND_CNN2D = 0, KIND_CNN1D = 1, KIND_CAE = 2 };
+
+struct dfs_model {
+  int kind = -1;
+  int device = 0;
+  int chunk = 0;
+  int conv_impl = 0;
+  int num_sms = 148;
+  std::vector<void*> allocs;  // everything cudaMalloc'ed for this model
+  size_t ws_bytes = 0;
+  // ---- CNN2D ----
+  Conv1Weights c1{};
+  uint16_t* w2pack = nullptr;
+  uint16_t* w3pack = nullptr;
+  float b2[64] = {0}, b3[128] = {0};
+  float* b2_dev = nullptr;
+  float* b3_dev = nullptr;
+  float* fcw_dev = nullptr;
+  float fcb = 0.f;
+  ActBuf act1{}, act2{};
+  float* emb = nullptr;
+  CUtensorMap tmap1{}, tmap2{};
+  // ---- CNN1D / CAE (CUDA-core path) ----
+  SimtConv sc[8];
+  float* work = nullptr;
+  float* norm_mean = nullptr;
+  float* norm_std = nullptr;
+  float final_bias = 0.f;
+  // ---- per-kernel device timing (option "profile"): event pairs around every launch ----
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
+  std::vector<int> prof_kid;          // kernel id of each pair
+  size_t prof_used = 0;               // pairs in use since the last reset
+  // ---- host-buffer pipeline ----
+  float* stage_in[2] = {nullptr, nullptr};
+  float* stage_out[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+static int dev_alloc(dfs_model* m, void** p, size_t bytes, bool zero) {
+  DFS_CUDA_CHECK(cudaMalloc(p, bytes));
+  m->allocs.push_back(*p);
+  m->ws_bytes += bytes;
+  if (zero) DFS_CUDA_CHECK(cudaMemset(*p, 0, bytes));
+  return DFS_OK;
+}
+template <typename T>
+static int dev_upload(dfs_model* m, T** p, const std::vector<T>& h) {
+  DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(p), h.size() * sizeof(T), false));
+  DFS_CUDA_CHECK(cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return DFS_OK;
+}
+
+static uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// BN fold in double: scale[co], shift[co] such that  y = scale*(conv_nobias) + shift
+static void bn_fold(const dfs_conv_bn& c, int co, std::vector<double>& scale, std::vector<double>& shift) {
+  scale.assign(co, 1.0);
+  shift.assign(co, 0.0);
+  for (int o = 0; o < co; ++o) {
+    const double b = c.bias ? (double)c.bias[o] : 0.0;
+    if (c.bn_weight) {
+      const double s = (double)c.bn_weight[o] / std::sqrt((double)c.bn_var[o] + 1e-5);
+      scale[o] = s;
+      shift[o] = (b - (double)c.bn_mean[o]) * s + (double)c.bn_bias[o];
+    } else {
+      shift[o] = b;
+    }
+  }
+}
+
+static bool conv_ok(const dfs_conv_bn& c, bool need_bn) {
+  if (!c.weight || !c.bias) return false;
+  const int nbn = (c.bn_weight != nullptr) + (c.bn_bias != nullptr) + (c.bn_mean != nullptr) + (c.bn_var != nullptr);
+  return need_bn ? nbn == 4 : (nbn == 0 || nbn == 4);
+}
+
+static int model_common_init(dfs_model* m, int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    dfs_set_error("no CUDA device available (%s); this engine has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return DFS_ERR_CUDA;
+  }
+  DFS_REQUIRE(device >= 0 && device < count, DFS_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  DFS_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DFS_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  DFS_REQUIRE(prop.major == 10, DFS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+              prop.major, prop.minor);
+  m->device = device;
+  m->num_sms = prop.multiProcessorCount;
+  return DFS_OK;
+}
+
+static int model_stage_init(dfs_model* m) {
+  if (m->copy_stream) return DFS_OK;
+  DFS_CUDA_CHECK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&m->stage_in[b]), (size_t)m->chunk * kT * kF * 4, false));
+    DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&m->stage_out[b]), (size_t)m->chunk * 4, false));
+    DFS_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_in[b], cudaEventDisableTiming));
+    DFS_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_done[b], cudaEventDisableTiming));
+  }
+  return DFS_OK;
+}
+
+// event-pair bracket around one launch when profiling is on
+struct ProfScope {
+  dfs_model* m;
+  cudaStream_t s;
+  cudaEvent_t stop = nullptr;
+  ProfScope(dfs_model* m_, int kid, cudaStream_t s_) : m(m_), s(s_) {
+    if (!m->profile) return;
+    if (m->prof_used * 2 + 2 > m->prof_ev.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      m->prof_ev.push_back(a);
+      m->prof_ev.push_back(b);
+      m->prof_kid.push_back(kid);
+    }
+    m->prof_kid[m->prof_used] = kid;
+    cudaEventRecord(m->prof_ev[2 * m->prof_used], s);
+    stop = m->prof_ev[2 * m->prof_used + 1];
+    ++m->prof_used;
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, s);
+  }
+};
+
+extern "C" int dfs_model_profile(dfs_model* m, double* ms_out, int64_t* launches_out, int n_ids, int reset) {
+  DFS_REQUIRE(m && ms_out && launches_out && n_ids > 0, DFS_ERR_INVALID, "dfs_model_profile: bad argument");
+  for (int i = 0; i < n_ids; ++i) { ms_out[i] = 0.0; launches_out[i] = 0; }
+  for (size_t i = 0; i < m->prof_used; ++i) {
+    DFS_CUDA_CHECK(cudaEventSynchronize(m->prof_ev[2 * i + 1]));
+    float ms = 0.f;
+    DFS_CUDA_CHECK(cudaEventElapsedTime(&ms, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]));
+    const int k = m->prof_kid[i];
+    if (k >= 0 && k < n_ids) { ms_out[k] += ms; launches_out[k] += 1; }
+  }
+  if (reset) m->prof_used = 0;
+  return DFS_OK;
+}
+
+extern "C" int dfs_model_destroy(dfs_model* m) {
+  if (!m) return DFS_OK;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+  for (void* p : m->allocs) cudaFree(p);
+  for (int b = 0; b < 2; ++b) {
+    if (m->ev_in[b]) cudaEventDestroy(m->ev_in[b]);
+    if (m->ev_done[b]) cudaEventDestroy(m->ev_done[b]);
+  }
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  delete m;
+  return DFS_OK;
+}
+
+extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value) {
+  DFS_REQUIRE(m && key, DFS_ERR_INVALID, "dfs_model_set_option: NULL argument");
+  if (strcmp(key, "conv_impl") == 0) {
+    DFS_REQUIRE(value == 0 || value == 1, DFS_ERR_INVALID, "conv_impl must be 0 (tcgen05) or 1 (CUDA-core cross-check)");
+    m->conv_impl = (int)value;
+    return DFS_OK;
+  }
+  if (strcmp(key, "profile") == 0) {
+    m->profile = value != 0;
+    m->prof_used = 0;
+    return DFS_OK;
+  }
+  dfs_set_error("unknown option '%s'", key);
+  return DFS_ERR_INVALID;
+}
+
+extern "C" int64_t dfs_model_workspace_bytes(const dfs_model* m) { return m ? (int64_t)m->ws_bytes : 0; }
+
+// ------------------------------------------------------------------------------------------
+// CNN2D
+// ------------------------------------------------------------------------------------------
+// pack a folded 3x3 conv weight (Co,Ci,3,3) into [tap][ci/8][co][ci%8] bf16
+static std::vector<uint16_t> pack_conv3x3_bf16(const dfs_conv_bn& c, int co, int ci, std::vector<float>& bias_out) {
+  std::vector<double> scale, shift;
+  bn_fold(c, co, scale, shift);
+  bias_out.resize(co);
+  for (int o = 0; o < co; ++o) bias_out[o] = (float)shift[o];
+  std::vector<uint16_t> out((size_t)9 * ci * co);
+  for (int tap = 0; tap < 9; ++tap)
+    for (int i = 0; i < ci; ++i)
+      for (int o = 0; o < co; ++o) {
+        const double w = (double)c.weight[((size_t)o * ci + i) * 9 + tap] * scale[o];
+        out[(((size_t)tap * (ci / 8) + (i >> 3)) * co + o) * 8 + (i & 7)] = f32_to_bf16_rn((float)w);
+      }
+  return out;
+}
+
+static void fold_conv1(const dfs_conv_bn& c, Conv1Weights& w) {
+  std::vector<double> scale, shift;
+  bn_fold(c, 32, scale, shift);
+  for (int o = 0; o < 32; ++o) {
+    for (int k = 0; k < 9; ++k) w.w[o * 9 + k] = (float)((double)c.weight[o * 9 + k] * scale[o]);
+    w.b[o] = (float)shift[o];
+  }
+}
+
+extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_weights* w, int max_chunk) {
+  DFS_REQUIRE(out && w, DFS_ERR_INVALID, "dfs_cnn2d_create: NULL argument");
+  *out = nullptr;
+  DFS_REQUIRE(w->in_features == kF && w->base_channels == 32, DFS_ERR_UNSUPPORTED,
+              "CNN2D kernels are built for in_features=180, base_channels=32 (got %d, %d)", w->in_features, w->base_channels);
+  for (int i = 0; i < 3; ++i) DFS_REQUIRE(conv_ok(w->conv[i], true), DFS_ERR_INVALID, "dfs_cnn2d_create: conv[%d] has NULL tensors", i);
+  DFS_REQUIRE(w->fc_weight && w->fc_bias, DFS_ERR_INVALID, "dfs_cnn2d_create: classifier tensors are NULL");
+  dfs_model* m = new (std::nothrow) dfs_model();
+  DFS_REQUIRE(m, DFS_ERR_NOMEM, "out of host memory");
+  m->kind = KIND_CNN2D;
+  int st = model_common_init(m, device);
+  if (st != DFS_OK) { delete m; return st; }
+  m->chunk = max_chunk > 0 ? max_chunk : 208;  // 208 * 182 / 16 column tiles = 16 full waves of 148 CTAs
+  auto fail = [&](int s) { dfs_model_destroy(m); return s; };
+
+  fold_conv1(w->conv[0], m->c1);
+  std::vector<float> b2, b3;
+  std::vector<uint16_t> p2 = pack_conv3x3_bf16(w->conv[1], 64, 32, b2);
+  std::vector<uint16_t> p3 = pack_conv3x3_bf16(w->conv[2], 128, 64, b3);
+  memcpy(m->b2, b2.data(), sizeof(m->b2));
+  memcpy(m->b3, b3.data(), sizeof(m->b3));
+  if ((st = dev_upload(m, &m->w2pack, p2)) != DFS_OK) return fail(st);
+  if ((st = dev_upload(m, &m->w3pack, p3)) != DFS_OK) return fail(st);
+  if ((st = dev_upload(m, &m->b2_dev, b2)) != DFS_OK) return fail(st);
+  if ((st = dev_upload(m, &m->b3_dev, b3)) != DFS_OK) return fail(st);
+  // classifier: [f][c] order of the time-sum buffer, 1/80 (mean over time, model.py:37) folded in
+  std::vector<float> fcw((size_t)kF * 128);
+  for (int f = 0; f < kF; ++f)
+    for (int c = 0; c < 128; ++c) fcw[(size_t)f * 128 + c] = (float)((double)w->fc_weight[(size_t)c * kF + f] / 80.0);
+  if ((st = dev_upload(m, &m->fcw_dev, fcw)) != DFS_OK) return fail(st);
+  m->fcb = w->fc_bias[0];
+
+  const int64_t ncols = (int64_t)m->chunk * kCols + 32;
+  m->act1 = ActBuf{nullptr, 4, 160 + 2, ncols};
+  m->act2 = ActBuf{nullptr, 8, 80 + 2, ncols};
+  if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->act1.ptr), m->act1.bytes(), true)) != DFS_OK) return fail(st);
+  if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->act2.ptr), m->act2.bytes(), true)) != DFS_OK) return fail(st);
+  if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->emb), (size_t)m->chunk * kF * 128 * 4, true)) != DFS_OK) return fail(st);
+  if ((st = make_act_tensor_map(&m->tmap1, m->act1, conv2_tc_window_rows())) != DFS_OK) return fail(st);
+  if ((st = make_act_tensor_map(&m->tmap2, m->act2, conv3_tc_window_rows())) != DFS_OK) return fail(st);
+  *out = m;
+  return DFS_OK;
+}
+
+static int check_feats(const dfs_features* f, const char* who) {
+  DFS_REQUIRE(f != nullptr, DFS_ERR_INVALID, "%s: features is NULL", who);
+  DFS_REQUIRE(f->n >= 0 && f->n < (1ll << 31), DFS_ERR_INVALID, "%s: n = %lld out of range", who, (long long)f->n);
+  DFS_REQUIRE(f->n == 0 || f->x != nullptr, DFS_ERR_INVALID, "%s: features pointer is NULL", who);
+  DFS_REQUIRE(f->stride_t > 0 && f->stride_f > 0 && (f->n <= 1 || f->stride_n > 0), DFS_ERR_INVALID, "%s: strides must be positive", who);
+  return DFS_OK;
+}
+
+extern "C" int dfs_cnn2d_score(dfs_model* m, const dfs_features* feats, float* out_dev, float* embedding_dev, int apply_sigmoid,
+                               void* stream_) {
+  DFS_REQUIRE(m && m->kind == KIND_CNN2D, DFS_ERR_INVALID, "dfs_cnn2d_score: not a CNN2D handle");
+  DFS_PROPAGATE(check_feats(feats, "dfs_cnn2d_score"));
+  DFS_REQUIRE(feats->n == 0 || out_dev, DFS_ERR_INVALID, "dfs_cnn2d_score: out_dev is NULL");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DFS_CUDA_CHECK(cudaSetDevice(m->device));
+  for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk) {
+    const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
+    const float* x = feats->x + i0 * feats->stride_n;
+    {
+      ProfScope ps(m, 0, stream);
+      DFS_PROPAGATE(launch_conv1(x, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->c1, nullptr, nullptr, false, m->act1, stream));
+    }
+    {
+      ProfScope ps(m, 1, stream);
+      if (m->conv_impl == 0) DFS_PROPAGATE(launch_cnn2d_conv2_tc(m->tmap1, m->w2pack, m->b2, nk, m->act2, m->num_sms, stream));
+      else DFS_PROPAGATE(launch_cnn2d_conv2_simt(m->act1, m->w2pack, m->b2_dev, nk, m->act2, stream));
+    }
+    {
+      ProfScope ps(m, 2, stream);
+      if (m->conv_impl == 0) DFS_PROPAGATE(launch_cnn2d_conv3_tc(m->tmap2, m->w3pack, m->b3, nk, m->emb, m->num_sms, stream));
+      else DFS_PROPAGATE(launch_cnn2d_conv3_simt(m->act2, m->w3pack, m->b3_dev, nk, m->emb, stream));
+    }
+    {
+      ProfScope ps(m, 3, stream);
+      DFS_PROPAGATE(launch_cnn2d_head(m->emb, m->fcw_dev, m->fcb, nk, apply_sigmoid, out_dev + i0, stream));
+    }
+    if (embedding_dev) DFS_PROPAGATE(launch_cnn2d_embedding_export(m->emb, nk, embedding_dev + i0 * (int64_t)kF * 128, stream));
+  }
+  return DFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// CNN1D / CAE (CUDA-core path): fold + repack to [tap][ci][co]
+// ------------------------------------------------------------------------------------------
+// conv weight (Co,Ci,taps) -> [tap][ci][co]
+static int make_simt_conv(dfs_model* m, const dfs_conv_bn& c, int co, int ci, int taps, SimtConv* out) {
+  std::vector<double> scale, shift;
+  bn_fold(c, co, scale, shift);
+  std::vector<float> w((size_t)taps * ci * co), b(co);
+  for (int o = 0; o < co; ++o) {
+    b[o] = (float)shift[o];
+    for (int i = 0; i < ci; ++i)
+      for (int k = 0; k < taps; ++k) w[((size_t)k * ci + i) * co + o] = (float)((double)c.weight[((size_t)o * ci + i) * taps + k] * scale[o]);
+  }
+  out->ci = ci;
+  out->co = co;
+  DFS_PROPAGATE(dev_upload(m, &out->w, w));
+  DFS_PROPAGATE(dev_upload(m, &out->b, b));
+  return DFS_OK;
+}
+// transposed-conv weight (Ci,Co,2,2) -> [a*2+b][ci][co]
+static int make_simt_convT(dfs_model* m, const dfs_conv_bn& c, int ci, int co, SimtConv* out) {
+  std::vector<double> scale, shift;
+  bn_fold(c, co, scale, shift);
+  std::vector<float> w((size_t)4 * ci * co), b(co);
+  for (int o = 0; o < co; ++o) {
+    b[o] = (float)shift[o];
+    for (int i = 0; i < ci; ++i)
+      for (int k = 0; k < 4; ++k) w[((size_t)k * ci + i) * co + o] = (float)((double)c.weight[((size_t)i * co + o) * 4 + k] * scale[o]);
+  }
+  out->ci = ci;
+  out->co = co;
+  DFS_PROPAGATE(dev_upload(m, &out->w, w));
+  DFS_PROPAGATE(dev_upload(m, &out->b, b));
+  return DFS_OK;
+}
+
+extern "C" int dfs_cnn1d_create(dfs_model** out, int device, const dfs_cnn1d_weights* w, int max_chunk) {
+  DFS_REQUIRE(out && w, DFS_ERR_INVALID, "dfs_cnn1d_create: NULL argument");
+  *out = nullptr;
+  DFS_REQUIRE(w->in_features == kF && w->base_channels == 32, DFS_ERR_UNSUPPORTED,
+              "CNN1D kernels are built for in_features=180, base_channels=32 (got %d, %d)", w->in_features, w->base_channels);
+  for (int i = 0; i < 3; ++i) DFS_REQUIRE(conv_ok(w->conv[i], true), DFS_ERR_INVALID, "dfs_cnn1d_create: conv[%d] has NULL tensors", i);
+  DFS_REQUIRE(w->fc_weight && w->fc_bias, DFS_ERR_INVALID, "dfs_cnn1d_create: classifier tensors are NULL");
+  dfs_model* m = new (std::nothrow) dfs_model();
+  DFS_REQUIRE(m, DFS_ERR_NOMEM, "out of host memory");
+  m->kind = KIND_CNN1D;
+  int st = model_common_init(m, device);
+  if (st != DFS_OK) { delete m; return st; }
+  m->chunk = max_chunk > 0 ? max_chunk : 256;
+  auto fail = [&](int s) { dfs_model_destroy(m); return s; };
+  const int ci[3] = {kF, 32, 64}, co[3] = {32, 64, 128};
+  for (int i = 0; i < 3; ++i)
+    if ((st = make_simt_conv(m, w->conv[i], co[i], ci[i], 3, &m->sc[i])) != DFS_OK) return fail(st);
+  std::vector<float> fcw(w->fc_weight, w->fc_weight + 128);
+  if ((st = dev_upload(m, &m->fcw_dev, fcw)) != DFS_OK) return fail(st);
+  m->fcb = w->fc_bias[0];
+  if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->work), cnn1d_simt_work_floats(m->chunk) * 4, false)) != DFS_OK) return fail(st);
+  *out = m;
+  return DFS_OK;
+}
+
+extern "C" int dfs_cnn1d_score(dfs_model* m, const dfs_features* feats, float* out_dev, int apply_sigmoid, void* stream_) {
+  DFS_REQUIRE(m && m->kind == KIND_CNN1D, DFS_ERR_INVALID, "dfs_cnn1d_score: not a CNN1D handle");
+  DFS_PROPAGATE(check_feats(feats, "dfs_cnn1d_score"));
+  DFS_REQUIRE(feats->n == 0 || out_dev, DFS_ERR_INVALID, "dfs_cnn1d_score: out_dev is NULL");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DFS_CUDA_CHECK(cudaSetDevice(m->device));
+  for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk) {
+    const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
+    DFS_PROPAGATE(launch_cnn1d_simt(feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->sc, m->fcw_dev,
+                                    m->fcb, apply_sigmoid, m->work, out_dev + i0, stream));
+  }
+  return DFS_OK;
+}
+
+extern "C" int dfs_cae_create(dfs_model** out, int device, const dfs_cae_weights* w, int max_chunk) {
+  DFS_REQUIRE(out && w, DFS_ERR_INVALID, "dfs_cae_create: NULL argument");
+  *out = nullptr;
+  DFS_REQUIRE(w->base_channels == 32, DFS_ERR_UNSUPPORTED, "CAE kernels are built for base_channels=32 (got %d)", w->base_channels);
+  for (int i = 0; i < 4; ++i) {
+    DFS_REQUIRE(conv_ok(w->enc[i], true), DFS_ERR_INVALID, "dfs_cae_create: enc[%d] has NULL tensors", i);
+    DFS_REQUIRE(conv_ok(w->dec[i], i < 3), DFS_ERR_INVALID, "dfs_cae_create: dec[%d] has NULL tensors", i);
+  }
+  DFS_REQUIRE((w->norm_mean == nullptr) == (w->norm_std == nullptr), DFS_ERR_INVALID, "dfs_cae_create: give both norm_mean and norm_std or neither");
+  dfs_model* m = new (std::nothrow) dfs_model();
+  DFS_REQUIRE(m, DFS_ERR_NOMEM, "out of host memory");
+  m->kind = KIND_CAE;
+  int st = model_common_init(m, device);
+  if (st != DFS_OK) { delete m; return st; }
+  m->chunk = max_chunk > 0 ? max_chunk : 64;
+  auto fail = [&](int s) { dfs_model_destroy(m); return s; };
+  const int eci[4] = {1, 32, 64, 128}, eco[4] = {32, 64, 128, 256};
+  for (int i = 0; i < 4; ++i)
+    if ((st = make_simt_conv(m, w->enc[i], eco[i], eci[i], 9, &m->sc[i])) != DFS_OK) return fail(st);
+  const int dci[4] = {256, 128, 64, 32}, dco[4] = {128, 64, 32, 1};
+  for (int i = 0; i < 4; ++i)
+    if ((st = make_simt_convT(m, w->dec[i], dci[i], dco[i], &m->sc[4 + i])) != DFS_OK) return fail(st);
+  m->final_bias = w->dec[3].bias[0];
+  if (w->norm_mean) {
+    std::vector<float> mean(w->norm_mean, w->norm_mean + kF), sd(w->norm_std, w->norm_std + kF);
+    if ((st = dev_upload(m, &m->norm_mean, mean)) != DFS_OK) return fail(st);
+    if ((st = dev_upload(m, &m->norm_std, sd)) != DFS_OK) return fail(st);
+  }
+  if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->work), cae_simt_work_floats(m->chunk) * 4, false)) != DFS_OK) return fail(st);
+  *out = m;
+  return DFS_OK;
+}
+
+static int cae_run(dfs_model* m, const dfs_features* feats, int apply_normalizer, float* mse_dev, float* recon_dev, float* latent_dev,
+                   cudaStream_t stream) {
+  DFS_REQUIRE(!apply_normalizer || m->norm_mean, DFS_ERR_INVALID, "CAE handle was created without normaliser statistics");
+  DFS_CUDA_CHECK(cudaSetDevice(m->device));
+  const float* mean = apply_normalizer ? m->norm_mean : nullptr;
+  const float* sd = apply_normalizer ? m->norm_std : nullptr;
+  for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk) {
+    const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
+    DFS_PROPAGATE(launch_cae_simt(feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->sc, m->sc + 4,
+                                  m->final_bias, mean, sd, m->work, mse_dev ? mse_dev + i0 : nullptr,
+                                  recon_dev ? recon_dev + i0 * (int64_t)kT * kF : nullptr,
+                                  latent_dev ? latent_dev + i0 * (int64_t)256 * 20 * 11 : nullptr, stream));
+  }
+  return DFS_OK;
+}
+
+extern "C" int dfs_cae_score(dfs_model* m, const dfs_features* feats, int apply_normalizer, float* mse_dev, void* stream_) {
+  DFS_REQUIRE(m && m->kind == KIND_CAE, DFS_ERR_INVALID, "dfs_cae_score: not a CAE handle");
+  DFS_PROPAGATE(check_feats(feats, "dfs_cae_score"));
+  DFS_REQUIRE(feats->n == 0 || mse_dev, DFS_ERR_INVALID, "dfs_cae_score: mse_dev is NULL");
+  return cae_run(m, feats, apply_normalizer, mse_dev, nullptr, nullptr, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int dfs_cae_forward(dfs_model* m, const dfs_features* feats, float* recon_dev, float* latent_dev, void* stream_) {
+  DFS_REQUIRE(m && m->kind == KIND_CAE, DFS_ERR_INVALID, "dfs_cae_forward: not a CAE handle");
+  DFS_PROPAGATE(check_feats(feats, "dfs_cae_forward"));
+  return cae_run(m, feats, 0, nullptr, recon_dev, latent_dev, static_cast<cudaStream_t>(stream_));
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer pipeline: H2D of chunk k+1 (copy stream) overlaps the kernels of chunk k
+// ------------------------------------------------------------------------------------------
+extern "C" int dfs_score_host(dfs_model* m, const dfs_features* feats, int flag, float* out_host, void* stream_) {
+  DFS_REQUIRE(m, DFS_ERR_INVALID, "dfs_score_host: model is NULL");
+  DFS_PROPAGATE(check_feats(feats, "dfs_score_host"));
+  DFS_REQUIRE(feats->n == 0 || out_host, DFS_ERR_INVALID, "dfs_score_host: out_host is NULL");
+  const int64_t per_utt = (int64_t)kT * kF;
+  const bool dense = (feats->stride_f == 1 && feats->stride_t == kF) || (feats->stride_t == 1 && feats->stride_f == kT);
+  DFS_REQUIRE(dense && (feats->n <= 1 || feats->stride_n == per_utt), DFS_ERR_UNSUPPORTED,
+              "dfs_score_host: each utterance must be one dense 321x180 (or 180x321) block, utterances back to back");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DFS_CUDA_CHECK(cudaSetDevice(m->device));
+  DFS_PROPAGATE(model_stage_init(m));
+  int k = 0;
+  for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk, ++k) {
+    const int b = k & 1;
+    const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
+    if (k >= 2) DFS_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_done[b], 0));
+    DFS_CUDA_CHECK(cudaMemcpyAsync(m->stage_in[b], feats->x + i0 * per_utt, (size_t)nk * per_utt * 4, cudaMemcpyHostToDevice, m->copy_stream));
+    DFS_CUDA_CHECK(cudaEventRecord(m->ev_in[b], m->copy_stream));
+    DFS_CUDA_CHECK(cudaStreamWaitEvent(stream, m->ev_in[b], 0));
+    dfs_features dv{m->stage_in[b], nk, per_utt, feats->stride_t, feats->stride_f};
+    int st;
+    if (m->kind == KIND_CNN2D) st = dfs_cnn2d_score(m, &dv, m->stage_out[b], nullptr, flag, stream);
+    else if (m->kind == KIND_CNN1D) st = dfs_cnn1d_score(m, &dv, m->stage_out[b], flag, stream);
+    else st = dfs_cae_score(m, &dv, flag, m->stage_out[b], stream);
+    DFS_PROPAGATE(st);
+    DFS_CUDA_CHECK(cudaMemcpyAsync(out_host + i0, m->stage_out[b], (size_t)nk * 4, cudaMemcpyDeviceToHost, stream));
+    DFS_CUDA_CHECK(cudaEventRecord(m->ev_done[b], stream));
+  }
+  DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return DFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// metric / blend / synthetic / probes: thin forwards
+// ------------------------------------------------------------------------------------------
+extern "C" int dfs_blend_f64(const double* const* scores, int m, const double* weights, const int* minmax, double divisor, int64_t n,
+                             double* out_dev, void* stream) {
+  DFS_REQUIRE(divisor != 0.0, DFS_ERR_INVALID, "dfs_blend_f64: divisor is 0");
+  return blend_device(scores, m, weights, minmax, divisor, n, out_dev, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dfs_widen_f32_f64(const float* in_dev, int64_t n, double* out_dev, void* stream) {
+  return widen_device(in_dev, n, out_dev, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dfs_eer(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, dfs_eer_result* result_host,
+                       uint32_t* perm_dev, void* sorted_dev, void* stream) {
+  return eer_device(scores_dev, key_bytes, labels_dev, n, result_host, perm_dev, sorted_dev, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,
+                             int64_t* out4_host, void* stream) {
+  return confusion_device(scores_dev, key_bytes, labels_dev, n, threshold, out4_host, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dfs_fill_features(float* out_dev, int64_t n, int64_t first_utt, uint64_t seed, float std_, void* stream) {
+  return fill_features_device(out_dev, n, first_utt, seed, std_, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dfs_probe_umma(const uint16_t* a_dev, const uint16_t* b_dev, int rows_a, int n, int k, int row_shift, int group_rows,
+                              float* out_dev, void* stream) {
+  return probe_umma(a_dev, b_dev, rows_a, n, k, row_shift, group_rows, out_dev, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dfs_probe_tma_window(const uint16_t* act_dev, int planes, int rs, int64_t ncols, int wrows, int row0, int col0,
+                                    uint16_t* out_dev, void* stream) {
+  return probe_tma_window(act_dev, planes, rs, ncols, wrows, row0, col0, out_dev, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,70 @@
+// kernels.h -- host-callable launchers shared between the .cu translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dfs_b200.h"
+#include "layout.cuh"
+
+namespace dfs {
+
+// ---- conv_tc.cu (tcgen05 implicit GEMM) ----
+int make_act_tensor_map(CUtensorMap* out, const ActBuf& a, int wrows);
+int conv2_tc_window_rows();
+int conv3_tc_window_rows();
+int launch_cnn2d_conv2_tc(const CUtensorMap& tmap_act1, const uint16_t* wpack, const float* bias, int n_utts, ActBuf act2,
+                          int num_sms, cudaStream_t stream);
+int launch_cnn2d_conv3_tc(const CUtensorMap& tmap_act2, const uint16_t* wpack, const float* bias, int n_utts, float* emb,
+                          int num_sms, cudaStream_t stream);
+
+// ---- cnn2d.cu (CUDA-core stages of the 2D-CNN) ----
+struct Conv1Weights {
+  float w[32 * 9];  // folded, [co][kh][kw]
+  float b[32];
+};
+// conv1 + BN + ReLU + AvgPool (2,1) [or (2,2) for the CAE encoder] -> FT8 bf16.
+// x element (i,t,f) at x[i*sn + t*st + f*sf]; optional per-feature normaliser (mean, 1/std) applied first.
+int launch_conv1(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const Conv1Weights& w, const float* norm_mean,
+                 const float* norm_std, bool pool_f, ActBuf out, cudaStream_t stream);
+// debug cross-check of the tensor-core path: same inputs / packed weights / outputs, CUDA cores only
+int launch_cnn2d_conv2_simt(ActBuf act1, const uint16_t* wpack, const float* bias_dev, int n_utts, ActBuf act2, cudaStream_t stream);
+int launch_cnn2d_conv3_simt(ActBuf act2, const uint16_t* wpack, const float* bias_dev, int n_utts, float* emb, cudaStream_t stream);
+// logits[n] = fc_b + sum_{f,c} emb[n][f][c] * wfc[f][c]  (wfc already carries 1/T); optional sigmoid
+int launch_cnn2d_head(const float* emb, const float* wfc, float fcb, int n_utts, int apply_sigmoid, float* out, cudaStream_t stream);
+// embedding[n][c*180+f] = emb[n][f][c] / 80   (src/model.py:37-38 flatten order)
+int launch_cnn2d_embedding_export(const float* emb, int n_utts, float* embedding, cudaStream_t stream);
+
+// ---- simt_models.cu (CUDA-core CNN1D and CAE) ----
+struct SimtConv {        // BN-folded fp32 weights on device, re-packed [tap][ci][co] (co fastest)
+  float* w = nullptr;
+  float* b = nullptr;    // [co] folded bias
+  int ci = 0, co = 0;
+};
+int launch_cnn1d_simt(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const SimtConv* conv3, const float* fcw,
+                      float fcb, int apply_sigmoid, float* work, float* out, cudaStream_t stream);
+size_t cnn1d_simt_work_floats(int n_utts);
+int launch_cae_simt(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const SimtConv* enc4, const SimtConv* dec4,
+                    float final_bias, const float* norm_mean, const float* norm_std, float* work, float* mse_out, float* recon_out,
+                    float* latent_out, cudaStream_t stream);
+size_t cae_simt_work_floats(int n_utts);
+
+// ---- eer.cu ----
+int eer_device(const void* scores, int key_bytes, const uint8_t* labels, int64_t n, dfs_eer_result* result_host, uint32_t* perm,
+               void* sorted, cudaStream_t stream);
+int confusion_device(const void* scores, int key_bytes, const uint8_t* labels, int64_t n, double thr, int64_t* out4_host,
+                     cudaStream_t stream);
+int blend_device(const double* const* scores, int m, const double* weights, const int* minmax, double divisor, int64_t n, double* out,
+                 cudaStream_t stream);
+int widen_device(const float* in, int64_t n, double* out, cudaStream_t stream);
+
+// ---- synth.cu ----
+int fill_features_device(float* out, int64_t n, int64_t first_utt, uint64_t seed, float std, cudaStream_t stream);
+
+// ---- probe.cu ----
+int probe_umma(const uint16_t* a, const uint16_t* b, int rows_a, int n, int k, int row_shift, int group_rows, float* out,
+               cudaStream_t stream);
+int probe_tma_window(const uint16_t* act, int planes, int RS, int64_t ncols, int wrows, int row0, int col0, uint16_t* out,
+                     cudaStream_t stream);
+
+}  // namespace dfs

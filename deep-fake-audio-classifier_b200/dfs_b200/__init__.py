@@ -1,0 +1,11 @@
+"""dfs_b200 -- B200-native scoring engine for the Deep-Fake-Audio-Classifier hot path.
+
+Host side only (ctypes over libdfs_b200.so); see DESIGN.md for the path and its boundary.
+"""
+from . import _native  # noqa: F401
+from .engine import CaeScorer, Cnn1dScorer, Cnn2dScorer, fill_features  # noqa: F401
+from .metrics import (blend, calculate_eer, confusion_at_threshold, eer_details, ensemble_mean,  # noqa: F401
+                      hybrid_blend, normalise_01)
+
+__all__ = ["Cnn2dScorer", "Cnn1dScorer", "CaeScorer", "fill_features", "calculate_eer", "confusion_at_threshold",
+           "eer_details", "normalise_01", "hybrid_blend", "ensemble_mean", "blend"]

@@ -1,0 +1,247 @@
+"""Host side of the scoring engine: state dicts in, device pointers across the C ABI, scores out.
+
+PyTorch is used for device memory, streams and (in bench.py) torch.distributed only; every
+arithmetic step of the scoring path runs in libdfs_b200.so.  Mirrors, per scorer, the reference's
+batch loops (src/predict.py:100-111, src/predict_hybrid.py:52-78) and ``forward`` signatures.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+T_FRAMES, N_FEATS = N.T_FRAMES, N.N_FEATS
+
+
+def _np32(v):
+    """state-dict value (numpy or torch, any device) -> contiguous fp32 numpy array."""
+    if hasattr(v, "detach"):
+        v = v.detach().to("cpu").numpy()
+    return np.ascontiguousarray(np.asarray(v), dtype=np.float32)
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _conv_bn(sd, conv_key, bn_key, keep):
+    w, b = _np32(sd[conv_key + ".weight"]), _np32(sd[conv_key + ".bias"])
+    keep += [w, b]
+    c = N.ConvBn()
+    c.weight, c.bias = _fptr(w), _fptr(b)
+    if bn_key is not None:
+        arrs = [_np32(sd[f"{bn_key}.{k}"]) for k in ("weight", "bias", "running_mean", "running_var")]
+        keep += arrs
+        c.bn_weight, c.bn_bias, c.bn_mean, c.bn_var = (_fptr(a) for a in arrs)
+    return c
+
+
+def _require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("dfs_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _features_struct(x):
+    """torch CUDA fp32 tensor (B, 321, 180) with arbitrary strides -> dfs_features."""
+    if x.dim() != 3 or x.shape[1] != T_FRAMES or x.shape[2] != N_FEATS:
+        raise ValueError(f"expected features of shape (B, {T_FRAMES}, {N_FEATS}), got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("dfs_b200 scoring takes CUDA tensors (no CPU fallback); use score_host() for host buffers")
+    if x.dtype != _require_cuda().float32:
+        x = x.float()
+    sn, st, sf = x.stride()
+    if min(st, sf) <= 0 or (x.shape[0] > 1 and sn <= 0):
+        x = x.contiguous()
+        sn, st, sf = x.stride()
+    f = N.Features(x.data_ptr(), x.shape[0], sn, st, sf)
+    return f, x
+
+
+def _stream_ptr(torch, device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _Scorer:
+    KIND = ""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        self.device_index = 0
+        self._lib = N.load()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.dfs_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        N.check(self._lib.dfs_model_set_option(self._h, key.encode(), int(value)), "dfs_model_set_option")
+
+    def profile(self, n_ids: int = 4, reset: bool = True):
+        """(ms per kernel id, launches per kernel id) since the last reset; needs set_option('profile', 1)."""
+        ms = (C.c_double * n_ids)()
+        cnt = (C.c_int64 * n_ids)()
+        N.check(self._lib.dfs_model_profile(self._h, ms, cnt, n_ids, int(reset)), "dfs_model_profile")
+        return list(ms), list(cnt)
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self._lib.dfs_model_workspace_bytes(self._h))
+
+    def _device(self, torch):
+        return torch.device("cuda", self.device_index)
+
+    # -- host buffers: H2D / D2H inside (the e2e path of bench.py) --
+    def score_host(self, feats, flag: int = 1):
+        """feats: pinned torch CPU tensor or numpy array (B,321,180) fp32, dense. Returns numpy fp32 (B,)."""
+        torch = _require_cuda()
+        if hasattr(feats, "numpy") and not isinstance(feats, np.ndarray):
+            t = feats
+            ptr, shape, strides = t.data_ptr(), tuple(t.shape), t.stride()
+        else:
+            a = np.asarray(feats, dtype=np.float32)
+            ptr, shape, strides = a.ctypes.data, a.shape, tuple(s // 4 for s in a.strides)
+            t = a
+        if len(shape) != 3 or shape[1] != T_FRAMES or shape[2] != N_FEATS:
+            raise ValueError(f"expected features of shape (B, {T_FRAMES}, {N_FEATS}), got {shape}")
+        out = torch.empty(shape[0], dtype=torch.float32, pin_memory=True)
+        f = N.Features(ptr, shape[0], strides[0], strides[1], strides[2])
+        with torch.cuda.device(self.device_index):
+            N.check(self._lib.dfs_score_host(self._h, C.byref(f), int(flag), C.c_void_p(out.data_ptr()),
+                                             _stream_ptr(torch, self._device(torch))), "dfs_score_host")
+        del t
+        return out.numpy()
+
+
+class Cnn2dScorer(_Scorer):
+    """CNN2D (src/model.py:12-42) on the tcgen05 path."""
+    KIND = "cnn2d"
+
+    def __init__(self, state_dict, device: int = 0, max_chunk: int = 0):
+        super().__init__()
+        _require_cuda()
+        keep = []
+        w = N.Cnn2dWeights()
+        w.base_channels = int(np.asarray(_np32(state_dict["conv.0.weight"])).shape[0])
+        fcw, fcb = _np32(state_dict["classifier.weight"]), _np32(state_dict["classifier.bias"])
+        w.in_features = int(fcw.shape[1] // max(4 * w.base_channels, 1))
+        for i, (ck, bk) in enumerate((("conv.0", "conv.1"), ("conv.5", "conv.6"), ("conv.10", "conv.11"))):
+            w.conv[i] = _conv_bn(state_dict, ck, bk, keep)
+        keep += [fcw, fcb]
+        w.fc_weight, w.fc_bias = _fptr(fcw), _fptr(fcb)
+        self.device_index = int(device)
+        N.check(self._lib.dfs_cnn2d_create(C.byref(self._h), int(device), C.byref(w), int(max_chunk)), "dfs_cnn2d_create")
+
+    def score(self, x, apply_sigmoid: bool = False, return_embedding: bool = False):
+        """x: CUDA fp32 (B,321,180), any strides.  Returns (B,) logits/scores [, (B,23040) embedding]."""
+        torch = _require_cuda()
+        f, x = _features_struct(x)
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        emb = torch.empty((x.shape[0], 128 * N_FEATS), dtype=torch.float32, device=x.device) if return_embedding else None
+        with torch.cuda.device(x.device):
+            N.check(self._lib.dfs_cnn2d_score(self._h, C.byref(f), C.c_void_p(out.data_ptr()),
+                                              C.c_void_p(emb.data_ptr()) if emb is not None else None,
+                                              int(bool(apply_sigmoid)), _stream_ptr(torch, x.device)), "dfs_cnn2d_score")
+        return (out, emb) if return_embedding else out
+
+
+class Cnn1dScorer(_Scorer):
+    """CNN1D (src/model_cnn1d.py:12-46)."""
+    KIND = "cnn1d"
+
+    def __init__(self, state_dict, device: int = 0, max_chunk: int = 0):
+        super().__init__()
+        _require_cuda()
+        keep = []
+        w = N.Cnn1dWeights()
+        w0 = _np32(state_dict["conv.0.weight"])
+        w.base_channels, w.in_features = int(w0.shape[0]), int(w0.shape[1])
+        for i, (ck, bk) in enumerate((("conv.0", "conv.1"), ("conv.4", "conv.5"), ("conv.8", "conv.9"))):
+            w.conv[i] = _conv_bn(state_dict, ck, bk, keep)
+        fcw, fcb = _np32(state_dict["classifier.weight"]), _np32(state_dict["classifier.bias"])
+        keep += [fcw, fcb]
+        w.fc_weight, w.fc_bias = _fptr(fcw), _fptr(fcb)
+        self.device_index = int(device)
+        N.check(self._lib.dfs_cnn1d_create(C.byref(self._h), int(device), C.byref(w), int(max_chunk)), "dfs_cnn1d_create")
+
+    def score(self, x, apply_sigmoid: bool = False):
+        torch = _require_cuda()
+        f, x = _features_struct(x)
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            N.check(self._lib.dfs_cnn1d_score(self._h, C.byref(f), C.c_void_p(out.data_ptr()), int(bool(apply_sigmoid)),
+                                              _stream_ptr(torch, x.device)), "dfs_cnn1d_score")
+        return out
+
+
+class CaeScorer(_Scorer):
+    """ConvAutoencoder reconstruction-MSE scorer (src/model_cae.py:23-125 + src/predict_hybrid.py:66-78).
+    ``mean``/``std`` are the FeatureNormalizer statistics (src/dataset_cae.py:18-52), optional."""
+    KIND = "cae"
+
+    def __init__(self, state_dict, mean=None, std=None, device: int = 0, max_chunk: int = 0):
+        super().__init__()
+        _require_cuda()
+        keep = []
+        w = N.CaeWeights()
+        w.base_channels = int(_np32(state_dict["encoder.0.weight"]).shape[0])
+        for i, (ck, bk) in enumerate((("encoder.0", "encoder.1"), ("encoder.4", "encoder.5"), ("encoder.8", "encoder.9"),
+                                      ("encoder.12", "encoder.13"))):
+            w.enc[i] = _conv_bn(state_dict, ck, bk, keep)
+        for i, (ck, bk) in enumerate((("decoder.0", "decoder.1"), ("decoder.3", "decoder.4"), ("decoder.6", "decoder.7"),
+                                      ("decoder.9", None))):
+            w.dec[i] = _conv_bn(state_dict, ck, bk, keep)
+        self.has_normalizer = mean is not None
+        if mean is not None:
+            m, s = _np32(mean), _np32(std)
+            keep += [m, s]
+            w.norm_mean, w.norm_std = _fptr(m), _fptr(s)
+        self.device_index = int(device)
+        N.check(self._lib.dfs_cae_create(C.byref(self._h), int(device), C.byref(w), int(max_chunk)), "dfs_cae_create")
+
+    def score(self, x, apply_normalizer: bool | None = None):
+        """Per-utterance MSE between the (normalised) input and its reconstruction; recon never hits HBM."""
+        torch = _require_cuda()
+        if apply_normalizer is None:
+            apply_normalizer = self.has_normalizer
+        f, x = _features_struct(x)
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            N.check(self._lib.dfs_cae_score(self._h, C.byref(f), int(bool(apply_normalizer)), C.c_void_p(out.data_ptr()),
+                                            _stream_ptr(torch, x.device)), "dfs_cae_score")
+        return out
+
+    def forward(self, x):
+        """Compat path of ConvAutoencoder.forward: (recon (B,321,180), latent (B,256,20,11)); x already normalised."""
+        torch = _require_cuda()
+        f, x = _features_struct(x)
+        recon = torch.empty((x.shape[0], T_FRAMES, N_FEATS), dtype=torch.float32, device=x.device)
+        latent = torch.empty((x.shape[0], 256, 20, 11), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            N.check(self._lib.dfs_cae_forward(self._h, C.byref(f), C.c_void_p(recon.data_ptr()), C.c_void_p(latent.data_ptr()),
+                                              _stream_ptr(torch, x.device)), "dfs_cae_forward")
+        return recon, latent
+
+    def score_host(self, feats, flag: int | None = None):
+        return super().score_host(feats, int(self.has_normalizer if flag is None else flag))
+
+
+def fill_features(n: int, first_utt: int = 0, seed: int = 1234, std: float = 3.2, device: int = 0):
+    """Device-generated synthetic [n,321,180] fp32 maps (csrc/synth.cu)."""
+    torch = _require_cuda()
+    dev = torch.device("cuda", device)
+    out = torch.empty((n, T_FRAMES, N_FEATS), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.load().dfs_fill_features(C.c_void_p(out.data_ptr()), n, first_utt, seed, std, _stream_ptr(torch, dev)),
+                "dfs_fill_features")
+    return out

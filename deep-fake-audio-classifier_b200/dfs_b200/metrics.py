@@ -1,0 +1,160 @@
+"""Device implementations of the metric half of the hot path, with the reference's signatures:
+
+    calculate_eer(scores, labels) -> (eer, threshold)              scripts/evaluation.py:7-39
+    confusion_at_threshold(scores, labels, thr) -> (tp,fp,tn,fn,far,frr)   scripts/evaluation.py:42-56
+    normalise_01(scores)                                             src/predict_hybrid.py:81-85
+    hybrid_blend(sup, cae, alpha)                                    src/predict_hybrid.py:149-151
+    ensemble_mean(all_scores)                                        src/ensemble.py:121
+
+Inputs may be lists, numpy arrays, or torch tensors (CPU or CUDA); fp32 arrays are sorted as fp32
+keys, everything else as float64, exactly like ``np.array(scores)`` would type them.  Tie order is
+stable by original index (DESIGN.md "EER tie contract").
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("dfs_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _stream(torch, dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _scores_to_device(scores, device=None):
+    """-> contiguous CUDA tensor of dtype float32 or float64 (numpy's typing of the input)."""
+    torch = _torch()
+    if isinstance(scores, torch.Tensor):
+        t = scores.detach()
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.double()
+    else:
+        a = np.array(scores)                       # scripts/evaluation.py:8
+        if a.dtype != np.float32:
+            a = a.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    dev = device if device is not None else (t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+    return t.to(dev).contiguous().reshape(-1)
+
+
+def _labels_to_device(labels, dev):
+    torch = _torch()
+    if isinstance(labels, torch.Tensor):
+        t = labels.detach().to(dev)
+        return (t != 0).to(torch.uint8).contiguous().reshape(-1), t
+    a = np.array(labels)
+    return torch.from_numpy(np.ascontiguousarray((a != 0).astype(np.uint8))).to(dev).reshape(-1), a
+
+
+def eer_details(scores, labels, want_perm=False, want_sorted=False, device=None):
+    """dict(eer, threshold, eer_idx, n_bonafide, n_spoof[, perm][, sorted]) -- eer_idx = -1 on the
+    single-class early-out (scripts/evaluation.py:18-19)."""
+    torch = _torch()
+    s = _scores_to_device(scores, device)
+    lab, _ = _labels_to_device(labels, s.device)
+    if s.numel() != lab.numel():
+        raise ValueError("scores and labels must have the same length")
+    n = s.numel()
+    if n == 0:
+        raise ValueError("calculate_eer needs at least one score")
+    res = N.EerResult()
+    perm = torch.empty(n, dtype=torch.int32, device=s.device) if want_perm else None
+    srt = torch.empty_like(s) if want_sorted else None
+    with torch.cuda.device(s.device):
+        N.check(N.load().dfs_eer(C.c_void_p(s.data_ptr()), s.element_size(), C.c_void_p(lab.data_ptr()), n, C.byref(res),
+                                 C.c_void_p(perm.data_ptr()) if perm is not None else None,
+                                 C.c_void_p(srt.data_ptr()) if srt is not None else None, _stream(torch, s.device)), "dfs_eer")
+    out = dict(eer=float(res.eer), threshold=float(res.threshold), eer_idx=int(res.eer_idx),
+               n_bonafide=int(res.n_bonafide), n_spoof=int(res.n_spoof))
+    if want_perm:
+        out["perm"] = perm
+    if want_sorted:
+        out["sorted"] = srt
+    return out
+
+
+def calculate_eer(scores, labels):
+    d = eer_details(scores, labels)
+    return d["eer"], d["threshold"]
+
+
+def confusion_at_threshold(scores, labels, threshold):
+    torch = _torch()
+    s = _scores_to_device(scores)
+    lab_u8, lab_raw = _labels_to_device(labels, s.device)
+    # the reference counts label == 1 / label == 0 after .astype(int); keep other values out of both classes
+    if isinstance(lab_raw, np.ndarray):
+        li = lab_raw.astype(int)
+        lab_dev = torch.from_numpy(np.where(li == 1, 1, np.where(li == 0, 0, 2)).astype(np.uint8)).to(s.device)
+    else:
+        li = lab_raw.to(torch.int64)
+        lab_dev = torch.where(li == 1, 1, torch.where(li == 0, 0, 2)).to(torch.uint8)
+    out4 = (C.c_int64 * 4)()
+    with torch.cuda.device(s.device):
+        N.check(N.load().dfs_confusion(C.c_void_p(s.data_ptr()), s.element_size(), C.c_void_p(lab_dev.data_ptr()), s.numel(),
+                                       float(threshold), out4, _stream(torch, s.device)), "dfs_confusion")
+    tp, fp, tn, fn = (int(v) for v in out4)
+    far = fp / (fp + tn) if (fp + tn) > 0 else 0.0
+    frr = fn / (tp + fn) if (tp + fn) > 0 else 0.0
+    return tp, fp, tn, fn, float(far), float(frr)
+
+
+def _f64_device(x, dev=None):
+    torch = _torch()
+    if isinstance(x, torch.Tensor):
+        t = x.detach()
+        d = dev if dev is not None else (t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+        t = t.to(d)
+        if t.dtype == torch.float32:            # fp32 model scores -> float64 column, on the device
+            out = torch.empty(t.numel(), dtype=torch.float64, device=d)
+            t = t.contiguous().reshape(-1)
+            with torch.cuda.device(d):
+                N.check(N.load().dfs_widen_f32_f64(C.c_void_p(t.data_ptr()), t.numel(), C.c_void_p(out.data_ptr()), _stream(torch, d)),
+                        "dfs_widen_f32_f64")
+            return out
+        return t.double().contiguous().reshape(-1)
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64)).reshape(-1)
+    d = dev if dev is not None else torch.device("cuda", torch.cuda.current_device())
+    return torch.from_numpy(a).to(d)
+
+
+def blend(score_list, weights, minmax_flags, divisor=1.0, as_numpy=True):
+    """out = (sum_m weights[m] * (minmax? normalise_01(s_m) : s_m)) / divisor in float64 on the device."""
+    torch = _torch()
+    if not (len(score_list) == len(weights) == len(minmax_flags)) or not 1 <= len(score_list) <= 8:
+        raise ValueError("blend takes 1..8 score vectors with one weight and one min-max flag each")
+    ts = [_f64_device(score_list[0])]
+    ts += [_f64_device(s, ts[0].device) for s in score_list[1:]]
+    n = ts[0].numel()
+    if any(t.numel() != n for t in ts):
+        raise ValueError("all score vectors must have the same length")
+    out = torch.empty(n, dtype=torch.float64, device=ts[0].device)
+    m = len(ts)
+    ptrs = (C.c_void_p * m)(*[t.data_ptr() for t in ts])
+    w = (C.c_double * m)(*[float(v) for v in weights])
+    f = (C.c_int * m)(*[int(bool(v)) for v in minmax_flags])
+    with torch.cuda.device(out.device):
+        N.check(N.load().dfs_blend_f64(ptrs, m, w, f, float(divisor), n, C.c_void_p(out.data_ptr()), _stream(torch, out.device)),
+                "dfs_blend_f64")
+    return out.cpu().numpy() if as_numpy else out
+
+
+def normalise_01(scores, as_numpy=True):
+    return blend([scores], [1.0], [1], 1.0, as_numpy)
+
+
+def hybrid_blend(sup_scores, cae_scores, alpha=0.80, as_numpy=True):
+    return blend([sup_scores, cae_scores], [alpha, 1 - alpha], [1, 1], 1.0, as_numpy)
+
+
+def ensemble_mean(all_scores, as_numpy=True):
+    return blend(list(all_scores), [1.0] * len(all_scores), [0] * len(all_scores), float(len(all_scores)), as_numpy)

@@ -1,0 +1,189 @@
+/* dfs_b200.h -- C ABI of the B200-native scoring engine (libdfs_b200.so).
+ *
+ * The reference (kingdomseed/Deep-Fake-Audio-Classifier) is pure Python and has no FFI; its
+ * seams for this path are Python call signatures.  Each entry point below
+ * names the reference interface it stands behind.  The Python host (dfs_b200/_native.py,
+ * ctypes) is the only caller; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - plain C types only: pointers, sizes, ints.  No torch / C++ types cross this boundary.
+ *  - every call returns an int status (DFS_OK = 0, < 0 = error); dfs_last_error() gives a
+ *    thread-local message.  No exceptions, no callbacks.
+ *  - "dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensors);
+ *    "host" pointers are host memory (pinned for the *_host entry points to overlap copies).
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ *    Calls that return results through host pointers synchronise that stream before returning.
+ *  - a dfs_model owns its folded/re-packed weights and its activation workspace; it is bound
+ *    to one device and is not thread-safe (one handle per device per thread, like the
+ *    reference's single-threaded host loop, SURVEY.md §8b "Threading").
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *    DFS_ERR_CUDA.
+ */
+#ifndef DFS_B200_H
+#define DFS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFS_OK 0
+#define DFS_ERR_INVALID (-1)     /* bad argument (NULL, negative size, unsupported shape) */
+#define DFS_ERR_CUDA (-2)        /* CUDA runtime / driver error, message has the detail   */
+#define DFS_ERR_UNSUPPORTED (-3) /* architecture parameters the kernels are not built for */
+#define DFS_ERR_NOMEM (-4)
+
+#define DFS_T_FRAMES 321 /* time frames of an utterance map (README.md:76 of the reference) */
+#define DFS_N_FEATS 180  /* LFCC + delta + delta-delta                                        */
+
+typedef struct dfs_model dfs_model; /* opaque */
+
+/* One Conv(+BatchNorm) block as the reference state_dict stores it (fp32, HOST pointers,
+ * un-folded).  bn_* may all be NULL for a conv without BatchNorm (CAE decoder.9).
+ * BN is folded in double precision at create time:  w' = w*g/sqrt(var+1e-5),
+ * b' = (b-mean)*g/sqrt(var+1e-5)+beta.                                                    */
+typedef struct {
+  const float* weight; /* Conv2d (Co,Ci,3,3) | Conv1d (Co,Ci,3) | ConvTranspose2d (Ci,Co,2,2) */
+  const float* bias;   /* (Co)                                                               */
+  const float* bn_weight;
+  const float* bn_bias;
+  const float* bn_mean;
+  const float* bn_var;
+} dfs_conv_bn;
+
+/* src/model.py:12-31  CNN2D(in_features=180, base_channels=32, num_classes=1) */
+typedef struct {
+  int in_features;    /* must be 180 */
+  int base_channels;  /* must be 32  */
+  dfs_conv_bn conv[3];    /* conv.{0,5,10} + BN conv.{1,6,11}        */
+  const float* fc_weight; /* classifier.weight (1, 128*in_features)  */
+  const float* fc_bias;   /* classifier.bias (1)                     */
+} dfs_cnn2d_weights;
+
+/* src/model_cnn1d.py:12-35  CNN1D(in_features=180, base_channels=32, num_classes=1) */
+typedef struct {
+  int in_features;
+  int base_channels;
+  dfs_conv_bn conv[3];    /* conv.{0,4,8} + BN conv.{1,5,9} */
+  const float* fc_weight; /* (1, 128) */
+  const float* fc_bias;
+} dfs_cnn1d_weights;
+
+/* src/model_cae.py:23-81  ConvAutoencoder(base_channels=32) (+ FeatureNormalizer stats,
+ * src/dataset_cae.py:18-52; NULL = input is already normalised) */
+typedef struct {
+  int base_channels;
+  dfs_conv_bn enc[4];     /* encoder.{0,4,8,12} + BN encoder.{1,5,9,13}                   */
+  dfs_conv_bn dec[4];     /* decoder.{0,3,6,9} + BN decoder.{1,4,7}; dec[3] has no BN      */
+  const float* norm_mean; /* (180) or NULL */
+  const float* norm_std;  /* (180) or NULL */
+} dfs_cae_weights;
+
+/* Strided view of the feature maps: element (i, t, f) is at x[i*stride_n + t*stride_t + f*stride_f]
+ * (strides in ELEMENTS).  The reference hands its models a transposed, non-contiguous
+ * (B,321,180) view of (B,180,321) storage (src/predict.py:103-105): stride_t = 1,
+ * stride_f = 321 there; the benchmark layout is contiguous [N,321,180].                   */
+typedef struct {
+  const float* x;
+  int64_t n;
+  int64_t stride_n, stride_t, stride_f;
+} dfs_features;
+
+int dfs_version(void);
+const char* dfs_last_error(void);
+/* number of kernels this library has launched in the calling process (bench "gpu_launches") */
+int64_t dfs_launch_count(void);
+
+/* ---- model handles ------------------------------------------------------------------- */
+/* `max_chunk` = utterances processed per internal pass (workspace is sized for it); 0 = default. */
+int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_weights* w, int max_chunk);
+int dfs_cnn1d_create(dfs_model** out, int device, const dfs_cnn1d_weights* w, int max_chunk);
+int dfs_cae_create(dfs_model** out, int device, const dfs_cae_weights* w, int max_chunk);
+int dfs_model_destroy(dfs_model* m);
+/* options: "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = CUDA-core direct conv (debug
+ * cross-check, same layouts); "profile" 0/1 = per-kernel event timing (dfs_model_profile). */
+int dfs_model_set_option(dfs_model* m, const char* key, int64_t value);
+int64_t dfs_model_workspace_bytes(const dfs_model* m);
+/* With option "profile" = 1 every kernel launch of the scoring loop is bracketed by a CUDA event
+ * pair on the launching stream.  This call synchronises those events and returns, per kernel id
+ * (CNN2D: 0 conv1, 1 conv2, 2 conv3, 3 head), the summed device time in ms and the launch count
+ * since the last reset.  Used by bench.py for the live roofline figure.                     */
+int dfs_model_profile(dfs_model* m, double* ms_out, int64_t* launches_out, int n_ids, int reset);
+
+/* ---- scoring (device-resident features) --------------------------------------------- */
+/* CNN2D.forward + squeeze(-1) [+ torch.sigmoid]  (src/model.py:33-42, src/predict.py:106-108).
+ * out_dev: [n] fp32 logits (apply_sigmoid=0) or scores.  embedding_dev: NULL or [n,23040] fp32
+ * in the reference's flatten order c*180+f (src/model.py:38, return_embedding=True).       */
+int dfs_cnn2d_score(dfs_model* m, const dfs_features* feats, float* out_dev, float* embedding_dev,
+                    int apply_sigmoid, void* stream);
+/* CNN1D.forward (src/model_cnn1d.py:37-46) */
+int dfs_cnn1d_score(dfs_model* m, const dfs_features* feats, float* out_dev, int apply_sigmoid, void* stream);
+/* get_cae_scores (src/predict_hybrid.py:66-78): per-utterance reconstruction MSE, the
+ * reconstruction is never written to HBM.  apply_normalizer!=0 applies (x-mean)/std first
+ * (src/predict_hybrid.py:45-49); the residual is taken against the normalised input.      */
+int dfs_cae_score(dfs_model* m, const dfs_features* feats, int apply_normalizer, float* mse_dev, void* stream);
+/* ConvAutoencoder.forward compat path (src/model_cae.py:83-125): materialises recon [n,321,180]
+ * and latent [n,256,20,11] (either may be NULL).  Input must already be normalised.        */
+int dfs_cae_forward(dfs_model* m, const dfs_features* feats, float* recon_dev, float* latent_dev, void* stream);
+
+/* ---- scoring (HOST features; copies are pipelined inside) --------------------------- */
+/* The batch loop of src/predict.py:100-111 / src/predict_hybrid.py:52-78 behind one call:
+ * feats->x and out_host are HOST pointers; H2D copies of chunk k+1 overlap the kernels of
+ * chunk k; returns after the scores are in out_host.  `kind`: 0 cnn2d, 1 cnn1d, 2 cae-mse.
+ * `flag` = apply_sigmoid (cnn) / apply_normalizer (cae).                                   */
+int dfs_score_host(dfs_model* m, const dfs_features* feats, int flag, float* out_host, void* stream);
+
+/* ---- ensemble blend (float64, like numpy) ------------------------------------------- */
+/* out[i] = (sum_m weights[m] * (minmax_flags[m] ? normalise_01(scores[m])[i] : scores[m][i])) / divisor
+ * evaluated left to right with separately rounded IEEE multiply / add / divide, like numpy:
+ *   src/ensemble.py:121 np.mean(all_scores, axis=0)          -> weights 1, no min-max, divisor M
+ *   src/predict_hybrid.py:81-85,149-151 alpha*a + (1-alpha)*b -> weights {alpha, 1-alpha}, min-max on, divisor 1
+ * scores_host_array: m (<= 8) DEVICE pointers to [n] float64; out_dev [n] float64. */
+int dfs_blend_f64(const double* const* scores_host_array, int m, const double* weights_host, const int* minmax_flags_host,
+                  double divisor, int64_t n, double* out_dev, void* stream);
+/* fp32 model scores -> float64 column (what .cpu().tolist() + np.array does, src/predict.py:111) */
+int dfs_widen_f32_f64(const float* in_dev, int64_t n, double* out_dev, void* stream);
+
+/* ---- EER (scripts/evaluation.py:7-39 == src/evaluation.py:12-48) -------------------- */
+typedef struct {
+  double eer;
+  double threshold;
+  int64_t eer_idx;    /* argmin index into the (n+1)-point FAR/FRR curves; -1 = single-class early-out */
+  int64_t n_bonafide;
+  int64_t n_spoof;
+} dfs_eer_result;
+/* scores_dev [n] fp32 or fp64 (key_bytes 4|8), labels_dev [n] uint8 in {0,1}.  Sort is a stable
+ * LSD radix sort (ties keep original index order -- the kind="stable" contract of DESIGN.md);
+ * perm_dev (NULL or [n] uint32) receives the permutation, sorted_dev (NULL or [n] same dtype as
+ * the scores) the sorted scores.  Synchronises `stream`.                                    */
+int dfs_eer(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, dfs_eer_result* result_host,
+            uint32_t* perm_dev, void* sorted_dev, void* stream);
+/* confusion_at_threshold (scripts/evaluation.py:42-56): out4_host = {tp, fp, tn, fn}. */
+int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,
+                  int64_t* out4_host, void* stream);
+
+/* ---- synthetic data (BASELINE.json north_star: "pinned synthetic feature tensors") --- */
+/* Fill [n,321,180] fp32 with N(0, std^2) from a counter-based generator keyed by
+ * (seed, first_utt + i, element) so every rank / GPU count sees the same global data set. */
+int dfs_fill_features(float* out_dev, int64_t n, int64_t first_utt, uint64_t seed, float std, void* stream);
+
+/* ---- bring-up probes (tests only) --------------------------------------------------- */
+/* One tcgen05.mma tile D[128,N] = A'[128,K] * B[N,K]^T.  A [rows_a,K] and B [N,K] are row-major
+ * bf16 bit patterns in device memory; they are staged in shared memory in the layout the conv
+ * kernels use and read through the same SWIZZLE_NONE K-major descriptors.  D row r = 8g+i reads
+ * staged A row (row_shift + g*group_rows + i) -- the addressing of a 3x3 tap on a 16x8 tile.
+ * out_dev [128*N] fp32.                                                                     */
+int dfs_probe_umma(const uint16_t* a_dev, const uint16_t* b_dev, int rows_a, int n, int k, int row_shift, int group_rows,
+                   float* out_dev, void* stream);
+/* One 3-D TMA box load (wrows rows x 18 columns x all planes) from an FT8 activation buffer
+ * (planes, rs rows per column, ncols columns) at (row0, col0); the shared-memory image is
+ * copied to out_dev [planes*18*wrows*8] bf16 bits.                                          */
+int dfs_probe_tma_window(const uint16_t* act_dev, int planes, int rs, int64_t ncols, int wrows, int row0, int col0,
+                         uint16_t* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFS_B200_H */

@@ -1,0 +1,117 @@
+"""GPU parity for the metric half: device radix sort + FAR/FRR sweep vs the reference's goldens
+(bit-exact on tie-free scores) and vs the kind="stable" oracle on tie-heavy scores; blend known
+answer; confusion counts."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from conftest import GOLDEN  # noqa: E402
+import dfs_b200 as D  # noqa: E402
+from dfs_b200 import synthetic as syn  # noqa: E402
+from oracle import eer as oeer  # noqa: E402
+
+E = np.load(os.path.join(GOLDEN, "eer_cases.npz"))
+CASES = sorted({k.split("/")[0] for k in E.files})
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_eer_goldens(case):
+    s, l = E[case + "/scores"], E[case + "/labels"]
+    ref_eer, ref_thr = E[case + "/eer_thr"]
+    d = D.eer_details(s, l, want_perm=True, want_sorted=True)
+    stable = oeer.eer_details(s, l, kind="stable")
+    # the device contract: identical to the reference algorithm with a stable argsort
+    assert (d["eer"], d["threshold"]) == (stable["eer"], stable["threshold"])
+    assert d["eer_idx"] == stable["eer_idx"]
+    assert np.array_equal(d["perm"].cpu().numpy().astype(np.int64), stable["perm"])
+    assert np.array_equal(d["sorted"].cpu().numpy(), np.array(s)[stable["perm"]])
+    if not case.startswith("ties_mixed"):
+        # tie-free (or single-label tie groups): bit-exact with the unmodified reference itself
+        assert (d["eer"], d["threshold"]) == (ref_eer, ref_thr)
+    if case.startswith("tiefree"):
+        assert np.array_equal(d["perm"].cpu().numpy().astype(np.int64), E[case + "/ref_argsort"])
+    thr = d["threshold"]
+    assert D.confusion_at_threshold(s, l, thr) == oeer.confusion_at_threshold(s, l, thr)
+    if not case.startswith("ties_mixed"):
+        assert tuple(D.confusion_at_threshold(s, l, ref_thr)[:4]) == tuple(E[case + "/confusion"])
+
+
+def test_eer_accepts_lists_and_tensors():
+    assert D.calculate_eer([0.1, 0.2, 0.8, 0.9], [0, 0, 1, 1]) == (0.0, 0.2)
+    assert D.calculate_eer([0.1, 0.2, 0.8, 0.9], [1, 1, 0, 0])[0] == 1.0
+    assert D.calculate_eer([0.3, 0.4], [1, 1]) == (0.0, 0.0)
+    s = torch.tensor([0.1, 0.2, 0.8, 0.9], device="cuda")
+    lab = torch.tensor([0.0, 0.0, 1.0, 1.0], device="cuda")          # float labels as evaluate() passes them
+    eer, thr = D.calculate_eer(s, lab)
+    assert eer == 0.0 and thr == float(np.float32(0.2))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_eer_threshold_edges(dtype):
+    # eer_idx == 0 and eer_idx == n use +-1e-6 in the score dtype (evaluation.py:31-35)
+    for s, l in (([0.9, 0.8, 0.1], [0, 0, 1]), ([0.1, 0.2, 0.3, 0.9], [1, 0, 0, 0])):
+        s = np.array(s, dtype=dtype)
+        assert D.calculate_eer(s, l) == oeer.calculate_eer(s, l)
+
+
+@pytest.mark.parametrize("n", [1, 2, 4095, 4096, 4097, 1_000_003])
+def test_eer_sizes_and_negative_scores(n):
+    rng = np.random.default_rng(n)
+    s = rng.standard_normal(n).astype(np.float32) * 4
+    s[::7] = -s[::7]
+    l = (rng.random(n) < 0.45).astype(np.uint8)
+    d = D.eer_details(s, l, want_perm=True)
+    o = oeer.eer_details(s, l, kind="stable")
+    assert (d["eer"], d["threshold"], d["eer_idx"]) == (o["eer"], o["threshold"], o["eer_idx"])
+    assert np.array_equal(d["perm"].cpu().numpy().astype(np.int64), o["perm"])
+
+
+def test_eer_ten_million_tie_free_bit_exact():
+    s, l = syn.tie_free_scores(10_000_000, seed=5)
+    d = D.eer_details(s, l)
+    o = oeer.eer_details(s, l)            # the reference's own (unstable) argsort: tie-free => same order
+    assert (d["eer"], d["threshold"], d["eer_idx"]) == (o["eer"], o["threshold"], o["eer_idx"])
+    assert 0.05 < d["eer"] < 0.45
+
+
+def test_eer_hundred_million_properties():
+    """BASELINE config 5 size: checked through size-independent properties (the CPU oracle needs ~40 s
+    and 10 GB here): sortedness, permutation checksum, and FAR/FRR consistency at the reported index."""
+    n = 100_000_000
+    s, l = syn.tie_free_scores(n, seed=6)
+    sd, ld = torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda()
+    d = D.eer_details(sd, ld, want_perm=True, want_sorted=True)
+    srt, perm = d["sorted"], d["perm"].long()
+    assert bool((srt[1:] > srt[:-1]).all())                              # strictly sorted (tie-free)
+    assert int(perm.sum()) == n * (n - 1) // 2                           # a permutation of 0..n-1
+    assert bool((sd[perm[:1000]] == srt[:1000]).all()) and bool((sd[perm[-1000:]] == srt[-1000:]).all())
+    k = d["eer_idx"]
+    c1 = int(ld[perm[:k]].sum())
+    far = (d["n_spoof"] - (k - c1)) / d["n_spoof"]
+    frr = c1 / d["n_bonafide"]
+    assert d["eer"] == (far + frr) / 2.0
+    assert d["threshold"] == float(srt[k - 1])
+    assert abs(far - frr) < 1e-6
+
+
+def test_blend_known_answer_bit_exact():
+    B = np.load(os.path.join(GOLDEN, "blend_known_answer.npz"))
+    alpha = float(B["alpha"])
+    got = D.blend([B["sup"], B["cae_minmaxed"]], [alpha, 1 - alpha], [1, 0])
+    assert np.array_equal(got, B["hybrid"])                              # the reference's shipped result, bit for bit
+    assert np.array_equal(D.normalise_01(B["sup"]), oeer.normalise_01(B["sup"]))
+    assert np.array_equal(D.hybrid_blend(B["sup"], B["cae_minmaxed"], alpha), oeer.hybrid_blend(B["sup"], B["cae_minmaxed"], alpha))
+    assert np.array_equal(D.normalise_01(np.full(17, 0.25)), np.zeros(17))   # flat input -> zeros (predict_hybrid.py:83-84)
+
+
+def test_ensemble_mean_and_fp32_inputs():
+    rng = np.random.default_rng(3)
+    a, b, c = (rng.random(5001).astype(np.float32) for _ in range(3))
+    ref = oeer.ensemble_mean([a.astype(np.float64), b.astype(np.float64), c.astype(np.float64)])
+    assert np.array_equal(D.ensemble_mean([a, b, c]), ref)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    assert np.array_equal(D.hybrid_blend(ta, tb, 0.8), oeer.hybrid_blend(a, b, 0.8))

@@ -1,0 +1,126 @@
+"""GPU parity: the three scorers through the C ABI vs the golden outputs of the unmodified
+reference (tests/golden/models.npz) and vs the numpy oracle on the same seeded inputs.
+Tolerance (BASELINE.json north_star): per-utterance scores within 1e-3 relative."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from conftest import GOLDEN  # noqa: E402
+from dfs_b200 import CaeScorer, Cnn1dScorer, Cnn2dScorer, fill_features, synthetic as syn  # noqa: E402
+from oracle import models_np as onp  # noqa: E402
+
+G = np.load(os.path.join(GOLDEN, "models.npz"))
+N_G = int(G["n"])
+REL = 1e-3  # north_star tolerance on per-utterance scores
+
+
+@pytest.fixture(scope="module")
+def feats():
+    x = syn.features(N_G, seed=1234)
+    assert syn.state_digest([x]) == str(G["features_sha256"])
+    return torch.from_numpy(x).cuda()
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30))
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["cuda-core-crosscheck", "tcgen05"])
+def test_cnn2d_matches_reference_golden(feats, impl):
+    sc = Cnn2dScorer(syn.cnn2d_state(0))
+    sc.set_option("conv_impl", impl)
+    logits, emb = sc.score(feats, apply_sigmoid=False, return_embedding=True)
+    scores = sc.score(feats, apply_sigmoid=True)
+    torch.cuda.synchronize()
+    logits, emb, scores = logits.cpu().numpy(), emb.cpu().numpy(), scores.cpu().numpy()
+    assert _rel(scores, G["cnn2d_init_sigmoid"]) <= REL
+    np.testing.assert_allclose(logits, G["cnn2d_init_logits"], atol=2e-4)
+    # embedding = mean over time of the conv stack, flatten order c*180+f (model.py:37-38); bf16 operands
+    np.testing.assert_allclose(emb[:, :512], G["cnn2d_init_embedding_head"], rtol=3e-2, atol=3e-3)
+    np.testing.assert_allclose(emb.sum(1), G["cnn2d_init_embedding_sum"], rtol=2e-3)
+
+
+def test_cnn2d_tcgen05_equals_cuda_core_crosscheck(feats):
+    sc = Cnn2dScorer(syn.cnn2d_state(0))
+    a, ea = sc.score(feats, return_embedding=True)
+    sc.set_option("conv_impl", 1)
+    b, eb = sc.score(feats, return_embedding=True)
+    torch.cuda.synchronize()
+    # same bf16 operands, fp32 accumulation: only summation order differs
+    np.testing.assert_allclose(ea.cpu().numpy(), eb.cpu().numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=2e-5)
+
+
+def test_cnn2d_layouts_chunking_and_host_path(feats):
+    sd = syn.cnn2d_state(0)
+    base = Cnn2dScorer(sd).score(feats, apply_sigmoid=True).cpu().numpy()
+    # the reference's transposed non-contiguous view of (B,180,321) storage (predict.py:103-105)
+    xt = feats.transpose(1, 2).contiguous().transpose(1, 2)
+    assert not xt.is_contiguous()
+    np.testing.assert_allclose(Cnn2dScorer(sd).score(xt, apply_sigmoid=True).cpu().numpy(), base, rtol=1e-6, atol=1e-7)
+    # ragged chunking: 12 utterances through chunks of 5
+    small = Cnn2dScorer(sd, max_chunk=5)
+    np.testing.assert_allclose(small.score(feats, apply_sigmoid=True).cpu().numpy(), base, rtol=1e-6, atol=1e-7)
+    # host-buffer pipeline (pinned) == device path
+    host = feats.cpu().pin_memory()
+    np.testing.assert_allclose(small.score_host(host, 1), base, rtol=1e-6, atol=1e-7)
+    # empty batch
+    assert Cnn2dScorer(sd).score(feats[:0]).numel() == 0
+
+
+def test_cnn2d_trained_like_regime_is_reported(feats):
+    """Classifier rescaled so logits span +-20: bf16 convs are NOT expected to hold
+    1e-3 on saturated sigmoids; the logit error relative to the logit range must stay small."""
+    sc = Cnn2dScorer(syn.cnn2d_state(0, logit_scale=2000.0))
+    logits = sc.score(feats).cpu().numpy()
+    ref = G["cnn2d_trained_logits"]
+    assert np.max(np.abs(logits - ref)) <= 5e-3 * (np.max(np.abs(ref)) + 1.0)
+
+
+def test_cnn2d_oracle_on_fresh_inputs():
+    x = syn.features(3, seed=99)
+    sd = syn.cnn2d_state(3)
+    ref = onp.sigmoid(onp.cnn2d_forward(sd, x)[:, 0])
+    got = Cnn2dScorer(sd).score(torch.from_numpy(x).cuda(), apply_sigmoid=True).cpu().numpy()
+    assert _rel(got, ref) <= REL
+
+
+def test_cnn1d_matches_reference_golden(feats):
+    sc = Cnn1dScorer(syn.cnn1d_state(0))
+    logits = sc.score(feats).cpu().numpy()
+    scores = sc.score(feats, apply_sigmoid=True).cpu().numpy()
+    np.testing.assert_allclose(logits, G["cnn1d_init_logits"], rtol=1e-4, atol=1e-5)
+    assert _rel(scores, G["cnn1d_init_sigmoid"]) <= REL
+    sc = Cnn1dScorer(syn.cnn1d_state(0, logit_scale=100.0))
+    np.testing.assert_allclose(sc.score(feats).cpu().numpy(), G["cnn1d_trained_logits"], rtol=1e-4, atol=1e-3)
+    xt = feats.transpose(1, 2).contiguous().transpose(1, 2)
+    np.testing.assert_allclose(Cnn1dScorer(syn.cnn1d_state(0), max_chunk=7).score(xt).cpu().numpy(), logits, rtol=1e-6, atol=1e-7)
+
+
+def test_cae_mse_matches_reference_golden(feats):
+    mean, std = syn.normalizer_stats(1)
+    sc = CaeScorer(syn.cae_state(0), mean, std, max_chunk=5)
+    mse = sc.score(feats).cpu().numpy()
+    assert _rel(mse, G["cae_mse"]) <= REL
+    np.testing.assert_allclose(sc.score_host(feats.cpu().pin_memory()), mse, rtol=1e-6)
+    # compat forward: recon (B,321,180) with a zero last row, latent (B,256,20,11)
+    xn = (feats - torch.from_numpy(mean).cuda()) / torch.from_numpy(std).cuda()
+    recon, latent = sc.forward(xn)
+    assert tuple(recon.shape) == (N_G, 321, 180) and tuple(latent.shape) == (N_G, 256, 20, 11)
+    assert float(recon[:, 320].abs().max()) == 0.0
+    np.testing.assert_allclose(recon[:, 0, :].cpu().numpy(), G["cae_recon_row0"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(latent.double().sum((1, 2, 3)).cpu().numpy(), G["cae_latent_sum"], rtol=1e-4)
+    # un-normalised scoring on a pre-normalised input gives the same MSE
+    np.testing.assert_allclose(sc.score(xn, apply_normalizer=False).cpu().numpy(), mse, rtol=1e-5)
+
+
+def test_device_generated_features_have_the_right_statistics():
+    x = fill_features(64, first_utt=0, seed=1234)
+    assert tuple(x.shape) == (64, 321, 180)
+    assert abs(float(x.mean())) < 0.02 and abs(float(x.std()) - 3.2) < 0.02
+    y = fill_features(8, first_utt=56, seed=1234)      # keyed by (seed, utterance index): shards line up
+    assert torch.equal(x[56:64], y)
