@@ -89,12 +89,12 @@ static int dev_upload(dfs_model* m, T** p, const std::vector<T>& h) {
   return DFS_OK;
 }
 
-static uint16_t f32_to_bf16_rn(float f) {
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
-  u += 0x7fffu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
+// fp32 -> IEEE fp16 bits, round to nearest even (the operand type of the conv GEMMs)
+static uint16_t f32_to_act_bits(float f) {
+  const __half h = __float2half_rn(f);
+  uint16_t b;
+  memcpy(&b, &h, 2);
+  return b;
 }
 
 // BN fold in double: scale[co], shift[co] such that  y = scale*(conv_nobias) + shift
@@ -223,8 +223,8 @@ extern "C" int64_t dfs_model_workspace_bytes(const dfs_model* m) { return m ? (i
 // ------------------------------------------------------------------------------------------
 // CNN2D
 // ------------------------------------------------------------------------------------------
-// pack a folded 3x3 conv weight (Co,Ci,3,3) into [tap][ci/8][co][ci%8] bf16
-static std::vector<uint16_t> pack_conv3x3_bf16(const dfs_conv_bn& c, int co, int ci, std::vector<float>& bias_out) {
+// pack a folded 3x3 conv weight (Co,Ci,3,3) into [tap][ci/8][co][ci%8] fp16
+static std::vector<uint16_t> pack_conv3x3_f16(const dfs_conv_bn& c, int co, int ci, std::vector<float>& bias_out) {
   std::vector<double> scale, shift;
   bn_fold(c, co, scale, shift);
   bias_out.resize(co);
@@ -234,7 +234,7 @@ static std::vector<uint16_t> pack_conv3x3_bf16(const dfs_conv_bn& c, int co, int
     for (int i = 0; i < ci; ++i)
       for (int o = 0; o < co; ++o) {
         const double w = (double)c.weight[((size_t)o * ci + i) * 9 + tap] * scale[o];
-        out[(((size_t)tap * (ci / 8) + (i >> 3)) * co + o) * 8 + (i & 7)] = f32_to_bf16_rn((float)w);
+        out[(((size_t)tap * (ci / 8) + (i >> 3)) * co + o) * 8 + (i & 7)] = f32_to_act_bits((float)w);
       }
   return out;
 }
@@ -265,8 +265,8 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
 
   fold_conv1(w->conv[0], m->c1);
   std::vector<float> b2, b3;
-  std::vector<uint16_t> p2 = pack_conv3x3_bf16(w->conv[1], 64, 32, b2);
-  std::vector<uint16_t> p3 = pack_conv3x3_bf16(w->conv[2], 128, 64, b3);
+  std::vector<uint16_t> p2 = pack_conv3x3_f16(w->conv[1], 64, 32, b2);
+  std::vector<uint16_t> p3 = pack_conv3x3_f16(w->conv[2], 128, 64, b3);
   memcpy(m->b2, b2.data(), sizeof(m->b2));
   memcpy(m->b3, b3.data(), sizeof(m->b3));
   if ((st = dev_upload(m, &m->w2pack, p2)) != DFS_OK) return fail(st);
@@ -288,6 +288,10 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
   if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->emb), (size_t)m->chunk * kF * 128 * 4, true)) != DFS_OK) return fail(st);
   if ((st = make_act_tensor_map(&m->tmap1, m->act1, conv2_tc_window_rows())) != DFS_OK) return fail(st);
   if ((st = make_act_tensor_map(&m->tmap2, m->act2, conv3_tc_window_rows())) != DFS_OK) return fail(st);
+  if (cudaDeviceSynchronize() != cudaSuccess) {  // the zero padding must be in place before any stream uses it
+    dfs_set_error("dfs_cnn2d_create: device synchronize failed");
+    return fail(DFS_ERR_CUDA);
+  }
   *out = m;
   return DFS_OK;
 }
@@ -534,4 +538,13 @@ extern "C" int dfs_probe_umma(const uint16_t* a_dev, const uint16_t* b_dev, int 
 extern "C" int dfs_probe_tma_window(const uint16_t* act_dev, int planes, int rs, int64_t ncols, int wrows, int row0, int col0,
                                     uint16_t* out_dev, void* stream) {
   return probe_tma_window(act_dev, planes, rs, ncols, wrows, row0, col0, out_dev, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dfs_probe_umma_bench(int n, int nmma, int iters, const uint32_t* a_off_host, const uint32_t* b_off_host, uint32_t a_lbo,
+                                    uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t layout, uint32_t use_base_offset,
+                                    int64_t* cycles_host, void* stream) {
+  long long c = 0;
+  int st = probe_umma_bench(n, nmma, iters, a_off_host, b_off_host, a_lbo, a_sbo, b_lbo, b_sbo, layout, use_base_offset, &c,
+                            static_cast<cudaStream_t>(stream));
+  if (cycles_host) *cycles_host = c;
+  return st;
 }

@@ -1,7 +1,7 @@
 // cnn2d.cu -- the CUDA-core stages around the tensor-core convolutions of the 2D-CNN scorer
 // (/root/reference/src/model.py:12-42):
-//   conv1_kernel      Conv2d(1,32,3,p=1)+BN+ReLU+AvgPool2d((2,1))  (model.py:15-18) -> FT8 bf16
-//                     (Cin = 1, K = 9 is not a tensor-core shape; also the fp32 -> bf16 / layout producer)
+//   conv1_kernel      Conv2d(1,32,3,p=1)+BN+ReLU+AvgPool2d((2,1))  (model.py:15-18) -> FT8 fp16
+//                     (Cin = 1, K = 9 is not a tensor-core shape; also the fp32 -> fp16 / layout producer)
 //                     with POOLF it is the CAE encoder block 1 (model_cae.py:34-37, AvgPool2d(2)).
 //   head_kernel       x.mean(dim=2) -> flatten -> Linear(23040,1) [-> sigmoid]  (model.py:37-39, predict.py:108)
 //   *_simt kernels    conv2 / conv3 on CUDA cores over the SAME packed weights and layouts: a debug
@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x,
           }
         r[e] = acc * (POOLF ? 0.25f : 0.5f);
       }
-      st_global_v4(dst + pj * plane_elems, pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
-                   pack_bf16x2(r[6], r[7]));
+      st_global_v4(dst + pj * plane_elems, pack_act2(r[0], r[1]), pack_act2(r[2], r[3]), pack_act2(r[4], r[5]),
+                   pack_act2(r[6], r[7]));
     }
   }
 }
@@ -155,8 +155,8 @@ __device__ __forceinline__ float conv_at(const ActBuf& a, const uint16_t* __rest
     const int kh = tap / 3, kw = tap % 3;
     const uint16_t* src = a.ptr + ((gc + kw - 1) * a.RS + (tp + kh - 1)) * 8;
     for (int ci = 0; ci < CIN; ++ci) {
-      const float xv = bf16_bits_to_float(src[(ci >> 3) * plane_elems + (ci & 7)]);
-      const float wv = bf16_bits_to_float(wpack[(((long long)tap * (CIN / 8) + (ci >> 3)) * COUT + co) * 8 + (ci & 7)]);
+      const float xv = act_bits_to_float(src[(ci >> 3) * plane_elems + (ci & 7)]);
+      const float wv = act_bits_to_float(wpack[(((long long)tap * (CIN / 8) + (ci >> 3)) * COUT + co) * 8 + (ci & 7)]);
       acc = fmaf(xv, wv, acc);
     }
   }
@@ -175,7 +175,7 @@ __global__ void cnn2d_conv2_simt_kernel(ActBuf act1, const uint16_t* __restrict_
   const long long gc = n * kCols + f + 1;
   float s = 0.0f;
   for (int d = 0; d < 2; ++d) s += fmaxf(conv_at<32, 64>(act1, wpack, gc, 2 * to + 1 + d, co) + bias[co], 0.0f);
-  const __nv_bfloat16 b = __float2bfloat16_rn(0.5f * s);
+  const __half b = __float2half_rn(fminf(0.5f * s, 65504.0f));
   act2.ptr[(co >> 3) * act2.plane_elems() + (gc * act2.RS + to + 1) * 8 + (co & 7)] = *reinterpret_cast<const uint16_t*>(&b);
 }
 

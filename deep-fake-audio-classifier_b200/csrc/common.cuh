@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -61,6 +62,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+
+// Activation / weight operand type of the conv GEMMs: IEEE fp16 (kind::f16 runs fp16 and bf16 at
+// the same rate; fp16's 11-bit significand keeps the score error ~8x below bf16, DESIGN.md
+// "Precision").  Values are clamped to the fp16 range (post-ReLU activations are >= 0).
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(fminf(lo, 65504.0f), fminf(hi, 65504.0f));
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float act_bits_to_float(uint16_t b) {
+  return __half2float(*reinterpret_cast<const __half*>(&b));
+}
 
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred = 0;
@@ -167,6 +179,21 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // | [17,23) N>>3 | [24,29) M>>4          (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same, FP16 x FP16 -> FP32 (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MMA with descriptors given as (low word, shared high word): the per-tap / per-K-step variation of
+// a descriptor is a 32-bit add on the low word (start address field), so the issue loop costs one
+// uniform add per operand instead of re-encoding the descriptor.
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // Shared-memory matrix descriptor, SWIZZLE_NONE ("interleave"), K-major canonical layout
 //   ((8,m),(8 elem,2)) : ((16 B, SBO),(2 B, LBO))

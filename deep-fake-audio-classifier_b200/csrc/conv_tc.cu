@@ -10,12 +10,12 @@
 //   N             = COUT (64 / 128), K = 9 taps x CIN, issued as 9*CIN/16 tcgen05.mma of K = 16
 //   A (activations): SWIZZLE_NONE K-major smem descriptor straight into the TMA-loaded window;
 //                    tap (kh,kw) = +((kw*WROWS + kh) * 16) bytes on the start address
-//   B (weights)    : BN-folded bf16, resident in shared memory for the whole kernel
+//   B (weights)    : BN-folded fp16, resident in shared memory for the whole kernel
 //   D              : TMEM, NACC accumulators of COUT columns, so the epilogue of tile i overlaps
 //                    the MMAs of tile i+1.
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warp 2 = TMEM allocator, warp 3 idle, warps 4..11 = epilogue (lane quarter = warp%4, column
-// half = (warp-4)/4).
+// Warp roles (352 threads): warps 0..7 = epilogue (TMEM lane quarter = warp%4, column half = warp/4),
+// warp 8 = TMA producer, warp 9 = MMA issuer (one lane; highest warp id on its scheduler so the
+// hi-warp-id-first arbiter never starves it behind spinning epilogue warps), warp 10 = TMEM allocator.
 // Work unit = one column tile (16 feature columns, all T time steps); units are dealt round-robin
 // to a persistent grid of one CTA per SM.
 #include "common.cuh"
@@ -42,8 +42,12 @@ struct ConvCfg {
   static constexpr int TMEM_COLS = NACC * COUT;
   static constexpr int BAR_B = 256;
   static constexpr int SMEM_B = WGT_B_AL + NSTAGE * WIN_B_AL + BAR_B;
-  static constexpr int THREADS = 384;
+  static constexpr int THREADS = 352;
+  // two CTAs per SM when shared memory and TMEM allow: the second CTA's epilogue / issue latencies
+  // overlap the first one's MMAs (conv2: 101 KB smem, 256 TMEM columns each)
+  static constexpr int OCC = (SMEM_B <= 113 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
   static_assert(T % (8 * MT) == 0, "T must be a multiple of the super-tile height");
+  static_assert(NACC % MT == 0, "the accumulators of one window must be consecutive");
   static_assert(WROWS * 8 <= 256, "TMA box inner dimension limit");
   static_assert(TMEM_COLS == 32 || TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
   static_assert(COUT % 64 == 0 && COUT <= 256 && CIN % 16 == 0, "shape");
@@ -51,13 +55,13 @@ struct ConvCfg {
 };
 
 struct ConvParams {
-  const uint16_t* wpack;  // [9][CIN/8][COUT][8] bf16, BN folded
+  const uint16_t* wpack;  // [9][CIN/8][COUT][8] fp16, BN folded
   float bias[128];        // folded bias per output channel
   int n_units;            // column tiles
   int n_utts;
   int cols;               // padded feature columns per utterance (F + 2)
   int feats;              // F
-  // EPI_POOL_T: pooled bf16 activations in FT8 layout with RS = T/2 + 2
+  // EPI_POOL_T: pooled fp16 activations in FT8 layout with RS = T/2 + 2
   uint16_t* out;
   long long out_ncols;
   // EPI_MEAN_T: per-utterance time SUMS, [n][F][COUT] fp32 (the head applies 1/T)
@@ -65,7 +69,7 @@ struct ConvParams {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::OCC)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvParams p) {
   constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, MT = Cfg::MT, NSTAGE = Cfg::NSTAGE, NACC = Cfg::NACC;
   constexpr int KCH = Cfg::KCH, WROWS = Cfg::WROWS, PLANE_B = Cfg::PLANE_B;
@@ -82,14 +86,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap);
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 10) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -98,7 +102,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(wbar, Cfg::WGT_B);
@@ -117,11 +121,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, COUT);
+      constexpr uint32_t idesc = umma_idesc_f16(128, COUT);
       const uint32_t wsm_a = smem_u32(wsm);
+      // descriptor = (low word: start address >> 4 | LBO >> 4 << 16, high word: SBO >> 4 | version); taps and
+      // K steps only move the start address, i.e. add a compile-time constant to the low word
+      const uint64_t b_desc0 = umma_smem_desc(wsm_a, COUT * 16, 128);
+      const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
+      const uint64_t a_desc0 = umma_smem_desc(smem_u32(win0), PLANE_B, WROWS * 16);
+      const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
       mbar_wait(wbar, 0, 2);
       uint32_t ws = 0, it = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
@@ -129,33 +139,38 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           const int stage = ws % NSTAGE;
           mbar_wait(&full[stage], (ws / NSTAGE) & 1, 3);
           tc_fence_after();
-          const uint32_t win = smem_u32(win0 + stage * Cfg::WIN_B_AL);
-#pragma unroll 1
-          for (int m = 0; m < MT; ++m, ++it) {
-            const int acc = it % NACC;
-            mbar_wait(&tempty[acc], ((it / NACC) & 1) ^ 1, 4);
-            tc_fence_after();
-            const uint32_t d = tmem_base + acc * COUT;
+          const uint32_t a_lo_stage = a_lo0 + (uint32_t)(stage * (Cfg::WIN_B_AL >> 4));
+          // The MT tiles of a window are issued INTERLEAVED (tile index innermost): consecutive MMAs then
+          // accumulate into different TMEM tiles, so the ~90-cycle accumulate latency of one MMA (measured,
+          // tools/umma_bench.py) is hidden behind the next one instead of serialising the K loop.
+          const int acc0 = it % NACC;  // NACC % MT == 0: the MT accumulators of a window are consecutive
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int kh = tap / 3, kw = tap % 3;
+          for (int m = 0; m < MT; ++m) mbar_wait(&tempty[acc0 + m], (((it + m) / NACC) & 1) ^ 1, 4);
+          tc_fence_after();
 #pragma unroll
-              for (int kk = 0; kk < CIN / 16; ++kk) {
-                const uint64_t a = umma_smem_desc(win + (2 * kk) * PLANE_B + (kw * WROWS + m * 8 + kh) * 16, PLANE_B, WROWS * 16);
-                const uint64_t b = umma_smem_desc(wsm_a + ((tap * KCH + 2 * kk) * COUT) * 16, COUT * 16, 128);
-                umma_bf16(d, a, b, idesc, (tap | kk) != 0 ? 1u : 0u);
-              }
+          for (int tap = 0; tap < 9; ++tap) {
+            const int kh = tap / 3, kw = tap % 3;
+#pragma unroll
+            for (int kk = 0; kk < CIN / 16; ++kk) {
+              const uint32_t a_off = (uint32_t)(((2 * kk) * PLANE_B + (kw * WROWS + kh) * 16) >> 4);
+              const uint32_t b_off = (uint32_t)((((tap * KCH + 2 * kk) * COUT) * 16) >> 4);
+#pragma unroll
+              for (int m = 0; m < MT; ++m)  // tile m = rows 8m.. of the window: +8 rows of 16 B
+                umma_f16_lohi(tmem_base + (acc0 + m) * COUT, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc,
+                              (tap | kk) != 0 ? 1u : 0u);
             }
-            umma_commit(&tfull[acc]);  // accumulator ready for the epilogue
           }
+#pragma unroll
+          for (int m = 0; m < MT; ++m) umma_commit(&tfull[acc0 + m]);  // accumulators ready for the epilogue
+          it += MT;
           umma_commit(&empty[stage]);  // window may be overwritten once these MMAs retire
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ===================== epilogue =====================
     const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int h = (warp - 4) >> 2;    // column half
+    const int h = warp >> 2;    // column half
     constexpr int HC = COUT / 2;      // columns per thread
     const int r = 32 * q + lane;      // accumulator row = TMEM lane
     const int g = r >> 3;             // feature column within the tile
@@ -200,8 +215,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               uint16_t* dst = p.out + (long long)(chbase / 8 + k) * plane_elems + rowoff;
-              st_global_v4(dst, pack_bf16x2(o[8 * k + 0], o[8 * k + 1]), pack_bf16x2(o[8 * k + 2], o[8 * k + 3]),
-                           pack_bf16x2(o[8 * k + 4], o[8 * k + 5]), pack_bf16x2(o[8 * k + 6], o[8 * k + 7]));
+              st_global_v4(dst, pack_act2(o[8 * k + 0], o[8 * k + 1]), pack_act2(o[8 * k + 2], o[8 * k + 3]),
+                           pack_act2(o[8 * k + 4], o[8 * k + 5]), pack_act2(o[8 * k + 6], o[8 * k + 7]));
             }
           }
         }
@@ -269,7 +284,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 10) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -318,7 +333,7 @@ static int launch_conv(const CUtensorMap& tmap, const ConvParams& p, int num_sms
     configured = true;
   }
   if (p.n_units <= 0) return DFS_OK;
-  const int grid = p.n_units < num_sms ? p.n_units : num_sms;
+  const int grid = p.n_units < num_sms * Cfg::OCC ? p.n_units : num_sms * Cfg::OCC;
   conv3x3_tc_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_B, stream>>>(tmap, p);
   DFS_LAUNCH_CHECK();
   return DFS_OK;
@@ -327,7 +342,7 @@ static int launch_conv(const CUtensorMap& tmap, const ConvParams& p, int num_sms
 // CNN2D conv2: 32 -> 64 channels on 160 x 180, pooled to 80 rows.
 using Conv2Cfg = ConvCfg<32, 64, 160, 2, 3, 4, EPI_POOL_T>;
 // CNN2D conv3: 64 -> 128 channels on 80 x 180, summed over time.
-using Conv3Cfg = ConvCfg<64, 128, 80, 1, 3, 2, EPI_MEAN_T>;
+using Conv3Cfg = ConvCfg<64, 128, 80, 2, 2, 4, EPI_MEAN_T>;
 
 int conv2_tc_window_rows() { return Conv2Cfg::WROWS; }
 int conv3_tc_window_rows() { return Conv3Cfg::WROWS; }

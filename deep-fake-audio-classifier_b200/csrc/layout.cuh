@@ -1,6 +1,6 @@
 // layout.cuh -- the activation layout shared by the CUDA-core producers and the tcgen05 conv kernels.
 //
-// "FT8" padded planar layout, bf16:
+// "FT8" padded planar layout, fp16:
 //     elem(plane j, column gc, row t', e) at  ((j * ncols + gc) * RS + t') * 8 + e
 //   * channel c = 8*j + e            -- a "plane" holds 8 channels = one 16-byte K chunk of an MMA
 //   * column  gc = n * COLS + f'     -- utterance n, padded feature index f' in [0, F+1], COLS = F+2
@@ -26,7 +26,7 @@ constexpr int kColTile = 16;  // feature columns per MMA tile
 constexpr int kRowTile = 8;   // time steps per MMA tile
 
 struct ActBuf {
-  uint16_t* ptr;   // bf16 bits
+  uint16_t* ptr;   // fp16 bits
   int planes;      // C / 8
   int RS;          // T + 2
   int64_t ncols;   // allocated columns per plane (n_max * COLS + slack)

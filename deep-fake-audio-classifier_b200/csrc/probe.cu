@@ -82,6 +82,93 @@ int probe_umma(const uint16_t* a, const uint16_t* b, int rows_a, int n, int k, i
   return DFS_OK;
 }
 
+// Issue-rate / operand-fetch micro-benchmark: one thread issues `iters` rounds of `nmma` MMAs
+// (M=128, N=n, K=16) whose A start addresses walk a caller-given list of byte offsets (e.g. the 9
+// tap offsets of a conv tile), commits once per round and waits; reports SM cycles per MMA.
+// Operand CONTENT is irrelevant (shared memory is zero-filled), only the addressing is timed.
+struct UmmaBenchParams {
+  int n, nmma, iters;
+  uint32_t a_off[40];      // byte offsets of the A start address per MMA of a round
+  uint32_t b_off[40];      // byte offsets of the B start address per MMA
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
+  uint32_t layout;         // descriptor layout_type field (0 none, 2 SW128, 4 SW64, 6 SW32)
+  uint32_t use_base_offset;
+};
+
+__global__ void __launch_bounds__(128) probe_umma_bench_kernel(const __grid_constant__ UmmaBenchParams p, long long* __restrict__ cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int A_BYTES = 96 * 1024, B_BYTES = 64 * 1024;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < (A_BYTES + B_BYTES) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if ((threadIdx.x >> 5) == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, p.n);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + A_BYTES);
+    uint64_t* ad = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES + 64);   // descriptor tables in shared memory
+    uint64_t* bd = ad + 40;
+    for (int i = 0; i < p.nmma; ++i) {
+      const uint32_t aa = a0 + p.a_off[i], bb = b0 + p.b_off[i];
+      ad[i] = umma_smem_desc(aa, p.a_lbo, p.a_sbo) | ((uint64_t)p.layout << 61) | (p.use_base_offset ? ((uint64_t)((aa >> 7) & 7) << 49) : 0ull);
+      bd[i] = umma_smem_desc(bb, p.b_lbo, p.b_sbo) | ((uint64_t)p.layout << 61) | (p.use_base_offset ? ((uint64_t)((bb >> 7) & 7) << 49) : 0ull);
+    }
+    uint32_t phase = 0;
+    // warm-up round
+    for (int i = 0; i < p.nmma; ++i) umma_bf16(tmem_base, ad[i], bd[i], idesc, i != 0);
+    umma_commit(bar);
+    mbar_wait(bar, phase, 11);
+    phase ^= 1;
+    const long long t0 = clock64();
+    for (int it = 0; it < p.iters; ++it) {
+#pragma unroll 4
+      for (int i = 0; i < p.nmma; ++i) umma_bf16(tmem_base, ad[i], bd[i], idesc, i != 0);
+      umma_commit(bar);
+      mbar_wait(bar, phase, 12);
+      phase ^= 1;
+    }
+    const long long t1 = clock64();
+    cycles_out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int probe_umma_bench(int n, int nmma, int iters, const uint32_t* a_off, const uint32_t* b_off, uint32_t a_lbo, uint32_t a_sbo,
+                     uint32_t b_lbo, uint32_t b_sbo, uint32_t layout, uint32_t use_base_offset, long long* cycles_host, cudaStream_t stream) {
+  DFS_REQUIRE(n % 16 == 0 && n >= 16 && n <= 256 && nmma >= 1 && nmma <= 40 && iters >= 1, DFS_ERR_INVALID, "probe_umma_bench: bad argument");
+  UmmaBenchParams p{};
+  p.n = n; p.nmma = nmma; p.iters = iters;
+  for (int i = 0; i < nmma; ++i) { p.a_off[i] = a_off[i]; p.b_off[i] = b_off[i]; }
+  p.a_lbo = a_lbo; p.a_sbo = a_sbo; p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.layout = layout; p.use_base_offset = use_base_offset;
+  long long* d = nullptr;
+  DFS_CUDA_CHECK(cudaMalloc(&d, 8));
+  const int smem = 160 * 1024 + 64 + 80 * 8;
+  DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe_umma_bench_kernel<<<1, 128, smem, stream>>>(p, d);
+  dfs_count_launch();
+  cudaError_t e = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  DFS_REQUIRE(e == cudaSuccess, DFS_ERR_CUDA, "probe_umma_bench: %s", cudaGetErrorString(e));
+  return DFS_OK;
+}
+
 __global__ void __launch_bounds__(128) probe_tma_kernel(const __grid_constant__ CUtensorMap tmap, int c0, int c1, int bytes,
                                                          uint16_t* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];

@@ -70,6 +70,8 @@ SIGNATURES = {
     "dfs_confusion": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.POINTER(C.c_int64), C.c_void_p]),
     "dfs_fill_features": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_float, C.c_void_p]),
     "dfs_probe_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dfs_probe_umma_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32,
+                                       C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int64), C.c_void_p]),
     "dfs_probe_tma_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 

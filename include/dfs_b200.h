@@ -183,6 +183,13 @@ int dfs_probe_umma(const uint16_t* a_dev, const uint16_t* b_dev, int rows_a, int
 int dfs_probe_tma_window(const uint16_t* act_dev, int planes, int rs, int64_t ncols, int wrows, int row0, int col0,
                          uint16_t* out_dev, void* stream);
 
+/* Issue-rate / operand-fetch micro-benchmark of tcgen05.mma (M=128, N=n, K=16): `iters` rounds of
+ * `nmma` MMAs whose A/B descriptor start addresses are smem_base + a_off[i] / b_off[i] (bytes);
+ * cycles_host receives the SM cycles of the timed rounds.  Data content is zero.           */
+int dfs_probe_umma_bench(int n, int nmma, int iters, const uint32_t* a_off_host, const uint32_t* b_off_host, uint32_t a_lbo,
+                         uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t layout, uint32_t use_base_offset,
+                         int64_t* cycles_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

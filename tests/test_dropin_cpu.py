@@ -1,0 +1,87 @@
+"""CPU gate for the drop-in boundary: constructors, state-dict keys/shapes, checkpoint
+shapes, train-mode fall-through, eval-mode-on-CPU refusal, prediction.pkl format."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, PKG
+
+torch = pytest.importorskip("torch")
+sys.path.insert(0, os.path.join(PKG, "dropin"))
+
+from dfs_b200 import synthetic as syn  # noqa: E402
+import model as m2  # noqa: E402
+import model_cae as mc  # noqa: E402
+import model_cnn1d as m1  # noqa: E402
+import scoring  # noqa: E402
+
+
+def _t(sd):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("cls,factory,kwargs", [
+    (m2.CNN2D, syn.cnn2d_state, {"in_features": 180, "dropout": 0.3}),     # predict.py:51-52,76
+    (m1.CNN1D, syn.cnn1d_state, {"in_features": 180, "dropout": 0.2}),     # ensemble.py:35-39
+    (mc.ConvAutoencoder, syn.cae_state, {}),                               # predict_hybrid.py:133
+])
+def test_state_dict_contract(cls, factory, kwargs, tmp_path):
+    model = cls(**kwargs)
+    sd = factory(0)
+    own = model.state_dict()
+    assert list(own.keys()) == list(sd.keys())                            # the reference's key names, in order
+    assert all(tuple(own[k].shape) == tuple(sd[k].shape) for k in sd)
+    model.load_state_dict(_t(sd))                                          # strict
+    # both checkpoint shapes the scoring scripts accept (predict.py:82-85), loadable with weights_only=True
+    for payload in ({"model_state": model.state_dict(), "epoch": 3}, model.state_dict()):
+        p = tmp_path / "ckpt.pt"
+        torch.save(payload, p)
+        ck = torch.load(p, map_location="cpu", weights_only=True)
+        cls(**kwargs).load_state_dict(ck["model_state"] if "model_state" in ck else ck)
+
+
+def test_train_mode_uses_torch_layers_and_eval_cpu_refuses():
+    x = torch.randn(2, 321, 180)
+    model = m2.CNN2D()
+    model.train()
+    logits, emb = model(x, return_embedding=True)
+    assert tuple(logits.shape) == (2, 1) and tuple(emb.shape) == (2, 23040)          # model.py:45-49 smoke shapes
+    assert tuple(m1.CNN1D().train()(x).shape) == (2, 1)
+    recon, latent = mc.ConvAutoencoder().train()(x)
+    assert tuple(recon.shape) == (2, 321, 180) and tuple(latent.shape) == (2, 256, 20, 11)
+    model.eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(x)
+
+
+def test_train_mode_matches_oracle_in_eval_semantics():
+    """The torch layer tree of the drop-in is the reference architecture: with BN in eval it reproduces the golden logits."""
+    G = np.load(os.path.join(GOLDEN, "models.npz"))
+    x = torch.from_numpy(syn.features(2, seed=1234))
+    model = m2.CNN2D()
+    model.load_state_dict(_t(syn.cnn2d_state(0)))
+    model.train()
+    for mod in model.modules():
+        if isinstance(mod, (torch.nn.BatchNorm2d, torch.nn.Dropout)):
+            mod.eval()
+    with torch.no_grad():
+        logits = model(x).squeeze(-1).numpy()
+    np.testing.assert_allclose(logits, G["cnn2d_init_logits"][:2], rtol=1e-5, atol=1e-6)
+
+
+def test_prediction_pickle_format(tmp_path):
+    import pandas as pd
+    with open(os.path.join(GOLDEN, "prediction_format.json")) as f:
+        facts = json.load(f)
+    df = scoring.write_predictions(["raw_1", "raw_2", "raw_3"], np.array([0.1, 0.5, 0.9], dtype=np.float32), tmp_path / "prediction.pkl")
+    back = pd.read_pickle(tmp_path / "prediction.pkl")
+    assert list(back.columns) == facts["columns"]
+    assert {c: str(t) for c, t in back.dtypes.items()} == facts["dtypes"]
+    assert type(back.index).__name__ == facts["index_type"]
+    assert back["predictions"].iloc[0] == float(np.float32(0.1))                     # fp32 score widened exactly
+    with pytest.raises(ValueError):
+        scoring.write_predictions(["a"], [0.1, 0.2], tmp_path / "x.pkl")              # predict.py:113-114
+    assert len(df) == 3

@@ -38,7 +38,7 @@ def test_cnn2d_matches_reference_golden(feats, impl):
     torch.cuda.synchronize()
     logits, emb, scores = logits.cpu().numpy(), emb.cpu().numpy(), scores.cpu().numpy()
     assert _rel(scores, G["cnn2d_init_sigmoid"]) <= REL
-    np.testing.assert_allclose(logits, G["cnn2d_init_logits"], atol=2e-4)
+    np.testing.assert_allclose(logits, G["cnn2d_init_logits"], atol=1e-3)
     # embedding = mean over time of the conv stack, flatten order c*180+f (model.py:37-38); bf16 operands
     np.testing.assert_allclose(emb[:, :512], G["cnn2d_init_embedding_head"], rtol=3e-2, atol=3e-3)
     np.testing.assert_allclose(emb.sum(1), G["cnn2d_init_embedding_sum"], rtol=2e-3)

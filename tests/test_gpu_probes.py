@@ -18,7 +18,7 @@ def _bf16_bits(a):
 
 
 @pytest.mark.parametrize("n,k,row_shift,group_rows", [(64, 32, 0, 8), (128, 64, 0, 8), (128, 64, 3, 8), (64, 32, 1, 10),
-                                                      (128, 64, 11, 10), (64, 64, 19, 18), (128, 576, 0, 8)])
+                                                      (128, 64, 11, 10), (64, 64, 19, 18), (128, 288, 2, 10)])
 def test_umma_descriptor_addressing(n, k, row_shift, group_rows):
     rng = np.random.default_rng(n + k + row_shift)
     rows_a = row_shift + 15 * group_rows + 8 + 5

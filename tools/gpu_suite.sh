@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
 for t in probes eer models; do
-  timeout 600 python -m pytest tests/test_gpu_$t.py -m gpu -q -x --tb=short > gpurun_out/test_$t.log 2>&1
+  timeout 600 python -m pytest tests/test_gpu_$t.py -m gpu -q --tb=short > gpurun_out/test_$t.log 2>&1
   echo "test_$t exit $?" | tee -a gpurun_out/summary.txt
   tail -n 30 gpurun_out/test_$t.log
 done

@@ -1,0 +1,70 @@
+"""Turn the ncu artefacts brought back in gpurun_out/ into the small text summaries kept under profiles/.
+
+    python tools/summarize_ncu.py <tag>      # reads gpurun_out/launches.csv and gpurun_out/prof_conv.ncu-rep
+"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+GP = os.path.join(ROOT, "gpurun_out")
+KEYS = ["gpu__time_duration.sum", "sm__cycles_active.avg", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg",
+        "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]
+
+
+def launch_share(tag):
+    path = os.path.join(GP, "launches.csv")
+    if not os.path.exists(path):
+        return
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    tot, cnt = collections.defaultdict(float), collections.Counter()
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v
+        name = re.sub(r"\(.*", "", r[ki])[:100]
+        tot[name] += v
+        cnt[name] += 1
+    s = sum(tot.values())
+    with open(os.path.join(OUT, f"{tag}_launch_share.txt"), "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
+        f.write(f"# total {s:.1f} us over {sum(cnt.values())} profiled launches\n")
+        for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
+            f.write(f"{v / s * 100:6.2f}%  {v:10.1f} us  n={cnt[k]:4d}  avg {v / cnt[k]:8.1f} us  {k}\n")
+
+
+def full_set(tag):
+    rep = os.path.join(GP, "prof_conv.ncu-rep")
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(os.path.join(OUT, f"{tag}_conv_kernels_ncu_full.txt"), "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc (one launch of each conv kernel)\n")
+        for r in rows[2:]:
+            f.write(f"\n== {r[hdr.index('Kernel Name')]}\n")
+            for i, h in enumerate(hdr):
+                if any(h.endswith(k) for k in KEYS) and r[i] not in ("",):
+                    f.write(f"  {h:95s} {units[i]:16s} {r[i]}\n")
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    os.makedirs(OUT, exist_ok=True)
+    launch_share(tag)
+    full_set(tag)
+    print(os.listdir(OUT))

@@ -1,0 +1,58 @@
+"""tcgen05.mma cost model on this GPU: cycles per MMA for the addressing patterns the conv kernels use.
+Run on the GPU box:  python tools/umma_bench.py > gpurun_out/umma_bench.txt"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "deep-fake-audio-classifier_b200"))
+import torch  # noqa: E402
+
+from dfs_b200 import _native as N  # noqa: E402
+
+torch.zeros(1, device="cuda")
+lib = N.load()
+
+
+def run(name, n, a_off, b_off, a_lbo, a_sbo, b_lbo, b_sbo, layout=0, base=0, iters=200):
+    nm = len(a_off)
+    A = (C.c_uint32 * nm)(*a_off)
+    B = (C.c_uint32 * nm)(*b_off)
+    cyc = C.c_int64()
+    N.check(lib.dfs_probe_umma_bench(n, nm, iters, A, B, a_lbo, a_sbo, b_lbo, b_sbo, layout, base, C.byref(cyc), None), name)
+    per = cyc.value / (iters * nm)
+    print(f"{name:58s} N={n:3d} nmma={nm:2d}  {per:7.1f} cyc/MMA   ideal {128 * n / 256:5.1f}")
+
+
+# --- no swizzle, conv3-like: CIN=64 (4 k-steps), WROWS=10, plane = 18*10*16 = 2880 B
+P3 = 2880
+taps3 = [(2 * kk) * P3 + (kw * 10 + kh) * 16 for kh in range(3) for kw in range(3) for kk in range(4)]
+b3 = [((t * 8 + 2 * kk) * 128) * 16 % 65536 for t in range(9) for kk in range(4)]
+run("none  conv3 taps (SBO=160, 16B-granular shifts)", 128, taps3, b3, P3, 160, 2048, 128)
+al3 = [(2 * kk) * P3 for _ in range(9) for kk in range(4)]
+run("none  conv3 K-steps only, start aligned, SBO=160", 128, al3, b3, P3, 160, 2048, 128)
+P3a = 18 * 8 * 16
+run("none  aligned core matrices (SBO=128, 128B shifts)", 128, [(2 * kk) * P3a + kw * 128 for kh in range(3) for kw in range(3) for kk in range(4)], b3, P3a, 128, 2048, 128)
+run("none  aligned, fixed A (same address every MMA)", 128, [0] * 36, [0] * 36, P3a, 128, 2048, 128)
+run("none  aligned, N=256", 256, [0] * 16, [0] * 16, P3a, 128, 4096, 128)
+run("none  aligned, N=64", 64, [0] * 18, [0] * 18, P3a, 128, 1024, 128)
+# --- conv2-like: CIN=32 (2 k-steps), WROWS=18, plane = 18*18*16 = 5184
+P2 = 5184
+taps2 = [(2 * kk) * P2 + (kw * 18 + kh) * 16 for kh in range(3) for kw in range(3) for kk in range(2)]
+b2 = [((t * 4 + 2 * kk) * 64) * 16 for t in range(9) for kk in range(2)]
+run("none  conv2 taps (SBO=288), N=64", 64, taps2, b2, P2, 288, 1024, 128)
+run("none  conv2 taps (SBO=288), N=128 (as if 2 tiles shared B)", 128, taps2, b2, P2, 288, 2048, 128)
+# --- 128B swizzle, K-major: rows of 128 B (64 ch); group of 8 rows = 1024 B
+sw_al = [kk * 32 for _ in range(9) for kk in range(4)]
+bsw = [(t * 16384 + kk * 32) % 65536 for t in range(9) for kk in range(4)]
+run("SW128 aligned tile (SBO=1024), K advance by +32 B", 128, sw_al, bsw, 16, 1024, 16, 1024, layout=2)
+sw_taps = [(kw * 10 + kh) * 128 + kk * 32 for kh in range(3) for kw in range(3) for kk in range(4)]
+run("SW128 conv3 taps: row shifts of 128 B, SBO=1280", 128, sw_taps, bsw, 16, 1280, 16, 1024, layout=2)
+run("SW128 conv3 taps + base_offset field", 128, sw_taps, bsw, 16, 1280, 16, 1024, layout=2, base=1)
+sw_taps8 = [(kw * 8) * 128 + kh * 128 + kk * 32 for kh in range(3) for kw in range(3) for kk in range(4)]
+run("SW128 taps, window rows = 8 (SBO=1024)", 128, sw_taps8, bsw, 16, 1024, 16, 1024, layout=2)
+# --- 64B swizzle (CIN=32 rows of 64 B)
+sw64 = [(kw * 18 + kh) * 64 + kk * 32 for kh in range(3) for kw in range(3) for kk in range(2)]
+b64 = [(t * 4096 + kk * 32) for t in range(9) for kk in range(2)]
+run("SW64  conv2 taps: row shifts of 64 B, SBO=18*64, N=64", 64, sw64, b64, 16, 18 * 64, 16, 512, layout=4)
+run("SW64  aligned (SBO=512), N=64", 64, [kk * 32 for _ in range(9) for kk in range(2)], b64, 16, 512, 16, 512, layout=4)
