@@ -57,6 +57,10 @@ struct dfs_model {
   ActBuf act1{}, act2{};
   float* emb = nullptr;
   CUtensorMap tmap1{}, tmap2{};
+  int conv1_impl = 0;          // 0 = tensor-core Toeplitz GEMM, 1 = CUDA-core cross-check
+  uint16_t* xt = nullptr;      // fp16 time-major copy of the features (conv1_tc A operand)
+  uint16_t* w1pack = nullptr;  // Toeplitz weights [kw][2][256][8]
+  float b1h[32] = {0};         // 0.5 * folded conv1 bias
   // ---- CNN1D / CAE (CUDA-core path) ----
   SimtConv sc[8];
   float* work = nullptr;
@@ -209,6 +213,11 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     m->conv_impl = (int)value;
     return DFS_OK;
   }
+  if (strcmp(key, "conv1_impl") == 0) {
+    DFS_REQUIRE(value == 0 || value == 1, DFS_ERR_INVALID, "conv1_impl must be 0 (tcgen05) or 1 (CUDA-core cross-check)");
+    m->conv1_impl = (int)value;
+    return DFS_OK;
+  }
   if (strcmp(key, "profile") == 0) {
     m->profile = value != 0;
     m->prof_used = 0;
@@ -279,6 +288,21 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
     for (int c = 0; c < 128; ++c) fcw[(size_t)f * 128 + c] = (float)((double)w->fc_weight[(size_t)c * kF + f] / 80.0);
   if ((st = dev_upload(m, &m->fcw_dev, fcw)) != DFS_OK) return fail(st);
   m->fcb = w->fc_bias[0];
+  // conv1 as a Toeplitz-in-time GEMM (conv1_tc.cu): B_kw[n = jj*32 + c][o] = 0.5 * w'[c][o - jj][kw] for 0 <= o-jj <= 2,
+  // stored [kw][K chunk o/8][n][o%8]; 0.5 = the (2,1) average pool folded through the ReLU (positively homogeneous)
+  {
+    std::vector<uint16_t> p1((size_t)3 * 2 * 256 * 8, 0);
+    for (int kw = 0; kw < 3; ++kw)
+      for (int jj = 0; jj < 8; ++jj)
+        for (int c = 0; c < 32; ++c)
+          for (int kh = 0; kh < 3; ++kh) {
+            const int o = jj + kh, nn = jj * 32 + c;
+            p1[(((size_t)kw * 2 + (o >> 3)) * 256 + nn) * 8 + (o & 7)] = f32_to_act_bits(0.5f * m->c1.w[c * 9 + kh * 3 + kw]);
+          }
+    for (int c = 0; c < 32; ++c) m->b1h[c] = 0.5f * m->c1.b[c];
+    if ((st = dev_upload(m, &m->w1pack, p1)) != DFS_OK) return fail(st);
+    if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->xt), (size_t)conv1_xt_rows(m->chunk) * 16, true)) != DFS_OK) return fail(st);
+  }
 
   const int64_t ncols = (int64_t)m->chunk * kCols + 32;
   m->act1 = ActBuf{nullptr, 4, 160 + 2, ncols};
@@ -316,7 +340,11 @@ extern "C" int dfs_cnn2d_score(dfs_model* m, const dfs_features* feats, float* o
     const float* x = feats->x + i0 * feats->stride_n;
     {
       ProfScope ps(m, 0, stream);
-      DFS_PROPAGATE(launch_conv1(x, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->c1, nullptr, nullptr, false, m->act1, stream));
+      if (m->conv1_impl == 0)
+        DFS_PROPAGATE(launch_conv1_tc(x, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->xt, m->w1pack, m->b1h, m->act1, m->num_sms,
+                                      stream));
+      else
+        DFS_PROPAGATE(launch_conv1(x, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->c1, nullptr, nullptr, false, m->act1, stream));
     }
     {
       ProfScope ps(m, 1, stream);

@@ -1,0 +1,252 @@
+// conv1_tc.cu -- CNN2D block 1 on the tensor cores:
+//   nn.Conv2d(1,32,3,p=1) + BatchNorm2d + ReLU + AvgPool2d((2,1))      /root/reference/src/model.py:15-18
+//
+// Cin = 1 gives K = 9 per output, not a tensor-core shape as an im2col GEMM.  Instead the conv is
+// written as a *Toeplitz-in-time* GEMM whose A operand is the raw (fp16, time-major) input itself:
+//   row  R = (feature column f', time block tb)          -> 8 conv outputs t = 8tb .. 8tb+7
+//   col  n = jj*32 + c  (jj = time offset in the block, c = output channel), N = 256
+//   K    = 3 feature taps kw  x  16 consecutive input samples x[8tb-1 .. 8tb+14][f'+kw-1]
+//   B_kw[n][o] = 0.5*w'[c][o-jj][kw] if 0 <= o-jj <= 2 else 0      (BN folded, 0.5 = the (2,1) average)
+// With the input stored as xT[column][1+t] (fp16, 328 samples = 41 blocks of 16 B per column) row
+// R's two 16-byte K chunks are xT rows R and R+1, i.e. the SWIZZLE_NONE K-major descriptor has
+// LBO = 16 B, SBO = 128 B, and the feature tap kw is a +-41-row shift of the start address.  One
+// 1-D bulk copy of 212 rows x 16 B (3.4 KB) feeds a 128-row tile: 3 tcgen05.mma (M=128, N=256, K=16)
+// produce 1024 conv outputs x 32 channels.  Epilogue: +bias, ReLU, add the two time steps of a pool
+// window (columns n and n+32 of the same thread -- no shuffles), fp16, FT8 stores.
+// Issued MACs are 3.5x the useful ones (Toeplitz zeros) but run ~30x faster than CUDA-core FMAs.
+//
+// conv1_prep_kernel converts the caller's strided fp32 features into xT.
+#include "common.cuh"
+#include "kernels.h"
+#include "layout.cuh"
+
+namespace dfs {
+
+constexpr int kXtBlocks = 41;            // 16-byte blocks (8 samples) per xT column: samples t = -1 .. 326
+constexpr int kXtLead = 48;              // zero rows before column 0 (halo of the first tile)
+constexpr int kC1WinRows = 128 + 2 * kXtBlocks + 2;   // 212
+constexpr int kC1WinB = kC1WinRows * 16;               // 3392
+constexpr int kC1WinBAl = 3456;
+constexpr int kC1Stages = 4;
+constexpr int kC1WgtB = 3 * 256 * 16 * 2;              // 24576
+constexpr int kC1EpiWarps = 16;
+constexpr int kC1Threads = (kC1EpiWarps + 3) * 32;     // 608
+constexpr int kC1StageWarpB = 2 * 128 * 16;              // epilogue staging per warp: 2 planes x 128 chunks x 16 B
+constexpr int kC1BarOff = kC1WgtB + kC1Stages * kC1WinBAl;
+constexpr int kC1StageOff = kC1BarOff + 256;
+constexpr int kC1SmemB = kC1StageOff + kC1EpiWarps * kC1StageWarpB + kC1EpiWarps * 32 * 4;
+
+int64_t conv1_xt_rows(int64_t n_utts) { return kXtLead + n_utts * kCols * kXtBlocks + 128 + 2 * kXtBlocks + 16; }
+
+// ------------------------------------------------------------------------------------------
+// prep: fp32 strided features -> xT fp16 (row = 8 consecutive samples of one feature column)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1_prep_kernel(const float* __restrict__ x, long long sn, long long st, long long sf, long long total,
+                                                          uint16_t* __restrict__ xt) {
+  // item = (n, f, blk); thread mapping chosen so that global reads coalesce for the given storage order
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int f, blk;
+  long long n;
+  if (sf == 1) {  // feature-contiguous storage: consecutive threads -> consecutive features
+    f = (int)(idx % kF);
+    blk = (int)((idx / kF) % kXtBlocks);
+    n = idx / ((long long)kF * kXtBlocks);
+  } else {        // time-contiguous storage (the reference's transposed view): consecutive threads -> consecutive blocks
+    blk = (int)(idx % kXtBlocks);
+    f = (int)((idx / kXtBlocks) % kF);
+    n = idx / ((long long)kF * kXtBlocks);
+  }
+  const float* src = x + n * sn + (long long)f * sf;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int t = 8 * blk - 1 + e;
+    v[e] = (t >= 0 && t < kT) ? src[(long long)t * st] : 0.0f;
+  }
+  uint16_t* dst = xt + ((long long)kXtLead + (n * kCols + f + 1) * kXtBlocks + blk) * 8;
+  const float lim = 65504.0f;
+  st_global_v4(dst, pack_act2(fmaxf(v[0], -lim), fmaxf(v[1], -lim)), pack_act2(fmaxf(v[2], -lim), fmaxf(v[3], -lim)),
+               pack_act2(fmaxf(v[4], -lim), fmaxf(v[5], -lim)), pack_act2(fmaxf(v[6], -lim), fmaxf(v[7], -lim)));
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM kernel
+// ------------------------------------------------------------------------------------------
+struct Conv1TcParams {
+  const uint16_t* xt;      // xT rows (16 B each)
+  const uint16_t* wpack;   // [kw][chunk 2][n 256][8] fp16 Toeplitz weights
+  float bias[32];          // 0.5 * folded bias
+  int n_tiles;
+  int n_utts;
+  uint16_t* out;           // act1, FT8, RS = 162
+  long long out_ncols;
+};
+
+__global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_constant__ Conv1TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* wsm = smem;
+  uint8_t* win0 = smem + kC1WgtB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kC1BarOff);
+  uint8_t* stage0 = smem + kC1StageOff;
+  uint64_t* full = bars;                 // [stages]
+  uint64_t* empty = bars + kC1Stages;    // [stages]
+  uint64_t* tfull = empty + kC1Stages;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kC1EpiWarps && lane == 0) {
+    for (int i = 0; i < kC1Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == kC1EpiWarps + 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kC1EpiWarps) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, kC1WgtB);
+      for (int off = 0; off < kC1WgtB; off += 8192) bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, 8192, wbar);
+      uint32_t ws = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ws) {
+        const int stage = ws % kC1Stages;
+        mbar_wait(&empty[stage], ((ws / kC1Stages) & 1) ^ 1, 21);
+        mbar_arrive_expect_tx(&full[stage], kC1WinB);
+        // window = xT rows [R0 - 41, R0 + 128 + 41 + 2), R0 = 128*tile, shifted by the lead margin
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.xt) + ((long long)kXtLead + 128ll * tile - kXtBlocks) * 16;
+        bulk_g2s(win0 + stage * kC1WinBAl, src, kC1WinB, &full[stage]);
+      }
+    }
+  } else if (warp == kC1EpiWarps + 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, 256);
+      const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 256 * 16, 128);
+      const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
+      const uint64_t a_desc0 = umma_smem_desc(smem_u32(win0), 16, 128);   // LBO = 16 B: K chunk 1 of row R is row R+1
+      const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
+      mbar_wait(wbar, 0, 22);
+      uint32_t ws = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ws) {
+        const int stage = ws % kC1Stages, acc = ws & 1;
+        mbar_wait(&full[stage], (ws / kC1Stages) & 1, 23);
+        mbar_wait(&tempty[acc], ((ws >> 1) & 1) ^ 1, 24);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (kC1WinBAl >> 4));
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kw * kXtBlocks), a_hi, b_lo0 + (uint32_t)(kw * (8192 >> 4)), b_hi, idesc,
+                        kw != 0 ? 1u : 0u);
+        umma_commit(&tfull[acc]);
+        umma_commit(&empty[stage]);
+      }
+    }
+  } else if (warp < kC1EpiWarps) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;          // TMEM lane quarter
+    const int h = (warp >> 2) & 1;   // channel half: channels 16h .. 16h+15 = output planes 2h, 2h+1
+    const int grp = warp >> 3;       // accumulator / tile parity this warp serves
+    const long long plane_elems = p.out_ncols * 162 * 8;
+    // Per-warp staging: a thread owns 4 pooled rows x 2 planes = 8 chunks of 16 B, but its rows are 64 B apart from
+    // the next lane's, which would make every global store instruction touch 32 sectors.  The chunks go through
+    // shared memory (XOR-swizzled, conflict-free both ways) and are stored so that lane l of store j writes chunk
+    // 32j + l of the warp's contiguous 2 KB run per plane.
+    uint4* stage = reinterpret_cast<uint4*>(stage0 + warp * kC1StageWarpB);            // [2 planes][128 chunks]
+    int* dsttab = reinterpret_cast<int*>(stage0 + kC1EpiWarps * kC1StageWarpB) + warp * 32;  // first output row of each lane
+    uint32_t ws = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ws) {
+      if ((int)(ws & 1) != grp) continue;
+      const int acc = grp;
+      const long long R = 128ll * tile + 32 * q + lane;
+      const long long gcx = R / kXtBlocks;
+      const int tb = (int)(R - gcx * kXtBlocks);
+      const long long n = gcx / kCols;
+      const int fp = (int)(gcx - n * kCols);
+      const bool valid = (tb < 40) && (fp >= 1) && (fp <= kF) && (n < p.n_utts);
+      dsttab[lane] = valid ? (int)(gcx * 162 + 4 * tb + 1) : -1;
+      mbar_wait(&tfull[acc], (ws >> 1) & 1, 25);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * h;
+      const int sw = (lane >> 1) & 3;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // pooled row within the block: conv time offsets jj = 2k, 2k+1
+        float a[16], b[16];
+        tmem_ld_32x16(taddr + (2 * k) * 32, a);
+        tmem_ld_32x16(taddr + (2 * k + 1) * 32, b);
+        tmem_ld_wait();
+        if (k == 3) {  // all TMEM reads of this warp are done: release the accumulator early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          const float o0 = fmaxf(a[c] + p.bias[16 * h + c], 0.0f) + fmaxf(b[c] + p.bias[16 * h + c], 0.0f);
+          const float o1 = fmaxf(a[c + 1] + p.bias[16 * h + c + 1], 0.0f) + fmaxf(b[c + 1] + p.bias[16 * h + c + 1], 0.0f);
+          pk[c >> 1] = pack_act2(o0, o1);
+        }
+        const int slot = 4 * lane + (k ^ sw);
+        stage[slot] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        stage[128 + slot] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        uint16_t* pbase = p.out + (long long)(2 * h + pl) * plane_elems;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = 32 * j + lane, r = m >> 2, k = m & 3;
+          const int row = dsttab[r];
+          const uint4 v = stage[pl * 128 + 4 * r + (k ^ ((r >> 1) & 3))];
+          if (row >= 0) st_global_v4(pbase + (long long)(row + k) * 8, v.x, v.y, v.z, v.w);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kC1EpiWarps + 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, const uint16_t* wpack, const float* bias_half,
+                    ActBuf out, int num_sms, cudaStream_t stream) {
+  if (n_utts <= 0) return DFS_OK;
+  const long long total = (long long)n_utts * kF * kXtBlocks;
+  conv1_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, xt);
+  DFS_LAUNCH_CHECK();
+  static bool configured = false;
+  if (!configured) {
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1SmemB));
+    configured = true;
+  }
+  Conv1TcParams p{};
+  p.xt = xt;
+  p.wpack = wpack;
+  for (int i = 0; i < 32; ++i) p.bias[i] = bias_half[i];
+  p.n_tiles = (int)ceil_div64((long long)n_utts * kCols * kXtBlocks, 128);
+  p.n_utts = n_utts;
+  p.out = out.ptr;
+  p.out_ncols = out.ncols;
+  const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+  conv1_tc_kernel<<<grid, kC1Threads, kC1SmemB, stream>>>(p);
+  DFS_LAUNCH_CHECK();
+  return DFS_OK;
+}
+
+}  // namespace dfs

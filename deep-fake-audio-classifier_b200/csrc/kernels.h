@@ -18,6 +18,11 @@ int launch_cnn2d_conv2_tc(const CUtensorMap& tmap_act1, const uint16_t* wpack, c
 int launch_cnn2d_conv3_tc(const CUtensorMap& tmap_act2, const uint16_t* wpack, const float* bias, int n_utts, float* emb,
                           int num_sms, cudaStream_t stream);
 
+// ---- conv1_tc.cu (CNN2D block 1 as a Toeplitz-in-time tcgen05 GEMM) ----
+int64_t conv1_xt_rows(int64_t n_utts);   // 16-byte rows of the fp16 time-major feature copy for n utterances
+int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, const uint16_t* wpack, const float* bias_half,
+                    ActBuf out, int num_sms, cudaStream_t stream);
+
 // ---- cnn2d.cu (CUDA-core stages of the 2D-CNN) ----
 struct Conv1Weights {
   float w[32 * 9];  // folded, [co][kh][kw]

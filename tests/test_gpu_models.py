@@ -55,6 +55,21 @@ def test_cnn2d_tcgen05_equals_cuda_core_crosscheck(feats):
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=2e-5)
 
 
+def test_cnn2d_conv1_tensor_core_equals_cuda_core_crosscheck(feats):
+    """conv1 as a Toeplitz-in-time tcgen05 GEMM (fp16 input) vs the fp32 CUDA-core conv1: same pooled fp16 activations up
+    to the fp16 rounding of the input samples."""
+    sc = Cnn2dScorer(syn.cnn2d_state(0))
+    a, ea = sc.score(feats, return_embedding=True)
+    sc.set_option("conv1_impl", 1)
+    b, eb = sc.score(feats, return_embedding=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(ea.cpu().numpy(), eb.cpu().numpy(), rtol=5e-3, atol=1e-3)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=1e-4)
+    xt = feats.transpose(1, 2).contiguous().transpose(1, 2)          # time-contiguous storage takes the other prep mapping
+    sc.set_option("conv1_impl", 0)
+    np.testing.assert_allclose(sc.score(xt).cpu().numpy(), a.cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
 def test_cnn2d_layouts_chunking_and_host_path(feats):
     sd = syn.cnn2d_state(0)
     base = Cnn2dScorer(sd).score(feats, apply_sigmoid=True).cpu().numpy()
