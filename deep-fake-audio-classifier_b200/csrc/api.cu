@@ -269,12 +269,33 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
   m->kind = KIND_CNN2D;
   int st = model_common_init(m, device);
   if (st != DFS_OK) { delete m; return st; }
-  m->chunk = max_chunk > 0 ? max_chunk : 208;  // 208 * 182 / 16 column tiles = 16 full waves of 148 CTAs
+  // 416 * 182 / 16 column tiles = 32 full waves of 148 CTAs; measured plateau of the chunk sweep (tools/sweep.sh):
+  // smaller passes lose to launch gaps / tail waves, larger ones only delay the first H2D overlap of dfs_score_host
+  m->chunk = max_chunk > 0 ? max_chunk : 416;
   auto fail = [&](int s) { dfs_model_destroy(m); return s; };
 
   fold_conv1(w->conv[0], m->c1);
   std::vector<float> b2, b3;
-  std::vector<uint16_t> p2 = pack_conv3x3_f16(w->conv[1], 64, 32, b2);
+  // conv2 in the PAIR formulation (conv_tc.cu): B[tap = r*3+kw][ci/8][n = dt2*64 + co][ci%8] = 0.5 * w'[co][ci][kh = r-dt2][kw]
+  // for 0 <= r - dt2 <= 2, else 0; r = input time step relative to 2j-1, dt2 = which of the two pooled outputs.
+  std::vector<uint16_t> p2((size_t)12 * 32 * 128, 0);
+  {
+    std::vector<double> scale, shift;
+    bn_fold(w->conv[1], 64, scale, shift);
+    b2.resize(64);
+    for (int o = 0; o < 64; ++o) b2[o] = (float)(0.5 * shift[o]);
+    for (int r = 0; r < 4; ++r)
+      for (int kw = 0; kw < 3; ++kw)
+        for (int dt2 = 0; dt2 < 2; ++dt2) {
+          const int kh = r - dt2;
+          if (kh < 0 || kh > 2) continue;
+          for (int ci = 0; ci < 32; ++ci)
+            for (int o = 0; o < 64; ++o) {
+              const double wv = 0.5 * (double)w->conv[1].weight[((size_t)o * 32 + ci) * 9 + kh * 3 + kw] * scale[o];
+              p2[((((size_t)(r * 3 + kw)) * 4 + (ci >> 3)) * 128 + dt2 * 64 + o) * 8 + (ci & 7)] = f32_to_act_bits((float)wv);
+            }
+        }
+  }
   std::vector<uint16_t> p3 = pack_conv3x3_f16(w->conv[2], 128, 64, b3);
   memcpy(m->b2, b2.data(), sizeof(m->b2));
   memcpy(m->b3, b3.data(), sizeof(m->b3));
@@ -305,8 +326,8 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
   }
 
   const int64_t ncols = (int64_t)m->chunk * kCols + 32;
-  m->act1 = ActBuf{nullptr, 4, 160 + 2, ncols};
-  m->act2 = ActBuf{nullptr, 8, 80 + 2, ncols};
+  m->act1 = ActBuf{nullptr, 8, kAct1RS, ncols};  // FT8P: 4 channel chunks x 2 time parities, 80 time pairs + 2 pads
+  m->act2 = ActBuf{nullptr, 8, kAct2RS, ncols};  // FT8 : 8 channel chunks, 80 time steps + 2 pads
   if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->act1.ptr), m->act1.bytes(), true)) != DFS_OK) return fail(st);
   if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->act2.ptr), m->act2.bytes(), true)) != DFS_OK) return fail(st);
   if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->emb), (size_t)m->chunk * kF * 128 * 4, true)) != DFS_OK) return fail(st);

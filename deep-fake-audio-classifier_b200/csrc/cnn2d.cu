@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x,
       for (int b = 0; b < NC; ++b) xin[a][b] = xs[(2 * j + a) * XW + fc0 + b];
     const int fo = blockIdx.x * FO + fl;
     const long long gc = (long long)n * cols_out + fo + 1;
-    uint16_t* dst = out.ptr + (gc * out.RS + (j + 1)) * 8;
+    // CNN2D: FT8P (time parity planes, row = j/2 + 1); CAE block 1 (POOLF): plain FT8 (row = j + 1)
+    uint16_t* dst = POOLF ? out.ptr + (gc * out.RS + (j + 1)) * 8
+                          : out.ptr + (long long)((j & 1) * 4) * plane_elems + (gc * out.RS + (j >> 1) + 1) * 8;
 #pragma unroll
     for (int pj = 0; pj < 4; ++pj) {
       float r[8];
@@ -173,9 +175,26 @@ __global__ void cnn2d_conv2_simt_kernel(ActBuf act1, const uint16_t* __restrict_
   const int f = (int)((pos / 80) % kF);
   const long long n = pos / (80 * kF);
   const long long gc = n * kCols + f + 1;
-  float s = 0.0f;
-  for (int d = 0; d < 2; ++d) s += fmaxf(conv_at<32, 64>(act1, wpack, gc, 2 * to + 1 + d, co) + bias[co], 0.0f);
-  const __half b = __float2half_rn(fminf(0.5f * s, 65504.0f));
+  // Same GEMM as the PAIR formulation of conv_tc.cu, evaluated naively: output pair `to`, column dt2*64 + co,
+  // K = (input time step r of 2*to-1 .. 2*to+2, feature tap kw, channel); act1 is FT8P (row = t/2 + 1, parity planes);
+  // wpack = [r*3+kw][ci/8][128][8] with the 0.5 of the average pool folded in (bias too).
+  const long long plane_elems = act1.plane_elems();
+  float acc[2] = {0.0f, 0.0f};
+  for (int r = 0; r < 4; ++r) {
+    const int t_in = 2 * to - 1 + r;                       // -1 .. 160; s = t_in + 2 = 2*row + par
+    const int par = (t_in + 2) & 1, row = (t_in + 2) >> 1;
+    for (int kw = 0; kw < 3; ++kw) {
+      const uint16_t* src = act1.ptr + (long long)(par * 4) * plane_elems + ((gc + kw - 1) * act1.RS + row) * 8;
+      for (int ci = 0; ci < 32; ++ci) {
+        const float xv = act_bits_to_float(src[(ci >> 3) * plane_elems + (ci & 7)]);
+        const uint16_t* wrow = wpack + ((((long long)(r * 3 + kw)) * 4 + (ci >> 3)) * 128) * 8 + (ci & 7);
+        acc[0] = fmaf(xv, act_bits_to_float(wrow[(long long)co * 8]), acc[0]);
+        acc[1] = fmaf(xv, act_bits_to_float(wrow[(long long)(64 + co) * 8]), acc[1]);
+      }
+    }
+  }
+  const float s = fmaxf(acc[0] + bias[co], 0.0f) + fmaxf(acc[1] + bias[co], 0.0f);
+  const __half b = __float2half_rn(fminf(s, 65504.0f));
   act2.ptr[(co >> 3) * act2.plane_elems() + (gc * act2.RS + to + 1) * 8 + (co & 7)] = *reinterpret_cast<const uint16_t*>(&b);
 }
 

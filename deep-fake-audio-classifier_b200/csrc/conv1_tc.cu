@@ -156,12 +156,14 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
     const int q = warp & 3;          // TMEM lane quarter
     const int h = (warp >> 2) & 1;   // channel half: channels 16h .. 16h+15 = output planes 2h, 2h+1
     const int grp = warp >> 3;       // accumulator / tile parity this warp serves
-    const long long plane_elems = p.out_ncols * 162 * 8;
-    // Per-warp staging: a thread owns 4 pooled rows x 2 planes = 8 chunks of 16 B, but its rows are 64 B apart from
-    // the next lane's, which would make every global store instruction touch 32 sectors.  The chunks go through
-    // shared memory (XOR-swizzled, conflict-free both ways) and are stored so that lane l of store j writes chunk
-    // 32j + l of the warp's contiguous 2 KB run per plane.
-    uint4* stage = reinterpret_cast<uint4*>(stage0 + warp * kC1StageWarpB);            // [2 planes][128 chunks]
+    const long long plane_elems = p.out_ncols * kAct1RS * 8;
+    // Output layout FT8P (layout.cuh): pooled time step j = 4tb + k goes to parity plane j&1, row j/2 + 1.
+    // Per-warp staging: a thread owns 2 channel chunks x 2 parities x 2 rows = 8 chunks of 16 B, its two rows of a
+    // (chunk, parity) plane are contiguous but 32 B apart from the next lane's, which would make every global
+    // store instruction touch 32 half-used sectors.  The chunks go through shared memory (XOR-swizzled,
+    // conflict-free both ways) and are stored so that lane l of store j writes chunk 32j + l of the warp's
+    // contiguous 1 KB run per plane.
+    uint4* stage = reinterpret_cast<uint4*>(stage0 + warp * kC1StageWarpB);            // [2 chunks][2 parities][64]
     int* dsttab = reinterpret_cast<int*>(stage0 + kC1EpiWarps * kC1StageWarpB) + warp * 32;  // first output row of each lane
     uint32_t ws = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ws) {
@@ -173,11 +175,11 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
       const long long n = gcx / kCols;
       const int fp = (int)(gcx - n * kCols);
       const bool valid = (tb < 40) && (fp >= 1) && (fp <= kF) && (n < p.n_utts);
-      dsttab[lane] = valid ? (int)(gcx * 162 + 4 * tb + 1) : -1;
+      dsttab[lane] = valid ? (int)(gcx * kAct1RS + 2 * tb + 1) : -1;
       mbar_wait(&tfull[acc], (ws >> 1) & 1, 25);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * h;
-      const int sw = (lane >> 1) & 3;
+      const int sw = (lane >> 2) & 1;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {  // pooled row within the block: conv time offsets jj = 2k, 2k+1
         float a[16], b[16];
@@ -196,20 +198,24 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
           const float o1 = fmaxf(a[c + 1] + p.bias[16 * h + c + 1], 0.0f) + fmaxf(b[c + 1] + p.bias[16 * h + c + 1], 0.0f);
           pk[c >> 1] = pack_act2(o0, o1);
         }
-        const int slot = 4 * lane + (k ^ sw);
+        // pooled step j = 4tb + k: parity k&1, row offset k>>1 within the lane's two rows of that parity plane
+        const int slot = (k & 1) * 64 + 2 * lane + ((k >> 1) ^ sw);
         stage[slot] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         stage[128 + slot] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
       __syncwarp();
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl) {
-        uint16_t* pbase = p.out + (long long)(2 * h + pl) * plane_elems;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int m = 32 * j + lane, r = m >> 2, k = m & 3;
-          const int row = dsttab[r];
-          const uint4 v = stage[pl * 128 + 4 * r + (k ^ ((r >> 1) & 3))];
-          if (row >= 0) st_global_v4(pbase + (long long)(row + k) * 8, v.x, v.y, v.z, v.w);
+        for (int par = 0; par < 2; ++par) {
+          uint16_t* pbase = p.out + (long long)(par * 4 + 2 * h + pl) * plane_elems;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int m = 32 * j + lane, r = m >> 1, c = m & 1;
+            const int row = dsttab[r];
+            const uint4 v = stage[pl * 128 + par * 64 + 2 * r + (c ^ ((r >> 2) & 1))];
+            if (row >= 0) st_global_v4(pbase + (long long)(row + c) * 8, v.x, v.y, v.z, v.w);
+          }
         }
       }
       __syncwarp();
