@@ -61,7 +61,9 @@ struct dfs_model {
   uint16_t* xt = nullptr;      // fp16 time-major copy of the features (conv1_tc A operand)
   uint16_t* w1pack = nullptr;  // Toeplitz weights [kw][2][256][8]
   float b1h[32] = {0};         // 0.5 * folded conv1 bias
-  // ---- CNN1D / CAE (CUDA-core path) ----
+  // ---- CAE on the tcgen05 template (cae_tc.cu) ----
+  CaeTcState* cae = nullptr;
+  // ---- CNN1D / CAE (CUDA-core path; for the CAE it is the conv_impl = 1 cross-check) ----
   SimtConv sc[8];
   float* work = nullptr;
   float* norm_mean = nullptr;
@@ -197,6 +199,7 @@ extern "C" int dfs_model_destroy(dfs_model* m) {
   cudaDeviceSynchronize();
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   for (void* p : m->allocs) cudaFree(p);
+  delete m->cae;
   for (int b = 0; b < 2; ++b) {
     if (m->ev_in[b]) cudaEventDestroy(m->ev_in[b]);
     if (m->ev_done[b]) cudaEventDestroy(m->ev_done[b]);
@@ -331,8 +334,7 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
   if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->act1.ptr), m->act1.bytes(), true)) != DFS_OK) return fail(st);
   if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->act2.ptr), m->act2.bytes(), true)) != DFS_OK) return fail(st);
   if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->emb), (size_t)m->chunk * kF * 128 * 4, true)) != DFS_OK) return fail(st);
-  if ((st = make_act_tensor_map(&m->tmap1, m->act1, conv2_tc_window_rows())) != DFS_OK) return fail(st);
-  if ((st = make_act_tensor_map(&m->tmap2, m->act2, conv3_tc_window_rows())) != DFS_OK) return fail(st);
+  if ((st = make_cnn2d_tensor_maps(&m->tmap1, &m->tmap2, m->act1, m->act2)) != DFS_OK) return fail(st);
   if (cudaDeviceSynchronize() != cudaSuccess) {  // the zero padding must be in place before any stream uses it
     dfs_set_error("dfs_cnn2d_create: device synchronize failed");
     return fail(DFS_ERR_CUDA);
@@ -461,6 +463,99 @@ extern "C" int dfs_cnn1d_score(dfs_model* m, const dfs_features* feats, float* o
   return DFS_OK;
 }
 
+// ---- fp16 weight images for the CAE tensor-core layers (layouts: conv_tc.cuh ConvParams::wpack) ----
+// 3x3 conv (Co,Ci,3,3) -> [group][tap][ci/8][gco][8], output channels split into groups of gco, weights and bias x factor
+static std::vector<uint16_t> pack_3x3_groups(const dfs_conv_bn& c, int co, int ci, int gco, double factor, float* bias_out) {
+  std::vector<double> scale, shift;
+  bn_fold(c, co, scale, shift);
+  for (int o = 0; o < co; ++o) bias_out[o] = (float)(factor * shift[o]);
+  std::vector<uint16_t> out((size_t)9 * ci * co);
+  for (int o = 0; o < co; ++o)
+    for (int i = 0; i < ci; ++i)
+      for (int tap = 0; tap < 9; ++tap) {
+        const double w = factor * (double)c.weight[((size_t)o * ci + i) * 9 + tap] * scale[o];
+        const size_t g = o / gco, ol = o % gco;
+        out[((((size_t)g * 9 + tap) * (ci / 8) + (i >> 3)) * gco + ol) * 8 + (i & 7)] = f32_to_act_bits((float)w);
+      }
+  return out;
+}
+// PAIR formulation: [tap = r*3+kw][ci/8][n = dt2*co + o][8] = factor * w'[o][ci][kh = r-dt2][kw] (0 outside the 3 taps)
+static std::vector<uint16_t> pack_pair(const dfs_conv_bn& c, int co, int ci, double factor, float* bias_out) {
+  std::vector<double> scale, shift;
+  bn_fold(c, co, scale, shift);
+  for (int o = 0; o < co; ++o) bias_out[o] = (float)(factor * shift[o]);
+  std::vector<uint16_t> out((size_t)12 * ci * 2 * co, 0);
+  for (int r = 0; r < 4; ++r)
+    for (int kw = 0; kw < 3; ++kw)
+      for (int dt2 = 0; dt2 < 2; ++dt2) {
+        const int kh = r - dt2;
+        if (kh < 0 || kh > 2) continue;
+        for (int i = 0; i < ci; ++i)
+          for (int o = 0; o < co; ++o) {
+            const double w = factor * (double)c.weight[((size_t)o * ci + i) * 9 + kh * 3 + kw] * scale[o];
+            out[((((size_t)(r * 3 + kw)) * (ci / 8) + (i >> 3)) * (2 * co) + dt2 * co + o) * 8 + (i & 7)] = f32_to_act_bits((float)w);
+          }
+      }
+  return out;
+}
+// ConvTranspose2d (Ci,Co,2,2) as 1x1 GEMMs: quadrant q = a*2+b; the quadrants are spread over `groups` groups of
+// qpg = 4/groups quadrants, column n = (q % qpg) * co + o  ->  [group][ci/8][qpg*co][8]
+static std::vector<uint16_t> pack_convT(const dfs_conv_bn& c, int ci, int co, int groups, float* bias_out) {
+  std::vector<double> scale, shift;
+  bn_fold(c, co, scale, shift);
+  for (int o = 0; o < co; ++o) bias_out[o] = (float)shift[o];
+  const int qpg = 4 / groups, ng = qpg * co;
+  std::vector<uint16_t> out((size_t)4 * ci * co);
+  for (int q = 0; q < 4; ++q)
+    for (int i = 0; i < ci; ++i)
+      for (int o = 0; o < co; ++o) {
+        const double w = (double)c.weight[((size_t)i * co + o) * 4 + q] * scale[o];
+        const size_t g = q / qpg, nn = (size_t)(q % qpg) * co + o;
+        out[(((size_t)g * (ci / 8) + (i >> 3)) * ng + nn) * 8 + (i & 7)] = f32_to_act_bits((float)w);
+      }
+  return out;
+}
+
+static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
+  CaeTcState* s = new (std::nothrow) CaeTcState();
+  DFS_REQUIRE(s, DFS_ERR_NOMEM, "out of host memory");
+  m->cae = s;
+  memset(s->bias, 0, sizeof(s->bias));
+  fold_conv1(w->enc[0], s->c1);
+  std::vector<uint16_t> packs[6];
+  packs[0] = pack_pair(w->enc[1], 64, 32, 0.25, s->bias[0]);             // enc2: 2x2 average folded (4 ReLU outputs are summed)
+  packs[1] = pack_3x3_groups(w->enc[2], 128, 64, 128, 0.25, s->bias[1]);  // enc3
+  packs[2] = pack_3x3_groups(w->enc[3], 256, 128, 64, 0.25, s->bias[2]);  // enc4: 4 groups of 64 output channels
+  packs[3] = pack_convT(w->dec[0], 256, 128, 4, s->bias[3]);              // dec1: one quadrant per group
+  packs[4] = pack_convT(w->dec[1], 128, 64, 2, s->bias[4]);               // dec2: group = a, columns (b, co)
+  packs[5] = pack_convT(w->dec[2], 64, 32, 1, s->bias[5]);                // dec3: columns (a, b, co)
+  for (int i = 0; i < 6; ++i) {
+    uint16_t* d = nullptr;
+    DFS_PROPAGATE(dev_upload(m, &d, packs[i]));
+    s->w[i] = d;
+  }
+  std::vector<float> wf(128);
+  for (int q = 0; q < 4; ++q)
+    for (int i = 0; i < 32; ++i) wf[q * 32 + i] = w->dec[3].weight[(size_t)i * 4 + q];
+  float* wfd = nullptr;
+  DFS_PROPAGATE(dev_upload(m, &wfd, wf));
+  s->w_final = wfd;
+  s->final_bias = w->dec[3].bias[0];
+  for (int l = 0; l < 7; ++l) {
+    int planes, cols, rs;
+    cae_tc_geometry(l, &planes, &cols, &rs);
+    s->act[l] = ActBuf{nullptr, planes, rs, (int64_t)m->chunk * cols + 32};
+    DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&s->act[l].ptr), s->act[l].bytes(), true));
+  }
+  DFS_PROPAGATE(cae_tc_make_maps(s));
+  std::vector<float> b2(s->bias[4], s->bias[4] + 64);
+  float* b2d = nullptr;
+  DFS_PROPAGATE(dev_upload(m, &b2d, b2));
+  DFS_PROPAGATE(cae_tc_init_constants(s, m->chunk, b2d, nullptr));
+  DFS_CUDA_CHECK(cudaDeviceSynchronize());
+  return DFS_OK;
+}
+
 extern "C" int dfs_cae_create(dfs_model** out, int device, const dfs_cae_weights* w, int max_chunk) {
   DFS_REQUIRE(out && w, DFS_ERR_INVALID, "dfs_cae_create: NULL argument");
   *out = nullptr;
@@ -475,8 +570,9 @@ extern "C" int dfs_cae_create(dfs_model** out, int device, const dfs_cae_weights
   m->kind = KIND_CAE;
   int st = model_common_init(m, device);
   if (st != DFS_OK) { delete m; return st; }
-  m->chunk = max_chunk > 0 ? max_chunk : 64;
+  m->chunk = max_chunk > 0 ? max_chunk : 256;
   auto fail = [&](int s) { dfs_model_destroy(m); return s; };
+  if ((st = cae_tc_create(m, w)) != DFS_OK) return fail(st);
   const int eci[4] = {1, 32, 64, 128}, eco[4] = {32, 64, 128, 256};
   for (int i = 0; i < 4; ++i)
     if ((st = make_simt_conv(m, w->enc[i], eco[i], eci[i], 9, &m->sc[i])) != DFS_OK) return fail(st);
@@ -502,11 +598,43 @@ static int cae_run(dfs_model* m, const dfs_features* feats, int apply_normalizer
   const float* sd = apply_normalizer ? m->norm_std : nullptr;
   for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk) {
     const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
-    DFS_PROPAGATE(launch_cae_simt(feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->sc, m->sc + 4,
-                                  m->final_bias, mean, sd, m->work, mse_dev ? mse_dev + i0 : nullptr,
-                                  recon_dev ? recon_dev + i0 * (int64_t)kT * kF : nullptr,
-                                  latent_dev ? latent_dev + i0 * (int64_t)256 * 20 * 11 : nullptr, stream));
+    const float* x = feats->x + i0 * feats->stride_n;
+    float* mse = mse_dev ? mse_dev + i0 : nullptr;
+    float* recon = recon_dev ? recon_dev + i0 * (int64_t)kT * kF : nullptr;
+    float* latent = latent_dev ? latent_dev + i0 * (int64_t)256 * 20 * 11 : nullptr;
+    if (m->conv_impl == 0)
+      DFS_PROPAGATE(launch_cae_tc(m->cae, x, feats->stride_n, feats->stride_t, feats->stride_f, nk, mean, sd, mse, recon, latent, 7, m->num_sms,
+                                  stream));
+    else
+      DFS_PROPAGATE(launch_cae_simt(x, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->sc, m->sc + 4, m->final_bias, mean, sd, m->work,
+                                    mse, recon, latent, stream));
   }
+  return DFS_OK;
+}
+
+// Debug: activations after CAE layer `layer` (0..6 = e1 e2 e3 e4 d1 d2 d3) as [n][H][W][C] fp32, from the tensor-core
+// path (impl 0) or the CUDA-core path (impl 1); n must not exceed the handle's chunk.
+extern "C" int dfs_cae_debug_layer(dfs_model* m, const dfs_features* feats, int impl, int layer, int apply_normalizer, float* out_dev,
+                                   void* stream_) {
+  DFS_REQUIRE(m && m->kind == KIND_CAE, DFS_ERR_INVALID, "dfs_cae_debug_layer: not a CAE handle");
+  DFS_PROPAGATE(check_feats(feats, "dfs_cae_debug_layer"));
+  DFS_REQUIRE(out_dev && layer >= 0 && layer < 7 && feats->n <= m->chunk, DFS_ERR_INVALID, "dfs_cae_debug_layer: bad argument");
+  DFS_REQUIRE(!apply_normalizer || m->norm_mean, DFS_ERR_INVALID, "CAE handle was created without normaliser statistics");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DFS_CUDA_CHECK(cudaSetDevice(m->device));
+  const float* mean = apply_normalizer ? m->norm_mean : nullptr;
+  const float* sd = apply_normalizer ? m->norm_std : nullptr;
+  const int nk = (int)feats->n;
+  if (impl == 0) {
+    DFS_PROPAGATE(launch_cae_tc(m->cae, feats->x, feats->stride_n, feats->stride_t, feats->stride_f, nk, mean, sd, nullptr, nullptr, nullptr, layer,
+                                m->num_sms, stream));
+    return cae_tc_dump_layer(m->cae, layer, nk, out_dev, stream);
+  }
+  DFS_PROPAGATE(launch_cae_simt(feats->x, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->sc, m->sc + 4, m->final_bias, mean, sd, m->work,
+                                nullptr, nullptr, nullptr, stream));
+  size_t per = 0;
+  const float* src = cae_simt_layer_ptr(m->work, nk, layer, &per);
+  DFS_CUDA_CHECK(cudaMemcpyAsync(out_dev, src, per * (size_t)nk * 4, cudaMemcpyDeviceToDevice, stream));
   return DFS_OK;
 }
 

@@ -53,9 +53,8 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x,
       for (int b = 0; b < NC; ++b) xin[a][b] = xs[(2 * j + a) * XW + fc0 + b];
     const int fo = blockIdx.x * FO + fl;
     const long long gc = (long long)n * cols_out + fo + 1;
-    // CNN2D: FT8P (time parity planes, row = j/2 + 1); CAE block 1 (POOLF): plain FT8 (row = j + 1)
-    uint16_t* dst = POOLF ? out.ptr + (gc * out.RS + (j + 1)) * 8
-                          : out.ptr + (long long)((j & 1) * 4) * plane_elems + (gc * out.RS + (j >> 1) + 1) * 8;
+    // FT8P (layout.cuh): pooled time step j -> parity plane group j&1, row j/2 + 1 (both consumers are PAIR GEMMs)
+    uint16_t* dst = out.ptr + (long long)((j & 1) * 4) * plane_elems + (gc * out.RS + (j >> 1) + 1) * 8;
 #pragma unroll
     for (int pj = 0; pj < 4; ++pj) {
       float r[8];

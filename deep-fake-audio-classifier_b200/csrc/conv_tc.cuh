@@ -1,0 +1,468 @@
+// conv_tc.cuh -- the tcgen05 implicit-GEMM convolution template shared by the 2D-CNN (conv_tc.cu) and
+// the convolutional autoencoder (cae_tc.cu).
+//
+// GEMM view (layouts: layout.cuh):
+//   one MMA tile  = 128 rows = 16 feature columns x 8 consecutive row indices of the input layout  (M = 128)
+//   A (activations): SWIZZLE_NONE K-major smem descriptor straight into the TMA-loaded window; a tap is a
+//                    compile-time constant added to the descriptor's start-address field
+//   B (weights)    : BN-folded fp16, resident in shared memory for the whole kernel
+//   D              : TMEM, NACC accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// MODE_3X3  : row = (feature column, time step); N = COUT; K = 9 taps x CIN.
+// MODE_PAIR : the input is stored with even/odd time steps in separate planes (FT8P), a row is a PAIR of output
+//             time steps (2j, 2j+1), N = 2 x COUT (columns [0,COUT) = output at 2j, [COUT,2 COUT) = at 2j+1),
+//             K = 4 input time steps x 3 feature taps x CIN (zero weights where a time step does not reach an
+//             output).  Chosen when COUT = 64: the measured single-CTA MMA cost is ~88 cycles for any N <= 128
+//             (DESIGN.md §4), so N = 128 with 4/3 of the MACs beats N = 64; the time pool becomes in-thread.
+// MODE_1X1  : one tap, no halo: the k=2,s=2 transposed convolutions of the CAE decoder are GEMMs over positions
+//             with N = (output quadrant, COUT) and a pixel-shuffle epilogue.
+// KSPLIT    : the CIN/8 channel planes of a window are loaded as KSPLIT separate pipeline stages ("pieces"),
+//             which bounds shared memory for CIN >= 128.
+// blockIdx.y: output-channel / quadrant group (weights, bias and output placement are offset per group).
+//
+// Warp roles (352 threads): warps 0..7 = epilogue (TMEM lane quarter = warp%4, column half = warp/4),
+// warp 8 = TMA producer, warp 9 = MMA issuer (one lane), warp 10 = TMEM allocator.
+// Work unit = one column tile (16 feature columns, all rows); units are dealt round-robin to a persistent grid.
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+#include "layout.cuh"
+
+namespace dfs {
+
+enum { MODE_3X3 = 0, MODE_PAIR = 1, MODE_1X1 = 2 };
+enum {
+  EPI_PAIR_POOL = 0,    // PAIR: relu both time steps, add (time pool), store FT8                    (CNN2D conv2)
+  EPI_MEAN_T = 1,       // 3x3 : relu, sum over all rows of the unit, store [n][F][COUT] fp32         (CNN2D conv3)
+  EPI_PAIR_POOL_F = 2,  // PAIR: time pool in-thread + feature pool with lane^8, store FT8            (CAE enc2)
+  EPI_POOL_TF = 3,      // 3x3 : relu, 2x2 pool with lane^1 (time) and lane^8 (feature), store FT8    (CAE enc3, enc4)
+  EPI_SHUFFLE = 4       // 1x1 : relu, pixel-shuffle store of the quadrant(s) held in the columns      (CAE dec1-3)
+};
+
+template <int MODE_, int CIN_, int COUT_, int NG_, int ROWS_, int MT_, int NSTAGE_, int NACC_, int KSPLIT_, int EPI_>
+struct ConvCfg {
+  static constexpr int MODE = MODE_, CIN = CIN_, COUT = COUT_, NG = NG_, ROWS = ROWS_, MT = MT_, NSTAGE = NSTAGE_, NACC = NACC_,
+                       KSPLIT = KSPLIT_, EPI = EPI_;
+  static constexpr bool PAIR = (MODE == MODE_PAIR);
+  static constexpr int HALO = (MODE == MODE_1X1) ? 0 : 1;
+  static constexpr int NTAP = PAIR ? 12 : (MODE == MODE_1X1 ? 1 : 9);
+  static constexpr int CCH = CIN / 8;                  // 16-byte channel chunks
+  static constexpr int KCH = PAIR ? 2 * CCH : CCH;     // planes of the input layout (PAIR: x2 time parities)
+  static constexpr int PPL = KCH / KSPLIT;             // planes per piece
+  static constexpr int CPP = CCH / KSPLIT;             // channel chunks per piece
+  static constexpr int WROWS = 8 * MT + 2 * HALO;      // window rows incl. halo
+  static constexpr int WCOLS = kColTile + 2 * HALO;    // window columns (feature) incl. halo
+  static constexpr int PLANE_B = WCOLS * WROWS * 16;   // bytes of one plane of the window
+  static constexpr int WIN_B = PPL * PLANE_B;          // TMA transaction bytes per piece
+  static constexpr int WIN_B_AL = (WIN_B + 1023) & ~1023;
+  static constexpr int WGT_B = NTAP * CIN * NG * 2;    // per output group
+  static constexpr int WGT_B_AL = (WGT_B + 1023) & ~1023;
+  static constexpr int ST = ROWS / (8 * MT);           // windows (super-tiles) per unit
+  static constexpr int TILES = ROWS / 8;               // MMA tiles per unit
+  static constexpr int TMEM_COLS = NACC * NG;
+  static constexpr int BAR_B = 256;
+  static constexpr int SMEM_B = WGT_B_AL + NSTAGE * WIN_B_AL + BAR_B;
+  static constexpr int THREADS = 352;
+  // two CTAs per SM when shared memory and TMEM allow
+  static constexpr int OCC = (SMEM_B <= 113 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
+  static_assert(ROWS % (8 * MT) == 0, "rows must be a multiple of the super-tile height");
+  static_assert(NACC % MT == 0, "the accumulators of one window must be consecutive");
+  static_assert(WROWS * 8 <= 256, "TMA box inner dimension limit");
+  static_assert(TMEM_COLS == 32 || TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
+  static_assert(NG % 64 == 0 && NG <= 256 && CIN % 16 == 0, "shape");
+  static_assert(!PAIR || KSPLIT == 1, "PAIR mode loads both parities in one piece");
+  static_assert(CCH % KSPLIT == 0 && CPP % 2 == 0, "a piece must hold whole K=16 steps");
+  static_assert(SMEM_B <= 227 * 1024, "shared memory budget");
+
+  // byte offset of the A start address for (tap, K step kk of the piece) relative to the tile's first row in the piece window
+  __host__ __device__ static constexpr int a_off(int tap, int kk) {
+    if (MODE == MODE_PAIR) {
+      // tap = r*3 + kw; input time step r in 0..3 relative to 2j-1: r=0 -> odd plane, row-1; r=1 -> even, row;
+      // r=2 -> odd, row; r=3 -> even, row+1  (rows are pair indices; the window starts one row early)
+      const int r = tap / 3, kw = tap % 3;
+      const int par = (r == 0 || r == 2) ? 1 : 0;
+      const int rowoff = (r == 0) ? 0 : (r == 3) ? 2 : 1;
+      return (par * CCH + 2 * kk) * PLANE_B + (kw * WROWS + rowoff) * 16;
+    }
+    if (MODE == MODE_1X1) return (2 * kk) * PLANE_B;
+    const int kh = tap / 3, kw = tap % 3;
+    return (2 * kk) * PLANE_B + (kw * WROWS + kh) * 16;
+  }
+  // byte offset of the B start address for (tap, piece, K step kk)
+  __host__ __device__ static constexpr int b_off(int tap, int piece, int kk) { return ((tap * CCH + piece * CPP + 2 * kk) * NG) * 16; }
+};
+
+struct ConvParams {
+  const uint16_t* wpack;  // [group][NTAP][CIN/8][NG][8] fp16, BN folded
+  float bias[256];        // folded bias per OUTPUT CHANNEL (all groups), pre-scaled like the weights
+  int n_units;            // column tiles
+  int n_utts;
+  int cols;               // padded feature columns per utterance of the INPUT layout
+  int feats;              // valid feature columns of the input
+  int rows_valid;         // valid rows of the input (<= ROWS; rows beyond are padding whose outputs are dropped)
+  // fp16 output (FT8): geometry of the OUTPUT layout
+  uint16_t* out;
+  long long out_ncols;    // allocated columns per plane
+  int out_rs;             // rows per column
+  int out_cols;           // padded feature columns per utterance
+  int out_feats;          // valid output feature columns (pooled outputs beyond are dropped)
+  // EPI_MEAN_T: per-utterance time SUMS, [n][F][COUT] fp32 (the head applies 1/T)
+  float* emb;
+};
+
+// ---- epilogue helpers -----------------------------------------------------------------------------
+template <int NCH>
+__device__ __forceinline__ void store_chunks(uint16_t* dst, long long plane_elems, const uint32_t* pk) {
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) st_global_v4(dst + k * plane_elems, pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::OCC)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvParams p) {
+  constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, MT = Cfg::MT, NSTAGE = Cfg::NSTAGE, NACC = Cfg::NACC, NG = Cfg::NG;
+  constexpr int WROWS = Cfg::WROWS, PLANE_B = Cfg::PLANE_B, KSPLIT = Cfg::KSPLIT, HALO = Cfg::HALO;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* wsm = smem;
+  uint8_t* win0 = smem + Cfg::WGT_B_AL;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::WGT_B_AL + NSTAGE * Cfg::WIN_B_AL);
+  uint64_t* full = bars;                    // [NSTAGE]  TMA -> MMA
+  uint64_t* empty = bars + NSTAGE;          // [NSTAGE]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * NSTAGE;      // [NACC]    MMA -> epilogue
+  uint64_t* tempty = tfull + NACC;          // [NACC]    epilogue -> MMA
+  uint64_t* wbar = tempty + NACC;           // weights resident
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.y;               // output-channel / quadrant group
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 10) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, Cfg::WGT_B);
+      constexpr int PIECE = 16384;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)grp * Cfg::WGT_B;
+      for (int off = 0; off < Cfg::WGT_B; off += PIECE) {
+        const int bytes = (Cfg::WGT_B - off) < PIECE ? (Cfg::WGT_B - off) : PIECE;
+        bulk_g2s(wsm + off, wsrc + off, bytes, wbar);
+      }
+      uint32_t ws = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        for (int st = 0; st < Cfg::ST; ++st) {
+#pragma unroll 1
+          for (int pc = 0; pc < KSPLIT; ++pc, ++ws) {
+            const int stage = ws % NSTAGE;
+            mbar_wait(&empty[stage], ((ws / NSTAGE) & 1) ^ 1, 1);
+            mbar_arrive_expect_tx(&full[stage], Cfg::WIN_B);
+            tma_load_3d(win0 + stage * Cfg::WIN_B_AL, &tmap, (1 + 8 * MT * st - HALO) * 8, 1 + u * kColTile - HALO, pc * Cfg::PPL,
+                        &full[stage]);
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, NG);
+      // descriptor = (low word: start address >> 4 | LBO >> 4 << 16, high word: SBO >> 4 | version); taps and
+      // K steps only move the start address, i.e. add a compile-time constant to the low word
+      const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), NG * 16, 128);
+      const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
+      const uint64_t a_desc0 = umma_smem_desc(smem_u32(win0), PLANE_B, WROWS * 16);
+      const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
+      mbar_wait(wbar, 0, 2);
+      uint32_t ws = 0, it = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        for (int st = 0; st < Cfg::ST; ++st) {
+          const int acc0 = it % NACC;  // NACC % MT == 0: the MT accumulators of a window are consecutive
+#pragma unroll
+          for (int pc = 0; pc < KSPLIT; ++pc, ++ws) {
+            const int stage = ws % NSTAGE;
+            mbar_wait(&full[stage], (ws / NSTAGE) & 1, 3);
+            if (pc == 0) {
+#pragma unroll
+              for (int m = 0; m < MT; ++m) mbar_wait(&tempty[acc0 + m], (((it + m) / NACC) & 1) ^ 1, 4);
+            }
+            tc_fence_after();
+            const uint32_t a_lo_stage = a_lo0 + (uint32_t)(stage * (Cfg::WIN_B_AL >> 4));
+            // the MT tiles of a window are issued interleaved (tile index innermost)
+#pragma unroll
+            for (int tap = 0; tap < Cfg::NTAP; ++tap) {
+#pragma unroll
+              for (int kk = 0; kk < Cfg::CPP / 2; ++kk) {
+                const uint32_t a_off = (uint32_t)(Cfg::a_off(tap, kk) >> 4);
+                const uint32_t b_off = (uint32_t)(Cfg::b_off(tap, pc, kk) >> 4);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)  // tile m = rows 8m.. of the window: +8 rows of 16 B
+                  umma_f16_lohi(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc,
+                                (pc | tap | kk) != 0 ? 1u : 0u);
+              }
+            }
+            if (pc == KSPLIT - 1) {
+#pragma unroll
+              for (int m = 0; m < MT; ++m) umma_commit(&tfull[acc0 + m]);  // accumulators ready for the epilogue
+            }
+            umma_commit(&empty[stage]);  // window may be overwritten once these MMAs retire
+          }
+          it += MT;
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int h = warp >> 2;          // column half
+    const int r = 32 * q + lane;      // accumulator row = TMEM lane
+    const int g = r >> 3;             // feature column within the tile
+    const int i = r & 7;              // row within the tile
+    const float* bias = p.bias;  // param space: uniform constant-bank reads
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int gc = 1 + kColTile * u + g;
+      const int n = gc / p.cols;
+      const int fp = gc - n * p.cols;
+      const bool colvalid = (n < p.n_utts) && (fp >= 1) && (fp <= p.feats);
+
+      if constexpr (Cfg::EPI == EPI_PAIR_POOL || Cfg::EPI == EPI_PAIR_POOL_F) {
+        constexpr int HC = COUT / 2;  // output channels per thread
+        const long long plane_elems = p.out_ncols * p.out_rs * 8;
+        for (int tt = 0; tt < Cfg::TILES; ++tt, ++it) {
+          const int acc = it % NACC;
+          mbar_wait(&tfull[acc], (it / NACC) & 1, 5);
+          tc_fence_after();
+          float a[32], b[32];  // conv outputs at time 2j (columns [0,COUT)) and 2j+1 (columns [COUT, 2 COUT))
+          const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * HC;
+          tmem_ld_32x32(taddr, a);
+          tmem_ld_32x32(taddr + COUT, b);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          // bias + ReLU on both time steps, sum = time pool (the pool's 1/2 or 1/4 is folded into weights and bias)
+          float o[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = fmaxf(a[c] + bias[h * HC + c], 0.0f) + fmaxf(b[c] + bias[h * HC + c], 0.0f);
+          const int row_out = 8 * tt + i + 1;  // pair index + 1 = padded output row
+          if constexpr (Cfg::EPI == EPI_PAIR_POOL) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) pk[c >> 1] = pack_act2(o[c], o[c + 1]);
+            if (colvalid) {
+              uint16_t* dst = p.out + ((long long)gc * p.out_rs + row_out) * 8 + (long long)(4 * h) * plane_elems;
+              store_chunks<4>(dst, plane_elems, pk);
+            }
+          } else {
+            // feature pool: columns g (odd f') and g+1 live in lanes l and l^8; each keeps 16 of the 32 channels
+            const int oddg = g & 1;
+            uint32_t pk[8];
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+              float v[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float send = oddg ? o[c + e] : o[c + e + 16];
+                const float mine = oddg ? o[c + e + 16] : o[c + e];
+                v[e] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+              pk[c >> 1] = pack_act2(v[0], v[1]);
+            }
+            const int fo = (fp - 1) >> 1;  // pooled feature index of the pair (same for both lanes)
+            const bool ok = (n < p.n_utts) && (fp >= 1) && (fo < p.out_feats);
+            if (ok) {
+              const long long gco = (long long)n * p.out_cols + fo + 1;
+              uint16_t* dst = p.out + (gco * p.out_rs + row_out) * 8 + (long long)(4 * h + 2 * oddg) * plane_elems;
+              store_chunks<2>(dst, plane_elems, pk);
+            }
+          }
+        }
+      } else if constexpr (Cfg::EPI == EPI_MEAN_T) {
+        constexpr int HC = COUT / 2;
+        // time-sum of ReLU outputs kept in registers across the unit's tiles; no atomics, fixed order
+        float sum[HC];
+#pragma unroll
+        for (int c = 0; c < HC; ++c) sum[c] = 0.0f;
+        for (int tt = 0; tt < Cfg::TILES; ++tt, ++it) {
+          const int acc = it % NACC;
+          mbar_wait(&tfull[acc], (it / NACC) & 1, 5);
+          tc_fence_after();
+#pragma unroll
+          for (int blk = 0; blk < HC / 32; ++blk) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * HC + blk * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) sum[blk * 32 + c] += fmaxf(v[c] + bias[h * HC + blk * 32 + c], 0.0f);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        // transpose-reduce over the 8 time lanes of a feature column: after the three steps each lane
+        // holds the complete sums of HC/8 consecutive channels.
+        constexpr int W1 = HC / 2, W2 = HC / 4, W3 = HC / 8;
+        {
+          const bool up = (lane & 4) != 0;
+#pragma unroll
+          for (int c = 0; c < W1; ++c) {
+            const float send = up ? sum[c] : sum[c + W1];
+            const float keep = up ? sum[c + W1] : sum[c];
+            sum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+        }
+        {
+          const bool up = (lane & 2) != 0;
+#pragma unroll
+          for (int c = 0; c < W2; ++c) {
+            const float send = up ? sum[c] : sum[c + W2];
+            const float keep = up ? sum[c + W2] : sum[c];
+            sum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+        }
+        {
+          const bool up = (lane & 1) != 0;
+#pragma unroll
+          for (int c = 0; c < W3; ++c) {
+            const float send = up ? sum[c] : sum[c + W3];
+            const float keep = up ? sum[c + W3] : sum[c];
+            sum[c] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+        }
+        if (colvalid) {
+          const int cstart = h * HC + ((lane & 4) ? W1 : 0) + ((lane & 2) ? W2 : 0) + ((lane & 1) ? W3 : 0);
+          float* dst = p.emb + ((long long)n * p.feats + (fp - 1)) * COUT + cstart;
+#pragma unroll
+          for (int c = 0; c < W3; c += 4)
+            *reinterpret_cast<float4*>(dst + c) = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
+        }
+      } else if constexpr (Cfg::EPI == EPI_POOL_TF) {
+        // relu, then 2x2 average pool: time partner = lane^1, feature partner = lane^8 (1/4 folded into weights/bias).
+        // Each exchange halves the channels a lane keeps: HC -> HC/2 -> HC/4.
+        constexpr int HC = COUT / 2, Q1 = HC / 2, Q2 = HC / 4;
+        static_assert(Cfg::EPI != EPI_POOL_TF || (HC % 32 == 0 && Q2 % 8 == 0), "pool epilogue channel split");
+        const long long plane_elems = p.out_ncols * p.out_rs * 8;
+        const int oddi = i & 1, oddg = g & 1;
+        for (int tt = 0; tt < Cfg::TILES; ++tt, ++it) {
+          const int acc = it % NACC;
+          mbar_wait(&tfull[acc], (it / NACC) & 1, 5);
+          tc_fence_after();
+          float v[HC];
+#pragma unroll
+          for (int blk = 0; blk < HC / 32; ++blk) tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * HC + blk * 32, v + blk * 32);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+#pragma unroll
+          for (int c = 0; c < HC; ++c) v[c] = fmaxf(v[c] + bias[grp * COUT + h * HC + c], 0.0f);
+#pragma unroll
+          for (int c = 0; c < Q1; ++c) {
+            const float send = oddi ? v[c] : v[c + Q1];
+            const float mine = oddi ? v[c + Q1] : v[c];
+            v[c] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+          uint32_t pk[Q2 / 2];
+#pragma unroll
+          for (int c = 0; c < Q2; c += 2) {
+            float w2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float send = oddg ? v[c + e] : v[c + e + Q2];
+              const float mine = oddg ? v[c + e + Q2] : v[c + e];
+              w2[e] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            pk[c >> 1] = pack_act2(w2[0], w2[1]);
+          }
+          const int tp = 1 + 8 * tt + i;           // padded input row
+          const int to = (tp - 1) >> 1;            // pooled row (same for both time lanes)
+          const int fo = (fp - 1) >> 1;
+          const bool ok = (n < p.n_utts) && (fp >= 1) && (fo < p.out_feats) && (tp - oddi + 1 <= p.rows_valid);
+          if (ok) {
+            const long long gco = (long long)n * p.out_cols + fo + 1;
+            const int cbase = grp * COUT + h * HC + oddi * Q1 + oddg * Q2;
+            uint16_t* dst = p.out + (gco * p.out_rs + to + 1) * 8 + (long long)(cbase / 8) * plane_elems;
+            store_chunks<Q2 / 8>(dst, plane_elems, pk);
+          }
+        }
+      } else {
+        // EPI_SHUFFLE: columns = (sub-quadrant, COUT); group index and column block give the 2x2 output offset (a, b):
+        //   quadrant id = grp * (NG / COUT) + column block, a = qid >> 1, b = qid & 1.
+        // Each thread handles the columns [h*NG/2, (h+1)*NG/2) of its row.
+        constexpr int HN = NG / 2;
+        constexpr int QPG = NG / COUT;              // quadrants per group
+        const long long plane_elems = p.out_ncols * p.out_rs * 8;
+        for (int tt = 0; tt < Cfg::TILES; ++tt, ++it) {
+          const int acc = it % NACC;
+          mbar_wait(&tfull[acc], (it / NACC) & 1, 5);
+          tc_fence_after();
+          float v[HN];
+#pragma unroll
+          for (int blk = 0; blk < HN / 32; ++blk) tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * HN + blk * 32, v + blk * 32);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          const int tp = 1 + 8 * tt + i;
+          const bool ok = colvalid && (tp <= p.rows_valid);
+          constexpr int CPT = (COUT < HN) ? COUT : HN;   // channels of one quadrant held by this thread
+#pragma unroll
+          for (int s = 0; s < HN / CPT; ++s) {
+            const int col0 = h * HN + s * CPT;            // first column of this block within the group
+            const int qid = grp * QPG + col0 / COUT;
+            const int c0 = col0 % COUT;                   // first output channel of the block
+            uint32_t pk[CPT / 2];
+#pragma unroll
+            for (int c = 0; c < CPT; c += 2)
+              pk[c >> 1] = pack_act2(fmaxf(v[s * CPT + c] + bias[c0 + c], 0.0f), fmaxf(v[s * CPT + c + 1] + bias[c0 + c + 1], 0.0f));
+            if (ok) {
+              const int to = 2 * (tp - 1) + (qid >> 1), fo = 2 * (fp - 1) + (qid & 1);
+              const long long gco = (long long)n * p.out_cols + fo + 1;
+              uint16_t* dst = p.out + (gco * p.out_rs + to + 1) * 8 + (long long)(c0 / 8) * plane_elems;
+              store_chunks<CPT / 8>(dst, plane_elems, pk);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <class Cfg>
+static int launch_conv_tc(const CUtensorMap& tmap, const ConvParams& p, int groups, int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_B));
+    configured = true;
+  }
+  if (p.n_units <= 0) return DFS_OK;
+  int gx = (num_sms * Cfg::OCC) / groups;
+  if (gx < 1) gx = 1;
+  if (gx > p.n_units) gx = p.n_units;
+  conv_tc_kernel<Cfg><<<dim3(gx, groups), Cfg::THREADS, Cfg::SMEM_B, stream>>>(tmap, p);
+  DFS_LAUNCH_CHECK();
+  return DFS_OK;
+}
+
+}  // namespace dfs

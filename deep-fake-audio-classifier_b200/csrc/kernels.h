@@ -10,9 +10,8 @@
 namespace dfs {
 
 // ---- conv_tc.cu (tcgen05 implicit GEMM) ----
-int make_act_tensor_map(CUtensorMap* out, const ActBuf& a, int wrows);
-int conv2_tc_window_rows();
-int conv3_tc_window_rows();
+int make_act_tensor_map(CUtensorMap* out, const ActBuf& a, int wrows, int wcols, int box_planes);
+int make_cnn2d_tensor_maps(CUtensorMap* tmap_act1, CUtensorMap* tmap_act2, const ActBuf& act1, const ActBuf& act2);
 int launch_cnn2d_conv2_tc(const CUtensorMap& tmap_act1, const uint16_t* wpack, const float* bias, int n_utts, ActBuf act2,
                           int num_sms, cudaStream_t stream);
 int launch_cnn2d_conv3_tc(const CUtensorMap& tmap_act2, const uint16_t* wpack, const float* bias, int n_utts, float* emb,
@@ -40,6 +39,24 @@ int launch_cnn2d_head(const float* emb, const float* wfc, float fcb, int n_utts,
 // embedding[n][c*180+f] = emb[n][f][c] / 80   (src/model.py:37-38 flatten order)
 int launch_cnn2d_embedding_export(const float* emb, int n_utts, float* embedding, cudaStream_t stream);
 
+// ---- cae_tc.cu (convolutional autoencoder on the tcgen05 template) ----
+struct CaeTcState {
+  Conv1Weights c1;        // folded encoder block 1 (fp32, CUDA cores)
+  ActBuf act[7];          // e1 e2 e3 e4(latent) d1 d2 d3
+  CUtensorMap tmap[6];    // inputs of enc2 enc3 enc4 dec1 dec2 dec3
+  const uint16_t* w[6];   // packed fp16 weights of those six layers (device)
+  float bias[6][256];     // folded biases per output channel, pre-scaled like the weights
+  const float* w_final;   // final ConvTranspose2d(32,1): [(a*2+b)*32 + ci] fp32 (device)
+  float final_bias;
+};
+void cae_tc_geometry(int layer, int* planes, int* cols, int* rs);
+int cae_tc_make_maps(CaeTcState* s);
+int cae_tc_init_constants(CaeTcState* s, int max_utts, const float* dec2_bias_dev, cudaStream_t stream);
+int cae_tc_dump_layer(const CaeTcState* s, int layer, int n_utts, float* out_nhwc, cudaStream_t stream);
+// stop_after_layer: 0..6 = stop after e1..d3 (debug), 7 = run the fused final + MSE
+int launch_cae_tc(const CaeTcState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const float* norm_mean, const float* norm_std,
+                  float* mse_out, float* recon_out, float* latent_out, int stop_after_layer, int num_sms, cudaStream_t stream);
+
 // ---- simt_models.cu (CUDA-core CNN1D and CAE) ----
 struct SimtConv {        // BN-folded fp32 weights on device, re-packed [tap][ci][co] (co fastest)
   float* w = nullptr;
@@ -53,6 +70,7 @@ int launch_cae_simt(const float* x, int64_t sn, int64_t st, int64_t sf, int n_ut
                     float final_bias, const float* norm_mean, const float* norm_std, float* work, float* mse_out, float* recon_out,
                     float* latent_out, cudaStream_t stream);
 size_t cae_simt_work_floats(int n_utts);
+const float* cae_simt_layer_ptr(const float* work, int n_utts, int layer, size_t* floats_per_utt);
 
 // ---- eer.cu ----
 int eer_device(const void* scores, int key_bytes, const uint8_t* labels, int64_t n, dfs_eer_result* result_host, uint32_t* perm,

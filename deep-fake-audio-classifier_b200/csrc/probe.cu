@@ -191,7 +191,7 @@ int probe_tma_window(const uint16_t* act, int planes, int RS, int64_t ncols, int
   DFS_REQUIRE(act && out, DFS_ERR_INVALID, "probe_tma_window: NULL argument");
   ActBuf a{const_cast<uint16_t*>(act), planes, RS, ncols};
   CUtensorMap tmap;
-  DFS_PROPAGATE(make_act_tensor_map(&tmap, a, wrows));
+  DFS_PROPAGATE(make_act_tensor_map(&tmap, a, wrows, kColTile + 2, planes));
   const int bytes = planes * (kColTile + 2) * wrows * 16;
   const size_t smem = ((bytes + 127) & ~127) + 64;
   DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -204,6 +204,13 @@ size_t cae_simt_work_floats(int n_utts) {
   return s * (size_t)n_utts;
 }
 
+const float* cae_simt_layer_ptr(const float* work, int n_utts, int layer, size_t* floats_per_utt) {
+  const float* p = work;
+  for (int i = 0; i < layer; ++i) p += kCaeWork[i] * (size_t)n_utts;
+  *floats_per_utt = kCaeWork[layer];
+  return p;
+}
+
 int launch_cae_simt(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const SimtConv* enc, const SimtConv* dec,
                     float final_bias, const float* norm_mean, const float* norm_std, float* work, float* mse_out, float* recon_out, float* latent_out,
                     cudaStream_t stream) {

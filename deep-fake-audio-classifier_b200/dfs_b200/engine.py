@@ -232,6 +232,21 @@ class CaeScorer(_Scorer):
                                               _stream_ptr(torch, x.device)), "dfs_cae_forward")
         return recon, latent
 
+    LAYER_SHAPES = ((160, 90, 32), (80, 45, 64), (40, 22, 128), (20, 11, 256), (40, 22, 128), (80, 45, 64), (160, 90, 32))
+
+    def debug_layer(self, x, layer: int, impl: int = 0, apply_normalizer: bool | None = None):
+        """Activations after layer 0..6 (enc1..enc4, dec1..dec3) as (B,H,W,C) fp32; impl 0 = tcgen05, 1 = CUDA cores."""
+        torch = _require_cuda()
+        if apply_normalizer is None:
+            apply_normalizer = self.has_normalizer
+        f, x = _features_struct(x)
+        h, w, c = self.LAYER_SHAPES[layer]
+        out = torch.empty((x.shape[0], h, w, c), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            N.check(self._lib.dfs_cae_debug_layer(self._h, C.byref(f), int(impl), int(layer), int(bool(apply_normalizer)),
+                                                  C.c_void_p(out.data_ptr()), _stream_ptr(torch, x.device)), "dfs_cae_debug_layer")
+        return out
+
     def score_host(self, feats, flag: int | None = None):
         return super().score_host(feats, int(self.has_normalizer if flag is None else flag))
 

@@ -128,6 +128,11 @@ int dfs_cae_score(dfs_model* m, const dfs_features* feats, int apply_normalizer,
  * and latent [n,256,20,11] (either may be NULL).  Input must already be normalised.        */
 int dfs_cae_forward(dfs_model* m, const dfs_features* feats, float* recon_dev, float* latent_dev, void* stream);
 
+/* Debug: activations after CAE layer `layer` (0..6 = enc1..enc4, dec1..dec3) as [n][H][W][C] fp32 from the tensor-core
+ * path (impl 0) or the CUDA-core cross-check path (impl 1); n <= the handle's chunk.  Tests only. */
+int dfs_cae_debug_layer(dfs_model* m, const dfs_features* feats, int impl, int layer, int apply_normalizer, float* out_dev,
+                        void* stream);
+
 /* ---- scoring (HOST features; copies are pipelined inside) --------------------------- */
 /* The batch loop of src/predict.py:100-111 / src/predict_hybrid.py:52-78 behind one call:
  * feats->x and out_host are HOST pointers; H2D copies of chunk k+1 overlap the kernels of
