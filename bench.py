@@ -31,6 +31,8 @@ CONV3_FLOP_PER_UTT = 2 * 1_061_683_200
 CONV2_FLOP_PER_UTT = 2 * 530_841_600
 BYTES_PER_UTT = 321 * 180 * 4
 METRIC = "utterances/sec scoring [321x180] LFCC maps (2D-CNN) + EER"
+WORKLOAD = ("BASELINE configs[1]: 2D-CNN (src/model.py) batch scoring of synthetic [321x180] utterances + EER per step "
+            "(ours: fp16 tensor-core operands / fp32 accumulate; reference arm: torch CPU fp32, predict.py loop, bs 32)")
 
 
 def parse():
@@ -45,6 +47,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cnn2d", choices=["cnn2d", "cae", "hybrid", "eer"],
+                    help="cnn2d = the headline BASELINE configs[1]; cae / hybrid / eer = configs 3 / 4 / 5 (informational lines)")
+    ap.add_argument("--eer-n", type=int, default=100_000_000)
     return ap.parse_args()
 
 
@@ -144,12 +149,106 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "2D-CNN scoring + EER, reference CPU path (predict.py loop, bs 32)", "utterances_per_step": per_step},
+        "config": {"workload": WORKLOAD, "utterances_per_step": per_step, "sample": "bounded sample of the same workload sized for a few-minute run"},
         "cpu_baseline": {"value": value, "unit": "utterances/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} utterances/step x {args.steps} steps, torch CPU fp32, {cores} threads"},
         "e2e": {"value": value, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def run_other_workload(args, rank, world, local):
+    """--workload cae | hybrid | eer: the other BASELINE configs (3, 4, 5), same timing discipline as the headline run;
+    informational lines (the driver's bench line is the default cnn2d workload)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import dfs_b200 as D
+    from dfs_b200 import synthetic as syn
+    from dfs_b200.distributed import gather_scores
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    P = args.pool
+    if args.workload == "eer":
+        n = args.eer_n
+        sc, lab = syn.tie_free_scores(n, seed=6)
+        sd_, ld_ = torch.from_numpy(sc).to(dev), torch.from_numpy(lab).to(dev)
+        units, unit_name, metric = n, "scores/s", "EER sweep (device radix sort + FAR/FRR crossing) on tie-free fp32 scores"
+
+        def step():
+            return D.eer_details(sd_, ld_)
+    else:
+        pool = D.fill_features(P, first_utt=rank * P, seed=1234, device=local)
+        labels_global = torch.from_numpy(syn.labels(P * world)).to(dev)
+        mean, std = syn.normalizer_stats(1)
+        cae = D.CaeScorer(syn.cae_state(0), mean, std, device=local, max_chunk=args.chunk)
+        units, unit_name = P * world, "utterances/s"
+        if args.workload == "cae":
+            metric = "utterances/sec CAE reconstruction-MSE scoring [321x180] + EER"
+
+            def step():
+                return D.eer_details(gather_scores(cae.score(pool), n_total=P * world), labels_global)
+        else:
+            metric = "utterances/sec hybrid scoring (2D-CNN + 1D-CNN + CAE-MSE, blend alpha=0.8) [321x180] + EER"
+            c2 = D.Cnn2dScorer(syn.cnn2d_state(0), device=local, max_chunk=args.chunk)
+            c1 = D.Cnn1dScorer(syn.cnn1d_state(0), device=local, max_chunk=args.chunk)
+
+            def step():
+                g2 = gather_scores(c2.score(pool, apply_sigmoid=True), n_total=P * world)
+                g1 = gather_scores(c1.score(pool, apply_sigmoid=True), n_total=P * world)
+                gm = gather_scores(cae.score(pool), n_total=P * world)
+                sup = D.ensemble_mean([g2, g1], as_numpy=False)                 # src/ensemble.py:121
+                hyb = D.hybrid_blend(sup, gm, 0.8, as_numpy=False)              # src/predict_hybrid.py:149-151
+                return D.eer_details(hyb, labels_global)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = D._native.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        res = step()
+    ev1.record()
+    barrier()
+    launches = D._native.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = units * args.steps / (ms * 1e-3)
+    if rank == 0:
+        if args.workload == "eer":
+            ach = 13.0 * value / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                    "note": "13 B/score algorithmic (SURVEY.md 8d); a 4-pass LSD radix sort with u32 payload moves ~77 B/score"}
+        else:
+            flop = FLOP_PER_UTT["cae"] if args.workload == "cae" else sum(FLOP_PER_UTT.values())
+            ach = value / world * flop / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
+                    "traffic": None, "note": "whole-path algorithmic FLOPs per utterance / wall time (no single dominant kernel)"}
+        print(json.dumps({"metric": metric, "value": value, "unit": unit_name, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload != "eer" else "replicas only",
+                          "vs_baseline": None, "dtype": "f16" if args.workload != "eer" else "f32/f64", "data": "synthetic",
+                          "config": {"workload": args.workload, "units_per_step": units, "l2": "inputs larger than L2"},
+                          "eer": {"value": res["eer"], "threshold": res["threshold"]}, "clocks": clocks, "gpu_launches": int(launches),
+                          "roofline": roof}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -159,6 +258,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload != "cnn2d":
+        run_other_workload(args, rank, world, local)
         return
 
     import numpy as np
@@ -269,7 +371,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
            "data": "synthetic",
-           "config": {"workload": "BASELINE configs[1]: 2D-CNN (src/model.py) batch scoring, fp16 tensor-core operands / fp32 accumulate (same tcgen05 rate as bf16, 8x finer mantissa), + EER per step",
+           "config": {"workload": WORKLOAD,
                       "utterances_per_step_per_gpu": P, "total_utterances": P * world * args.steps, "chunk": chunk,
                       "l2": "inputs larger than L2 (pool %.2f GB per GPU, cycled)" % (P * BYTES_PER_UTT / 1e9),
                       "weights": "random-init CNN2D, seeded (dfs_b200.synthetic.cnn2d_state(0)); no checkpoints ship with the reference",

@@ -61,8 +61,9 @@ struct dfs_model {
   uint16_t* xt = nullptr;      // fp16 time-major copy of the features (conv1_tc A operand)
   uint16_t* w1pack = nullptr;  // Toeplitz weights [kw][2][256][8]
   float b1h[32] = {0};         // 0.5 * folded conv1 bias
-  // ---- CAE on the tcgen05 template (cae_tc.cu) ----
+  // ---- CAE / 1D-CNN on the tcgen05 template (cae_tc.cu, cnn1d_tc.cu) ----
   CaeTcState* cae = nullptr;
+  Cnn1dTcState* c1d = nullptr;
   // ---- CNN1D / CAE (CUDA-core path; for the CAE it is the conv_impl = 1 cross-check) ----
   SimtConv sc[8];
   float* work = nullptr;
@@ -200,6 +201,7 @@ extern "C" int dfs_model_destroy(dfs_model* m) {
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   for (void* p : m->allocs) cudaFree(p);
   delete m->cae;
+  delete m->c1d;
   for (int b = 0; b < 2; ++b) {
     if (m->ev_in[b]) cudaEventDestroy(m->ev_in[b]);
     if (m->ev_done[b]) cudaEventDestroy(m->ev_done[b]);
@@ -424,6 +426,48 @@ static int make_simt_convT(dfs_model* m, const dfs_conv_bn& c, int ci, int co, S
   return DFS_OK;
 }
 
+// Conv1d weight (Co,Ci,3) -> [tap][ci_pad/8][co_pad][8] fp16 (zero padding), folded bias (co_pad)
+static std::vector<uint16_t> pack_conv1d(const dfs_conv_bn& c, int co, int ci, int co_pad, int ci_pad, float* bias_out) {
+  std::vector<double> scale, shift;
+  bn_fold(c, co, scale, shift);
+  for (int o = 0; o < co_pad; ++o) bias_out[o] = o < co ? (float)shift[o] : 0.0f;
+  std::vector<uint16_t> out((size_t)3 * ci_pad * co_pad, 0);
+  for (int k = 0; k < 3; ++k)
+    for (int i = 0; i < ci; ++i)
+      for (int o = 0; o < co; ++o)
+        out[(((size_t)k * (ci_pad / 8) + (i >> 3)) * co_pad + o) * 8 + (i & 7)] =
+            f32_to_act_bits((float)((double)c.weight[((size_t)o * ci + i) * 3 + k] * scale[o]));
+  return out;
+}
+
+static int cnn1d_tc_create(dfs_model* m, const dfs_cnn1d_weights* w) {
+  Cnn1dTcState* s = new (std::nothrow) Cnn1dTcState();
+  DFS_REQUIRE(s, DFS_ERR_NOMEM, "out of host memory");
+  m->c1d = s;
+  memset(s->bias, 0, sizeof(s->bias));
+  std::vector<uint16_t> packs[3];
+  packs[0] = pack_conv1d(w->conv[0], 32, kF, 64, 192, s->bias[0]);
+  packs[1] = pack_conv1d(w->conv[1], 64, 32, 64, 64, s->bias[1]);
+  packs[2] = pack_conv1d(w->conv[2], 128, 64, 128, 64, s->bias[2]);
+  for (int i = 0; i < 3; ++i) {
+    uint16_t* d = nullptr;
+    DFS_PROPAGATE(dev_upload(m, &d, packs[i]));
+    s->w[i] = d;
+  }
+  for (int b = 0; b < 3; ++b) {
+    int planes, rs;
+    cnn1d_tc_geometry(b, &planes, &rs);
+    s->act[b] = ActBuf{nullptr, planes, rs, (int64_t)m->chunk + 1 + 32};
+    DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&s->act[b].ptr), s->act[b].bytes(), true));
+  }
+  DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&s->sums), (size_t)m->chunk * 128 * 4, true));
+  DFS_PROPAGATE(cnn1d_tc_make_maps(s));
+  s->fcw = m->fcw_dev;
+  s->fcb = m->fcb;
+  DFS_CUDA_CHECK(cudaDeviceSynchronize());
+  return DFS_OK;
+}
+
 extern "C" int dfs_cnn1d_create(dfs_model** out, int device, const dfs_cnn1d_weights* w, int max_chunk) {
   DFS_REQUIRE(out && w, DFS_ERR_INVALID, "dfs_cnn1d_create: NULL argument");
   *out = nullptr;
@@ -436,7 +480,7 @@ extern "C" int dfs_cnn1d_create(dfs_model** out, int device, const dfs_cnn1d_wei
   m->kind = KIND_CNN1D;
   int st = model_common_init(m, device);
   if (st != DFS_OK) { delete m; return st; }
-  m->chunk = max_chunk > 0 ? max_chunk : 256;
+  m->chunk = max_chunk > 0 ? max_chunk : 1024;
   auto fail = [&](int s) { dfs_model_destroy(m); return s; };
   const int ci[3] = {kF, 32, 64}, co[3] = {32, 64, 128};
   for (int i = 0; i < 3; ++i)
@@ -445,6 +489,7 @@ extern "C" int dfs_cnn1d_create(dfs_model** out, int device, const dfs_cnn1d_wei
   if ((st = dev_upload(m, &m->fcw_dev, fcw)) != DFS_OK) return fail(st);
   m->fcb = w->fc_bias[0];
   if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->work), cnn1d_simt_work_floats(m->chunk) * 4, false)) != DFS_OK) return fail(st);
+  if ((st = cnn1d_tc_create(m, w)) != DFS_OK) return fail(st);
   *out = m;
   return DFS_OK;
 }
@@ -457,8 +502,12 @@ extern "C" int dfs_cnn1d_score(dfs_model* m, const dfs_features* feats, float* o
   DFS_CUDA_CHECK(cudaSetDevice(m->device));
   for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk) {
     const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
-    DFS_PROPAGATE(launch_cnn1d_simt(feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->sc, m->fcw_dev,
-                                    m->fcb, apply_sigmoid, m->work, out_dev + i0, stream));
+    if (m->conv_impl == 0)
+      DFS_PROPAGATE(launch_cnn1d_tc(m->c1d, feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk, apply_sigmoid,
+                                    out_dev + i0, m->num_sms, stream));
+    else
+      DFS_PROPAGATE(launch_cnn1d_simt(feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->sc, m->fcw_dev,
+                                      m->fcb, apply_sigmoid, m->work, out_dev + i0, stream));
   }
   return DFS_OK;
 }

@@ -1,0 +1,104 @@
+// cnn1d_tc.cu -- the 1D-CNN scorer on the tcgen05 template (conv_tc.cuh, MODE_3X1):
+//   x.transpose(1,2) -> 3 x [Conv1d(k=3,p=1) + BatchNorm1d + ReLU] -> AdaptiveAvgPool1d(1) -> Linear(128,1)
+//   /root/reference/src/model_cnn1d.py:37-46 (+ :14-35)
+// Channels-last GEMMs over time: out[t,co] = b[co] + sum_k sum_f W[co,f,k] x[t+k-1,f].  One "feature column" per
+// utterance (column index 1 + n), rows = time steps 1..321 padded to 328, so an MMA tile is 16 utterances x 8 time
+// steps and the three taps are +0/+16/+32-byte shifts of the A descriptor.
+//   prep    fp32 strided features -> FT8 fp16, 24 planes (180 features zero-padded to 192)
+//   layer 1 K = 3 x 192, N = 64 (32 real output channels + 32 zero ones)      EPI_RELU
+//   layer 2 K = 3 x 64 (upper 32 input channels are the zero ones), N = 64      EPI_RELU
+//   layer 3 K = 3 x 64, N = 128, time sum kept in registers over the 41 tiles   EPI_MEAN_T  -> [n][128] fp32
+//   head    logits = fc_b + sum_c fc_w[c] * sum[c] / 321   (+ sigmoid)
+// The arithmetic is ~31 MFLOP per utterance; the path is bound by the 231 KB/utterance fp32 input read.
+#include "conv_tc.cuh"
+
+namespace dfs {
+
+constexpr int kC1dRows = 328;   // 321 time steps padded to a multiple of 8
+constexpr int kC1dRS = 330;
+using C1dL1 = ConvCfg<MODE_3X1, 192, 64, 64, kC1dRows, 1, 2, 4, 1, EPI_RELU>;
+using C1dL2 = ConvCfg<MODE_3X1, 64, 64, 64, kC1dRows, 1, 3, 4, 1, EPI_RELU>;
+using C1dL3 = ConvCfg<MODE_3X1, 64, 128, 128, kC1dRows, 1, 3, 4, 1, EPI_MEAN_T>;
+
+void cnn1d_tc_geometry(int buf, int* planes, int* rs) {
+  *planes = buf == 0 ? 24 : 8;
+  *rs = kC1dRS;
+}
+
+int cnn1d_tc_make_maps(Cnn1dTcState* s) {
+  DFS_PROPAGATE(make_act_tensor_map(&s->tmap[0], s->act[0], C1dL1::WROWS, C1dL1::WCOLS, C1dL1::PPL));
+  DFS_PROPAGATE(make_act_tensor_map(&s->tmap[1], s->act[1], C1dL2::WROWS, C1dL2::WCOLS, C1dL2::PPL));
+  DFS_PROPAGATE(make_act_tensor_map(&s->tmap[2], s->act[2], C1dL3::WROWS, C1dL3::WCOLS, C1dL3::PPL));
+  return DFS_OK;
+}
+
+// item = (utterance, feature chunk of 8, time step); consecutive threads -> consecutive time steps (16-byte stores)
+__global__ void __launch_bounds__(256) cnn1d_prep_kernel(const float* __restrict__ x, long long sn, long long st, long long sf, long long total,
+                                                          ActBuf out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int t = (int)(idx % kT);
+  const int c8 = (int)((idx / kT) % 24);
+  const long long n = idx / ((long long)kT * 24);
+  const float* src = x + n * sn + (long long)t * st;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int f = 8 * c8 + e;
+    v[e] = f < kF ? fmaxf(src[(long long)f * sf], -65504.0f) : 0.0f;
+  }
+  uint16_t* dst = out.ptr + (long long)c8 * out.plane_elems() + ((n + 1) * out.RS + t + 1) * 8;
+  st_global_v4(dst, pack_act2(v[0], v[1]), pack_act2(v[2], v[3]), pack_act2(v[4], v[5]), pack_act2(v[6], v[7]));
+}
+
+// one warp per utterance
+__global__ void __launch_bounds__(128) cnn1d_tc_head_kernel(const float* __restrict__ sums /*[n][128]*/, const float* __restrict__ fcw, float fcb,
+                                                             int n_utts, int apply_sigmoid, float* __restrict__ out) {
+  const int n = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= n_utts) return;
+  float acc = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc = fmaf(sums[(long long)n * 128 + lane + 32 * k] / (float)kT, fcw[lane + 32 * k], acc);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const float z = acc + fcb;
+    out[n] = apply_sigmoid ? 1.0f / (1.0f + expf(-z)) : z;
+  }
+}
+
+static ConvParams c1d_params(const Cnn1dTcState* s, int layer, int n_utts) {
+  ConvParams p{};
+  p.wpack = s->w[layer];
+  for (int i = 0; i < 128; ++i) p.bias[i] = s->bias[layer][i];
+  p.n_units = (n_utts + kColTile - 1) / kColTile;   // columns 1 .. n_utts
+  p.n_utts = n_utts;
+  p.cols = 1;
+  p.feats = 1;
+  p.rows_valid = kT;
+  if (layer < 2) {
+    p.out = s->act[layer + 1].ptr;
+    p.out_ncols = s->act[layer + 1].ncols;
+    p.out_rs = s->act[layer + 1].RS;
+  }
+  p.out_cols = 1;
+  p.out_feats = 1;
+  p.emb = s->sums;
+  return p;
+}
+
+int launch_cnn1d_tc(const Cnn1dTcState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, int apply_sigmoid, float* out, int num_sms,
+                    cudaStream_t stream) {
+  if (n_utts <= 0) return DFS_OK;
+  const long long total = (long long)n_utts * kT * 24;
+  cnn1d_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, s->act[0]);
+  DFS_LAUNCH_CHECK();
+  DFS_PROPAGATE(launch_conv_tc<C1dL1>(s->tmap[0], c1d_params(s, 0, n_utts), 1, num_sms, stream));
+  DFS_PROPAGATE(launch_conv_tc<C1dL2>(s->tmap[1], c1d_params(s, 1, n_utts), 1, num_sms, stream));
+  DFS_PROPAGATE(launch_conv_tc<C1dL3>(s->tmap[2], c1d_params(s, 2, n_utts), 1, num_sms, stream));
+  cnn1d_tc_head_kernel<<<(n_utts + 3) / 4, 128, 0, stream>>>(s->sums, s->fcw, s->fcb, n_utts, apply_sigmoid, out);
+  DFS_LAUNCH_CHECK();
+  return DFS_OK;
+}
+
+}  // namespace dfs

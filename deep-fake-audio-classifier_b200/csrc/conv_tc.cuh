@@ -16,6 +16,8 @@
 //             (DESIGN.md §4), so N = 128 with 4/3 of the MACs beats N = 64; the time pool becomes in-thread.
 // MODE_1X1  : one tap, no halo: the k=2,s=2 transposed convolutions of the CAE decoder are GEMMs over positions
 //             with N = (output quadrant, COUT) and a pixel-shuffle epilogue.
+// MODE_3X1  : three taps along the row (time) axis only, no column halo: the Conv1d(k=3) layers of the 1D-CNN with one
+//             "feature column" per utterance (cols = 1: a tile is 16 utterances x 8 time steps).
 // KSPLIT    : the CIN/8 channel planes of a window are loaded as KSPLIT separate pipeline stages ("pieces"),
 //             which bounds shared memory for CIN >= 128.
 // blockIdx.y: output-channel / quadrant group (weights, bias and output placement are offset per group).
@@ -30,13 +32,14 @@
 
 namespace dfs {
 
-enum { MODE_3X3 = 0, MODE_PAIR = 1, MODE_1X1 = 2 };
+enum { MODE_3X3 = 0, MODE_PAIR = 1, MODE_1X1 = 2, MODE_3X1 = 3 };
 enum {
   EPI_PAIR_POOL = 0,    // PAIR: relu both time steps, add (time pool), store FT8                    (CNN2D conv2)
   EPI_MEAN_T = 1,       // 3x3 : relu, sum over all rows of the unit, store [n][F][COUT] fp32         (CNN2D conv3)
   EPI_PAIR_POOL_F = 2,  // PAIR: time pool in-thread + feature pool with lane^8, store FT8            (CAE enc2)
   EPI_POOL_TF = 3,      // 3x3 : relu, 2x2 pool with lane^1 (time) and lane^8 (feature), store FT8    (CAE enc3, enc4)
-  EPI_SHUFFLE = 4       // 1x1 : relu, pixel-shuffle store of the quadrant(s) held in the columns      (CAE dec1-3)
+  EPI_SHUFFLE = 4,      // 1x1 : relu, pixel-shuffle store of the quadrant(s) held in the columns      (CAE dec1-3)
+  EPI_RELU = 5          // any : relu, store FT8 at the same position                                   (CNN1D layers 1, 2)
 };
 
 template <int MODE_, int CIN_, int COUT_, int NG_, int ROWS_, int MT_, int NSTAGE_, int NACC_, int KSPLIT_, int EPI_>
@@ -44,14 +47,15 @@ struct ConvCfg {
   static constexpr int MODE = MODE_, CIN = CIN_, COUT = COUT_, NG = NG_, ROWS = ROWS_, MT = MT_, NSTAGE = NSTAGE_, NACC = NACC_,
                        KSPLIT = KSPLIT_, EPI = EPI_;
   static constexpr bool PAIR = (MODE == MODE_PAIR);
-  static constexpr int HALO = (MODE == MODE_1X1) ? 0 : 1;
-  static constexpr int NTAP = PAIR ? 12 : (MODE == MODE_1X1 ? 1 : 9);
+  static constexpr int HALO = (MODE == MODE_1X1) ? 0 : 1;                       // row halo
+  static constexpr int HALO_C = (MODE == MODE_1X1 || MODE == MODE_3X1) ? 0 : 1;  // column halo
+  static constexpr int NTAP = PAIR ? 12 : (MODE == MODE_1X1 ? 1 : (MODE == MODE_3X1 ? 3 : 9));
   static constexpr int CCH = CIN / 8;                  // 16-byte channel chunks
   static constexpr int KCH = PAIR ? 2 * CCH : CCH;     // planes of the input layout (PAIR: x2 time parities)
   static constexpr int PPL = KCH / KSPLIT;             // planes per piece
   static constexpr int CPP = CCH / KSPLIT;             // channel chunks per piece
   static constexpr int WROWS = 8 * MT + 2 * HALO;      // window rows incl. halo
-  static constexpr int WCOLS = kColTile + 2 * HALO;    // window columns (feature) incl. halo
+  static constexpr int WCOLS = kColTile + 2 * HALO_C;  // window columns (feature) incl. halo
   static constexpr int PLANE_B = WCOLS * WROWS * 16;   // bytes of one plane of the window
   static constexpr int WIN_B = PPL * PLANE_B;          // TMA transaction bytes per piece
   static constexpr int WIN_B_AL = (WIN_B + 1023) & ~1023;
@@ -85,6 +89,7 @@ struct ConvCfg {
       return (par * CCH + 2 * kk) * PLANE_B + (kw * WROWS + rowoff) * 16;
     }
     if (MODE == MODE_1X1) return (2 * kk) * PLANE_B;
+    if (MODE == MODE_3X1) return (2 * kk) * PLANE_B + tap * 16;
     const int kh = tap / 3, kw = tap % 3;
     return (2 * kk) * PLANE_B + (kw * WROWS + kh) * 16;
   }
@@ -121,7 +126,7 @@ template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::OCC)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvParams p) {
   constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, MT = Cfg::MT, NSTAGE = Cfg::NSTAGE, NACC = Cfg::NACC, NG = Cfg::NG;
-  constexpr int WROWS = Cfg::WROWS, PLANE_B = Cfg::PLANE_B, KSPLIT = Cfg::KSPLIT, HALO = Cfg::HALO;
+  constexpr int WROWS = Cfg::WROWS, PLANE_B = Cfg::PLANE_B, KSPLIT = Cfg::KSPLIT, HALO = Cfg::HALO, HALO_C = Cfg::HALO_C;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* wsm = smem;
   uint8_t* win0 = smem + Cfg::WGT_B_AL;
@@ -170,7 +175,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             const int stage = ws % NSTAGE;
             mbar_wait(&empty[stage], ((ws / NSTAGE) & 1) ^ 1, 1);
             mbar_arrive_expect_tx(&full[stage], Cfg::WIN_B);
-            tma_load_3d(win0 + stage * Cfg::WIN_B_AL, &tmap, (1 + 8 * MT * st - HALO) * 8, 1 + u * kColTile - HALO, pc * Cfg::PPL,
+            tma_load_3d(win0 + stage * Cfg::WIN_B_AL, &tmap, (1 + 8 * MT * st - HALO) * 8, 1 + u * kColTile - HALO_C, pc * Cfg::PPL,
                         &full[stage]);
           }
         }
@@ -235,8 +240,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     uint32_t it = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int gc = 1 + kColTile * u + g;
-      const int n = gc / p.cols;
-      const int fp = gc - n * p.cols;
+      // padded layouts: column gc = n*cols + f' (f' = 0 and cols-1 are zero pads); cols == 1: one column per utterance at gc = 1 + n
+      const int n = (p.cols == 1) ? gc - 1 : gc / p.cols;
+      const int fp = (p.cols == 1) ? 1 : gc - n * p.cols;
       const bool colvalid = (n < p.n_utts) && (fp >= 1) && (fp <= p.feats);
 
       if constexpr (Cfg::EPI == EPI_PAIR_POOL || Cfg::EPI == EPI_PAIR_POOL_F) {
@@ -306,8 +312,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * HC + blk * 32, v);
             tmem_ld_wait();
+            if (8 * tt + i + 1 <= p.rows_valid) {  // rows beyond the valid range are padding (1D-CNN: 321 of 328)
 #pragma unroll
-            for (int c = 0; c < 32; ++c) sum[blk * 32 + c] += fmaxf(v[c] + bias[h * HC + blk * 32 + c], 0.0f);
+              for (int c = 0; c < 32; ++c) sum[blk * 32 + c] += fmaxf(v[c] + bias[h * HC + blk * 32 + c], 0.0f);
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -397,6 +405,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             const int cbase = grp * COUT + h * HC + oddi * Q1 + oddg * Q2;
             uint16_t* dst = p.out + (gco * p.out_rs + to + 1) * 8 + (long long)(cbase / 8) * plane_elems;
             store_chunks<Q2 / 8>(dst, plane_elems, pk);
+          }
+        }
+      } else if constexpr (Cfg::EPI == EPI_RELU) {
+        constexpr int HC = COUT / 2;
+        static_assert(Cfg::EPI != EPI_RELU || HC % 32 == 0, "relu epilogue: 32-column blocks");
+        const long long plane_elems = p.out_ncols * p.out_rs * 8;
+        for (int tt = 0; tt < Cfg::TILES; ++tt, ++it) {
+          const int acc = it % NACC;
+          mbar_wait(&tfull[acc], (it / NACC) & 1, 5);
+          tc_fence_after();
+          float v[HC];
+#pragma unroll
+          for (int blk = 0; blk < HC / 32; ++blk) tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * HC + blk * 32, v + blk * 32);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          uint32_t pk[HC / 2];
+#pragma unroll
+          for (int c = 0; c < HC; c += 2) pk[c >> 1] = pack_act2(fmaxf(v[c] + bias[h * HC + c], 0.0f), fmaxf(v[c + 1] + bias[h * HC + c + 1], 0.0f));
+          const int tp = 1 + 8 * tt + i;
+          if (colvalid && tp <= p.rows_valid) {
+            uint16_t* dst = p.out + ((long long)gc * p.out_rs + tp) * 8 + (long long)(h * HC / 8) * plane_elems;
+            store_chunks<HC / 8>(dst, plane_elems, pk);
           }
         }
       } else {

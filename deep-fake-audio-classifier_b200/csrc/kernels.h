@@ -57,6 +57,21 @@ int cae_tc_dump_layer(const CaeTcState* s, int layer, int n_utts, float* out_nhw
 int launch_cae_tc(const CaeTcState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const float* norm_mean, const float* norm_std,
                   float* mse_out, float* recon_out, float* latent_out, int stop_after_layer, int num_sms, cudaStream_t stream);
 
+// ---- cnn1d_tc.cu (1D-CNN on the tcgen05 template) ----
+struct Cnn1dTcState {
+  ActBuf act[3];          // fp16 input copy (24 planes), layer-1 output, layer-2 output (8 planes each)
+  CUtensorMap tmap[3];
+  const uint16_t* w[3];   // packed fp16 weights [tap][ci/8][co][8] (channel counts zero-padded to 192/64, 64/64, 64/128)
+  float bias[3][128];
+  float* sums;            // [n][128] time sums of the last layer
+  const float* fcw;       // classifier weight (128) on the device
+  float fcb;
+};
+void cnn1d_tc_geometry(int buf, int* planes, int* rs);
+int cnn1d_tc_make_maps(Cnn1dTcState* s);
+int launch_cnn1d_tc(const Cnn1dTcState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, int apply_sigmoid, float* out, int num_sms,
+                    cudaStream_t stream);
+
 // ---- simt_models.cu (CUDA-core CNN1D and CAE) ----
 struct SimtConv {        // BN-folded fp32 weights on device, re-packed [tap][ci][co] (co fastest)
   float* w = nullptr;
