@@ -3,11 +3,11 @@
 //   confusion_at_threshold   /root/reference/scripts/evaluation.py:42-56
 //   normalise_01 + blend     /root/reference/src/predict_hybrid.py:81-85,149-151, src/ensemble.py:121
 //
-// EER = stable LSD radix sort (one-sweep: per-pass decoupled look-back, 8-bit digits, key =
+// EER = stable LSD radix sort (8-bit digits, per pass: count -> scan -> stable scatter, key =
 // order-preserving integer image of the fp32/fp64 score, payload = original index | label<<31)
 // followed by a prefix-count FAR/FRR sweep in IEEE fp64 and a (value, lowest index) arg-min.
 // All kernels are HBM-bound streaming kernels: 16-byte vector accesses where the layout allows,
-// one tile of 4096 keys per CTA, tiles dealt by an atomic ticket so look-back cannot deadlock.
+// one super-tile of 16 x 4096 keys per CTA; no kernel waits on another CTA.
 #include <algorithm>
 
 #include "common.cuh"
@@ -18,7 +18,6 @@ namespace dfs {
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096
-constexpr uint32_t kFlagAgg = 1u << 30, kFlagIncl = 2u << 30, kValMask = (1u << 30) - 1;
 
 // ---- order-preserving key transforms (-0.0 is canonicalised to +0.0: numpy treats them as ties) ----
 __device__ __forceinline__ uint32_t to_key(float s) {
@@ -41,156 +40,97 @@ template <typename K> struct ScoreOf;
 template <> struct ScoreOf<uint32_t> { using type = float; };
 template <> struct ScoreOf<uint64_t> { using type = double; };
 
-// ---- pass 0: keys, payloads, all digit histograms, label count -------------------------------
+// ---- pass 0: keys, payloads, label count, AND / OR of all keys --------------------------------
+// A radix pass whose digit is identical in every key is the identity; that is the case exactly when the bitwise AND
+// and OR of all keys agree on that byte (common: sigmoid scores share their exponent byte), so the host can skip it.
+struct SortHeader {
+  unsigned long long ones;      // number of labels != 0
+  unsigned long long key_and;   // AND of all keys (zero-extended)
+  unsigned long long key_or;    // OR of all keys
+};
+
 template <typename K>
 __global__ void __launch_bounds__(256) sort_prep_kernel(const typename ScoreOf<K>::type* __restrict__ scores,
                                                          const uint8_t* __restrict__ labels, long long n, K* __restrict__ keys,
-                                                         uint32_t* __restrict__ pay, uint32_t* __restrict__ ghist /*[passes][256]*/,
-                                                         unsigned long long* __restrict__ n_ones) {
-  constexpr int PASSES = sizeof(K);
-  __shared__ uint32_t hist[PASSES][256];
-  for (int i = threadIdx.x; i < PASSES * 256; i += blockDim.x) (&hist[0][0])[i] = 0;
-  __syncthreads();
+                                                         uint32_t* __restrict__ pay, SortHeader* __restrict__ hdr) {
   uint32_t ones = 0;
-  // warp-uniform trip count so the match/ballot below always sees the full warp
-  for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
-    const long long i = i0 + (threadIdx.x & 31);
-    const bool ok = i < n;
-    K k = 0;
-    if (ok) {
-      k = to_key(scores[i]);
-      const uint32_t lab = labels[i] != 0;
-      keys[i] = k;
-      pay[i] = (uint32_t)i | (lab << 31);
-      ones += lab;
-    }
-    // warp-aggregated: real score vectors share their high digits, plain atomics would serialise
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) {
-      const uint32_t d = ok ? ((uint32_t)(k >> (8 * ps)) & 0xffu) : 0xffffffffu;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      if (ok && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[ps][d], (uint32_t)__popc(peers));
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < PASSES * 256; i += blockDim.x) {
-    const uint32_t v = (&hist[0][0])[i];
-    if (v) atomicAdd(&ghist[i], v);
+  K kand = ~(K)0, kor = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const K k = to_key(scores[i]);
+    const uint32_t lab = labels[i] != 0;
+    keys[i] = k;
+    pay[i] = (uint32_t)i | (lab << 31);
+    ones += lab;
+    kand &= k;
+    kor |= k;
   }
 #pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, o);
-  if ((threadIdx.x & 31) == 0 && ones) atomicAdd(n_ones, (unsigned long long)ones);
-}
-
-// exclusive scan of each pass's 256-bin histogram; skip[pass] = 1 when one bin holds every key
-__global__ void __launch_bounds__(256) sort_scan_hist_kernel(uint32_t* __restrict__ ghist, uint32_t* __restrict__ skip, long long n) {
-  __shared__ uint32_t s[256];
-  const uint32_t v = ghist[blockIdx.x * 256 + threadIdx.x];
-  s[threadIdx.x] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    bool one_bin = false;
-    for (int i = 0; i < 256; ++i) {
-      const uint32_t c = s[i];
-      if ((long long)c == n) one_bin = true;
-      s[i] = run;
-      run += c;
-    }
-    skip[blockIdx.x] = one_bin ? 1u : 0u;
+  for (int o = 16; o >= 1; o >>= 1) {
+    ones += __shfl_xor_sync(0xffffffffu, ones, o);
+    kand &= (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)kand, o);
+    kor |= (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)kor, o);
   }
-  __syncthreads();
-  ghist[blockIdx.x * 256 + threadIdx.x] = s[threadIdx.x];
+  if ((threadIdx.x & 31) == 0) {
+    if (ones) atomicAdd(&hdr->ones, (unsigned long long)ones);
+    atomicAnd(&hdr->key_and, (unsigned long long)kand);
+    atomicOr(&hdr->key_or, (unsigned long long)kor);
+  }
 }
 
-// ---- one radix pass ----------------------------------------------------------------------
+// ---- one radix pass = upsweep (per-super-tile digit counts) -> scan -> downsweep (stable scatter) ----
+// A super-tile is kSuperTiles consecutive tiles handled by ONE CTA in order, carrying its per-digit global write cursors in
+// shared memory, so no CTA ever waits on another one (a decoupled look-back walks hundreds of predecessors when ~600 tiles
+// are in flight: measured 8.5 ms per 100 M keys; this form is bandwidth-bound).
+constexpr int kSuperTiles = 16;
+constexpr int kSuperKeys = kSuperTiles * kSortTile;   // 65,536 keys per CTA
+
+// lanes holding the same 8-bit digit (8 ballots; no shared-memory atomics: those cost ~2 cycles per active lane)
+__device__ __forceinline__ uint32_t warp_peers8(uint32_t d, bool ok) {
+  uint32_t peers = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
+}
+
 template <typename K>
-__global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ pin,
-                                                                      K* __restrict__ kout, uint32_t* __restrict__ pout, long long n,
-                                                                      int shift, const uint32_t* __restrict__ bucket_base,
-                                                                      uint32_t* __restrict__ tile_counter, uint32_t* status) {
-  __shared__ uint32_t s_tile;
-  __shared__ uint32_t cnt[8][256];
-  __shared__ uint32_t digit_start[256];
-  __shared__ uint32_t gbase[256];
-  __shared__ uint32_t wsum[8];
-  extern __shared__ __align__(16) uint8_t dyn[];
-  K* skeys = reinterpret_cast<K*>(dyn);
-  uint32_t* spay = reinterpret_cast<uint32_t*>(dyn + sizeof(K) * kSortTile);
-
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-  for (int i = tid; i < 8 * 256; i += kSortThreads) (&cnt[0][0])[i] = 0;
+__global__ void __launch_bounds__(256) radix_upsweep_kernel(const K* __restrict__ kin, long long n, int shift, uint32_t* __restrict__ counts /*[supers][256]*/) {
+  __shared__ uint32_t whist[8][256];   // one private histogram per warp: the group leader does a plain read-modify-write
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) (&whist[0][0])[i] = 0;
   __syncthreads();
-  const uint32_t tile = s_tile;
-  const long long base = (long long)tile * kSortTile;
-  const int valid = (int)((n - base) < kSortTile ? (n - base) : kSortTile);
-
-  K key[kSortItems];
-  uint32_t pay[kSortItems];
-  uint32_t rnk[kSortItems];
-#pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    const int local = w * (32 * kSortItems) + i * 32 + lane;
-    if (local < valid) {
-      key[i] = kin[base + local];
-      pay[i] = pin[base + local];
-    } else {
-      key[i] = ~(K)0;  // sorts after every valid key of the tile in every pass; never written out
-      pay[i] = 0;
-    }
-  }
-  const uint32_t lt_mask = (1u << lane) - 1u;
-#pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (lane == leader) {
-      old = cnt[w][d];
-      cnt[w][d] = old + __popc(peers);
-    }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rnk[i] = old + __popc(peers & lt_mask);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long base = (long long)blockIdx.x * kSuperKeys;
+  const long long end = (base + kSuperKeys) < n ? (base + kSuperKeys) : n;
+  for (long long i0 = base + (threadIdx.x & ~31); i0 < end; i0 += 256) {   // warp-uniform trip count
+    const long long i = i0 + lane;
+    const bool ok = i < end;
+    const uint32_t d = ok ? ((uint32_t)(kin[i] >> shift) & 0xffu) : 0u;
+    const uint32_t peers = warp_peers8(d, ok);
+    if (ok && lane == __ffs(peers) - 1) whist[w][d] += (uint32_t)__popc(peers);
     __syncwarp();
   }
   __syncthreads();
-
-  // thread d owns digit d: prefix over the 8 warps, publish, look back, tile-local digit offsets
   uint32_t tot = 0;
 #pragma unroll
-  for (int ww = 0; ww < 8; ++ww) {
-    const uint32_t c = cnt[ww][tid];
-    cnt[ww][tid] = tot;
-    tot += c;
+  for (int ww = 0; ww < 8; ++ww) tot += whist[ww][threadIdx.x];
+  counts[(size_t)blockIdx.x * 256 + threadIdx.x] = tot;
+}
+
+// counts[s][d] -> exclusive prefix over super-tiles s (per digit), in place; thread d walks the rows (coalesced 1 KB rows);
+// bucket_base[d] = exclusive prefix over digits of the per-digit totals
+__global__ void __launch_bounds__(256) radix_scan_kernel(uint32_t* __restrict__ counts, int supers, uint32_t* __restrict__ bucket_base) {
+  uint32_t run = 0;
+  for (int s = 0; s < supers; ++s) {
+    const uint32_t c = counts[(size_t)s * 256 + threadIdx.x];
+    counts[(size_t)s * 256 + threadIdx.x] = run;
+    run += c;
   }
-  volatile uint32_t* vstatus = status;
-  vstatus[(size_t)tile * 256 + tid] = (tile == 0 ? kFlagIncl : kFlagAgg) | tot;
-  uint32_t excl = 0;
-  if (tile > 0) {
-    long long t = (long long)tile - 1;
-    uint64_t t0 = 0;
-    uint32_t spins = 0;
-    while (true) {
-      const uint32_t v = vstatus[(size_t)t * 256 + tid];
-      const uint32_t flag = v & ~kValMask;
-      if (flag == 0) {
-        if ((++spins & 0xfff) == 0) {
-          if (t0 == 0) t0 = global_timer_ns();
-          else if (global_timer_ns() - t0 > DFS_WAIT_LIMIT_NS) { printf("dfs_b200: radix look-back timeout\n"); __trap(); }
-        }
-        continue;
-      }
-      excl += v & kValMask;
-      if (flag == kFlagIncl) break;
-      --t;
-    }
-    vstatus[(size_t)tile * 256 + tid] = kFlagIncl | (excl + tot);
-  }
-  gbase[tid] = bucket_base[tid] + excl;
-  // block exclusive scan of tot over the 256 digits
-  uint32_t incl = tot;
+  __shared__ uint32_t wsum[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t incl = run;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
@@ -199,29 +139,111 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(const K* __
   if (lane == 31) wsum[w] = incl;
   __syncthreads();
   uint32_t woff = 0;
+  for (int ww = 0; ww < w; ++ww) woff += wsum[ww];
+  bucket_base[threadIdx.x] = woff + incl - run;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads) radix_downsweep_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ pin,
+                                                                        K* __restrict__ kout, uint32_t* __restrict__ pout, long long n,
+                                                                        int shift, const uint32_t* __restrict__ bucket_base,
+                                                                        const uint32_t* __restrict__ super_prefix) {
+  __shared__ uint32_t cnt[8][256];
+  __shared__ uint32_t digit_start[256];
+  __shared__ uint32_t gbase[256];
+  __shared__ uint32_t cursor[256];   // next global write position of each digit for this super-tile
+  __shared__ uint32_t wsum[8];
+  extern __shared__ __align__(16) uint8_t dyn[];
+  K* skeys = reinterpret_cast<K*>(dyn);
+  uint32_t* spay = reinterpret_cast<uint32_t*>(dyn + sizeof(K) * kSortTile);
+
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  cursor[tid] = bucket_base[tid] + super_prefix[(size_t)blockIdx.x * 256 + tid];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  for (int sub = 0; sub < kSuperTiles; ++sub) {
+    const long long base = (long long)blockIdx.x * kSuperKeys + (long long)sub * kSortTile;
+    if (base >= n) break;
+    const int valid = (int)((n - base) < kSortTile ? (n - base) : kSortTile);
+    for (int i = tid; i < 8 * 256; i += kSortThreads) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    K key[kSortItems];
+    uint32_t pay[kSortItems];
+    uint32_t rnk[kSortItems];
 #pragma unroll
-  for (int ww = 0; ww < 8; ++ww) woff += (ww < w) ? wsum[ww] : 0u;
-  digit_start[tid] = woff + incl - tot;
-  __syncthreads();
+    for (int i = 0; i < kSortItems; ++i) {
+      const int local = w * (32 * kSortItems) + i * 32 + lane;
+      if (local < valid) {
+        key[i] = kin[base + local];
+        pay[i] = pin[base + local];
+      } else {
+        key[i] = ~(K)0;  // sorts after every valid key of the tile in every pass; never written out
+        pay[i] = 0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+      const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
+      const uint32_t peers = warp_peers8(d, true);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader) {
+        old = cnt[w][d];
+        cnt[w][d] = old + __popc(peers);
+      }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      rnk[i] = old + __popc(peers & lt_mask);
+      __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d owns digit d: prefix over the 8 warps, tile-local digit offsets, global cursor
+    uint32_t tot = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) {
+      const uint32_t c = cnt[ww][tid];
+      cnt[ww][tid] = tot;
+      tot += c;
+    }
+    // padding keys (digit 255, ranked last) are counted in tot but never written; keep them out of the cursor
+    const uint32_t pad = (tid == 255) ? (uint32_t)(kSortTile - valid) : 0u;
+    gbase[tid] = cursor[tid];
+    cursor[tid] += tot - pad;
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) woff += (ww < w) ? wsum[ww] : 0u;
+    digit_start[tid] = woff + incl - tot;
+    __syncthreads();
 
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
-    const uint32_t pos = digit_start[d] + cnt[w][d] + rnk[i];
-    skeys[pos] = key[i];
-    spay[pos] = pay[i];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    const int pos = tid + i * kSortThreads;
-    if (pos < valid) {
-      const K k = skeys[pos];
-      const uint32_t d = (uint32_t)(k >> shift) & 0xffu;
-      const size_t dst = (size_t)gbase[d] + (uint32_t)(pos - digit_start[d]);
-      kout[dst] = k;
-      pout[dst] = spay[pos];
+    for (int i = 0; i < kSortItems; ++i) {
+      const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
+      const uint32_t pos = digit_start[d] + cnt[w][d] + rnk[i];
+      skeys[pos] = key[i];
+      spay[pos] = pay[i];
     }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+      const int pos = tid + i * kSortThreads;
+      if (pos < valid) {
+        const K k = skeys[pos];
+        const uint32_t d = (uint32_t)(k >> shift) & 0xffu;
+        const size_t dst = (size_t)gbase[d] + (uint32_t)(pos - digit_start[d]);
+        kout[dst] = k;
+        pout[dst] = spay[pos];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -439,9 +461,10 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_k0 = carve(sizeof(K) * n), o_k1 = carve(sizeof(K) * n);
   const size_t o_p0 = carve(4 * (size_t)n), o_p1 = carve(4 * (size_t)n);
-  const size_t o_status = carve((size_t)tiles * 256 * 4);
-  const size_t o_hist = carve(PASSES * 256 * 4);
-  const size_t o_small = carve(256);  // [0] n_ones (u64), [8..] tile counter, [64..] skip flags
+  const long long supers = ceil_div64(n, kSuperKeys);
+  const size_t o_counts = carve((size_t)supers * 256 * 4);
+  const size_t o_hist = carve(256 * 4);   // bucket bases of the current pass
+  const size_t o_small = carve(256);      // SortHeader
   const size_t o_bones = carve((size_t)tiles * 4), o_bexcl = carve((size_t)tiles * 8), o_bbest = carve((size_t)tiles * sizeof(SweepBest));
   const size_t o_res = carve(sizeof(dfs_eer_result));
   void* base = nullptr;
@@ -449,18 +472,17 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   uint8_t* b8 = static_cast<uint8_t*>(base);
   K* keys[2] = {reinterpret_cast<K*>(b8 + o_k0), reinterpret_cast<K*>(b8 + o_k1)};
   uint32_t* pay[2] = {reinterpret_cast<uint32_t*>(b8 + o_p0), reinterpret_cast<uint32_t*>(b8 + o_p1)};
-  uint32_t* status = reinterpret_cast<uint32_t*>(b8 + o_status);
+  uint32_t* counts = reinterpret_cast<uint32_t*>(b8 + o_counts);
   uint32_t* hist = reinterpret_cast<uint32_t*>(b8 + o_hist);
-  unsigned long long* n_ones = reinterpret_cast<unsigned long long*>(b8 + o_small);
-  uint32_t* tile_counter = reinterpret_cast<uint32_t*>(b8 + o_small + 8);
-  uint32_t* skip = reinterpret_cast<uint32_t*>(b8 + o_small + 64);
+  SortHeader* hdr = reinterpret_cast<SortHeader*>(b8 + o_small);
   uint32_t* bones = reinterpret_cast<uint32_t*>(b8 + o_bones);
   unsigned long long* bexcl = reinterpret_cast<unsigned long long*>(b8 + o_bexcl);
   SweepBest* bbest = reinterpret_cast<SweepBest*>(b8 + o_bbest);
   dfs_eer_result* res_dev = reinterpret_cast<dfs_eer_result*>(b8 + o_res);
 
-  DFS_CUDA_CHECK(cudaMemsetAsync(hist, 0, PASSES * 256 * 4, stream));
-  DFS_CUDA_CHECK(cudaMemsetAsync(b8 + o_small, 0, 256, stream));
+  SortHeader h0{0ull, ~0ull, 0ull};
+  DFS_CUDA_CHECK(cudaMemcpyAsync(hdr, &h0, sizeof(h0), cudaMemcpyHostToDevice, stream));
+  DFS_CUDA_CHECK(cudaStreamSynchronize(stream));  // h0 is a stack buffer
   int num_sms = 148;
   {
     int dev = 0;
@@ -468,30 +490,30 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const unsigned prep_grid = (unsigned)std::min<long long>(ceil_div64(n, 256), (long long)num_sms * 8);
-  sort_prep_kernel<K><<<prep_grid, 256, 0, stream>>>(static_cast<const S*>(scores), labels, n, keys[0], pay[0], hist, n_ones);
+  sort_prep_kernel<K><<<prep_grid, 256, 0, stream>>>(static_cast<const S*>(scores), labels, n, keys[0], pay[0], hdr);
   DFS_LAUNCH_CHECK();
-  sort_scan_hist_kernel<<<PASSES, 256, 0, stream>>>(hist, skip, n);
-  DFS_LAUNCH_CHECK();
-  // the label counts and skip flags decide the host control flow (single-class early-out; skipped passes)
-  struct { unsigned long long ones; uint32_t counter; uint32_t pad[13]; uint32_t skip[8]; } small_host;
-  DFS_CUDA_CHECK(cudaMemcpyAsync(&small_host, b8 + o_small, sizeof(small_host), cudaMemcpyDeviceToHost, stream));
+  // the label count and the key AND/OR decide the host control flow (single-class early-out; skipped passes)
+  SortHeader small_host;
+  DFS_CUDA_CHECK(cudaMemcpyAsync(&small_host, hdr, sizeof(small_host), cudaMemcpyDeviceToHost, stream));
   DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
   const long long n_bona = (long long)small_host.ones, n_spoof = n - n_bona;
 
   static bool configured = false;
   const size_t dyn_smem = (sizeof(K) + 4) * kSortTile;
   if (!configured) {
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(onesweep_pass_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kSortTile));
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(onesweep_pass_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kSortTile));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kSortTile));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kSortTile));
     configured = true;
   }
   int cur = 0;
   for (int ps = 0; ps < PASSES; ++ps) {
-    if (small_host.skip[ps]) continue;  // every key shares this digit: the pass is the identity
-    DFS_CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t)tiles * 256 * 4, stream));
-    DFS_CUDA_CHECK(cudaMemsetAsync(tile_counter, 0, 4, stream));
-    onesweep_pass_kernel<K><<<(unsigned)tiles, kSortThreads, dyn_smem, stream>>>(keys[cur], pay[cur], keys[cur ^ 1], pay[cur ^ 1], n, 8 * ps,
-                                                                                 hist + ps * 256, tile_counter, status);
+    if ((((small_host.key_and ^ small_host.key_or) >> (8 * ps)) & 0xffull) == 0) continue;  // every key shares this digit: identity pass
+    radix_upsweep_kernel<K><<<(unsigned)supers, 256, 0, stream>>>(keys[cur], n, 8 * ps, counts);
+    DFS_LAUNCH_CHECK();
+    radix_scan_kernel<<<1, 256, 0, stream>>>(counts, (int)supers, hist);
+    DFS_LAUNCH_CHECK();
+    radix_downsweep_kernel<K><<<(unsigned)supers, kSortThreads, dyn_smem, stream>>>(keys[cur], pay[cur], keys[cur ^ 1], pay[cur ^ 1], n, 8 * ps,
+                                                                                    hist, counts);
     DFS_LAUNCH_CHECK();
     cur ^= 1;
   }
