@@ -358,7 +358,7 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f)["dram_bytes_per_utterance"] * utt_per_launch
-    roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel<64,128> (CNN2D conv3, 66% of the FLOPs)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel<MODE_3X3S,64,128,N=256> (CNN2D conv3, 66% of the FLOPs)", "achieved": achieved,
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
                 "traffic_note": "DRAM bytes per launch (ncu); the tensor-bound kernel's algorithmic operand is the fp16 act2 read, 1.91 MB/utterance",
                 "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)",

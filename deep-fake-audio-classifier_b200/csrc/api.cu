@@ -330,7 +330,7 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
     if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->xt), (size_t)conv1_xt_rows(m->chunk) * 16, true)) != DFS_OK) return fail(st);
   }
 
-  const int64_t ncols = (int64_t)m->chunk * kCols + 32;
+  const int64_t ncols = (int64_t)m->chunk * kCols + 64;  // slack: the last 32-column tile window reaches past the last utterance
   m->act1 = ActBuf{nullptr, 8, kAct1RS, ncols};  // FT8P: 4 channel chunks x 2 time parities, 80 time pairs + 2 pads
   m->act2 = ActBuf{nullptr, 8, kAct2RS, ncols};  // FT8 : 8 channel chunks, 80 time steps + 2 pads
   if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->act1.ptr), m->act1.bytes(), true)) != DFS_OK) return fail(st);

@@ -49,6 +49,15 @@ void dfs_count_launch(int n = 1);
   } while (0)
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+// cudaFuncSetAttribute is per device: remember per (function instantiation, device) whether it has been applied
+static inline bool dfs_first_use_on_device(bool (&done)[32]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 32) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
 
 // ------------------------------------------------------------------------------------------
 // device helpers

@@ -236,11 +236,9 @@ int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_ut
   const long long total = (long long)n_utts * kF * kXtBlocks;
   conv1_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, xt);
   DFS_LAUNCH_CHECK();
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[32] = {false};
+  if (dfs_first_use_on_device(configured))
     DFS_CUDA_CHECK(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1SmemB));
-    configured = true;
-  }
   Conv1TcParams p{};
   p.xt = xt;
   p.wpack = wpack;

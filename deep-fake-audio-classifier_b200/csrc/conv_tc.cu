@@ -42,7 +42,8 @@ int make_act_tensor_map(CUtensorMap* out, const ActBuf& a, int wrows, int wcols,
 // CNN2D conv2: 32 -> 64 channels on 160 x 180 as 80 time PAIRS per column, pooled to 80 rows.
 using Conv2Cfg = ConvCfg<MODE_PAIR, 32, 64, 128, 80, 2, 3, 4, 1, EPI_PAIR_POOL>;
 // CNN2D conv3: 64 -> 128 channels on 80 x 180, summed over time.
-using Conv3Cfg = ConvCfg<MODE_3X3, 64, 128, 128, 80, 2, 2, 4, 1, EPI_MEAN_T>;
+using Conv3Cfg = ConvCfg<MODE_3X3S, 64, 128, 256, 80, 1, 3, 2, 2, EPI_MEAN_T_SWAP>;   // weights as A, 256 positions as N
+using Conv3PlainCfg = ConvCfg<MODE_3X3, 64, 128, 128, 80, 2, 2, 4, 1, EPI_MEAN_T>;   // positions as A (N = 128), kept for comparison
 
 int make_cnn2d_tensor_maps(CUtensorMap* tmap_act1, CUtensorMap* tmap_act2, const ActBuf& act1, const ActBuf& act2) {
   DFS_PROPAGATE(make_act_tensor_map(tmap_act1, act1, Conv2Cfg::WROWS, Conv2Cfg::WCOLS, Conv2Cfg::PPL));
@@ -73,7 +74,7 @@ int launch_cnn2d_conv3_tc(const CUtensorMap& tmap_act2, const uint16_t* wpack, c
   ConvParams p{};
   p.wpack = wpack;
   for (int i = 0; i < 128; ++i) p.bias[i] = bias[i];
-  p.n_units = num_col_tiles(n_utts, kCols);
+  p.n_units = (int)(((long long)n_utts * kCols - 1 + Conv3Cfg::CT - 1) / Conv3Cfg::CT);
   p.n_utts = n_utts;
   p.cols = kCols;
   p.feats = kF;

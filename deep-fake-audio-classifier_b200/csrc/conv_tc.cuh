@@ -16,6 +16,10 @@
 //             (DESIGN.md §4), so N = 128 with 4/3 of the MACs beats N = 64; the time pool becomes in-thread.
 // MODE_1X1  : one tap, no halo: the k=2,s=2 transposed convolutions of the CAE decoder are GEMMs over positions
 //             with N = (output quadrant, COUT) and a pixel-shuffle epilogue.
+// MODE_3X3S : 3x3 with SWAPPED operand roles: A = weights (M = COUT = 128 rows), B = activations with N = 256 positions
+//             (32 feature columns x 8 time steps).  Per the cost model N = 256 reaches 83 % of the tensor pipe instead
+//             of 73 % at N = 128, the accumulator row is an output channel, so the time sum is an in-thread add over
+//             8 consecutive columns and the [n][f][c] store is 128 contiguous bytes per warp.
 // MODE_3X1  : three taps along the row (time) axis only, no column halo: the Conv1d(k=3) layers of the 1D-CNN with one
 //             "feature column" per utterance (cols = 1: a tile is 16 utterances x 8 time steps).
 // KSPLIT    : the CIN/8 channel planes of a window are loaded as KSPLIT separate pipeline stages ("pieces"),
@@ -32,14 +36,15 @@
 
 namespace dfs {
 
-enum { MODE_3X3 = 0, MODE_PAIR = 1, MODE_1X1 = 2, MODE_3X1 = 3 };
+enum { MODE_3X3 = 0, MODE_PAIR = 1, MODE_1X1 = 2, MODE_3X1 = 3, MODE_3X3S = 4 };
 enum {
   EPI_PAIR_POOL = 0,    // PAIR: relu both time steps, add (time pool), store FT8                    (CNN2D conv2)
   EPI_MEAN_T = 1,       // 3x3 : relu, sum over all rows of the unit, store [n][F][COUT] fp32         (CNN2D conv3)
   EPI_PAIR_POOL_F = 2,  // PAIR: time pool in-thread + feature pool with lane^8, store FT8            (CAE enc2)
   EPI_POOL_TF = 3,      // 3x3 : relu, 2x2 pool with lane^1 (time) and lane^8 (feature), store FT8    (CAE enc3, enc4)
   EPI_SHUFFLE = 4,      // 1x1 : relu, pixel-shuffle store of the quadrant(s) held in the columns      (CAE dec1-3)
-  EPI_RELU = 5          // any : relu, store FT8 at the same position                                   (CNN1D layers 1, 2)
+  EPI_RELU = 5,         // any : relu, store FT8 at the same position                                   (CNN1D layers 1, 2)
+  EPI_MEAN_T_SWAP = 6   // 3x3S: lanes = output channels, columns = positions; relu, time sum in-thread   (CNN2D conv3)
 };
 
 template <int MODE_, int CIN_, int COUT_, int NG_, int ROWS_, int MT_, int NSTAGE_, int NACC_, int KSPLIT_, int EPI_>
@@ -47,6 +52,8 @@ struct ConvCfg {
   static constexpr int MODE = MODE_, CIN = CIN_, COUT = COUT_, NG = NG_, ROWS = ROWS_, MT = MT_, NSTAGE = NSTAGE_, NACC = NACC_,
                        KSPLIT = KSPLIT_, EPI = EPI_;
   static constexpr bool PAIR = (MODE == MODE_PAIR);
+  static constexpr bool SWAP = (MODE == MODE_3X3S);
+  static constexpr int CT = SWAP ? 32 : kColTile;      // feature columns per tile
   static constexpr int HALO = (MODE == MODE_1X1) ? 0 : 1;                       // row halo
   static constexpr int HALO_C = (MODE == MODE_1X1 || MODE == MODE_3X1) ? 0 : 1;  // column halo
   static constexpr int NTAP = PAIR ? 12 : (MODE == MODE_1X1 ? 1 : (MODE == MODE_3X1 ? 3 : 9));
@@ -55,11 +62,12 @@ struct ConvCfg {
   static constexpr int PPL = KCH / KSPLIT;             // planes per piece
   static constexpr int CPP = CCH / KSPLIT;             // channel chunks per piece
   static constexpr int WROWS = 8 * MT + 2 * HALO;      // window rows incl. halo
-  static constexpr int WCOLS = kColTile + 2 * HALO_C;  // window columns (feature) incl. halo
+  static constexpr int WCOLS = CT + 2 * HALO_C;        // window columns (feature) incl. halo
   static constexpr int PLANE_B = WCOLS * WROWS * 16;   // bytes of one plane of the window
   static constexpr int WIN_B = PPL * PLANE_B;          // TMA transaction bytes per piece
   static constexpr int WIN_B_AL = (WIN_B + 1023) & ~1023;
-  static constexpr int WGT_B = NTAP * CIN * NG * 2;    // per output group
+  static constexpr int WROWS_OUT = SWAP ? COUT : NG;   // rows of the weight operand image
+  static constexpr int WGT_B = NTAP * CIN * WROWS_OUT * 2;  // per output group
   static constexpr int WGT_B_AL = (WGT_B + 1023) & ~1023;
   static constexpr int ST = ROWS / (8 * MT);           // windows (super-tiles) per unit
   static constexpr int TILES = ROWS / 8;               // MMA tiles per unit
@@ -75,6 +83,7 @@ struct ConvCfg {
   static_assert(TMEM_COLS == 32 || TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
   static_assert(NG % 64 == 0 && NG <= 256 && CIN % 16 == 0, "shape");
   static_assert(!PAIR || KSPLIT == 1, "PAIR mode loads both parities in one piece");
+  static_assert(!SWAP || (MT == 1 && NG == 256 && COUT == 128), "swapped mode: one 128 x 256 tile per window");
   static_assert(CCH % KSPLIT == 0 && CPP % 2 == 0, "a piece must hold whole K=16 steps");
   static_assert(SMEM_B <= 227 * 1024, "shared memory budget");
 
@@ -94,7 +103,7 @@ struct ConvCfg {
     return (2 * kk) * PLANE_B + (kw * WROWS + kh) * 16;
   }
   // byte offset of the B start address for (tap, piece, K step kk)
-  __host__ __device__ static constexpr int b_off(int tap, int piece, int kk) { return ((tap * CCH + piece * CPP + 2 * kk) * NG) * 16; }
+  __host__ __device__ static constexpr int b_off(int tap, int piece, int kk) { return ((tap * CCH + piece * CPP + 2 * kk) * WROWS_OUT) * 16; }
 };
 
 struct ConvParams {
@@ -175,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             const int stage = ws % NSTAGE;
             mbar_wait(&empty[stage], ((ws / NSTAGE) & 1) ^ 1, 1);
             mbar_arrive_expect_tx(&full[stage], Cfg::WIN_B);
-            tma_load_3d(win0 + stage * Cfg::WIN_B_AL, &tmap, (1 + 8 * MT * st - HALO) * 8, 1 + u * kColTile - HALO_C, pc * Cfg::PPL,
+            tma_load_3d(win0 + stage * Cfg::WIN_B_AL, &tmap, (1 + 8 * MT * st - HALO) * 8, 1 + u * Cfg::CT - HALO_C, pc * Cfg::PPL,
                         &full[stage]);
           }
         }
@@ -187,7 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       constexpr uint32_t idesc = umma_idesc_f16(128, NG);
       // descriptor = (low word: start address >> 4 | LBO >> 4 << 16, high word: SBO >> 4 | version); taps and
       // K steps only move the start address, i.e. add a compile-time constant to the low word
-      const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), NG * 16, 128);
+      const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), Cfg::WROWS_OUT * 16, 128);
       const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
       const uint64_t a_desc0 = umma_smem_desc(smem_u32(win0), PLANE_B, WROWS * 16);
       const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
@@ -214,9 +223,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 const uint32_t a_off = (uint32_t)(Cfg::a_off(tap, kk) >> 4);
                 const uint32_t b_off = (uint32_t)(Cfg::b_off(tap, pc, kk) >> 4);
 #pragma unroll
-                for (int m = 0; m < MT; ++m)  // tile m = rows 8m.. of the window: +8 rows of 16 B
-                  umma_f16_lohi(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc,
-                                (pc | tap | kk) != 0 ? 1u : 0u);
+                for (int m = 0; m < MT; ++m) {  // tile m = rows 8m.. of the window: +8 rows of 16 B
+                  if constexpr (Cfg::SWAP)  // weights are the A (M) operand, the activation window is the B (N = 256) operand
+                    umma_f16_lohi(tmem_base + (acc0 + m) * NG, b_lo0 + b_off, b_hi, a_lo_stage + a_off, a_hi, idesc, (pc | tap | kk) != 0 ? 1u : 0u);
+                  else
+                    umma_f16_lohi(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc,
+                                  (pc | tap | kk) != 0 ? 1u : 0u);
+                }
               }
             }
             if (pc == KSPLIT - 1) {
@@ -239,7 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const float* bias = p.bias;  // param space: uniform constant-bank reads
     uint32_t it = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int gc = 1 + kColTile * u + g;
+      const int gc = 1 + Cfg::CT * u + g;
       // padded layouts: column gc = n*cols + f' (f' = 0 and cols-1 are zero pads); cols == 1: one column per utterance at gc = 1 + n
       const int n = (p.cols == 1) ? gc - 1 : gc / p.cols;
       const int fp = (p.cols == 1) ? 1 : gc - n * p.cols;
@@ -357,6 +370,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
           for (int c = 0; c < W3; c += 4)
             *reinterpret_cast<float4*>(dst + c) = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
+        }
+      } else if constexpr (Cfg::EPI == EPI_MEAN_T_SWAP) {
+        // accumulator row (TMEM lane) = output channel, column j = 8*(feature column) + time step; this thread sums the
+        // ReLU outputs over time for the 16 feature columns of its column half, across all tiles of the unit
+        const int ch = 32 * q + lane;
+        const float bc = bias[ch];
+        float tsum[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) tsum[c] = 0.0f;
+        for (int tt = 0; tt < Cfg::TILES; ++tt, ++it) {
+          const int acc = it % NACC;
+          mbar_wait(&tfull[acc], (it / NACC) & 1, 5);
+          tc_fence_after();
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * 128 + blk * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) tsum[blk * 4 + (k >> 3)] += fmaxf(v[k] + bc, 0.0f);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int gcc = 1 + Cfg::CT * u + h * 16 + c;
+          const int nn = gcc / p.cols;
+          const int fpp = gcc - nn * p.cols;
+          if (nn < p.n_utts && fpp >= 1 && fpp <= p.feats) p.emb[((long long)nn * p.feats + (fpp - 1)) * COUT + ch] = tsum[c];
         }
       } else if constexpr (Cfg::EPI == EPI_POOL_TF) {
         // relu, then 2x2 average pool: time partner = lane^1, feature partner = lane^8 (1/4 folded into weights/bias).
@@ -483,11 +527,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
 template <class Cfg>
 static int launch_conv_tc(const CUtensorMap& tmap, const ConvParams& p, int groups, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[32] = {false};
+  if (dfs_first_use_on_device(configured))
     DFS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_B));
-    configured = true;
-  }
   if (p.n_units <= 0) return DFS_OK;
   int gx = (num_sms * Cfg::OCC) / groups;
   if (gx < 1) gx = 1;

@@ -498,12 +498,11 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
   const long long n_bona = (long long)small_host.ones, n_spoof = n - n_bona;
 
-  static bool configured = false;
+  static bool configured[32] = {false};
   const size_t dyn_smem = (sizeof(K) + 4) * kSortTile;
-  if (!configured) {
+  if (dfs_first_use_on_device(configured)) {
     DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kSortTile));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kSortTile));
-    configured = true;
   }
   int cur = 0;
   for (int ps = 0; ps < PASSES; ++ps) {

@@ -147,3 +147,25 @@ def test_device_generated_features_have_the_right_statistics():
     assert abs(float(x.mean())) < 0.02 and abs(float(x.std()) - 3.2) < 0.02
     y = fill_features(8, first_utt=56, seed=1234)      # keyed by (seed, utterance index): shards line up
     assert torch.equal(x[56:64], y)
+
+
+def test_cnn2d_baseline_config0_2048_utterances_vs_cpu_reference_path():
+    """BASELINE configs[0]: 2D-CNN scoring of 2,048 synthetic utterances + EER, against the CPU reference path
+    (oracle port of the predict.py loop on torch CPU fp32 -- bit-identical to the reference classes, see
+    tests/test_oracle_golden.py::test_torch_oracle_bit_matches_reference)."""
+    from oracle import eer as oeer
+    from oracle import models_torch as ot
+    import dfs_b200 as D
+    n = 2048
+    x = fill_features(n, first_utt=0, seed=1234)
+    sd = syn.cnn2d_state(0)
+    got = Cnn2dScorer(sd).score(x, apply_sigmoid=True).cpu().numpy()
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = ot.reference_loop_supervised(ot.cnn2d_forward, sd, x.cpu())
+    assert _rel(got, ref) <= REL
+    ranks = np.argsort(np.argsort(ref, kind="stable"), kind="stable")
+    lab = (np.random.Generator(np.random.PCG64(7)).random(n) < 1 / (1 + np.exp(-6.0 * (ranks / n - 0.5)))).astype(np.uint8)
+    eer_ref = oeer.calculate_eer(ref, lab)[0]
+    eer_dev = D.calculate_eer(got, lab)[0]
+    assert abs(eer_ref - eer_dev) <= 2e-3        # reported: score ranks 3e-6 apart; see DESIGN.md "Precision"
+    assert D.calculate_eer(ref, lab) == oeer.calculate_eer(ref, lab)   # identical scores -> bit-exact EER and threshold
