@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--workload", default="cnn2d", choices=["cnn2d", "cae", "hybrid", "eer"],
                     help="cnn2d = the headline BASELINE configs[1]; cae / hybrid / eer = configs 3 / 4 / 5 (informational lines)")
     ap.add_argument("--eer-n", type=int, default=100_000_000)
+    ap.add_argument("--eer-method", default="sort", choices=["sort", "select"],
+                    help="eer workload: 'sort' = full stable radix sort + sweep (north_star wording; `value`), 'select' = radix select of "
+                         "the crossing (what calculate_eer() uses when no permutation is requested); the other one is timed as an extra key")
     return ap.parse_args()
 
 
@@ -180,8 +183,8 @@ def run_other_workload(args, rank, world, local):
         sd_, ld_ = torch.from_numpy(sc).to(dev), torch.from_numpy(lab).to(dev)
         units, unit_name, metric = n, "scores/s", "EER sweep (device radix sort + FAR/FRR crossing) on tie-free fp32 scores"
 
-        def step():
-            return D.eer_details(sd_, ld_)
+        def step(method=args.eer_method):
+            return D.eer_details(sd_, ld_, method=method)
     else:
         pool = D.fill_features(P, first_utt=rank * P, seed=1234, device=local)
         labels_global = torch.from_numpy(syn.labels(P * world)).to(dev)
@@ -231,11 +234,29 @@ def run_other_workload(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = units * args.steps / (ms * 1e-3)
+    extra = {}
+    if args.workload == "eer":
+        other = "select" if args.eer_method == "sort" else "sort"
+        for _ in range(3):
+            res_o = step(other)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            res_o = step(other)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms_o = ev0.elapsed_time(ev1) / args.steps
+        extra["eer_" + other] = {"value": units / (ms_o * 1e-3), "unit": unit_name, "ms_per_step": ms_o,
+                                 "identical_result": (res_o["eer"], res_o["threshold"], res_o["eer_idx"]) ==
+                                                     (res["eer"], res["threshold"], res["eer_idx"]),
+                                 "hbm_frac_at_13B_per_score": 13.0 * units / (ms_o * 1e-3) / 1e9 / pk["hbm_gbs"]}
+        extra["eer_method"] = args.eer_method
     if rank == 0:
         if args.workload == "eer":
             ach = 13.0 * value / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
-                    "note": "13 B/score algorithmic (SURVEY.md 8d); a 4-pass LSD radix sort with u32 payload moves ~77 B/score"}
+                    "note": "13 B/score algorithmic (SURVEY.md 8d). sort: 4 LSD passes x (4 B count + 16 B scatter) + 13 B prep + 8 B sweep "
+                            "~ 101 B/score; select: 5 B/score per varying key byte (<= 20 B/score fp32)"}
         else:
             flop = FLOP_PER_UTT["cae"] if args.workload == "cae" else sum(FLOP_PER_UTT.values())
             ach = value / world * flop / 1e12
@@ -246,7 +267,7 @@ def run_other_workload(args, rank, world, local):
                           "vs_baseline": None, "dtype": "f16" if args.workload != "eer" else "f32/f64", "data": "synthetic",
                           "config": {"workload": args.workload, "units_per_step": units, "l2": "inputs larger than L2"},
                           "eer": {"value": res["eer"], "threshold": res["threshold"]}, "clocks": clocks, "gpu_launches": int(launches),
-                          "roofline": roof}))
+                          "roofline": roof, **extra}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -750,6 +750,10 @@ extern "C" int dfs_eer(const void* scores_dev, int key_bytes, const uint8_t* lab
                        uint32_t* perm_dev, void* sorted_dev, void* stream) {
   return eer_device(scores_dev, key_bytes, labels_dev, n, result_host, perm_dev, sorted_dev, static_cast<cudaStream_t>(stream));
 }
+extern "C" int dfs_eer_select(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, dfs_eer_result* result_host,
+                              void* stream) {
+  return eer_select_device(scores_dev, key_bytes, labels_dev, n, result_host, static_cast<cudaStream_t>(stream));
+}
 extern "C" int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,
                              int64_t* out4_host, void* stream) {
   return confusion_device(scores_dev, key_bytes, labels_dev, n, threshold, out4_host, static_cast<cudaStream_t>(stream));

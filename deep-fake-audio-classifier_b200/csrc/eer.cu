@@ -96,26 +96,72 @@ __device__ __forceinline__ uint32_t warp_peers8(uint32_t d, bool ok) {
   return peers;
 }
 
+// ---- digit histograms with thread-private byte counters ---------------------------------------------------
+// Ballot ranking costs ~70 warp instructions per 32 keys and shared-memory atomics ~2 cycles per lane; a histogram needs
+// neither: thread t owns the byte column t of a [bins][kCntStride] table, so an increment is an unsynchronised
+// LDS.U8 / IADD / STS.U8 (rows 260 B apart: a warp's 32 accesses spread over the banks like 32 random words).  A thread
+// may add at most 255 keys between two flushes; a flush sums each row with dp4a (rows are conflict-free: word j of row r
+// sits in bank (r + j) % 32) and clears it.
+constexpr int kCntStride = 260;
+
+template <typename K> struct VecOf;
+template <> struct VecOf<uint32_t> { static constexpr int V = 4; };
+template <> struct VecOf<uint64_t> { static constexpr int V = 2; };
+
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T* __restrict__ p, T (&out)[V]) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  if constexpr (sizeof(T) == 4) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[e] = *reinterpret_cast<const T*>(&w[e]);
+  } else {
+    const uint64_t w[2] = {((uint64_t)q.y << 32) | q.x, ((uint64_t)q.w << 32) | q.z};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) out[e] = *reinterpret_cast<const T*>(&w[e]);
+  }
+}
+
+// sum and clear row `row` (256 counters) of a private-counter table
+__device__ __forceinline__ uint32_t flush_counter_row(uint8_t* cnt, int row) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(cnt + row * kCntStride);
+  uint32_t tot = 0;
+#pragma unroll 16
+  for (int j = 0; j < 64; ++j) {
+    tot = __dp4a(w[j], 0x01010101u, tot);
+    w[j] = 0u;
+  }
+  return tot;
+}
+
 template <typename K>
 __global__ void __launch_bounds__(256) radix_upsweep_kernel(const K* __restrict__ kin, long long n, int shift, uint32_t* __restrict__ counts /*[supers][256]*/) {
-  __shared__ uint32_t whist[8][256];   // one private histogram per warp: the group leader does a plain read-modify-write
-  for (int i = threadIdx.x; i < 8 * 256; i += 256) (&whist[0][0])[i] = 0;
+  extern __shared__ __align__(16) uint8_t cnt[];   // [256][kCntStride]
+  constexpr int V = VecOf<K>::V;
+  constexpr int kFlushKeys = 128;                  // keys per thread between flushes
+  for (int i = threadIdx.x; i < 256 * kCntStride / 4; i += 256) reinterpret_cast<uint32_t*>(cnt)[i] = 0u;
   __syncthreads();
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long base = (long long)blockIdx.x * kSuperKeys;
   const long long end = (base + kSuperKeys) < n ? (base + kSuperKeys) : n;
-  for (long long i0 = base + (threadIdx.x & ~31); i0 < end; i0 += 256) {   // warp-uniform trip count
-    const long long i = i0 + lane;
-    const bool ok = i < end;
-    const uint32_t d = ok ? ((uint32_t)(kin[i] >> shift) & 0xffu) : 0u;
-    const uint32_t peers = warp_peers8(d, ok);
-    if (ok && lane == __ffs(peers) - 1) whist[w][d] += (uint32_t)__popc(peers);
-    __syncwarp();
-  }
-  __syncthreads();
+  uint8_t* mine = cnt + threadIdx.x;
   uint32_t tot = 0;
+  for (long long c0 = base; c0 < end; c0 += 256ll * kFlushKeys) {
+#pragma unroll 4
+    for (int it = 0; it < kFlushKeys / V; ++it) {
+      const long long i = c0 + ((long long)it * 256 + threadIdx.x) * V;
+      if (i + V <= end) {
+        K k[V];
+        load_vec<K, V>(kin + i, k);
 #pragma unroll
-  for (int ww = 0; ww < 8; ++ww) tot += whist[ww][threadIdx.x];
+        for (int e = 0; e < V; ++e) mine[((uint32_t)(k[e] >> shift) & 0xffu) * kCntStride] += 1;
+      } else {
+        for (long long j = i; j < end; ++j) mine[((uint32_t)(kin[j] >> shift) & 0xffu) * kCntStride] += 1;
+      }
+    }
+    __syncthreads();
+    tot += flush_counter_row(cnt, threadIdx.x);
+    __syncthreads();
+  }
   counts[(size_t)blockIdx.x * 256 + threadIdx.x] = tot;
 }
 
@@ -304,8 +350,11 @@ __global__ void __launch_bounds__(1024) sweep_scan_kernel(const uint32_t* __rest
 
 __device__ __forceinline__ bool better(double d, long long i, double bd, long long bi) { return d < bd || (d == bd && i < bi); }
 
+// The curve points evaluated are k = k_base .. k_base + n, where the first k_base sorted scores (c1_base of them bonafide)
+// precede pay[0] (k_base = c1_base = 0 for the full sweep; the radix-select path sweeps one tie group only).
 __global__ void __launch_bounds__(256) sweep_min_kernel(const uint32_t* __restrict__ pay, long long n, long long n_bona, long long n_spoof,
-                                                         const unsigned long long* __restrict__ block_excl, SweepBest* __restrict__ block_best) {
+                                                         const unsigned long long* __restrict__ block_excl, SweepBest* __restrict__ block_best,
+                                                         long long k_base, long long c1_base) {
   // blocked arrangement: thread t owns sorted positions base + 16 t .. + 15
   const long long base = (long long)blockIdx.x * kSortTile + (long long)threadIdx.x * kSortItems;
   uint32_t lab[kSortItems];
@@ -337,18 +386,24 @@ __global__ void __launch_bounds__(256) sweep_min_kernel(const uint32_t* __restri
   uint32_t woff = 0;
 #pragma unroll
   for (int ww = 0; ww < 8; ++ww) woff += (ww < w) ? wsum[ww] : 0u;
-  long long c1 = (long long)block_excl[blockIdx.x] + woff + incl - ones;
+  long long c1 = c1_base + (long long)block_excl[blockIdx.x] + woff + incl - ones;
 
   const double dspoof = (double)n_spoof, dbona = (double)n_bona;
   double bd = 1.0e300;
   long long bi = 0x7fffffffffffffffll, bc1 = 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { bd = 1.0; bi = 0; bc1 = 0; }  // k = 0: FAR = 1, FRR = 0
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // first curve point (k = 0: FAR = 1, FRR = 0)
+    const double far0 = __ddiv_rn((double)(n_spoof - (k_base - c1_base)), dspoof);
+    const double frr0 = __ddiv_rn((double)c1_base, dbona);
+    bd = fabs(__dsub_rn(far0, frr0));
+    bi = k_base;
+    bc1 = c1_base;
+  }
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const long long j = base + i;
     if (j < n) {
       c1 += lab[i];
-      const long long k = j + 1;
+      const long long k = k_base + j + 1;
       const long long c0 = k - c1;
       const double far = __ddiv_rn((double)(n_spoof - c0), dspoof);   // evaluation.py:21-23
       const double frr = __ddiv_rn((double)c1, dbona);                // evaluation.py:24-26
@@ -503,11 +558,13 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   if (dfs_first_use_on_device(configured)) {
     DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kSortTile));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kSortTile));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_upsweep_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kCntStride));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_upsweep_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kCntStride));
   }
   int cur = 0;
   for (int ps = 0; ps < PASSES; ++ps) {
     if ((((small_host.key_and ^ small_host.key_or) >> (8 * ps)) & 0xffull) == 0) continue;  // every key shares this digit: identity pass
-    radix_upsweep_kernel<K><<<(unsigned)supers, 256, 0, stream>>>(keys[cur], n, 8 * ps, counts);
+    radix_upsweep_kernel<K><<<(unsigned)supers, 256, 256 * kCntStride, stream>>>(keys[cur], n, 8 * ps, counts);
     DFS_LAUNCH_CHECK();
     radix_scan_kernel<<<1, 256, 0, stream>>>(counts, (int)supers, hist);
     DFS_LAUNCH_CHECK();
@@ -534,13 +591,524 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   DFS_LAUNCH_CHECK();
   sweep_scan_kernel<<<1, 1024, 0, stream>>>(bones, tiles, bexcl);
   DFS_LAUNCH_CHECK();
-  sweep_min_kernel<<<(unsigned)tiles, 256, 0, stream>>>(pay[cur], n, n_bona, n_spoof, bexcl, bbest);
+  sweep_min_kernel<<<(unsigned)tiles, 256, 0, stream>>>(pay[cur], n, n_bona, n_spoof, bexcl, bbest, 0, 0);
   DFS_LAUNCH_CHECK();
   sweep_final_kernel<K><<<1, 256, 0, stream>>>(bbest, tiles, keys[cur], n, n_bona, n_spoof, res_dev);
   DFS_LAUNCH_CHECK();
   DFS_CUDA_CHECK(cudaMemcpyAsync(result_host, res_dev, sizeof(dfs_eer_result), cudaMemcpyDeviceToHost, stream));
   DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
   return DFS_OK;
+}
+
+// ---- EER by radix SELECT (no permutation requested) ------------------------------------------------------
+// FAR(k) - FRR(k) is strictly decreasing in k (every sorted score either removes 1/n_spoof from FAR or adds 1/n_bona to
+// FRR, both far above an fp64 ulp), so argmin |FAR - FRR| is the last k with a non-negative difference or the first
+// with a negative one.  That crossing is found like a quantile: an MSD radix descent over the key bytes with one
+// (digit, label) histogram per level -- 5 B/score per level instead of a full sort -- which pins down the key value G
+// holding the crossing, the label counts below G and the size of G's tie group.  A single-label tie group (always the
+// case for tie-free scores) is resolved in closed form; a mixed-label group is compacted in original index order (the
+// stable-sort contract) and swept with the same kernels as the full sort.  Every FAR/FRR value is produced by the same
+// IEEE fp64 operations as in sweep_min_kernel, so (eer, threshold, eer_idx) are bit-identical to the sort path.
+struct SelectState {
+  unsigned long long prefix;     // key bits decided so far
+  unsigned long long mask;       // which bits those are
+  unsigned long long c0_below;   // spoof / bonafide scores with key below the current prefix range
+  unsigned long long c1_below;
+  unsigned long long n_bona, n_spoof;
+  unsigned long long key_and, key_or;
+  unsigned long long g0, g1;     // spoof / bonafide scores inside the current prefix range
+  unsigned long long pred;       // largest key below G (filled on demand)
+  SweepBest best;                // chosen curve point
+  int status;                    // 1 = single-class input
+  int resolved;                  // best is valid
+};
+
+__global__ void select_init_kernel(SelectState* st, unsigned long long* hist) {
+  if (threadIdx.x == 0) {
+    SelectState z{};
+    z.key_and = ~0ull;
+    *st = z;
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) hist[i] = 0ull;
+}
+
+constexpr int kSelIters = 56;   // vector loads per thread between two flushes: <= 224 keys per thread
+constexpr int kSelUnroll = 8;
+
+template <typename K, bool FIRST>
+__global__ void __launch_bounds__(256, 1) select_hist_kernel(const typename ScoreOf<K>::type* __restrict__ scores,
+                                                              const uint8_t* __restrict__ labels, long long n, int shift,
+                                                              SelectState* __restrict__ st, unsigned long long* __restrict__ hist /*[2][256]*/) {
+  typedef typename ScoreOf<K>::type S;
+  constexpr int V = VecOf<K>::V;
+  extern __shared__ __align__(16) uint8_t cnt[];   // [512 = label*256 + digit][kCntStride]
+  for (int i = threadIdx.x; i < 512 * kCntStride / 4; i += 256) reinterpret_cast<uint32_t*>(cnt)[i] = 0u;
+  const K prefix = FIRST ? (K)0 : (K)st->prefix;
+  const K mask = FIRST ? (K)0 : (K)st->mask;
+  __syncthreads();
+  uint8_t* mine = cnt + threadIdx.x;
+  K kand = ~(K)0, kor = 0;
+  unsigned long long tot0 = 0, tot1 = 0;
+  constexpr long long kChunk = 256ll * V * kSelIters;
+  const long long nvec = n - (n % V);   // the last n % V scores are handled by one thread below
+  for (long long c0 = (long long)blockIdx.x * kChunk; c0 < nvec; c0 += (long long)gridDim.x * kChunk) {
+    for (int it0 = 0; it0 < kSelIters; it0 += kSelUnroll) {
+      S sv[kSelUnroll][V];
+      uint32_t lv[kSelUnroll];
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const long long i = c0 + ((long long)(it0 + u) * 256 + threadIdx.x) * V;
+        if (i < nvec) {
+          load_vec<S, V>(scores + i, sv[u]);
+          if constexpr (V == 4) lv[u] = __ldg(reinterpret_cast<const uint32_t*>(labels + i));
+          else lv[u] = __ldg(reinterpret_cast<const uint16_t*>(labels + i));
+        } else {
+          lv[u] = 0u;
+#pragma unroll
+          for (int e = 0; e < V; ++e) sv[u][e] = (S)0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const long long i = c0 + ((long long)(it0 + u) * 256 + threadIdx.x) * V;
+        if (i < nvec) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const K k = to_key(sv[u][e]);
+            const uint32_t lab = ((lv[u] >> (8 * e)) & 0xffu) != 0u;
+            if (FIRST) { kand &= k; kor |= k; }
+            if (FIRST || (k & mask) == prefix) mine[(((uint32_t)(k >> shift) & 0xffu) | (lab << 8)) * kCntStride] += 1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    tot0 += flush_counter_row(cnt, threadIdx.x);
+    tot1 += flush_counter_row(cnt, 256 + threadIdx.x);
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (long long i = nvec; i < n; ++i) {
+      const K k = to_key(scores[i]);
+      const uint32_t lab = labels[i] != 0;
+      if (FIRST) { kand &= k; kor |= k; }
+      if (FIRST || (k & mask) == prefix) atomicAdd(&hist[(((uint32_t)(k >> shift) & 0xffu)) + 256 * lab], 1ull);
+    }
+  }
+  if (tot0) atomicAdd(&hist[threadIdx.x], tot0);
+  if (tot1) atomicAdd(&hist[256 + threadIdx.x], tot1);
+  if (FIRST) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      kand &= (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)kand, o);
+      kor |= (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)kor, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAnd(&st->key_and, (unsigned long long)kand);   // zero-extended: the upper bits of a 32-bit key AND to 0, OR to 0
+      atomicOr(&st->key_or, (unsigned long long)kor);
+    }
+  }
+}
+
+// scalar-load variant for misaligned score / label pointers (same counters, same flush rule)
+template <typename K, bool FIRST>
+__global__ void __launch_bounds__(256, 1) select_hist_scalar_kernel(const typename ScoreOf<K>::type* __restrict__ scores,
+                                                                     const uint8_t* __restrict__ labels, long long n, int shift,
+                                                                     SelectState* __restrict__ st, unsigned long long* __restrict__ hist) {
+  extern __shared__ __align__(16) uint8_t cnt[];
+  for (int i = threadIdx.x; i < 512 * kCntStride / 4; i += 256) reinterpret_cast<uint32_t*>(cnt)[i] = 0u;
+  const K prefix = FIRST ? (K)0 : (K)st->prefix;
+  const K mask = FIRST ? (K)0 : (K)st->mask;
+  __syncthreads();
+  uint8_t* mine = cnt + threadIdx.x;
+  K kand = ~(K)0, kor = 0;
+  unsigned long long tot0 = 0, tot1 = 0;
+  constexpr long long kChunk = 256ll * 224;
+  for (long long c0 = (long long)blockIdx.x * kChunk; c0 < n; c0 += (long long)gridDim.x * kChunk) {
+    for (int it = 0; it < 224; ++it) {
+      const long long i = c0 + (long long)it * 256 + threadIdx.x;
+      if (i < n) {
+        const K k = to_key(scores[i]);
+        const uint32_t lab = labels[i] != 0;
+        if (FIRST) { kand &= k; kor |= k; }
+        if (FIRST || (k & mask) == prefix) mine[(((uint32_t)(k >> shift) & 0xffu) | (lab << 8)) * kCntStride] += 1;
+      }
+    }
+    __syncthreads();
+    tot0 += flush_counter_row(cnt, threadIdx.x);
+    tot1 += flush_counter_row(cnt, 256 + threadIdx.x);
+    __syncthreads();
+  }
+  if (tot0) atomicAdd(&hist[threadIdx.x], tot0);
+  if (tot1) atomicAdd(&hist[256 + threadIdx.x], tot1);
+  if (FIRST) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      kand &= (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)kand, o);
+      kor |= (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)kor, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAnd(&st->key_and, (unsigned long long)kand);
+      atomicOr(&st->key_or, (unsigned long long)kor);
+    }
+  }
+}
+
+__device__ __forceinline__ double eer_curve_diff(long long c0, long long c1, long long n_spoof, long long n_bona) {
+  const double far = __ddiv_rn((double)(n_spoof - c0), (double)n_spoof);   // evaluation.py:21-23
+  const double frr = __ddiv_rn((double)c1, (double)n_bona);                // evaluation.py:24-26
+  return __dsub_rn(far, frr);
+}
+
+// One level of the descent: pick the first digit whose END lies beyond the crossing (difference < 0 after all its keys).
+// skip != 0: every key shares this byte (key AND == OR); no histogram was taken.
+__global__ void __launch_bounds__(256) select_pick_kernel(unsigned long long* __restrict__ hist, SelectState* __restrict__ st, int shift,
+                                                           int first, int skip) {
+  if (skip) {
+    if (threadIdx.x == 0) {
+      st->prefix |= st->key_and & (0xffull << shift);
+      st->mask |= 0xffull << shift;
+    }
+    return;
+  }
+  __shared__ unsigned long long w0[8], w1[8];
+  __shared__ int wfirst[8];
+  __shared__ int single;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const unsigned long long c0 = hist[tid], c1 = hist[256 + tid];
+  hist[tid] = 0ull;
+  hist[256 + tid] = 0ull;
+  unsigned long long i0 = c0, i1 = c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long u0 = __shfl_up_sync(0xffffffffu, i0, o), u1 = __shfl_up_sync(0xffffffffu, i1, o);
+    if (lane >= o) { i0 += u0; i1 += u1; }
+  }
+  if (lane == 31) { w0[w] = i0; w1[w] = i1; }
+  __syncthreads();
+  unsigned long long t0 = 0, t1 = 0;
+  for (int ww = 0; ww < 8; ++ww) {
+    if (ww < w) { i0 += w0[ww]; i1 += w1[ww]; }
+    t0 += w0[ww];
+    t1 += w1[ww];
+  }
+  if (first) {
+    if (tid == 0) {
+      st->n_spoof = t0;
+      st->n_bona = t1;
+      st->g0 = t0;
+      st->g1 = t1;
+      single = (t0 == 0 || t1 == 0);
+      if (single) st->status = 1;
+    }
+    __syncthreads();
+    if (single) return;
+  }
+  const long long n_spoof = (long long)(first ? t0 : st->n_spoof), n_bona = (long long)(first ? t1 : st->n_bona);
+  if (!first && st->status != 0) return;
+  const long long C0 = (long long)(st->c0_below + i0), C1 = (long long)(st->c1_below + i1);
+  const bool neg = eer_curve_diff(C0, C1, n_spoof, n_bona) < 0.0;
+  const uint32_t bal = __ballot_sync(0xffffffffu, neg);
+  if (lane == 0) wfirst[w] = bal ? (32 * w + __ffs(bal) - 1) : 256;
+  __syncthreads();
+  int b = 256;
+  for (int ww = 0; ww < 8; ++ww) b = wfirst[ww] < b ? wfirst[ww] : b;
+  __syncthreads();   // everybody has read c*_below before the owner updates them
+  if (tid == b) {
+    st->c0_below += i0 - c0;
+    st->c1_below += i1 - c1;
+    st->prefix |= (unsigned long long)b << shift;
+    st->mask |= 0xffull << shift;
+    st->g0 = c0;
+    st->g1 = c1;
+  }
+}
+
+// After the last level: prefix = G.  A single-label tie group is resolved here (binary search for the first negative difference).
+__global__ void select_uniform_group_kernel(SelectState* __restrict__ st) {
+  if (threadIdx.x != 0 || st->status != 0) return;
+  const long long g0 = (long long)st->g0, g1 = (long long)st->g1;
+  if (g0 > 0 && g1 > 0) return;   // mixed labels: needs the compaction path
+  const long long n_spoof = (long long)st->n_spoof, n_bona = (long long)st->n_bona;
+  const long long b0 = (long long)st->c0_below, b1 = (long long)st->c1_below;
+  const long long m = g0 + g1;
+  const int lab = g1 > 0;
+  // first j in [1, m] with diff(start + j) < 0 (exists: the pick step chose this group because its end is negative)
+  long long lo = 1, hi = m;
+  while (lo < hi) {
+    const long long mid = lo + (hi - lo) / 2;
+    const bool neg = eer_curve_diff(b0 + (lab ? 0 : mid), b1 + (lab ? mid : 0), n_spoof, n_bona) < 0.0;
+    if (neg) hi = mid; else lo = mid + 1;
+  }
+  const long long j = lo;
+  const long long c0a = b0 + (lab ? 0 : j - 1), c1a = b1 + (lab ? j - 1 : 0);
+  const long long c0b = b0 + (lab ? 0 : j), c1b = b1 + (lab ? j : 0);
+  const double da = fabs(eer_curve_diff(c0a, c1a, n_spoof, n_bona)), db = fabs(eer_curve_diff(c0b, c1b, n_spoof, n_bona));
+  SweepBest best;
+  if (da <= db) { best.diff = da; best.idx = c0a + c1a; best.c1 = c1a; }   // np.argmin keeps the lowest index among equals
+  else { best.diff = db; best.idx = c0b + c1b; best.c1 = c1b; }
+  st->best = best;
+  st->resolved = 1;
+}
+
+// ---- mixed-label tie group: labels of the scores equal to G, in original index order ----
+template <typename K>
+__global__ void __launch_bounds__(256) group_count_kernel(const typename ScoreOf<K>::type* __restrict__ scores, long long n,
+                                                           const SelectState* __restrict__ st, uint32_t* __restrict__ tile_cnt) {
+  const K G = (K)st->prefix;
+  const long long base = (long long)blockIdx.x * kSortTile;
+  uint32_t c = 0;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const long long j = base + threadIdx.x + i * 256;
+    if (j < n) c += to_key(scores[j]) == G;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  __shared__ uint32_t part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+    for (int i = 0; i < 8; ++i) s += part[i];
+    tile_cnt[blockIdx.x] = s;
+  }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(256) group_write_kernel(const typename ScoreOf<K>::type* __restrict__ scores, const uint8_t* __restrict__ labels,
+                                                           long long n, const SelectState* __restrict__ st,
+                                                           const unsigned long long* __restrict__ tile_excl, uint32_t* __restrict__ pay_out) {
+  const K G = (K)st->prefix;
+  // blocked arrangement: thread t owns positions base + 16 t .. + 15, so ranks follow the original index order
+  const long long base = (long long)blockIdx.x * kSortTile + (long long)threadIdx.x * kSortItems;
+  uint32_t hit = 0, labs = 0;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const long long j = base + i;
+    if (j < n && to_key(scores[j]) == G) {
+      hit |= 1u << i;
+      labs |= (uint32_t)(labels[j] != 0) << i;
+    }
+  }
+  const uint32_t mine = __popc(hit);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  __shared__ uint32_t wsum[8];
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+#pragma unroll
+  for (int ww = 0; ww < 8; ++ww) woff += (ww < w) ? wsum[ww] : 0u;
+  unsigned long long dst = tile_excl[blockIdx.x] + woff + incl - mine;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i)
+    if (hit & (1u << i)) pay_out[dst++] = ((uint32_t)(base + i) & 0x7fffffffu) | (((labs >> i) & 1u) << 31);
+}
+
+__global__ void __launch_bounds__(256) select_reduce_best_kernel(const SweepBest* __restrict__ block_best, long long nb, SelectState* __restrict__ st) {
+  double bd = 1.0e300;
+  long long bi = 0x7fffffffffffffffll, bc1 = 0;
+  for (long long i = threadIdx.x; i < nb; i += blockDim.x) {
+    const SweepBest b = block_best[i];
+    if (better(b.diff, b.idx, bd, bi)) { bd = b.diff; bi = b.idx; bc1 = b.c1; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    const long long oc = __shfl_xor_sync(0xffffffffu, bc1, o);
+    if (better(od, oi, bd, bi)) { bd = od; bi = oi; bc1 = oc; }
+  }
+  __shared__ SweepBest part[8];
+  if (lane == 0) part[w] = SweepBest{bd, bi, bc1};
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SweepBest b = part[0];
+    for (int i = 1; i < 8; ++i)
+      if (better(part[i].diff, part[i].idx, b.diff, b.idx)) b = part[i];
+    st->best = b;
+    st->resolved = 1;
+  }
+}
+
+// largest key strictly below G: the threshold when the chosen curve point is the start of G's group (evaluation.py:37)
+template <typename K>
+__global__ void __launch_bounds__(256) select_pred_kernel(const typename ScoreOf<K>::type* __restrict__ scores, long long n, SelectState* __restrict__ st) {
+  const K G = (K)st->prefix;
+  K best = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const K k = to_key(scores[i]);
+    if (k < G && k > best) best = k;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const K other = (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)best, o);
+    best = other > best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0 && best != 0) atomicMax(&st->pred, (unsigned long long)best);
+}
+
+template <typename K>
+__global__ void select_finish_kernel(const SelectState* __restrict__ st, long long n, dfs_eer_result* __restrict__ res) {
+  if (threadIdx.x != 0) return;
+  typedef typename ScoreOf<K>::type S;
+  const long long n_spoof = (long long)st->n_spoof, n_bona = (long long)st->n_bona;
+  const long long k = st->best.idx, c1 = st->best.c1, c0 = k - c1;
+  const long long start = (long long)(st->c0_below + st->c1_below);
+  const double far = __ddiv_rn((double)(n_spoof - c0), (double)n_spoof);
+  const double frr = __ddiv_rn((double)c1, (double)n_bona);
+  res->eer = __ddiv_rn(__dadd_rn(far, frr), 2.0);                      // evaluation.py:29
+  const K G = (K)st->prefix;
+  const S eps = (S)1e-6;
+  double thr;
+  if (k == 0) thr = (double)(S)(from_key(G) - eps);                    // evaluation.py:32-33 (the smallest score is G)
+  else if (k == n) thr = (double)(S)(from_key(G) + eps);               // :34-35 (the largest score is G)
+  else if (k > start) thr = (double)from_key(G);                       // :37, sorted_scores[k-1] lies in G's group
+  else thr = (double)from_key((K)st->pred);                            //      ... or is the largest score below G
+  res->threshold = thr;
+  res->eer_idx = k;
+  res->n_bonafide = n_bona;
+  res->n_spoof = n_spoof;
+}
+
+struct SelectScratch {
+  SelectState* state = nullptr;          // device
+  unsigned long long* hist = nullptr;    // device [512]
+  dfs_eer_result* res = nullptr;         // device
+};
+static SelectScratch g_sel[16];
+
+template <typename K>
+static int eer_select_impl(const void* scores_v, const uint8_t* labels, int64_t n, dfs_eer_result* result_host, cudaStream_t stream) {
+  typedef typename ScoreOf<K>::type S;
+  constexpr int LEVELS = sizeof(K);
+  constexpr int V = VecOf<K>::V;
+  const S* scores = static_cast<const S*>(scores_v);
+  int dev = 0, num_sms = 148;
+  DFS_CUDA_CHECK(cudaGetDevice(&dev));
+  DFS_REQUIRE(dev >= 0 && dev < 16, DFS_ERR_INVALID, "device index %d out of range", dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  SelectScratch& sc = g_sel[dev];
+  if (sc.state == nullptr) {
+    void* p = nullptr;
+    DFS_CUDA_CHECK(cudaMalloc(&p, 8192));
+    sc.state = static_cast<SelectState*>(p);
+    sc.hist = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(p) + 1024);
+    sc.res = reinterpret_cast<dfs_eer_result*>(static_cast<uint8_t*>(p) + 1024 + 4096);
+  }
+  static bool configured[32] = {false};
+  constexpr int kHistSmem = 512 * kCntStride;
+  if (dfs_first_use_on_device(configured)) {
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_scalar_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_scalar_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_scalar_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_scalar_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
+  }
+  const bool aligned = (reinterpret_cast<uintptr_t>(scores) % 16 == 0) && (reinterpret_cast<uintptr_t>(labels) % V == 0);
+  const long long chunk = aligned ? 256ll * V * kSelIters : 256ll * 224;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ceil_div64(n, chunk), num_sms));
+
+  select_init_kernel<<<1, 256, 0, stream>>>(sc.state, sc.hist);
+  DFS_LAUNCH_CHECK();
+  SelectState host{};
+  for (int lv = LEVELS - 1; lv >= 0; --lv) {
+    const int shift = 8 * lv;
+    const bool first = (lv == LEVELS - 1);
+    const bool skip = !first && ((((host.key_and ^ host.key_or) >> shift) & 0xffull) == 0);
+    if (!skip) {
+      if (aligned) {
+        if (first) select_hist_kernel<K, true><<<grid, 256, kHistSmem, stream>>>(scores, labels, n, shift, sc.state, sc.hist);
+        else select_hist_kernel<K, false><<<grid, 256, kHistSmem, stream>>>(scores, labels, n, shift, sc.state, sc.hist);
+      } else {
+        if (first) select_hist_scalar_kernel<K, true><<<grid, 256, kHistSmem, stream>>>(scores, labels, n, shift, sc.state, sc.hist);
+        else select_hist_scalar_kernel<K, false><<<grid, 256, kHistSmem, stream>>>(scores, labels, n, shift, sc.state, sc.hist);
+      }
+      DFS_LAUNCH_CHECK();
+    }
+    select_pick_kernel<<<1, 256, 0, stream>>>(sc.hist, sc.state, shift, first ? 1 : 0, skip ? 1 : 0);
+    DFS_LAUNCH_CHECK();
+    if (first) {  // label totals (single-class early-out, evaluation.py:18-19) and the key AND / OR (constant bytes are skipped)
+      DFS_CUDA_CHECK(cudaMemcpyAsync(&host, sc.state, sizeof(host), cudaMemcpyDeviceToHost, stream));
+      DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
+      if (host.status != 0) {
+        result_host->eer = 0.0;
+        result_host->threshold = 0.0;
+        result_host->eer_idx = -1;
+        result_host->n_bonafide = (int64_t)host.n_bona;
+        result_host->n_spoof = (int64_t)host.n_spoof;
+        return DFS_OK;
+      }
+    }
+  }
+  select_uniform_group_kernel<<<1, 32, 0, stream>>>(sc.state);
+  DFS_LAUNCH_CHECK();
+  DFS_CUDA_CHECK(cudaMemcpyAsync(&host, sc.state, sizeof(host), cudaMemcpyDeviceToHost, stream));
+  DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
+  const long long start = (long long)(host.c0_below + host.c1_below);
+  if (!host.resolved) {
+    // mixed-label tie group of m scores: compact its labels in index order, sweep the m + 1 curve points it spans
+    const long long m = (long long)(host.g0 + host.g1);
+    const long long tiles_n = ceil_div64(n, kSortTile), tiles_m = ceil_div64(m, kSortTile);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_cnt = carve((size_t)tiles_n * 4), o_excl = carve((size_t)tiles_n * 8), o_pay = carve((size_t)m * 4);
+    const size_t o_bones = carve((size_t)tiles_m * 4), o_bexcl = carve((size_t)tiles_m * 8), o_bbest = carve((size_t)tiles_m * sizeof(SweepBest));
+    void* base = nullptr;
+    DFS_PROPAGATE(get_workspace(off, &base));
+    uint8_t* b8 = static_cast<uint8_t*>(base);
+    uint32_t* tcnt = reinterpret_cast<uint32_t*>(b8 + o_cnt);
+    unsigned long long* texcl = reinterpret_cast<unsigned long long*>(b8 + o_excl);
+    uint32_t* gpay = reinterpret_cast<uint32_t*>(b8 + o_pay);
+    uint32_t* bones = reinterpret_cast<uint32_t*>(b8 + o_bones);
+    unsigned long long* bexcl = reinterpret_cast<unsigned long long*>(b8 + o_bexcl);
+    SweepBest* bbest = reinterpret_cast<SweepBest*>(b8 + o_bbest);
+    group_count_kernel<K><<<(unsigned)tiles_n, 256, 0, stream>>>(scores, n, sc.state, tcnt);
+    DFS_LAUNCH_CHECK();
+    sweep_scan_kernel<<<1, 1024, 0, stream>>>(tcnt, tiles_n, texcl);
+    DFS_LAUNCH_CHECK();
+    group_write_kernel<K><<<(unsigned)tiles_n, 256, 0, stream>>>(scores, labels, n, sc.state, texcl, gpay);
+    DFS_LAUNCH_CHECK();
+    sweep_count_kernel<<<(unsigned)tiles_m, 256, 0, stream>>>(gpay, m, bones);
+    DFS_LAUNCH_CHECK();
+    sweep_scan_kernel<<<1, 1024, 0, stream>>>(bones, tiles_m, bexcl);
+    DFS_LAUNCH_CHECK();
+    sweep_min_kernel<<<(unsigned)tiles_m, 256, 0, stream>>>(gpay, m, (long long)host.n_bona, (long long)host.n_spoof, bexcl, bbest, start,
+                                                           (long long)host.c1_below);
+    DFS_LAUNCH_CHECK();
+    select_reduce_best_kernel<<<1, 256, 0, stream>>>(bbest, tiles_m, sc.state);
+    DFS_LAUNCH_CHECK();
+    DFS_CUDA_CHECK(cudaMemcpyAsync(&host, sc.state, sizeof(host), cudaMemcpyDeviceToHost, stream));
+    DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
+  if (host.best.idx == start && start > 0) {
+    select_pred_kernel<K><<<(unsigned)std::max<long long>(1, std::min<long long>(ceil_div64(n, 256), (long long)num_sms * 8)), 256, 0, stream>>>(
+        scores, n, sc.state);
+    DFS_LAUNCH_CHECK();
+  }
+  select_finish_kernel<K><<<1, 32, 0, stream>>>(sc.state, n, sc.res);
+  DFS_LAUNCH_CHECK();
+  DFS_CUDA_CHECK(cudaMemcpyAsync(result_host, sc.res, sizeof(dfs_eer_result), cudaMemcpyDeviceToHost, stream));
+  DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return DFS_OK;
+}
+
+int eer_select_device(const void* scores, int key_bytes, const uint8_t* labels, int64_t n, dfs_eer_result* result_host, cudaStream_t stream) {
+  DFS_REQUIRE(scores && labels && result_host, DFS_ERR_INVALID, "dfs_eer_select: NULL argument");
+  DFS_REQUIRE(n > 0 && n < (1ll << 30), DFS_ERR_INVALID, "dfs_eer_select: n = %lld outside [1, 2^30)", (long long)n);
+  DFS_REQUIRE(key_bytes == 4 || key_bytes == 8, DFS_ERR_INVALID, "dfs_eer_select: key_bytes must be 4 (fp32) or 8 (fp64)");
+  return key_bytes == 4 ? eer_select_impl<uint32_t>(scores, labels, n, result_host, stream)
+                        : eer_select_impl<uint64_t>(scores, labels, n, result_host, stream);
 }
 
 int eer_device(const void* scores, int key_bytes, const uint8_t* labels, int64_t n, dfs_eer_result* result_host, uint32_t* perm,

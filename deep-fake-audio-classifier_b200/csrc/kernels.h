@@ -90,6 +90,7 @@ const float* cae_simt_layer_ptr(const float* work, int n_utts, int layer, size_t
 // ---- eer.cu ----
 int eer_device(const void* scores, int key_bytes, const uint8_t* labels, int64_t n, dfs_eer_result* result_host, uint32_t* perm,
                void* sorted, cudaStream_t stream);
+int eer_select_device(const void* scores, int key_bytes, const uint8_t* labels, int64_t n, dfs_eer_result* result_host, cudaStream_t stream);
 int confusion_device(const void* scores, int key_bytes, const uint8_t* labels, int64_t n, double thr, int64_t* out4_host,
                      cudaStream_t stream);
 int blend_device(const double* const* scores, int m, const double* weights, const int* minmax, double divisor, int64_t n, double* out,

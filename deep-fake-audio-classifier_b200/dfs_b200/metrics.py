@@ -50,14 +50,27 @@ def _labels_to_device(labels, dev):
     torch = _torch()
     if isinstance(labels, torch.Tensor):
         t = labels.detach().to(dev)
+        if t.dtype == torch.uint8:      # the kernels read "label != 0": a uint8 tensor is used in place
+            return t.contiguous().reshape(-1), t
+        if t.dtype == torch.bool:
+            return t.contiguous().reshape(-1).view(torch.uint8), t
         return (t != 0).to(torch.uint8).contiguous().reshape(-1), t
     a = np.array(labels)
     return torch.from_numpy(np.ascontiguousarray((a != 0).astype(np.uint8))).to(dev).reshape(-1), a
 
 
-def eer_details(scores, labels, want_perm=False, want_sorted=False, device=None):
+def eer_details(scores, labels, want_perm=False, want_sorted=False, device=None, method="auto"):
     """dict(eer, threshold, eer_idx, n_bonafide, n_spoof[, perm][, sorted]) -- eer_idx = -1 on the
-    single-class early-out (scripts/evaluation.py:18-19)."""
+    single-class early-out (scripts/evaluation.py:18-19).
+
+    method: "sort" = full stable radix sort + sweep (dfs_eer; the only one that can return perm /
+    sorted), "select" = MSD radix select of the FAR/FRR crossing (dfs_eer_select; bit-identical
+    result, ~5 B/score per key byte instead of a sort), "auto" = select unless perm / sorted is wanted."""
+    if method not in ("auto", "sort", "select"):
+        raise ValueError("method must be 'auto', 'sort' or 'select'")
+    if method == "select" and (want_perm or want_sorted):
+        raise ValueError("the select path does not materialise the permutation; use method='sort'")
+    use_select = method == "select" or (method == "auto" and not (want_perm or want_sorted))
     torch = _torch()
     s = _scores_to_device(scores, device)
     lab, _ = _labels_to_device(labels, s.device)
@@ -70,9 +83,13 @@ def eer_details(scores, labels, want_perm=False, want_sorted=False, device=None)
     perm = torch.empty(n, dtype=torch.int32, device=s.device) if want_perm else None
     srt = torch.empty_like(s) if want_sorted else None
     with torch.cuda.device(s.device):
-        N.check(N.load().dfs_eer(C.c_void_p(s.data_ptr()), s.element_size(), C.c_void_p(lab.data_ptr()), n, C.byref(res),
-                                 C.c_void_p(perm.data_ptr()) if perm is not None else None,
-                                 C.c_void_p(srt.data_ptr()) if srt is not None else None, _stream(torch, s.device)), "dfs_eer")
+        if use_select:
+            N.check(N.load().dfs_eer_select(C.c_void_p(s.data_ptr()), s.element_size(), C.c_void_p(lab.data_ptr()), n, C.byref(res),
+                                            _stream(torch, s.device)), "dfs_eer_select")
+        else:
+            N.check(N.load().dfs_eer(C.c_void_p(s.data_ptr()), s.element_size(), C.c_void_p(lab.data_ptr()), n, C.byref(res),
+                                     C.c_void_p(perm.data_ptr()) if perm is not None else None,
+                                     C.c_void_p(srt.data_ptr()) if srt is not None else None, _stream(torch, s.device)), "dfs_eer")
     out = dict(eer=float(res.eer), threshold=float(res.threshold), eer_idx=int(res.eer_idx),
                n_bonafide=int(res.n_bonafide), n_spoof=int(res.n_spoof))
     if want_perm:
@@ -82,8 +99,8 @@ def eer_details(scores, labels, want_perm=False, want_sorted=False, device=None)
     return out
 
 
-def calculate_eer(scores, labels):
-    d = eer_details(scores, labels)
+def calculate_eer(scores, labels, method="auto"):
+    d = eer_details(scores, labels, method=method)
     return d["eer"], d["threshold"]
 
 

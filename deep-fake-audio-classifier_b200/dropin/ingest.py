@@ -1,0 +1,100 @@
+"""Feature ingestion for the scoring path.
+
+The reference reads ``features.pkl`` -- a pandas DataFrame whose ``features`` column holds one
+``torch.Tensor[180, 321]`` per utterance (README.md:41-48) -- through a ``Dataset.__getitem__`` that does
+``features.iloc[idx].float()`` per row, a bs-32 DataLoader collate and a ``.transpose(1, 2)`` per batch
+(src/predict.py:55-63,88-105; src/dataset.py:24-56).  Here the table is repacked ONCE into a single pinned
+``[N, 180, 321]`` fp32 slab plus the uttid index; the engine then reads it in place as the transposed
+``(N, 321, 180)`` view (strides, no copy) and streams it to the device in double-buffered chunks
+(``dfs_score_host``).
+
+    table = load_feature_table("features.pkl")          # or a DataFrame
+    table.view()                                        # (N, 321, 180) strided view the models expect
+    idx, labels = merge_labels(table, labels_df)        # inner merge on uttid, like AudioDeepfakeDataset
+
+Errors mirror the reference: ``ValueError`` on a missing column or a malformed row.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from dataclasses import dataclass
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+
+import torch  # noqa: E402
+
+N_FEATS, T_FRAMES = 180, 321
+
+
+@dataclass
+class FeatureTable:
+    uttids: np.ndarray            # object array, file order
+    slab: "torch.Tensor"          # [N, 180, 321] fp32, pinned when a CUDA device is present
+
+    def __len__(self):
+        return int(self.slab.shape[0])
+
+    def view(self):
+        """(N, 321, 180) view with stride_t = 1, stride_f = 321 -- what ``features.transpose(1, 2)`` gives the models."""
+        return self.slab.transpose(1, 2)
+
+    def take(self, index):
+        """Sub-table in the given row order (rows are copied into a fresh pinned slab)."""
+        index = np.asarray(index, dtype=np.int64)
+        out = _alloc(len(index))
+        if len(index):
+            torch.index_select(self.slab, 0, torch.from_numpy(index), out=out)
+        return FeatureTable(self.uttids[index], out)
+
+
+def _alloc(n):
+    return torch.empty((n, N_FEATS, T_FRAMES), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+
+
+def pack_features(rows) -> "torch.Tensor":
+    """list / Series of per-utterance tensors (or arrays) [180, 321] of any float dtype -> one pinned fp32 slab.
+    fp32 rows are stacked by a single multi-threaded ``torch.stack(out=)``; other dtypes are cast like the
+    reference's ``.float()`` (src/predict.py:63)."""
+    rows = list(rows)
+    n = len(rows)
+    if n == 0:
+        raise ValueError("features.pkl has no rows")
+    fixed = []
+    for i, r in enumerate(rows):
+        t = r if isinstance(r, torch.Tensor) else torch.as_tensor(np.asarray(r))
+        if tuple(t.shape) != (N_FEATS, T_FRAMES):
+            raise ValueError(f"features row {i} has shape {tuple(t.shape)}, expected ({N_FEATS}, {T_FRAMES})")
+        if t.dtype != torch.float32 or t.device.type != "cpu":
+            t = t.detach().to("cpu").float()
+        fixed.append(t.detach())
+    slab = _alloc(n)
+    torch.stack(fixed, out=slab)
+    return slab
+
+
+def load_feature_table(source) -> FeatureTable:
+    """``source``: path of a features.pkl or the DataFrame itself ({uttid, features})."""
+    import pandas as pd
+    df = pd.read_pickle(source) if isinstance(source, (str, os.PathLike)) else source
+    if "uttid" not in df.columns:
+        raise ValueError("features.pkl must contain 'uttid'")              # src/predict.py:89-90
+    if "features" not in df.columns:
+        raise ValueError("features.pkl must contain 'features'")
+    uttids = np.asarray(df["uttid"].values, dtype=object)
+    return FeatureTable(uttids, pack_features(df["features"].reset_index(drop=True)))
+
+
+def merge_labels(table: FeatureTable, labels_df):
+    """Inner merge on uttid in feature order (``pd.merge(features, labels, on='uttid', how='inner')``,
+    src/dataset.py:29-33): returns (row indices into the table, labels as uint8)."""
+    import pandas as pd
+    if "uttid" not in labels_df.columns or "label" not in labels_df.columns:
+        raise ValueError("labels.pkl must have 'uttid' and 'label' columns")   # scripts/evaluation.py:75-76
+    left = pd.DataFrame({"uttid": table.uttids, "_row": np.arange(len(table), dtype=np.int64)})
+    merged = pd.merge(left, labels_df[["uttid", "label"]], on="uttid", how="inner")
+    return merged["_row"].to_numpy(dtype=np.int64), (merged["label"].to_numpy() != 0).astype(np.uint8)

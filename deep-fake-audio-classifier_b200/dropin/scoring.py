@@ -23,17 +23,12 @@ from dfs_b200.metrics import ensemble_mean, hybrid_blend, normalise_01  # noqa: 
 
 def features_slab(features_df):
     """features.pkl rows are torch.Tensor[180,321] (README.md:41-48): pack once into a pinned
-    [N,180,321] fp32 slab; the engine reads it through strides as the (N,321,180) view the reference
-    builds with .transpose(1,2) (predict.py:103-105)."""
-    col = features_df["features"].reset_index(drop=True)
-    n = len(col)
-    if n == 0:
-        raise ValueError("features.pkl has no rows")
-    first = col.iloc[0]
-    slab = torch.empty((n,) + tuple(first.shape), dtype=torch.float32, pin_memory=torch.cuda.is_available())
-    for i in range(n):
-        slab[i].copy_(col.iloc[i])
-    return slab
+    [N,180,321] fp32 slab (ingest.pack_features); the engine reads it through strides as the (N,321,180) view the
+    reference builds with .transpose(1,2) (predict.py:103-105).  Accepts a DataFrame or an ingest.FeatureTable."""
+    from ingest import FeatureTable, pack_features
+    if isinstance(features_df, FeatureTable):
+        return features_df.slab
+    return pack_features(features_df["features"].reset_index(drop=True))
 
 
 def _device_index(device):

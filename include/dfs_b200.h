@@ -165,6 +165,12 @@ typedef struct {
  * the scores) the sorted scores.  Synchronises `stream`.                                    */
 int dfs_eer(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, dfs_eer_result* result_host,
             uint32_t* perm_dev, void* sorted_dev, void* stream);
+/* Same (eer, threshold, eer_idx) without materialising the sort: FAR - FRR is strictly decreasing along the sorted
+ * order, so the crossing is located by an MSD radix SELECT (one (digit, label) histogram per key byte, 5 B/score per
+ * level) and only the tie group that holds it is put in stable order.  Bit-identical to dfs_eer on every input;
+ * this is what calculate_eer(scores, labels) -> (eer, threshold) needs (scripts/evaluation.py:7-39).  Synchronises `stream`. */
+int dfs_eer_select(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, dfs_eer_result* result_host,
+                   void* stream);
 /* confusion_at_threshold (scripts/evaluation.py:42-56): out4_host = {tp, fp, tn, fn}. */
 int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,
                   int64_t* out4_host, void* stream);

@@ -34,6 +34,11 @@ def test_eer_goldens(case):
         assert (d["eer"], d["threshold"]) == (ref_eer, ref_thr)
     if case.startswith("tiefree"):
         assert np.array_equal(d["perm"].cpu().numpy().astype(np.int64), E[case + "/ref_argsort"])
+    # the radix-select path must agree with the sort path bit for bit on every golden
+    for method in ("select", "sort"):
+        e = D.eer_details(s, l, method=method)
+        assert (e["eer"], e["threshold"], e["eer_idx"], e["n_bonafide"], e["n_spoof"]) == \
+               (d["eer"], d["threshold"], d["eer_idx"], d["n_bonafide"], d["n_spoof"]), method
     thr = d["threshold"]
     assert D.confusion_at_threshold(s, l, thr) == oeer.confusion_at_threshold(s, l, thr)
     if not case.startswith("ties_mixed"):
@@ -68,14 +73,80 @@ def test_eer_sizes_and_negative_scores(n):
     o = oeer.eer_details(s, l, kind="stable")
     assert (d["eer"], d["threshold"], d["eer_idx"]) == (o["eer"], o["threshold"], o["eer_idx"])
     assert np.array_equal(d["perm"].cpu().numpy().astype(np.int64), o["perm"])
+    e = D.eer_details(s, l, method="select")
+    assert (e["eer"], e["threshold"], e["eer_idx"]) == (o["eer"], o["threshold"], o["eer_idx"])
 
 
 def test_eer_ten_million_tie_free_bit_exact():
     s, l = syn.tie_free_scores(10_000_000, seed=5)
-    d = D.eer_details(s, l)
     o = oeer.eer_details(s, l)            # the reference's own (unstable) argsort: tie-free => same order
-    assert (d["eer"], d["threshold"], d["eer_idx"]) == (o["eer"], o["threshold"], o["eer_idx"])
+    for method in ("sort", "select"):
+        d = D.eer_details(s, l, method=method)
+        assert (d["eer"], d["threshold"], d["eer_idx"]) == (o["eer"], o["threshold"], o["eer_idx"]), method
     assert 0.05 < d["eer"] < 0.45
+
+
+def _select_vs_oracle(s, l):
+    o = oeer.eer_details(s, l, kind="stable")
+    for method in ("select", "sort"):
+        d = D.eer_details(s, l, method=method)
+        assert (d["eer"], d["threshold"], d["eer_idx"]) == (o["eer"], o["threshold"], o["eer_idx"]), (method, d, o)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("levels", [2, 3, 17, 1000])
+def test_eer_select_tie_groups(dtype, levels):
+    """Heavily tied scores: the crossing falls inside a mixed-label tie group, whose stable (index) order decides the
+    argmin -- the compaction path of dfs_eer_select."""
+    rng = np.random.default_rng(levels)
+    for n in (50, 4097, 300_001):
+        s = (rng.integers(0, levels, n) / levels - 0.3).astype(dtype)
+        l = (rng.random(n) < 0.2 + 0.6 * (s - s.min()) / (np.ptp(s) + 1e-9)).astype(np.uint8)
+        if l.min() == l.max():
+            l[0], l[1] = 0, 1
+        _select_vs_oracle(s, l)
+    # every score equal: one group holds the whole curve
+    s = np.full(70_001, 0.25, dtype=dtype)
+    l = (rng.random(s.size) < 0.5).astype(np.uint8)
+    _select_vs_oracle(s, l)
+
+
+def test_eer_select_crossing_at_group_boundaries():
+    """The chosen curve point is the START of the group that holds the first negative difference: the threshold is the
+    largest score below that group (predecessor pass), incl. eer_idx = 0 and eer_idx = n."""
+    _select_vs_oracle(np.array([0.1, 0.2, 0.8, 0.9], dtype=np.float32), np.array([0, 0, 1, 1], dtype=np.uint8))
+    _select_vs_oracle(np.array([0.1, 0.2, 0.8, 0.9], dtype=np.float64), np.array([1, 1, 0, 0], dtype=np.uint8))
+    _select_vs_oracle(np.array([0.9, 0.8, 0.1], dtype=np.float32), np.array([0, 0, 1], dtype=np.uint8))
+    _select_vs_oracle(np.array([0.1, 0.2, 0.3, 0.9], dtype=np.float64), np.array([1, 0, 0, 0], dtype=np.uint8))
+    _select_vs_oracle(np.array([-1.5, -0.0, 0.0, 2.0, 2.0, 7.0], dtype=np.float32), np.array([0, 1, 0, 1, 0, 1], dtype=np.uint8))
+    rng = np.random.default_rng(11)
+    for n in (3, 10, 257, 65_537):
+        for _ in range(6):
+            s = rng.standard_normal(n).astype(np.float32)
+            l = (rng.random(n) < 0.5).astype(np.uint8)
+            if l.min() == l.max():
+                l[0], l[-1] = 0, 1
+            _select_vs_oracle(s, l)
+    # logits-like scores sharing most key bytes (constant bytes are skipped via key AND / OR)
+    s = (0.5 + rng.random(200_000) * 1e-3).astype(np.float32)
+    l = (rng.random(s.size) < 0.5).astype(np.uint8)
+    _select_vs_oracle(s, l)
+
+
+def test_eer_select_misaligned_device_pointers():
+    rng = np.random.default_rng(3)
+    n = 100_003
+    s = torch.from_numpy(rng.standard_normal(n + 1).astype(np.float32)).cuda()[1:]      # 4-byte aligned only
+    l = torch.from_numpy((rng.random(n + 3) < 0.4).astype(np.uint8)).cuda()[3:]         # 1-byte aligned only
+    o = oeer.eer_details(s.cpu().numpy(), l.cpu().numpy(), kind="stable")
+    d = D.eer_details(s, l, method="select")
+    assert (d["eer"], d["threshold"], d["eer_idx"]) == (o["eer"], o["threshold"], o["eer_idx"])
+
+
+def test_eer_select_single_class():
+    for lab in (0, 1):
+        d = D.eer_details(np.linspace(0, 1, 1000, dtype=np.float32), np.full(1000, lab, dtype=np.uint8), method="select")
+        assert (d["eer"], d["threshold"], d["eer_idx"]) == (0.0, 0.0, -1)
 
 
 def test_eer_hundred_million_properties():
@@ -96,6 +167,8 @@ def test_eer_hundred_million_properties():
     assert d["eer"] == (far + frr) / 2.0
     assert d["threshold"] == float(srt[k - 1])
     assert abs(far - frr) < 1e-6
+    e = D.eer_details(sd, ld, method="select")                           # the radix-select path, same answer
+    assert (e["eer"], e["threshold"], e["eer_idx"]) == (d["eer"], d["threshold"], d["eer_idx"])
 
 
 def test_blend_known_answer_bit_exact():
