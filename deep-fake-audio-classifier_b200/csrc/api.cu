@@ -754,6 +754,9 @@ extern "C" int dfs_eer_select(const void* scores_dev, int key_bytes, const uint8
                               void* stream) {
   return eer_select_device(scores_dev, key_bytes, labels_dev, n, result_host, static_cast<cudaStream_t>(stream));
 }
+extern "C" int dfs_bce_with_logits(const float* logits_dev, const float* labels_dev, int64_t n, double* mean_host, void* stream) {
+  return bce_with_logits_device(logits_dev, labels_dev, n, mean_host, static_cast<cudaStream_t>(stream));
+}
 extern "C" int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,
                              int64_t* out4_host, void* stream) {
   return confusion_device(scores_dev, key_bytes, labels_dev, n, threshold, out4_host, static_cast<cudaStream_t>(stream));

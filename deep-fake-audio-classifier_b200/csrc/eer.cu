@@ -1269,4 +1269,50 @@ int widen_device(const float* in, int64_t n, double* out, cudaStream_t stream) {
   return DFS_OK;
 }
 
+// ---- BCEWithLogitsLoss(reduction='mean') over a whole score vector ---------------------------------------
+// src/evaluation.py:83-86 accumulates criterion(logits, labels).item() * batch per batch; here the per-element loss
+//   max(x, 0) - x*y + log1p(exp(-|x|))        (torch's numerically stable form, evaluated in fp32 like torch)
+// is summed once over all n scores in fp64 (fixed order per launch geometry: per-thread -> warp shuffle -> one
+// atomicAdd(double) per warp is NOT order-deterministic, so the warp partials go to a buffer reduced by one thread).
+__global__ void __launch_bounds__(256) bce_partial_kernel(const float* __restrict__ logits, const float* __restrict__ labels, long long n,
+                                                           double* __restrict__ partial /*[gridDim.x]*/) {
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = logits[i], y = labels[i];
+    const float l = fmaxf(x, 0.0f) - x * y + log1pf(expf(-fabsf(x)));
+    acc += (double)l;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += part[i];
+    partial[blockIdx.x] = s;
+  }
+}
+__global__ void bce_final_kernel(const double* __restrict__ partial, int nb, long long n, double* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  double s = 0.0;
+  for (int i = 0; i < nb; ++i) s += partial[i];
+  out[0] = s / (double)n;
+}
+
+int bce_with_logits_device(const float* logits, const float* labels, int64_t n, double* mean_host, cudaStream_t stream) {
+  DFS_REQUIRE(logits && labels && mean_host && n > 0, DFS_ERR_INVALID, "dfs_bce_with_logits: bad argument");
+  const int nb = (int)std::min<long long>(ceil_div64(n, 256), 148 * 4);
+  void* base = nullptr;
+  DFS_PROPAGATE(get_workspace((size_t)(nb + 1) * 8, &base));
+  double* partial = static_cast<double*>(base);
+  bce_partial_kernel<<<nb, 256, 0, stream>>>(logits, labels, n, partial);
+  DFS_LAUNCH_CHECK();
+  bce_final_kernel<<<1, 32, 0, stream>>>(partial, nb, n, partial + nb);
+  DFS_LAUNCH_CHECK();
+  DFS_CUDA_CHECK(cudaMemcpyAsync(mean_host, partial + nb, 8, cudaMemcpyDeviceToHost, stream));
+  DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return DFS_OK;
+}
+
 }  // namespace dfs

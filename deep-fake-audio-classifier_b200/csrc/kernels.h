@@ -95,6 +95,7 @@ int confusion_device(const void* scores, int key_bytes, const uint8_t* labels, i
                      cudaStream_t stream);
 int blend_device(const double* const* scores, int m, const double* weights, const int* minmax, double divisor, int64_t n, double* out,
                  cudaStream_t stream);
+int bce_with_logits_device(const float* logits, const float* labels, int64_t n, double* mean_host, cudaStream_t stream);
 int widen_device(const float* in, int64_t n, double* out, cudaStream_t stream);
 
 // ---- synth.cu ----

@@ -175,3 +175,50 @@ def hybrid_blend(sup_scores, cae_scores, alpha=0.80, as_numpy=True):
 
 def ensemble_mean(all_scores, as_numpy=True):
     return blend(list(all_scores), [1.0] * len(all_scores), [0] * len(all_scores), float(len(all_scores)), as_numpy)
+
+
+def alpha_sweep(sup_scores, cae_scores, labels, alphas=None, alpha_steps=21):
+    """The alpha sweep of src/hybrid_ensemble.py:131-151 on the device: both score vectors are min-max normalised
+    once (float64), then for every alpha the blend ``alpha*sup + (1-alpha)*cae`` and its EER are computed without the
+    vectors leaving the GPU (the reference re-sorts on the host 21 times via ``.tolist()``).
+
+    Returns dict(alphas, eer [A], threshold [A], best_alpha, best_eer) -- best = first strict improvement over 1.0,
+    like the reference's ``if eer < best_eer`` loop."""
+    torch = _torch()
+    if alphas is None:
+        alphas = np.linspace(0.0, 1.0, int(alpha_steps))                # hybrid_ensemble.py:132
+    sup_n = normalise_01(sup_scores, as_numpy=False)                    # :128-129
+    cae_n = _f64_device(normalise_01(cae_scores, as_numpy=False), sup_n.device)
+    lab, _ = _labels_to_device(labels, sup_n.device)
+    eers, thrs = [], []
+    best_eer, best_alpha = 1.0, 0.0
+    for a in alphas:
+        a = float(a)
+        combined = blend([sup_n, cae_n], [a, 1 - a], [0, 0], 1.0, as_numpy=False)   # :145, float64
+        d = eer_details(combined, lab)
+        eers.append(d["eer"])
+        thrs.append(d["threshold"])
+        if d["eer"] < best_eer:
+            best_eer, best_alpha = d["eer"], a
+    return dict(alphas=np.asarray(alphas, dtype=np.float64), eer=np.array(eers), threshold=np.array(thrs),
+                best_alpha=best_alpha, best_eer=best_eer)
+
+
+def bce_with_logits_mean(logits, labels):
+    """nn.BCEWithLogitsLoss()(logits, labels) over the whole vector in one fused device reduction (fp64 sum of the fp32
+    per-element loss) -- the avg_loss of src/evaluation.py::evaluate."""
+    torch = _torch()
+    x = logits.detach() if isinstance(logits, torch.Tensor) else torch.as_tensor(np.asarray(logits, dtype=np.float32))
+    dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    x = x.to(dev, torch.float32).contiguous().reshape(-1)
+    y = labels.detach() if isinstance(labels, torch.Tensor) else torch.as_tensor(np.asarray(labels, dtype=np.float32))
+    y = y.to(dev, torch.float32).contiguous().reshape(-1)
+    if x.numel() != y.numel():
+        raise ValueError("logits and labels must have the same length")
+    if x.numel() == 0:
+        raise ValueError("bce_with_logits_mean needs at least one score")
+    out = C.c_double()
+    with torch.cuda.device(dev):
+        N.check(N.load().dfs_bce_with_logits(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), x.numel(), C.byref(out), _stream(torch, dev)),
+                "dfs_bce_with_logits")
+    return float(out.value)

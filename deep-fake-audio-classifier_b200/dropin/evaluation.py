@@ -11,14 +11,25 @@ if _PKG not in sys.path:
 
 import torch  # noqa: E402
 
-from dfs_b200.metrics import calculate_eer, confusion_at_threshold, eer_details  # noqa: E402,F401
+from dfs_b200.metrics import bce_with_logits_mean, calculate_eer, confusion_at_threshold, eer_details  # noqa: E402,F401
+
+
+def _is_plain_bce(criterion):
+    """nn.BCEWithLogitsLoss() with default reduction and no weights: the loss the training loop evaluates with
+    (src/train.py); it is then computed once over all logits by one fused device reduction."""
+    return (isinstance(criterion, torch.nn.BCEWithLogitsLoss) and criterion.reduction == "mean"
+            and criterion.weight is None and criterion.pos_weight is None)
 
 
 def evaluate(model, dataloader, criterion=None, device="cpu", apply_sigmoid=False, swap_tf: bool = False):
-    """metrics dict (avg_loss, eer, threshold), scores, labels -- logits unless apply_sigmoid."""
+    """metrics dict (avg_loss, eer, threshold), scores, labels -- logits unless apply_sigmoid
+    (/root/reference/src/evaluation.py:51-104).  The model calls stay per batch (a DataLoader is the interface), but
+    nothing is synchronised per batch: logits stay on the device, a plain nn.BCEWithLogitsLoss() is evaluated once over
+    all of them (dfs_bce_with_logits) and the EER is the device radix select."""
     model.eval()
-    chunks, label_chunks = [], []
+    logit_chunks, label_chunks = [], []
     total_loss, total_count = 0.0, 0
+    fused_bce = criterion is not None and _is_plain_bce(criterion) and torch.device(device).type == "cuda"
     with torch.no_grad():
         for features, batch_labels in dataloader:
             features = features.to(device)
@@ -26,13 +37,19 @@ def evaluate(model, dataloader, criterion=None, device="cpu", apply_sigmoid=Fals
             if swap_tf:
                 features = features.transpose(1, 2)
             logits = model(features).squeeze(-1)
-            if criterion is not None:
+            if criterion is not None and not fused_bce:     # any other criterion: the caller's own torch op, per batch
                 total_loss += criterion(logits, batch_labels).item() * batch_labels.size(0)
                 total_count += batch_labels.size(0)
-            chunks.append(torch.sigmoid(logits) if apply_sigmoid else logits)
+            logit_chunks.append(logits)
             label_chunks.append(batch_labels)
-    scores = torch.cat(chunks).tolist() if chunks else []
-    labels = torch.cat(label_chunks).tolist() if label_chunks else []
+    scores, labels = [], []
+    if logit_chunks:
+        all_logits, all_labels = torch.cat(logit_chunks), torch.cat(label_chunks)
+        if fused_bce:
+            total_count = all_logits.numel()
+            total_loss = bce_with_logits_mean(all_logits, all_labels.float()) * total_count
+        scores = (torch.sigmoid(all_logits) if apply_sigmoid else all_logits).tolist()
+        labels = all_labels.tolist()
     eer, threshold = (None, None)
     if scores and labels:
         eer, threshold = calculate_eer(scores, labels)

@@ -175,6 +175,11 @@ int dfs_eer_select(const void* scores_dev, int key_bytes, const uint8_t* labels_
 int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,
                   int64_t* out4_host, void* stream);
 
+/* nn.BCEWithLogitsLoss() (mean) of a whole logit vector against float {0,1} labels -- the avg_loss of
+ * src/evaluation.py::evaluate (:83-86,94), one fused reduction instead of a .item() per batch.
+ * logits_dev / labels_dev [n] fp32 DEVICE pointers; *mean_host receives the loss.  Synchronises `stream`. */
+int dfs_bce_with_logits(const float* logits_dev, const float* labels_dev, int64_t n, double* mean_host, void* stream);
+
 /* ---- synthetic data (BASELINE.json north_star: "pinned synthetic feature tensors") --- */
 /* Fill [n,321,180] fp32 with N(0, std^2) from a counter-based generator keyed by
  * (seed, first_utt + i, element) so every rank / GPU count sees the same global data set. */

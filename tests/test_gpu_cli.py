@@ -1,0 +1,118 @@
+"""GPU parity for SURVEY.md §8(f) rows 1-4 against goldens written by the UNMODIFIED reference tools
+(tests/golden/make_golden_cli.py): the predict.py / predict_hybrid.py drop-in CLIs on rebuilt input files, the
+device alpha sweep of hybrid_ensemble.py, and evaluate() with the fused BCEWithLogits mean."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+pd = pytest.importorskip("pandas")
+
+from conftest import GOLDEN, PKG  # noqa: E402
+
+sys.path.insert(0, os.path.join(PKG, "dropin"))
+import cli_fixtures as fx  # noqa: E402
+import dfs_b200 as D  # noqa: E402
+import evaluation as dev_eval  # noqa: E402
+import hybrid_ensemble as dhe  # noqa: E402
+import ingest  # noqa: E402
+import model as m2  # noqa: E402
+import predict as dpredict  # noqa: E402
+import predict_hybrid as dhybrid  # noqa: E402
+
+CLI = np.load(os.path.join(GOLDEN, "cli_cases.npz"), allow_pickle=False)
+TOL = 1e-3   # north_star: per-utterance scores within 1e-3 relative
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    return fx.write_fixture_files(str(tmp_path_factory.mktemp("cli")))
+
+
+@pytest.mark.parametrize("model", ["cnn2d", "cnn1d"])
+@pytest.mark.parametrize("tag,flags", [("sigmoid", []), ("logits", ["--no-apply-sigmoid"])])
+def test_predict_cli_matches_reference_cli(files, tmp_path, model, tag, flags):
+    out = str(tmp_path / "prediction.pkl")
+    dpredict.main(["--features", files["features"], "--checkpoint", files[model], "--model", model, "--out", out, "--device", "cuda:0",
+                   "--num-workers", "0", "--dropout", "0.2"] + flags)
+    df = pd.read_pickle(out)
+    assert list(df.columns) == ["uttid", "predictions"] and list(df["uttid"].values) == list(CLI["uttids"])
+    assert str(df["predictions"].dtype) == str(CLI[f"predict_{model}_{tag}_dtype"]) == "float64"
+    got, ref = df["predictions"].to_numpy(), CLI[f"predict_{model}_{tag}"]
+    if tag == "sigmoid":
+        assert _rel(got, ref) <= TOL
+    else:   # logits cross zero: absolute error against the logit scale
+        assert float(np.max(np.abs(got - ref))) <= TOL * max(1.0, float(np.max(np.abs(ref))))
+
+
+def test_predict_hybrid_cli_matches_reference_cli(files, tmp_path, capsys):
+    out = str(tmp_path / "prediction_hybrid.pkl")
+    dhybrid.main(["--sup-checkpoint", files["cnn2d"], "--cae-checkpoint", files["cae"], "--cae-normalizer", files["normalizer"],
+                  "--test-features", files["features"], "--alpha", "0.8", "--out", out, "--device", "cuda"])
+    df = pd.read_pickle(out)
+    assert list(df["uttid"].values) == list(CLI["uttids"]) and str(df["predictions"].dtype) == "float64"
+    # min-max normalisation amplifies the per-score tolerance by value range / score range: compare in normalised units
+    assert float(np.max(np.abs(df["predictions"].to_numpy() - CLI["predict_hybrid"]))) <= 2e-2
+    assert "Saved hybrid predictions" in capsys.readouterr().out
+
+
+def test_alpha_sweep_on_reference_scores_is_bit_exact():
+    """Identical score inputs -> identical blends (float64) -> identical EER and threshold for all 21 alphas."""
+    best_alpha, best_eer, table = dhe.alpha_sweep(CLI["sup_scores"], CLI["cae_scores"], fx.labels(), alpha_steps=21)
+    assert np.array_equal(np.array([t[0] for t in table]), CLI["alpha_sweep_alphas"])
+    assert np.array_equal(np.array([[t[1], t[2]] for t in table]), CLI["alpha_sweep_eer_thr"])
+    ref = CLI["alpha_sweep_eer_thr"][:, 0]
+    b_eer, b_alpha = 1.0, 0.0
+    for a, e in zip(CLI["alpha_sweep_alphas"], ref):                     # hybrid_ensemble.py:147-151
+        if e < b_eer:
+            b_eer, b_alpha = e, a
+    assert (best_alpha, best_eer) == (b_alpha, b_eer)
+    # a larger, tie-heavy sweep against the oracle
+    from oracle import eer as oeer
+    rng = np.random.default_rng(5)
+    n = 50_000
+    lab = (rng.random(n) < 0.4).astype(np.int64)
+    sup = np.clip(rng.normal(0.35 + 0.3 * lab, 0.2), 0, 1).round(3)
+    cae = rng.gamma(2.0, 0.1 + 0.05 * (1 - lab))
+    res = D.alpha_sweep(sup, cae, lab, alpha_steps=11)
+    for a, e, t in zip(res["alphas"], res["eer"], res["threshold"]):
+        comb = a * oeer.normalise_01(sup) + (1 - a) * oeer.normalise_01(cae)
+        assert (e, t) == oeer.calculate_eer(comb.tolist(), lab.tolist(), kind="stable")
+
+
+def test_evaluate_with_fused_bce_matches_reference_evaluate(files):
+    from torch.utils.data import DataLoader, Dataset
+
+    table = ingest.load_feature_table(files["features"])
+    idx, lab = ingest.merge_labels(table, pd.read_pickle(files["labels"]))
+
+    class DS(Dataset):                                                    # what AudioDeepfakeDataset yields (dataset.py:36-56)
+        def __len__(self):
+            return len(idx)
+
+        def __getitem__(self, i):
+            return table.slab[idx[i]], torch.tensor(float(lab[i]), dtype=torch.float32)
+
+    model = dpredict.load_checkpoint_into(m2.CNN2D(in_features=180, dropout=0.2).cuda(), files["cnn2d"], "cuda")
+    metrics, scores, labels = dev_eval.evaluate(model, DataLoader(DS(), batch_size=5, shuffle=False), criterion=torch.nn.BCEWithLogitsLoss(),
+                                                device="cuda", swap_tf=True)
+    ref_loss, ref_eer, ref_thr = CLI["evaluate_metrics"]
+    assert labels == CLI["evaluate_labels"].tolist()
+    assert float(np.max(np.abs(np.array(scores) - CLI["evaluate_scores"]))) <= TOL * max(1.0, float(np.max(np.abs(CLI["evaluate_scores"]))))
+    assert abs(metrics["avg_loss"] - ref_loss) <= 1e-4 * abs(ref_loss)
+    # the fused loss on the reference's own logits: only the summation order differs (fp64 here, fp32 batch means there)
+    fused = D.bce_with_logits_mean(CLI["evaluate_scores"].astype(np.float32), CLI["evaluate_labels"].astype(np.float32))
+    assert abs(fused - ref_loss) <= 2e-6 * abs(ref_loss)
+    x = torch.randn(100_003, device="cuda") * 6
+    y = (torch.rand(100_003, device="cuda") < 0.5).float()
+    want = float(torch.nn.functional.binary_cross_entropy_with_logits(x.double(), y.double()))
+    assert abs(D.bce_with_logits_mean(x, y) - want) <= 1e-6 * want
+    # EER on 12 random-init scores a few 1e-6 apart is rank-sensitive (DESIGN.md "Tolerances"): check it on the reference's scores
+    assert D.calculate_eer(CLI["evaluate_scores"], CLI["evaluate_labels"]) == (ref_eer, ref_thr)
