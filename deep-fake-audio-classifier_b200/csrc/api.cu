@@ -757,6 +757,16 @@ extern "C" int dfs_eer_select(const void* scores_dev, int key_bytes, const uint8
 extern "C" int dfs_bce_with_logits(const float* logits_dev, const float* labels_dev, int64_t n, double* mean_host, void* stream) {
   return bce_with_logits_device(logits_dev, labels_dev, n, mean_host, static_cast<cudaStream_t>(stream));
 }
+namespace dfs { extern int g_select_use_tma; }
+extern "C" int dfs_set_global_option(const char* key, int64_t value) {
+  DFS_REQUIRE(key != nullptr, DFS_ERR_INVALID, "dfs_set_global_option: key is NULL");
+  if (strcmp(key, "eer_select_tma") == 0) {
+    dfs::g_select_use_tma = value != 0;
+    return DFS_OK;
+  }
+  dfs_set_error("dfs_set_global_option: unknown key '%s'", key);
+  return DFS_ERR_INVALID;
+}
 extern "C" int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,
                              int64_t* out4_host, void* stream) {
   return confusion_device(scores_dev, key_bytes, labels_dev, n, threshold, out4_host, static_cast<cudaStream_t>(stream));

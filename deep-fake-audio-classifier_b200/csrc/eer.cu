@@ -23,7 +23,7 @@ constexpr int kSortTile = kSortThreads * kSortItems;  // 4096
 __device__ __forceinline__ uint32_t to_key(float s) {
   uint32_t b = __float_as_uint(s);
   if (b == 0x80000000u) b = 0;
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);   // negative: flip all bits, else set the sign bit
 }
 __device__ __forceinline__ uint64_t to_key(double s) {
   uint64_t b = (uint64_t)__double_as_longlong(s);
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) radix_scan_kernel(uint32_t* __restrict__ 
 }
 
 template <typename K>
-__global__ void __launch_bounds__(kSortThreads) radix_downsweep_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ pin,
+__global__ void __launch_bounds__(kSortThreads, 4) radix_downsweep_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ pin,
                                                                         K* __restrict__ kout, uint32_t* __restrict__ pout, long long n,
                                                                         int shift, const uint32_t* __restrict__ bucket_base,
                                                                         const uint32_t* __restrict__ super_prefix) {
@@ -214,19 +214,14 @@ __global__ void __launch_bounds__(kSortThreads) radix_downsweep_kernel(const K* 
     for (int i = tid; i < 8 * 256; i += kSortThreads) (&cnt[0][0])[i] = 0;
     __syncthreads();
 
+    // keys only: the payloads are fetched after the ranking, straight into their staging slot, so they are not live in
+    // registers across the ballot loop (<= 64 registers -> 4 CTAs per SM instead of 2)
     K key[kSortItems];
-    uint32_t pay[kSortItems];
     uint32_t rnk[kSortItems];
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
       const int local = w * (32 * kSortItems) + i * 32 + lane;
-      if (local < valid) {
-        key[i] = kin[base + local];
-        pay[i] = pin[base + local];
-      } else {
-        key[i] = ~(K)0;  // sorts after every valid key of the tile in every pass; never written out
-        pay[i] = 0;
-      }
+      key[i] = (local < valid) ? kin[base + local] : ~(K)0;  // padding sorts after every valid key of the tile; never written out
     }
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
@@ -274,8 +269,9 @@ __global__ void __launch_bounds__(kSortThreads) radix_downsweep_kernel(const K* 
     for (int i = 0; i < kSortItems; ++i) {
       const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
       const uint32_t pos = digit_start[d] + cnt[w][d] + rnk[i];
+      const int local = w * (32 * kSortItems) + i * 32 + lane;
       skeys[pos] = key[i];
-      spay[pos] = pay[i];
+      spay[pos] = (local < valid) ? pin[base + local] : 0u;
     }
     __syncthreads();
 #pragma unroll
@@ -710,6 +706,140 @@ __global__ void __launch_bounds__(256, 1) select_hist_kernel(const typename Scor
   }
 }
 
+// TMA-fed variant (16-byte aligned score / label pointers): one producer lane keeps a ring of kSelStages stages, each one
+// 16 KB of scores + their labels, in flight with cp.async.bulk (~80 KB per SM: enough outstanding bytes to cover HBM
+// latency with a single resident CTA -- the counter table takes 130 KB of the SM's shared memory).  256 consumer threads
+// read the stage with conflict-free 16-byte LDS and bump their private counters.
+constexpr int kSelStages = 4;
+constexpr int kSelStageB = 16384 + 4096;
+constexpr int kSelRingOff = 513 * kCntStride + 60;                       // 133,440: 513 rows (row 512 = spare), 128-byte aligned
+constexpr int kSelBarOff = kSelRingOff + kSelStages * kSelStageB;        // 215,360
+constexpr int kSelTmaSmem = kSelBarOff + 2 * kSelStages * 8;
+
+template <typename K, bool FIRST>
+__global__ void __launch_bounds__(288, 1) select_hist_tma_kernel(const typename ScoreOf<K>::type* __restrict__ scores,
+                                                                  const uint8_t* __restrict__ labels, long long n, int shift,
+                                                                  SelectState* __restrict__ st, unsigned long long* __restrict__ hist /*[2][256]*/) {
+  typedef typename ScoreOf<K>::type S;
+  constexpr int V = VecOf<K>::V;
+  constexpr int KS = 16384 / (int)sizeof(S);          // scores per stage: 4096 (fp32) / 2048 (fp64)
+  constexpr int ITERS = KS / (256 * V);               // 16-byte loads per consumer thread per stage (4)
+  constexpr int FLUSH_STAGES = 224 / (ITERS * V);     // <= 224 counts per thread between flushes
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* cnt = smem;
+  uint8_t* ring = smem + kSelRingOff;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSelBarOff);
+  uint64_t* empty = full + kSelStages;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 513 * kCntStride / 4; i += 288) reinterpret_cast<uint32_t*>(cnt)[i] = 0u;
+  if (tid == 0) {
+    for (int i = 0; i < kSelStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    fence_mbar_init();
+  }
+  const K prefix = FIRST ? (K)0 : (K)st->prefix;
+  const K mask = FIRST ? (K)0 : (K)st->mask;
+  __syncthreads();
+  const long long n_stages = n / KS;                  // full stages; the tail (< KS scores) is read directly below
+  if (warp == 8) {
+    // ===================== producer =====================
+    if ((tid & 31) == 0) {
+      uint32_t it = 0;
+      for (long long g = blockIdx.x; g < n_stages; g += gridDim.x, ++it) {
+        const int s = it % kSelStages;
+        mbar_wait(&empty[s], ((it / kSelStages) & 1) ^ 1, 31);
+        mbar_arrive_expect_tx(&full[s], 16384 + KS);
+        bulk_g2s(ring + s * kSelStageB, scores + g * KS, 16384, &full[s]);
+        bulk_g2s(ring + s * kSelStageB + 16384, labels + g * KS, KS, &full[s]);
+      }
+    }
+    return;
+  }
+  // ===================== consumers (warps 0..7) =====================
+  uint8_t* mine = cnt + tid;
+  K kand = ~(K)0, kor = 0;
+  unsigned long long tot0 = 0, tot1 = 0;
+  uint32_t it = 0;
+  int since_flush = 0;
+  auto flush = [&]() {
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    tot0 += flush_counter_row(cnt, tid);
+    tot1 += flush_counter_row(cnt, 256 + tid);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  };
+  for (long long g = blockIdx.x; g < n_stages; g += gridDim.x, ++it) {
+    const int s = it % kSelStages;
+    mbar_wait(&full[s], (it / kSelStages) & 1, 32);
+    const uint8_t* base = ring + s * kSelStageB;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int v = i * 256 + tid;                    // 16-byte vector index within the stage
+      S sv[V];
+      const uint4 q = *reinterpret_cast<const uint4*>(base + v * 16);
+      if constexpr (V == 4) {
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sv[e] = *reinterpret_cast<const S*>(&w[e]);
+      } else {
+        const uint64_t w[2] = {((uint64_t)q.y << 32) | q.x, ((uint64_t)q.w << 32) | q.z};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) sv[e] = *reinterpret_cast<const S*>(&w[e]);
+      }
+      uint32_t lv;
+      if constexpr (V == 4) lv = *reinterpret_cast<const uint32_t*>(base + 16384 + v * 4);
+      else lv = *reinterpret_cast<const uint16_t*>(base + 16384 + v * 2);
+      // Below the first level almost no score carries the chosen prefix: test that first (4-5 instructions per score)
+      // and leave the counters alone unless some lane of the warp has a hit.  The update itself is branch-free per
+      // score: one outside the prefix bumps the spare row 512.
+      K kk[V];
+      bool hit[V];
+      bool any = FIRST;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        kk[e] = to_key(sv[e]);
+        hit[e] = FIRST || (kk[e] & mask) == prefix;
+        if (FIRST) { kand &= kk[e]; kor |= kk[e]; }
+        any |= hit[e];
+      }
+      if (FIRST || __any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const uint32_t lab = min((lv >> (8 * e)) & 0xffu, 1u);
+          const uint32_t row = hit[e] ? (((uint32_t)(kk[e] >> shift) & 0xffu) | (lab << 8)) : 512u;
+          mine[row * kCntStride] += 1;
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[s]);      // this warp is done reading the stage
+    if (++since_flush == FLUSH_STAGES) {
+      flush();
+      since_flush = 0;
+    }
+  }
+  if (blockIdx.x == 0) {                               // tail: fewer than KS scores, strided direct loads (<= 16 per thread)
+    for (long long i = n_stages * KS + tid; i < n; i += 256) {
+      const K k = to_key(scores[i]);
+      const uint32_t lab = labels[i] != 0;
+      if (FIRST) { kand &= k; kor |= k; }
+      if (FIRST || (k & mask) == prefix) atomicAdd(&hist[((uint32_t)(k >> shift) & 0xffu) + 256 * lab], 1ull);
+    }
+  }
+  flush();
+  if (tot0) atomicAdd(&hist[tid], tot0);
+  if (tot1) atomicAdd(&hist[256 + tid], tot1);
+  if (FIRST) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      kand &= (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)kand, o);
+      kor |= (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)kor, o);
+    }
+    if ((tid & 31) == 0) {
+      atomicAnd(&st->key_and, (unsigned long long)kand);
+      atomicOr(&st->key_or, (unsigned long long)kor);
+    }
+  }
+}
+
 // scalar-load variant for misaligned score / label pointers (same counters, same flush rule)
 template <typename K, bool FIRST>
 __global__ void __launch_bounds__(256, 1) select_hist_scalar_kernel(const typename ScoreOf<K>::type* __restrict__ scores,
@@ -978,6 +1108,9 @@ __global__ void select_finish_kernel(const SelectState* __restrict__ st, long lo
   res->n_spoof = n_spoof;
 }
 
+// 1 = cp.async.bulk ring (default), 0 = direct vector loads: kept switchable for the cross-check test (dfs_set_global_option)
+int g_select_use_tma = 1;
+
 struct SelectScratch {
   SelectState* state = nullptr;          // device
   unsigned long long* hist = nullptr;    // device [512]
@@ -1010,13 +1143,18 @@ static int eer_select_impl(const void* scores_v, const uint8_t* labels, int64_t 
     DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_tma_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelTmaSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_tma_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelTmaSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_tma_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelTmaSmem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_tma_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelTmaSmem));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_scalar_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_scalar_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_scalar_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(select_hist_scalar_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
   }
   const bool aligned = (reinterpret_cast<uintptr_t>(scores) % 16 == 0) && (reinterpret_cast<uintptr_t>(labels) % V == 0);
-  const long long chunk = aligned ? 256ll * V * kSelIters : 256ll * 224;
+  const bool tma = (reinterpret_cast<uintptr_t>(scores) % 16 == 0) && (reinterpret_cast<uintptr_t>(labels) % 16 == 0) && g_select_use_tma;
+  const long long chunk = tma ? (long long)(16384 / sizeof(S)) : aligned ? 256ll * V * kSelIters : 256ll * 224;
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ceil_div64(n, chunk), num_sms));
 
   select_init_kernel<<<1, 256, 0, stream>>>(sc.state, sc.hist);
@@ -1027,7 +1165,10 @@ static int eer_select_impl(const void* scores_v, const uint8_t* labels, int64_t 
     const bool first = (lv == LEVELS - 1);
     const bool skip = !first && ((((host.key_and ^ host.key_or) >> shift) & 0xffull) == 0);
     if (!skip) {
-      if (aligned) {
+      if (tma) {
+        if (first) select_hist_tma_kernel<K, true><<<grid, 288, kSelTmaSmem, stream>>>(scores, labels, n, shift, sc.state, sc.hist);
+        else select_hist_tma_kernel<K, false><<<grid, 288, kSelTmaSmem, stream>>>(scores, labels, n, shift, sc.state, sc.hist);
+      } else if (aligned) {
         if (first) select_hist_kernel<K, true><<<grid, 256, kHistSmem, stream>>>(scores, labels, n, shift, sc.state, sc.hist);
         else select_hist_kernel<K, false><<<grid, 256, kHistSmem, stream>>>(scores, labels, n, shift, sc.state, sc.hist);
       } else {

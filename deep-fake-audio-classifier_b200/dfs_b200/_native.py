@@ -70,6 +70,7 @@ SIGNATURES = {
     "dfs_eer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(EerResult), C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfs_eer_select": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(EerResult), C.c_void_p]),
     "dfs_bce_with_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_void_p]),
+    "dfs_set_global_option": (C.c_int, [C.c_char_p, C.c_int64]),
     "dfs_confusion": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.POINTER(C.c_int64), C.c_void_p]),
     "dfs_fill_features": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_float, C.c_void_p]),
     "dfs_probe_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -110,3 +111,7 @@ def check(status: int, what: str = "dfs_b200"):
 
 def launch_count() -> int:
     return int(load().dfs_launch_count())
+
+
+def set_global_option(key: str, value: int):
+    check(load().dfs_set_global_option(key.encode(), int(value)), "dfs_set_global_option")

@@ -171,6 +171,9 @@ int dfs_eer(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, in
  * this is what calculate_eer(scores, labels) -> (eer, threshold) needs (scripts/evaluation.py:7-39).  Synchronises `stream`. */
 int dfs_eer_select(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, dfs_eer_result* result_host,
                    void* stream);
+/* Library-wide switches for cross-checks (tests only; defaults are the product path):
+ *   "eer_select_tma" 1 (default) = cp.async.bulk-fed histogram kernel, 0 = direct vector loads.                 */
+int dfs_set_global_option(const char* key, int64_t value);
 /* confusion_at_threshold (scripts/evaluation.py:42-56): out4_host = {tp, fp, tn, fn}. */
 int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,
                   int64_t* out4_host, void* stream);

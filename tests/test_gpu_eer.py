@@ -188,3 +188,26 @@ def test_ensemble_mean_and_fp32_inputs():
     assert np.array_equal(D.ensemble_mean([a, b, c]), ref)
     ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     assert np.array_equal(D.hybrid_blend(ta, tb, 0.8), oeer.hybrid_blend(a, b, 0.8))
+
+
+def test_eer_select_tma_ring_matches_direct_loads():
+    """The cp.async.bulk-fed histogram kernel and the direct-load one must pick the same crossing (sizes around the
+    stage size 4096 / 2048 and the flush interval, fp32 and fp64)."""
+    rng = np.random.default_rng(21)
+    try:
+        for dtype in (np.float32, np.float64):
+            for n in (1, 2047, 4096, 4097, 14 * 4096 * 3 + 5, 2_000_003):
+                s = torch.from_numpy((rng.standard_normal(n) * 3).astype(dtype)).cuda()
+                l = torch.from_numpy((rng.random(n) < 0.5).astype(np.uint8)).cuda()
+                if n == 1:
+                    continue
+                l[0], l[1] = 0, 1
+                out = []
+                for tma in (1, 0):
+                    D._native.set_global_option("eer_select_tma", tma)
+                    d = D.eer_details(s, l, method="select")
+                    out.append((d["eer"], d["threshold"], d["eer_idx"], d["n_bonafide"]))
+                d = D.eer_details(s, l, method="sort")
+                assert out[0] == out[1] == (d["eer"], d["threshold"], d["eer_idx"], d["n_bonafide"]), (dtype, n)
+    finally:
+        D._native.set_global_option("eer_select_tma", 1)
