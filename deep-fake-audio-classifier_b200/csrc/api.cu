@@ -221,6 +221,7 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
   if (strcmp(key, "conv1_impl") == 0) {
     DFS_REQUIRE(value == 0 || value == 1, DFS_ERR_INVALID, "conv1_impl must be 0 (tcgen05) or 1 (CUDA-core cross-check)");
     m->conv1_impl = (int)value;
+    if (m->cae != nullptr) m->cae->enc1_impl = (int)value;
     return DFS_OK;
   }
   if (strcmp(key, "profile") == 0) {
@@ -480,7 +481,8 @@ extern "C" int dfs_cnn1d_create(dfs_model** out, int device, const dfs_cnn1d_wei
   m->kind = KIND_CNN1D;
   int st = model_common_init(m, device);
   if (st != DFS_OK) { delete m; return st; }
-  m->chunk = max_chunk > 0 ? max_chunk : 1024;
+  // an MMA tile is 16 utterances: 4736 = 148 SMs x 2 resident CTAs x 16 gives every CTA one column tile (1024 left 84 SMs idle)
+  m->chunk = max_chunk > 0 ? max_chunk : 4736;
   auto fail = [&](int s) { dfs_model_destroy(m); return s; };
   const int ci[3] = {kF, 32, 64}, co[3] = {32, 64, 128};
   for (int i = 0; i < 3; ++i)
@@ -571,6 +573,24 @@ static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
   m->cae = s;
   memset(s->bias, 0, sizeof(s->bias));
   fold_conv1(w->enc[0], s->c1);
+  {
+    // enc1 as a Toeplitz-in-time GEMM (cae_enc1_tc.cu): B_kw[n = jj*32 + c][o] = 0.25 * w'[c][o - jj][kw] for 0 <= o-jj <= 2,
+    // stored [kw][K chunk o/8][n][o%8]; 0.25 = the 2x2 average pool folded through the ReLU
+    std::vector<uint16_t> p1((size_t)3 * 2 * 256 * 8, 0);
+    for (int kw = 0; kw < 3; ++kw)
+      for (int jj = 0; jj < 8; ++jj)
+        for (int c = 0; c < 32; ++c)
+          for (int kh = 0; kh < 3; ++kh) {
+            const int o = jj + kh, nn = jj * 32 + c;
+            p1[(((size_t)kw * 2 + (o >> 3)) * 256 + nn) * 8 + (o & 7)] = f32_to_act_bits(0.25f * s->c1.w[c * 9 + kh * 3 + kw]);
+          }
+    for (int c = 0; c < 32; ++c) s->b1q[c] = 0.25f * s->c1.b[c];
+    uint16_t* d = nullptr;
+    DFS_PROPAGATE(dev_upload(m, &d, p1));
+    s->w1pack = d;
+    DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&s->xt1), (size_t)cae_enc1_xt_rows(m->chunk) * 16, true));
+    s->enc1_impl = 0;
+  }
   std::vector<uint16_t> packs[6];
   packs[0] = pack_pair(w->enc[1], 64, 32, 0.25, s->bias[0]);             // enc2: 2x2 average folded (4 ReLU outputs are summed)
   packs[1] = pack_3x3_groups(w->enc[2], 128, 64, 128, 0.25, s->bias[1]);  // enc3
@@ -589,7 +609,10 @@ static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
   float* wfd = nullptr;
   DFS_PROPAGATE(dev_upload(m, &wfd, wf));
   s->w_final = wfd;
+  memcpy(s->w_final_host, wf.data(), sizeof(s->w_final_host));
   s->final_bias = w->dec[3].bias[0];
+  DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&s->mse_partial), (size_t)m->chunk * kCaeFinalSplit * 4, true));
+  DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&s->mse_done), (size_t)m->chunk * 4, true));
   for (int l = 0; l < 7; ++l) {
     int planes, cols, rs;
     cae_tc_geometry(l, &planes, &cols, &rs);

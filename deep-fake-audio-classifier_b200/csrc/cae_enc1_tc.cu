@@ -1,0 +1,255 @@
+// cae_enc1_tc.cu -- CAE encoder block 1 on the tensor cores:
+//   FeatureNormalizer.transform + nn.Conv2d(1,32,3,p=1) + BatchNorm2d + ReLU + AvgPool2d(2)
+//   /root/reference/src/dataset_cae.py:37-41, /root/reference/src/model_cae.py:33-38
+//
+// Same Toeplitz-in-time GEMM as the 2D-CNN's first layer (conv1_tc.cu): a GEMM row = 8 consecutive conv outputs in time of
+// one feature column, N = 256 = (time offset jj, output channel c), K = 16 consecutive input samples per feature tap,
+// three taps -> 3 tcgen05.mma (M=128, N=256, K=16) per 1024 conv positions.  The input image is column-major,
+//     xT2[(gc * 41 + tb)] = 8 samples x[8tb-1 .. 8tb+6][f]  (normalised, fp16),  gc = n * 184 + f + 2
+// (pad columns 0, 1, 182, 183 of every utterance are zero), so K chunk 1 of a row is the next row (LBO = 16 B) and a
+// feature tap is a +-41-row shift of the descriptor start address.  The M = 128 rows of a tile are 16 COLUMNS x 8 TIME
+// BLOCKS: the stride between the 8-row core-matrix groups (SBO) is free, and SBO = 41 rows walks across columns.  That
+// puts the 2x2 pool's feature partner 8 TMEM lanes away (one __shfl_xor 8, as in conv_tc's EPI_POOL_TF), the time partner
+// in the same thread, and gives every 8 consecutive lanes 8 consecutive time blocks of one column = 256 contiguous bytes
+// of each output plane.  One bulk copy of 18 columns x 41 rows (11.8 KB) feeds the 5 tiles (tb 0..39) of a 16-column unit.
+// The 0.25 of the 2x2 average is folded into weights and bias (ReLU is positively homogeneous).  Output: e1 in the FT8P
+// layout enc2's PAIR GEMM reads (layout.cuh): pooled time step 4tb + k -> parity plane k & 1, row 2tb + (k >> 1) + 1.
+// Like conv1_tc the kernel is bound by the TMEM read-out of the fp32 accumulators (64 B/clk/SM), not by the MMAs.
+#include "common.cuh"
+#include "kernels.h"
+#include "layout.cuh"
+
+namespace dfs {
+
+constexpr int kE1Cols = 184;                            // padded feature columns per utterance: f'' = f + 2
+constexpr int kE1Blocks = 41;                           // 16-byte rows (8 samples) per column: samples t = -1 .. 326
+constexpr int kE1Lead = 48;                             // zero rows before column 0 (tap -1 of the first unit)
+constexpr int kE1UnitCols = 16;
+constexpr int kE1WinRows = (kE1UnitCols + 2) * kE1Blocks;   // 738
+constexpr int kE1WinB = kE1WinRows * 16;                // 11808
+constexpr int kE1WinBAl = 12288;
+constexpr int kE1Stages = 4;
+constexpr int kE1TilesPerUnit = 5;                      // time blocks 0..39 in tiles of 8 (block 40 only feeds K chunk 1)
+constexpr int kE1WgtB = 3 * 256 * 16 * 2;               // 24576
+constexpr int kE1EpiWarps = 16;
+constexpr int kE1Threads = (kE1EpiWarps + 3) * 32;      // 608
+constexpr int kE1BarOff = kE1WgtB + kE1Stages * kE1WinBAl;
+constexpr int kE1SmemB = kE1BarOff + 256;
+
+int64_t cae_enc1_xt_rows(int64_t n_utts) { return kE1Lead + (n_utts * kE1Cols + 2 * kE1UnitCols + 2) * kE1Blocks + 16; }
+
+// fp32 strided features -> normalised fp16 xT2 rows; pad columns / lead / tail rows are zeroed once at allocation
+__global__ void __launch_bounds__(256) cae_enc1_prep_kernel(const float* __restrict__ x, long long sn, long long st, long long sf, long long total,
+                                                             const float* __restrict__ mean, const float* __restrict__ sd,
+                                                             uint16_t* __restrict__ xt) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int f, tb;
+  long long n;
+  if (sf <= st) {  // feature-contiguous storage: consecutive threads -> consecutive features (coalesced reads)
+    f = (int)(idx % kF);
+    tb = (int)((idx / kF) % kE1Blocks);
+    n = idx / ((long long)kF * kE1Blocks);
+  } else {         // time-contiguous storage (the reference's transposed view): consecutive threads -> consecutive blocks
+    tb = (int)(idx % kE1Blocks);
+    f = (int)((idx / kE1Blocks) % kF);
+    n = idx / ((long long)kF * kE1Blocks);
+  }
+  const float* src = x + n * sn + (long long)f * sf;
+  const float m = mean != nullptr ? mean[f] : 0.0f, s = sd != nullptr ? sd[f] : 1.0f;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int t = 8 * tb - 1 + e;
+    float val = 0.0f;                               // zero padding is applied AFTER the normalisation
+    if (t >= 0 && t < kT) {
+      val = src[(long long)t * st];
+      if (mean != nullptr) val = (val - m) / s;
+      val = fmaxf(val, -65504.0f);
+    }
+    v[e] = val;
+  }
+  uint16_t* dst = xt + ((long long)kE1Lead + (n * kE1Cols + f + 2) * kE1Blocks + tb) * 8;
+  st_global_v4(dst, pack_act2(v[0], v[1]), pack_act2(v[2], v[3]), pack_act2(v[4], v[5]), pack_act2(v[6], v[7]));
+}
+
+struct Enc1TcParams {
+  const uint16_t* xt;      // xT2 rows (16 B each)
+  const uint16_t* wpack;   // [kw][chunk 2][n 256][8] fp16 Toeplitz weights, 0.25 folded
+  float bias[32];          // 0.25 * folded bias
+  int n_units;             // 16-column units over the global column index n * 184 + f''
+  int n_utts;
+  uint16_t* out;           // e1, FT8P, 8 planes x (92 columns per utterance) x RS 82
+  long long out_plane_elems;
+  int out_rs;
+  int out_cols;
+};
+
+__global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid_constant__ Enc1TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* wsm = smem;
+  uint8_t* win0 = smem + kE1WgtB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kE1BarOff);
+  uint64_t* full = bars;                 // [stages]
+  uint64_t* empty = bars + kE1Stages;    // [stages]
+  uint64_t* tfull = empty + kE1Stages;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kE1EpiWarps && lane == 0) {
+    for (int i = 0; i < kE1Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == kE1EpiWarps + 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kE1EpiWarps) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, kE1WgtB);
+      for (int off = 0; off < kE1WgtB; off += 8192) bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, 8192, wbar);
+      uint32_t ws = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ws) {
+        const int stage = ws % kE1Stages;
+        mbar_wait(&empty[stage], ((ws / kE1Stages) & 1) ^ 1, 41);
+        mbar_arrive_expect_tx(&full[stage], kE1WinB);
+        // window = columns 16u - 1 .. 16u + 16, all 41 rows each
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.xt) + ((long long)kE1Lead + (16ll * u - 1) * kE1Blocks) * 16;
+        bulk_g2s(win0 + stage * kE1WinBAl, src, kE1WinB, &full[stage]);
+      }
+    }
+  } else if (warp == kE1EpiWarps + 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, 256);
+      const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 256 * 16, 128);
+      const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
+      // A: K chunk 1 of a row is the next row (LBO = 16 B); the 16 core-matrix groups of a tile are 16 columns (SBO = 41 rows)
+      const uint64_t a_desc0 = umma_smem_desc(smem_u32(win0), 16, kE1Blocks * 16);
+      const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
+      mbar_wait(wbar, 0, 42);
+      uint32_t ws = 0, it = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ws) {
+        const int stage = ws % kE1Stages;
+        mbar_wait(&full[stage], (ws / kE1Stages) & 1, 43);
+        const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (kE1WinBAl >> 4));
+#pragma unroll 1
+        for (int tt = 0; tt < kE1TilesPerUnit; ++tt, ++it) {
+          const int acc = it & 1;
+          mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, 44);
+          tc_fence_after();
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)   // window column 0 is 16u - 1: tap kw starts kw columns in; tile tt starts at row 8 tt
+            umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kw * kE1Blocks + 8 * tt), a_hi, b_lo0 + (uint32_t)(kw * (8192 >> 4)), b_hi, idesc,
+                          kw != 0 ? 1u : 0u);
+          umma_commit(&tfull[acc]);
+        }
+        umma_commit(&empty[stage]);
+      }
+    }
+  } else if (warp < kE1EpiWarps) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;          // TMEM lane quarter
+    const int h = (warp >> 2) & 1;   // channel half: channels 16h .. 16h+15
+    const int grp = warp >> 3;       // accumulator / tile parity this warp serves
+    const int g = 4 * q + (lane >> 3);   // column within the unit
+    const int i = lane & 7;              // time block within the tile
+    const int odd = g & 1;               // feature parity: even column keeps channels 16h..16h+7, odd column 16h+8..16h+15
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const long long gc = 16ll * u + g;
+      const long long n = gc / kE1Cols;
+      const int fpp = (int)(gc - n * kE1Cols);
+      const bool valid = (fpp >= 2) && (fpp <= kF + 1) && (n < p.n_utts);
+      // the lane pair (f'' even, f'' + 1) is one pooled feature column fo = (f'' - 2) / 2
+      uint16_t* ocol = p.out + (long long)(2 * h + odd) * p.out_plane_elems + ((n * p.out_cols + ((fpp - 2) >> 1) + 1) * (long long)p.out_rs) * 8;
+      for (int tt = 0; tt < kE1TilesPerUnit; ++tt, ++it) {
+        if ((int)(it & 1) != grp) continue;
+        const int acc = grp;
+        const int tb = 8 * tt + i;
+        mbar_wait(&tfull[acc], (it >> 1) & 1, 45);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * h;
+        uint32_t pk[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // pooled time step within the block: conv time offsets jj = 2k, 2k+1
+          float a[16], b[16];
+          tmem_ld_32x16(taddr + (2 * k) * 32, a);
+          tmem_ld_32x16(taddr + (2 * k + 1) * 32, b);
+          tmem_ld_wait();
+          if (k == 3) {  // all TMEM reads of this warp are done: release the accumulator early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          float o[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[c] = fmaxf(a[c] + p.bias[16 * h + c], 0.0f) + fmaxf(b[c] + p.bias[16 * h + c], 0.0f);
+          float v[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float send = odd ? o[c] : o[c + 8];
+            const float mine = odd ? o[c + 8] : o[c];
+            v[c] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) pk[k][c] = pack_act2(v[2 * c], v[2 * c + 1]);
+        }
+        if (valid) {
+          // pooled step 4tb + k: parity plane k & 1 (4 planes further), rows 2tb + 1 (k < 2) and 2tb + 2: the two rows of a
+          // parity are 32 contiguous bytes, the 8 lanes of a column 256
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            uint16_t* dst = ocol + (long long)(par * 4) * p.out_plane_elems + (2 * tb + 1) * 8;
+            st_global_v4(dst, pk[par][0], pk[par][1], pk[par][2], pk[par][3]);
+            st_global_v4(dst + 8, pk[par + 2][0], pk[par + 2][1], pk[par + 2][2], pk[par + 2][3]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kE1EpiWarps + 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_cae_enc1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const float* norm_mean, const float* norm_std, uint16_t* xt,
+                       const uint16_t* wpack, const float* bias_quarter, ActBuf out, int out_cols, int num_sms, cudaStream_t stream) {
+  if (n_utts <= 0) return DFS_OK;
+  const long long total = (long long)n_utts * kF * kE1Blocks;
+  cae_enc1_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, norm_mean, norm_std, xt);
+  DFS_LAUNCH_CHECK();
+  static bool configured[32] = {false};
+  if (dfs_first_use_on_device(configured))
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(cae_enc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kE1SmemB));
+  Enc1TcParams p{};
+  p.xt = xt;
+  p.wpack = wpack;
+  for (int i = 0; i < 32; ++i) p.bias[i] = bias_quarter[i];
+  p.n_units = (int)ceil_div64((long long)n_utts * kE1Cols, kE1UnitCols);
+  p.n_utts = n_utts;
+  p.out = out.ptr;
+  p.out_plane_elems = out.plane_elems();
+  p.out_rs = out.RS;
+  p.out_cols = out_cols;
+  const int grid = p.n_units < num_sms ? p.n_units : num_sms;
+  cae_enc1_tc_kernel<<<grid, kE1Threads, kE1SmemB, stream>>>(p);
+  DFS_LAUNCH_CHECK();
+  return DFS_OK;
+}
+
+}  // namespace dfs

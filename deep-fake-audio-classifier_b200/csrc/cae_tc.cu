@@ -4,7 +4,7 @@
 //   score    MSELoss(reduction='none')(recon, x).view(B,-1).mean(1)   /root/reference/src/predict_hybrid.py:75-76
 //
 //   layer  in (C x T x F)      kernel                                              out layout (planes, cols, RS)
-//   enc1   1 x 321 x 180       conv1_kernel<POOLF> (CUDA cores; normaliser on load) e1 FT8P ( 8, 92,  82)
+//   enc1   1 x 321 x 180       Toeplitz-in-time GEMM N=256 (cae_enc1_tc.cu; normaliser in the prep) e1 FT8P ( 8, 92,  82)
 //   enc2   32 x 160 x 90       PAIR GEMM  N=128, K=384, time pool in-thread + lane^8 e2 FT8  ( 8, 48,  82)
 //   enc3   64 x 80 x 45        3x3 GEMM   N=128, K=576, 2x2 pool lane^1 / lane^8     e3 FT8  (16, 24,  42)
 //   enc4   128 x 40 x 22       3x3 GEMM   4 groups of N=64, K=1152 in 2 pieces       e4 FT8  (32, 14,  26)   = latent
@@ -15,6 +15,8 @@
 //                              zero row 320, per-utterance mean -- the reconstruction is never written.
 // AvgPool2d(2) floors: enc1 drops input row 320, enc3 drops feature column 44 (out_feats = 22); dec2's
 // output_padding column receives the bias only (constant, written once at handle creation).
+#include <string.h>
+
 #include "conv_tc.cuh"
 
 namespace dfs {
@@ -76,18 +78,31 @@ __device__ __forceinline__ float cae_in(const float* __restrict__ x, long long s
   return v;
 }
 
-__global__ void __launch_bounds__(256) cae_final_tc_kernel(ActBuf d3, const float* __restrict__ x, long long sn, long long st, long long sf,
-                                                            const float* __restrict__ mean, const float* __restrict__ sd,
-                                                            const float* __restrict__ w /*[(a*2+b)*32 + ci]*/, float bias,
-                                                            float* __restrict__ mse_out, float* __restrict__ recon_out) {
+// grid = (utterances, 20): block (n, s) handles the d3 rows to = 8s .. 8s+7 of all 90 columns, i.e. the 16 full input rows
+// t = 16s .. 16s+15 (block 0 also the zero-padded row 320).
+//   phase 1  thread -> (column fo, row to): eight consecutive threads read 128 contiguous bytes of each of the 4 channel
+//            planes of d3; 4 outputs x 32 MACs; the 2x2 reconstruction patch goes to shared memory [16][180]
+//   phase 2  the residual against the (normalised) input runs over that tile in the input's own storage order, so the
+//            global reads are contiguous whichever of (t, f) is the fast axis (the first version read x through the
+//            (to, fo) mapping: 4 useful bytes per 32-byte sector, and the kernel took as long as the 531 MFLOP layers).
+// The block that arrives last adds the 20 partial sums in index order (deterministic score).
+// The 4 x 32 weights travel in the kernel parameter space: every FFMA takes its weight as a constant-bank operand (no
+// shared-memory loads, no 128 weight registers -- the first version needed 164 registers and ran one block per SM).
+struct CaeFinalW {
+  float w[128];   // [(a*2+b)*32 + ci]
+  float bias;
+};
+__global__ void __launch_bounds__(256, 4) cae_final_tc_kernel(ActBuf d3, const float* __restrict__ x, long long sn, long long st, long long sf,
+                                                               const float* __restrict__ mean, const float* __restrict__ sd,
+                                                               const __grid_constant__ CaeFinalW fw,
+                                                               float* __restrict__ mse_out, float* __restrict__ recon_out,
+                                                               float* __restrict__ partial, unsigned int* __restrict__ done) {
   const long long n = blockIdx.x;
-  __shared__ float ws[128];
-  if (threadIdx.x < 128) ws[threadIdx.x] = w[threadIdx.x];
-  __syncthreads();
+  const int split = blockIdx.y;
+  __shared__ float rec[16][kF + 1];
   const long long plane_elems = d3.plane_elems();
-  float acc = 0.0f;
-  for (int pos = threadIdx.x; pos < 160 * 90; pos += blockDim.x) {
-    const int fo = pos / 160, to = pos - fo * 160;   // consecutive threads -> consecutive rows of one column (16 B apart)
+  for (int pos = threadIdx.x; pos < 90 * 8; pos += blockDim.x) {
+    const int fo = pos >> 3, tl = pos & 7, to = 8 * split + tl;
     const uint16_t* src = d3.ptr + ((n * 92 + fo + 1) * d3.RS + to + 1) * 8;
     float in[32];
 #pragma unroll
@@ -105,19 +120,38 @@ __global__ void __launch_bounds__(256) cae_final_tc_kernel(ActBuf d3, const floa
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
-        float r = bias;
+        float r = fw.bias;
 #pragma unroll
-        for (int ci = 0; ci < 32; ++ci) r = fmaf(in[ci], ws[(a * 2 + b) * 32 + ci], r);
-        const int t = 2 * to + a, f = 2 * fo + b;
-        if (recon_out != nullptr) recon_out[n * kT * kF + t * kF + f] = r;
-        const float d = r - cae_in(x, sn, st, sf, n, t, f, mean, sd);
-        acc = fmaf(d, d, acc);
+        for (int ci = 0; ci < 32; ++ci) r = fmaf(in[ci], fw.w[(a * 2 + b) * 32 + ci], r);
+        rec[2 * tl + a][2 * fo + b] = r;
       }
   }
-  for (int f = threadIdx.x; f < kF; f += blockDim.x) {  // reconstruction row 320 is zero padding (model_cae.py:116-119)
-    if (recon_out != nullptr) recon_out[n * kT * kF + 320 * kF + f] = 0.0f;
-    const float d = cae_in(x, sn, st, sf, n, 320, f, mean, sd);
-    acc = fmaf(d, d, acc);
+  __syncthreads();
+  float acc = 0.0f;
+  const int t0 = 16 * split;
+  if (sf <= st) {   // feature axis is the fast one (contiguous [N,321,180]): consecutive threads -> consecutive features
+    for (int i = threadIdx.x; i < 16 * kF; i += blockDim.x) {
+      const int tt = i / kF, f = i - tt * kF;
+      const float r = rec[tt][f];
+      if (recon_out != nullptr) recon_out[n * kT * kF + (t0 + tt) * kF + f] = r;
+      const float d = r - cae_in(x, sn, st, sf, n, t0 + tt, f, mean, sd);
+      acc = fmaf(d, d, acc);
+    }
+  } else {          // time axis is the fast one (the reference's transposed view of [N,180,321] storage)
+    for (int i = threadIdx.x; i < 16 * kF; i += blockDim.x) {
+      const int f = i >> 4, tt = i & 15;
+      const float r = rec[tt][f];
+      if (recon_out != nullptr) recon_out[n * kT * kF + (t0 + tt) * kF + f] = r;
+      const float d = r - cae_in(x, sn, st, sf, n, t0 + tt, f, mean, sd);
+      acc = fmaf(d, d, acc);
+    }
+  }
+  if (split == 0) {
+    for (int f = threadIdx.x; f < kF; f += blockDim.x) {  // reconstruction row 320 is zero padding (model_cae.py:116-119)
+      if (recon_out != nullptr) recon_out[n * kT * kF + 320 * kF + f] = 0.0f;
+      const float d = cae_in(x, sn, st, sf, n, 320, f, mean, sd);
+      acc = fmaf(d, d, acc);
+    }
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -127,7 +161,15 @@ __global__ void __launch_bounds__(256) cae_final_tc_kernel(ActBuf d3, const floa
   if (threadIdx.x == 0 && mse_out != nullptr) {
     float s = 0.0f;
     for (int i = 0; i < 8; ++i) s += part[i];
-    mse_out[n] = s / (float)(kT * kF);
+    partial[n * kCaeFinalSplit + split] = s;
+    __threadfence();
+    if (atomicAdd(&done[n], 1u) == kCaeFinalSplit - 1) {   // last block of this utterance
+      __threadfence();
+      float tot = 0.0f;
+      for (int i = 0; i < kCaeFinalSplit; ++i) tot += __ldcg(&partial[n * kCaeFinalSplit + i]);
+      mse_out[n] = tot / (float)(kT * kF);
+      done[n] = 0u;
+    }
   }
 }
 
@@ -192,7 +234,10 @@ static ConvParams base_params(const CaeTcState* s, int li /*weights index 0..5*/
 int launch_cae_tc(const CaeTcState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const float* norm_mean, const float* norm_std,
                   float* mse_out, float* recon_out, float* latent_out, int stop_after_layer, int num_sms, cudaStream_t stream) {
   if (n_utts <= 0) return DFS_OK;
-  DFS_PROPAGATE(launch_conv1(x, sn, st, sf, n_utts, s->c1, norm_mean, norm_std, true, s->act[0], stream));
+  if (s->enc1_impl == 0)
+    DFS_PROPAGATE(launch_cae_enc1_tc(x, sn, st, sf, n_utts, norm_mean, norm_std, s->xt1, s->w1pack, s->b1q, s->act[0], kCaeCols[0], num_sms, stream));
+  else
+    DFS_PROPAGATE(launch_conv1(x, sn, st, sf, n_utts, s->c1, norm_mean, norm_std, true, s->act[0], stream));
   if (stop_after_layer == 0) return DFS_OK;
   DFS_PROPAGATE(launch_conv_tc<Enc2Cfg>(s->tmap[0], base_params(s, 0, 0, 1, n_utts, 90, 80, 45), 1, num_sms, stream));
   if (stop_after_layer == 1) return DFS_OK;
@@ -212,7 +257,11 @@ int launch_cae_tc(const CaeTcState* s, const float* x, int64_t sn, int64_t st, i
   DFS_PROPAGATE(launch_conv_tc<Dec3Cfg>(s->tmap[5], base_params(s, 5, 5, 6, n_utts, 45, 80, 90), 1, num_sms, stream));
   if (stop_after_layer == 6) return DFS_OK;
   if (mse_out != nullptr || recon_out != nullptr) {
-    cae_final_tc_kernel<<<n_utts, 256, 0, stream>>>(s->act[6], x, sn, st, sf, norm_mean, norm_std, s->w_final, s->final_bias, mse_out, recon_out);
+    CaeFinalW fw;
+    memcpy(fw.w, s->w_final_host, sizeof(fw.w));
+    fw.bias = s->final_bias;
+    cae_final_tc_kernel<<<dim3(n_utts, kCaeFinalSplit), 256, 0, stream>>>(s->act[6], x, sn, st, sf, norm_mean, norm_std, fw, mse_out, recon_out,
+                                                                         s->mse_partial, s->mse_done);
     DFS_LAUNCH_CHECK();
   }
   return DFS_OK;

@@ -48,7 +48,19 @@ struct CaeTcState {
   float bias[6][256];     // folded biases per output channel, pre-scaled like the weights
   const float* w_final;   // final ConvTranspose2d(32,1): [(a*2+b)*32 + ci] fp32 (device)
   float final_bias;
+  float w_final_host[128];// same weights on the host: passed to the fused final kernel as a kernel parameter (constant bank)
+  uint16_t* xt1;          // enc1 input image xT2 (cae_enc1_tc.cu), zero padded
+  const uint16_t* w1pack; // enc1 Toeplitz weights [kw][K chunk][n 256][8] fp16, 0.25 folded
+  float b1q[32];          // 0.25 * folded enc1 bias
+  int enc1_impl;          // 0 = tensor-core Toeplitz GEMM, 1 = fp32 CUDA-core conv1_kernel<POOLF> (cross-check)
+  float* mse_partial;     // [chunk][kCaeFinalSplit] partial squared-error sums of the fused final layer
+  unsigned int* mse_done; // [chunk] arrival counters (self-resetting)
 };
+constexpr int kCaeFinalSplit = 20;  // blocks per utterance in the fused final ConvT + MSE kernel: 8 of the 160 d3 rows each
+// ---- cae_enc1_tc.cu ----
+int64_t cae_enc1_xt_rows(int64_t n_utts);
+int launch_cae_enc1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const float* norm_mean, const float* norm_std, uint16_t* xt,
+                       const uint16_t* wpack, const float* bias_quarter, ActBuf out, int out_cols, int num_sms, cudaStream_t stream);
 void cae_tc_geometry(int layer, int* planes, int* cols, int* rs);
 int cae_tc_make_maps(CaeTcState* s);
 int cae_tc_init_constants(CaeTcState* s, int max_utts, const float* dec2_bias_dev, cudaStream_t stream);

@@ -44,3 +44,37 @@ def test_cae_mse_tensor_core_vs_oracle_and_crosscheck(setup):
     assert np.max(np.abs(simt - ref) / ref) <= 1e-5
     xt = x.transpose(1, 2).contiguous().transpose(1, 2)
     np.testing.assert_allclose(sc.score(xt).cpu().numpy(), tc, rtol=1e-6)
+
+
+def test_cae_enc1_tensor_core_vs_fp32_cuda_core_conv(setup):
+    """enc1 as the Toeplitz-in-time tcgen05 GEMM (cae_enc1_tc.cu) against the fp32 CUDA-core conv1_kernel<POOLF> writing the
+    same FT8P buffer (option conv1_impl = 1), on contiguous and on the reference's transposed storage, with and without
+    the normaliser; and the end-to-end MSE with either enc1."""
+    x, sc = setup
+    xt = x.transpose(1, 2).contiguous().transpose(1, 2)
+    for feats in (x, xt):
+        for norm in (True, False):
+            tc = sc.debug_layer(feats, 0, impl=0, apply_normalizer=norm).cpu().numpy()
+            sc.set_option("conv1_impl", 1)
+            ref = sc.debug_layer(feats, 0, impl=0, apply_normalizer=norm).cpu().numpy()
+            sc.set_option("conv1_impl", 0)
+            scale = np.abs(ref).max()
+            assert np.abs(tc - ref).max() <= 2e-3 * scale, (norm, np.abs(tc - ref).max(), scale)
+            assert (ref > 0).mean() > 0.2 and np.array_equal(tc == 0, ref == 0) or np.abs(tc - ref).max() <= 2e-3 * scale
+    a = sc.score(x).cpu().numpy()
+    sc.set_option("conv1_impl", 1)
+    b = sc.score(x).cpu().numpy()
+    sc.set_option("conv1_impl", 0)
+    assert np.max(np.abs(a - b) / b) <= 2e-4
+
+
+def test_cae_chunk_boundaries_and_ragged_tail():
+    """More utterances than one internal pass (chunk 8): every pass reuses the zero-padded xT2 / activation buffers."""
+    mean, std = syn.normalizer_stats(1)
+    x = torch.from_numpy(syn.features(19, seed=5)).cuda()
+    sc = CaeScorer(syn.cae_state(0), mean, std, max_chunk=8)
+    got = sc.score(x).cpu().numpy()
+    ref = onp.cae_mse_scores(syn.cae_state(0), x.cpu().numpy(), mean, std)
+    assert np.max(np.abs(got - ref) / ref) <= 1e-3
+    one = CaeScorer(syn.cae_state(0), mean, std, max_chunk=32).score(x).cpu().numpy()
+    np.testing.assert_array_equal(got, one)          # chunking must not change a single bit
