@@ -224,6 +224,11 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     if (m->cae != nullptr) m->cae->enc1_impl = (int)value;
     return DFS_OK;
   }
+  if (strcmp(key, "l1_fused") == 0) {
+    DFS_REQUIRE(m->c1d != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "l1_fused is a CNN1D option (0 | 1)");
+    m->c1d->l1_fused = (int)value;
+    return DFS_OK;
+  }
   if (strcmp(key, "profile") == 0) {
     m->profile = value != 0;
     m->prof_used = 0;
@@ -465,6 +470,7 @@ static int cnn1d_tc_create(dfs_model* m, const dfs_cnn1d_weights* w) {
   DFS_PROPAGATE(cnn1d_tc_make_maps(s));
   s->fcw = m->fcw_dev;
   s->fcb = m->fcb;
+  s->l1_fused = 1;
   DFS_CUDA_CHECK(cudaDeviceSynchronize());
   return DFS_OK;
 }

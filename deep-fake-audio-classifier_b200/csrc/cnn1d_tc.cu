@@ -9,7 +9,8 @@
 //   layer 2 K = 3 x 64 (upper 32 input channels are the zero ones), N = 64      EPI_RELU
 //   layer 3 K = 3 x 64, N = 128, time sum kept in registers over the 41 tiles   EPI_MEAN_T  -> [n][128] fp32
 //   head    logits = fc_b + sum_c fc_w[c] * sum[c] / 321   (+ sigmoid)
-// The arithmetic is ~31 MFLOP per utterance; the path is bound by the 231 KB/utterance fp32 input read.
+// The arithmetic is ~31 MFLOP per utterance; the path is bound by the 231 KB/utterance fp32 input read.  On dense
+// feature-contiguous input, prep + layer 1 are replaced by cnn1d_l1_fused.cu (fp32 -> fp16 conversion in flight).
 #include "conv_tc.cuh"
 
 namespace dfs {
@@ -90,10 +91,14 @@ static ConvParams c1d_params(const Cnn1dTcState* s, int layer, int n_utts) {
 int launch_cnn1d_tc(const Cnn1dTcState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, int apply_sigmoid, float* out, int num_sms,
                     cudaStream_t stream) {
   if (n_utts <= 0) return DFS_OK;
-  const long long total = (long long)n_utts * kT * 24;
-  cnn1d_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, s->act[0]);
-  DFS_LAUNCH_CHECK();
-  DFS_PROPAGATE(launch_conv_tc<C1dL1>(s->tmap[0], c1d_params(s, 0, n_utts), 1, num_sms, stream));
+  if (s->l1_fused && cnn1d_l1_fused_supported(x, sn, st, sf)) {
+    DFS_PROPAGATE(launch_cnn1d_l1_fused(x, sn, n_utts, s->w[0], s->bias[0], s->act[1], num_sms, stream));
+  } else {
+    const long long total = (long long)n_utts * kT * 24;
+    cnn1d_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, s->act[0]);
+    DFS_LAUNCH_CHECK();
+    DFS_PROPAGATE(launch_conv_tc<C1dL1>(s->tmap[0], c1d_params(s, 0, n_utts), 1, num_sms, stream));
+  }
   DFS_PROPAGATE(launch_conv_tc<C1dL2>(s->tmap[1], c1d_params(s, 1, n_utts), 1, num_sms, stream));
   DFS_PROPAGATE(launch_conv_tc<C1dL3>(s->tmap[2], c1d_params(s, 2, n_utts), 1, num_sms, stream));
   cnn1d_tc_head_kernel<<<(n_utts + 3) / 4, 128, 0, stream>>>(s->sums, s->fcw, s->fcb, n_utts, apply_sigmoid, out);

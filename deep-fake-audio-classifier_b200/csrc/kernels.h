@@ -78,7 +78,11 @@ struct Cnn1dTcState {
   float* sums;            // [n][128] time sums of the last layer
   const float* fcw;       // classifier weight (128) on the device
   float fcb;
+  int l1_fused;           // 1 (default) = layer 1 converts the fp32 rows in flight (cnn1d_l1_fused.cu) when the layout allows
 };
+// ---- cnn1d_l1_fused.cu ----
+bool cnn1d_l1_fused_supported(const float* x, int64_t sn, int64_t st, int64_t sf);
+int launch_cnn1d_l1_fused(const float* x, int64_t sn, int n_utts, const uint16_t* wpack, const float* bias, ActBuf out, int num_sms, cudaStream_t stream);
 void cnn1d_tc_geometry(int buf, int* planes, int* rs);
 int cnn1d_tc_make_maps(Cnn1dTcState* s);
 int launch_cnn1d_tc(const Cnn1dTcState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, int apply_sigmoid, float* out, int num_sms,

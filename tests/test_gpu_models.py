@@ -124,6 +124,25 @@ def test_cnn1d_matches_reference_golden(feats, impl):
     np.testing.assert_allclose(small.score(xt).cpu().numpy(), logits, rtol=1e-6, atol=1e-7)
 
 
+def test_cnn1d_fused_first_layer_equals_prep_plus_template_path():
+    """Layer 1 converting the fp32 rows in flight (cnn1d_l1_fused.cu) must give the very bits of the prep + TMA path:
+    same fp16 operands, same MMA order.  37 utterances through passes of 20 (ragged 16-utterance column tiles)."""
+    x = torch.from_numpy(syn.features(37, seed=31)).cuda()
+    sc = Cnn1dScorer(syn.cnn1d_state(0), max_chunk=20)
+    fused = sc.score(x).cpu().numpy()
+    sc.set_option("l1_fused", 0)
+    plain = sc.score(x).cpu().numpy()
+    sc.set_option("l1_fused", 1)
+    np.testing.assert_array_equal(fused, plain)
+    ref = onp.cnn1d_forward(syn.cnn1d_state(0), x.cpu().numpy())[:, 0]
+    np.testing.assert_allclose(fused, ref, atol=1e-3)
+    # a view that starts 4 bytes off a 16-byte boundary cannot use the fused loads: falls back, same result
+    buf = torch.zeros(37 * 321 * 180 + 1, device="cuda")
+    off = buf[1:].view(37, 321, 180)
+    off.copy_(x)
+    np.testing.assert_array_equal(sc.score(off).cpu().numpy(), fused)
+
+
 def test_cae_mse_matches_reference_golden(feats):
     mean, std = syn.normalizer_stats(1)
     sc = CaeScorer(syn.cae_state(0), mean, std, max_chunk=5)
