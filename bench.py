@@ -47,8 +47,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cnn2d", choices=["cnn2d", "cae", "hybrid", "eer"],
-                    help="cnn2d = the headline BASELINE configs[1]; cae / hybrid / eer = configs 3 / 4 / 5 (informational lines)")
+    ap.add_argument("--workload", default="cnn2d", choices=["cnn2d", "cae", "cnn1d", "hybrid", "eer"],
+                    help="cnn2d = the headline BASELINE configs[1]; cae / hybrid / eer = configs 3 / 4 / 5, cnn1d = the 1D-CNN alone "
+                         "(informational lines)")
     ap.add_argument("--eer-n", type=int, default=100_000_000)
     ap.add_argument("--eer-method", default="sort", choices=["sort", "select"],
                     help="eer workload: 'sort' = full stable radix sort + sweep (north_star wording; `value`), 'select' = radix select of "
@@ -196,6 +197,12 @@ def run_other_workload(args, rank, world, local):
 
             def step():
                 return D.eer_details(gather_scores(cae.score(pool), n_total=P * world), labels_global)
+        elif args.workload == "cnn1d":
+            metric = "utterances/sec 1D-CNN scoring [321x180] + EER"
+            c1 = D.Cnn1dScorer(syn.cnn1d_state(0), device=local, max_chunk=args.chunk)
+
+            def step():
+                return D.eer_details(gather_scores(c1.score(pool, apply_sigmoid=True), n_total=P * world), labels_global)
         else:
             metric = "utterances/sec hybrid scoring (2D-CNN + 1D-CNN + CAE-MSE, blend alpha=0.8) [321x180] + EER"
             c2 = D.Cnn2dScorer(syn.cnn2d_state(0), device=local, max_chunk=args.chunk)
@@ -257,6 +264,10 @@ def run_other_workload(args, rank, world, local):
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
                     "note": "13 B/score algorithmic (SURVEY.md 8d). sort: 4 LSD passes x (4 B count + 16 B scatter) + 13 B prep + 8 B sweep "
                             "~ 101 B/score; select: 5 B/score per varying key byte (<= 20 B/score fp32)"}
+        elif args.workload == "cnn1d":
+            ach = value / world * BYTES_PER_UTT / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                    "note": "231,120 B/utterance algorithmic (the fp32 input read, SURVEY.md 8d); layer 1 converts the rows in flight"}
         else:
             flop = FLOP_PER_UTT["cae"] if args.workload == "cae" else sum(FLOP_PER_UTT.values())
             ach = value / world * flop / 1e12

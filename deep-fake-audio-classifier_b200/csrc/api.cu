@@ -453,7 +453,7 @@ static int cnn1d_tc_create(dfs_model* m, const dfs_cnn1d_weights* w) {
   memset(s->bias, 0, sizeof(s->bias));
   std::vector<uint16_t> packs[3];
   packs[0] = pack_conv1d(w->conv[0], 32, kF, 64, 192, s->bias[0]);
-  packs[1] = pack_conv1d(w->conv[1], 64, 32, 64, 64, s->bias[1]);
+  packs[1] = pack_conv1d(w->conv[1], 64, 32, 64, 32, s->bias[1]);
   packs[2] = pack_conv1d(w->conv[2], 128, 64, 128, 64, s->bias[2]);
   for (int i = 0; i < 3; ++i) {
     uint16_t* d = nullptr;

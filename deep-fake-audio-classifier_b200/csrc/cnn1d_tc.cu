@@ -6,7 +6,7 @@
 // steps and the three taps are +0/+16/+32-byte shifts of the A descriptor.
 //   prep    fp32 strided features -> FT8 fp16, 24 planes (180 features zero-padded to 192)
 //   layer 1 K = 3 x 192, N = 64 (32 real output channels + 32 zero ones)      EPI_RELU
-//   layer 2 K = 3 x 64 (upper 32 input channels are the zero ones), N = 64      EPI_RELU
+//   layer 2 K = 3 x 32 (the 32 real channels = planes 0..3 of the layer-1 buffer), N = 64   EPI_RELU
 //   layer 3 K = 3 x 64, N = 128, time sum kept in registers over the 41 tiles   EPI_MEAN_T  -> [n][128] fp32
 //   head    logits = fc_b + sum_c fc_w[c] * sum[c] / 321   (+ sigmoid)
 // The arithmetic is ~31 MFLOP per utterance; the path is bound by the 231 KB/utterance fp32 input read.  On dense
@@ -18,7 +18,7 @@ namespace dfs {
 constexpr int kC1dRows = 328;   // 321 time steps padded to a multiple of 8
 constexpr int kC1dRS = 330;
 using C1dL1 = ConvCfg<MODE_3X1, 192, 64, 64, kC1dRows, 1, 2, 4, 1, EPI_RELU>;
-using C1dL2 = ConvCfg<MODE_3X1, 64, 64, 64, kC1dRows, 1, 3, 4, 1, EPI_RELU>;
+using C1dL2 = ConvCfg<MODE_3X1, 32, 64, 64, kC1dRows, 1, 3, 4, 1, EPI_RELU>;   // reads planes 0..3 of the layer-1 buffer only
 using C1dL3 = ConvCfg<MODE_3X1, 64, 128, 128, kC1dRows, 1, 3, 4, 1, EPI_MEAN_T>;
 
 void cnn1d_tc_geometry(int buf, int* planes, int* rs) {

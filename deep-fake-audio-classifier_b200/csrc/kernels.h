@@ -73,7 +73,7 @@ int launch_cae_tc(const CaeTcState* s, const float* x, int64_t sn, int64_t st, i
 struct Cnn1dTcState {
   ActBuf act[3];          // fp16 input copy (24 planes), layer-1 output, layer-2 output (8 planes each)
   CUtensorMap tmap[3];
-  const uint16_t* w[3];   // packed fp16 weights [tap][ci/8][co][8] (channel counts zero-padded to 192/64, 64/64, 64/128)
+  const uint16_t* w[3];   // packed fp16 weights [tap][ci/8][co][8] (channel counts zero-padded to 192/64, 32/64, 64/128)
   float bias[3][128];
   float* sums;            // [n][128] time sums of the last layer
   const float* fcw;       // classifier weight (128) on the device
