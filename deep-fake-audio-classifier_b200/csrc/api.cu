@@ -224,6 +224,11 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     if (m->cae != nullptr) m->cae->enc1_impl = (int)value;
     return DFS_OK;
   }
+  if (strcmp(key, "final_fused") == 0) {
+    DFS_REQUIRE(m->cae != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "final_fused is a CAE option (0 | 1)");
+    m->cae->final_fused = (int)value;
+    return DFS_OK;
+  }
   if (strcmp(key, "l1_fused") == 0) {
     DFS_REQUIRE(m->c1d != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "l1_fused is a CNN1D option (0 | 1)");
     m->c1d->l1_fused = (int)value;
@@ -596,6 +601,7 @@ static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
     s->w1pack = d;
     DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&s->xt1), (size_t)cae_enc1_xt_rows(m->chunk) * 16, true));
     s->enc1_impl = 0;
+    s->final_fused = 1;
   }
   std::vector<uint16_t> packs[6];
   packs[0] = pack_pair(w->enc[1], 64, 32, 0.25, s->bias[0]);             // enc2: 2x2 average folded (4 ReLU outputs are summed)

@@ -11,8 +11,10 @@
 //   dec1   256 x 20 x 11       1x1 GEMM   4 quadrant groups of N=128, K=256          d1 FT8  (16, 24,  42)
 //   dec2   128 x 40 x 22       1x1 GEMM   2 groups (a) of N=(b,64), K=128            d2 FT8  ( 8, 48,  82)   col 45 = relu(bias)
 //   dec3   64 x 80 x 45        1x1 GEMM   N=(a,b,32), K=64                           d3 FT8  ( 4, 92, 162)
-//   final  32 x 160 x 90       CUDA cores: 4 outputs x 32 MACs per position, residual vs the (normalised) input,
-//                              zero row 320, per-utterance mean -- the reconstruction is never written.
+//   final  32 x 160 x 90       fused into dec3's epilogue on the scoring path (EPI_SHUFFLE_MSE: 4 outputs x 32 MACs per d3 vector,
+//                              residual vs the (normalised) input, one partial sum per 16-column unit; neither d3 nor the
+//                              reconstruction is written) + cae_mse_finish_kernel (zero row 320, per-utterance mean).
+//                              cae_final_tc_kernel (reads d3) serves forward()'s materialised reconstruction and the cross-check.
 // AvgPool2d(2) floors: enc1 drops input row 320, enc3 drops feature column 44 (out_feats = 22); dec2's
 // output_padding column receives the bias only (constant, written once at handle creation).
 #include <string.h>
@@ -27,6 +29,7 @@ using Enc4Cfg = ConvCfg<MODE_3X3, 128, 64, 64, 40, 1, 3, 4, 2, EPI_POOL_TF>;
 using Dec1Cfg = ConvCfg<MODE_1X1, 256, 128, 128, 24, 1, 3, 2, 4, EPI_SHUFFLE>;
 using Dec2Cfg = ConvCfg<MODE_1X1, 128, 64, 128, 40, 1, 3, 2, 2, EPI_SHUFFLE>;
 using Dec3Cfg = ConvCfg<MODE_1X1, 64, 32, 128, 80, 2, 3, 4, 1, EPI_SHUFFLE>;
+using Dec3MseCfg = ConvCfg<MODE_1X1, 64, 32, 128, 80, 2, 3, 4, 1, EPI_SHUFFLE_MSE>;   // dec3 + final ConvT + squared error, nothing written but partial sums
 
 // geometry of the seven activation buffers: planes, padded cols per utterance, rows per column
 static const int kCaePlanes[7] = {8, 8, 16, 32, 16, 8, 4};
@@ -173,6 +176,24 @@ __global__ void __launch_bounds__(256, 4) cae_final_tc_kernel(ActBuf d3, const f
   }
 }
 
+// scores of the fused dec3 + final path: an utterance is exactly three 16-column units of the d2 layout (48 columns), so
+// mse = (partial[3n] + partial[3n+1] + partial[3n+2] + sum_f x_norm[320][f]^2) / (321 * 180); the last term is the
+// reconstruction's zero-padded row 320 (model_cae.py:116-119).  One warp per utterance, fixed summation order.
+__global__ void __launch_bounds__(128) cae_mse_finish_kernel(const float* __restrict__ partial, const float* __restrict__ x, long long sn, long long st,
+                                                              long long sf, const float* __restrict__ mean, const float* __restrict__ sd, int n_utts,
+                                                              float* __restrict__ mse_out) {
+  const int n = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= n_utts) return;
+  float acc = 0.0f;
+  for (int f = lane; f < kF; f += 32) {
+    const float d = cae_in(x, sn, st, sf, n, 320, f, mean, sd);
+    acc = fmaf(d, d, acc);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) mse_out[n] = (((partial[3 * n] + partial[3 * n + 1]) + partial[3 * n + 2]) + acc) / (float)(kT * kF);
+}
+
 // FT8 / FT8P -> [n][H][W][C] fp32 (H = time, W = feature): latent export and the per-layer debug dump
 __global__ void ft8_unpack_kernel(ActBuf a, int cols, int parity_layout, int H, int W, int C, long long total, float* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,6 +275,24 @@ int launch_cae_tc(const CaeTcState* s, const float* x, int64_t sn, int64_t st, i
   if (stop_after_layer == 4) return DFS_OK;
   DFS_PROPAGATE(launch_conv_tc<Dec2Cfg>(s->tmap[4], base_params(s, 4, 4, 5, n_utts, 22, 40, 44), 2, num_sms, stream));
   if (stop_after_layer == 5) return DFS_OK;
+  if (s->final_fused && stop_after_layer == 7 && mse_out != nullptr && recon_out == nullptr) {
+    // scoring path: dec3's epilogue applies the final layer and accumulates the squared error; d3 never reaches HBM
+    ConvParams p = base_params(s, 5, 5, 6, n_utts, 45, 80, 90);
+    for (int k = 0; k < 128; ++k) p.bias[32 + k] = s->w_final_host[k];
+    p.bias[160] = s->final_bias;
+    p.x = x;
+    p.xsn = sn;
+    p.xst = st;
+    p.xsf = sf;
+    p.norm_mean = norm_mean;
+    p.norm_sd = norm_std;
+    p.partial = s->mse_partial;
+    p.x_vec4 = (sf == 1 && (st % 4) == 0 && (sn % 4) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0) ? 1 : 0;
+    DFS_PROPAGATE(launch_conv_tc<Dec3MseCfg>(s->tmap[5], p, 1, num_sms, stream));
+    cae_mse_finish_kernel<<<(n_utts + 3) / 4, 128, 0, stream>>>(s->mse_partial, x, sn, st, sf, norm_mean, norm_std, n_utts, mse_out);
+    DFS_LAUNCH_CHECK();
+    return DFS_OK;
+  }
   DFS_PROPAGATE(launch_conv_tc<Dec3Cfg>(s->tmap[5], base_params(s, 5, 5, 6, n_utts, 45, 80, 90), 1, num_sms, stream));
   if (stop_after_layer == 6) return DFS_OK;
   if (mse_out != nullptr || recon_out != nullptr) {

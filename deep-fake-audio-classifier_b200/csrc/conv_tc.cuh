@@ -44,7 +44,9 @@ enum {
   EPI_POOL_TF = 3,      // 3x3 : relu, 2x2 pool with lane^1 (time) and lane^8 (feature), store FT8    (CAE enc3, enc4)
   EPI_SHUFFLE = 4,      // 1x1 : relu, pixel-shuffle store of the quadrant(s) held in the columns      (CAE dec1-3)
   EPI_RELU = 5,         // any : relu, store FT8 at the same position                                   (CNN1D layers 1, 2)
-  EPI_MEAN_T_SWAP = 6   // 3x3S: lanes = output channels, columns = positions; relu, time sum in-thread   (CNN2D conv3)
+  EPI_MEAN_T_SWAP = 6,  // 3x3S: lanes = output channels, columns = positions; relu, time sum in-thread   (CNN2D conv3)
+  EPI_SHUFFLE_MSE = 7   // 1x1 : CAE dec3 with the final ConvTranspose2d(32,1) and the squared error against the input fused in:
+                        //        neither d3 nor the reconstruction is written; one partial sum per 16-column unit   (CAE dec3+final)
 };
 
 template <int MODE_, int CIN_, int COUT_, int NG_, int ROWS_, int MT_, int NSTAGE_, int NACC_, int KSPLIT_, int EPI_>
@@ -122,6 +124,14 @@ struct ConvParams {
   int out_feats;          // valid output feature columns (pooled outputs beyond are dropped)
   // EPI_MEAN_T: per-utterance time SUMS, [n][F][COUT] fp32 (the head applies 1/T)
   float* emb;
+  // EPI_SHUFFLE_MSE: the scorer's input (element (n,t,f) at x[n*xsn + t*xst + f*xsf]), the optional normaliser and the
+  // per-unit partial sums; the final layer's weights ride in bias[32..159] ([(a*2+b)*32 + ci]) and its bias in bias[160]
+  const float* x;
+  long long xsn, xst, xsf;
+  const float* norm_mean;
+  const float* norm_sd;
+  float* partial;
+  int x_vec4;             // 1 = x rows are 16-byte aligned with the feature axis contiguous: float4 loads
 };
 
 // ---- epilogue helpers -----------------------------------------------------------------------------
@@ -251,6 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int i = r & 7;              // row within the tile
     const float* bias = p.bias;  // param space: uniform constant-bank reads
     uint32_t it = 0;
+    [[maybe_unused]] uint32_t unit_seq = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int gc = 1 + Cfg::CT * u + g;
       // padded layouts: column gc = n*cols + f' (f' = 0 and cols-1 are zero pads); cols == 1: one column per utterance at gc = 1 + n
@@ -475,6 +486,86 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             store_chunks<HC / 8>(dst, plane_elems, pk);
           }
         }
+      } else if constexpr (Cfg::EPI == EPI_SHUFFLE_MSE) {
+        // dec3 (k=2,s=2 transposed conv as a 1x1 GEMM with N = (a, b, 32 channels)) + final ConvTranspose2d(32,1,k2,s2) +
+        // per-utterance squared error.  This thread holds, for input position (tp, fp), the d3 vectors at
+        // (2(tp-1)+h, 2(fp-1)+b), b = 0, 1; each expands to a 2x2 patch of the reconstruction, together the pixels
+        // t = 4(tp-1)+2h+{0,1}, f = 4(fp-1)+{0..3}: two runs of four contiguous input samples.  d3 is rounded to fp16
+        // exactly as the unfused path stores it, so both paths see the same reconstruction.
+        static_assert(Cfg::EPI != EPI_SHUFFLE_MSE || (COUT == 32 && NG == 128 && Cfg::MODE == MODE_1X1 && Cfg::BAR_B >= 224), "dec3 shape");
+        float acc_se = 0.0f;
+        const float fb = bias[160];
+        for (int tt = 0; tt < Cfg::TILES; ++tt, ++it) {
+          const int acc = it % NACC;
+          mbar_wait(&tfull[acc], (it / NACC) & 1, 5);
+          tc_fence_after();
+          float v[64];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * 64, v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * 64 + 32, v + 32);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          const int tp = 1 + 8 * tt + i;
+          if (colvalid && tp <= p.rows_valid) {
+            float rec[2][4];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              float d[32];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) d[c] = __half2float(__float2half_rn(fminf(fmaxf(v[b * 32 + c] + bias[c], 0.0f), 65504.0f)));
+#pragma unroll
+              for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) {
+                  float r = fb;
+#pragma unroll
+                  for (int c = 0; c < 32; ++c) r = fmaf(d[c], bias[32 + (a2 * 2 + b2) * 32 + c], r);
+                  rec[a2][2 * b + b2] = r;
+                }
+            }
+            const int t0 = 4 * (tp - 1) + 2 * h, f0 = 4 * (fp - 1);
+            float mu[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {1.f, 1.f, 1.f, 1.f};
+            if (p.norm_mean != nullptr) {
+              const float4 m4 = *reinterpret_cast<const float4*>(p.norm_mean + f0), s4 = *reinterpret_cast<const float4*>(p.norm_sd + f0);
+              mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
+              sg[0] = s4.x; sg[1] = s4.y; sg[2] = s4.z; sg[3] = s4.w;
+            }
+#pragma unroll
+            for (int a2 = 0; a2 < 2; ++a2) {
+              const float* xr = p.x + (long long)n * p.xsn + (long long)(t0 + a2) * p.xst + (long long)f0 * p.xsf;
+              float xv[4];
+              if (p.x_vec4) {
+                const float4 q4 = __ldg(reinterpret_cast<const float4*>(xr));
+                xv[0] = q4.x; xv[1] = q4.y; xv[2] = q4.z; xv[3] = q4.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) xv[e] = __ldg(xr + (long long)e * p.xsf);
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float xn = xv[e];
+                if (p.norm_mean != nullptr) xn = (xn - mu[e]) / sg[e];
+                const float df = rec[a2][e] - xn;
+                acc_se = fmaf(df, df, acc_se);
+              }
+            }
+          }
+        }
+        // one partial per unit: lanes -> warp (xor shuffles), 8 warps -> two alternating slot sets in the barrier page,
+        // summed in warp order by warp 0 (fixed order: the score does not depend on scheduling)
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) acc_se += __shfl_xor_sync(0xffffffffu, acc_se, o);
+        float* slots = reinterpret_cast<float*>(smem + Cfg::WGT_B_AL + NSTAGE * Cfg::WIN_B_AL + 160) + 8 * (unit_seq & 1);
+        if (lane == 0) slots[warp] = acc_se;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (warp == 0 && lane == 0) {
+          float tot = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) tot += slots[k];
+          p.partial[u] = tot;
+        }
+        ++unit_seq;
       } else {
         // EPI_SHUFFLE: columns = (sub-quadrant, COUT); group index and column block give the 2x2 output offset (a, b):
         //   quadrant id = grp * (NG / COUT) + column block, a = qid >> 1, b = qid & 1.

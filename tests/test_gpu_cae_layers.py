@@ -78,3 +78,24 @@ def test_cae_chunk_boundaries_and_ragged_tail():
     assert np.max(np.abs(got - ref) / ref) <= 1e-3
     one = CaeScorer(syn.cae_state(0), mean, std, max_chunk=32).score(x).cpu().numpy()
     np.testing.assert_array_equal(got, one)          # chunking must not change a single bit
+
+
+def test_cae_fused_final_layer_equals_separate_final_kernel():
+    """dec3's epilogue applying the final ConvTranspose2d + squared error (no d3, no reconstruction in HBM) against the
+    separate final kernel reading d3: same fp16-rounded d3, same FMA order for the reconstruction, only the order of the
+    57,780-term sum differs.  Contiguous and transposed storage, with and without the normaliser, ragged passes."""
+    mean, std = syn.normalizer_stats(1)
+    x = torch.from_numpy(syn.features(11, seed=13)).cuda()
+    xt = x.transpose(1, 2).contiguous().transpose(1, 2)
+    for scorer in (CaeScorer(syn.cae_state(0), mean, std, max_chunk=4), CaeScorer(syn.cae_state(2), None, None, max_chunk=16)):
+        for feats in (x, xt):
+            fused = scorer.score(feats).cpu().numpy()
+            scorer.set_option("final_fused", 0)
+            plain = scorer.score(feats).cpu().numpy()
+            scorer.set_option("final_fused", 1)
+            assert np.max(np.abs(fused - plain) / plain) <= 2e-6
+            again = scorer.score(feats).cpu().numpy()
+            np.testing.assert_array_equal(fused, again)      # deterministic
+    ref = onp.cae_mse_scores(syn.cae_state(0), x.cpu().numpy(), mean, std)
+    got = CaeScorer(syn.cae_state(0), mean, std).score(x).cpu().numpy()
+    assert np.max(np.abs(got - ref) / ref) <= 1e-3
