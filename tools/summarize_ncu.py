@@ -21,45 +21,63 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_active.avg", "sm__pipe_tensor_cycl
         "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]
 
 
+KEYS += ["dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.avg.per_cycle_elapsed",
+         "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "lts__t_sector_hit_rate.pct"]
+
+LISTS = (("launches.csv", "launch_share", "bench.py (2D-CNN headline workload)"),
+         ("launches_hybrid.csv", "hybrid_launch_share", "bench.py --workload hybrid (2D-CNN + 1D-CNN + CAE-MSE + blend + EER)"),
+         ("launches_cae.csv", "cae_launch_share", "bench.py --workload cae"),
+         ("eer_launches.csv", "eer_launch_share", "bench.py --workload eer (100 M scores: sort path, then select path)"))
+REPORTS = (("prof_conv.ncu-rep", "conv_kernels_ncu_full", "2D-CNN conv kernels"),
+           ("prof_hybrid.ncu-rep", "hybrid_kernels_ncu_full", "CAE enc1 / final and 1D-CNN fused layer 1"),
+           ("prof_eer.ncu-rep", "eer_kernels_ncu_full", "EER: select histogram, radix count and scatter passes"))
+
+
 def launch_share(tag):
-    path = os.path.join(GP, "launches.csv")
-    if not os.path.exists(path):
-        return
-    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
-    hdr = rows[0]
-    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-    tot, cnt = collections.defaultdict(float), collections.Counter()
-    for r in rows[1:]:
-        try:
-            v = float(r[vi].replace(",", ""))
-        except ValueError:
+    for fname, suffix, what in LISTS:
+        path = os.path.join(GP, fname)
+        if not os.path.exists(path):
             continue
-        v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v
-        name = re.sub(r"\(.*", "", r[ki])[:100]
-        tot[name] += v
-        cnt[name] += 1
-    s = sum(tot.values())
-    with open(os.path.join(OUT, f"{tag}_launch_share.txt"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
-        f.write(f"# total {s:.1f} us over {sum(cnt.values())} profiled launches\n")
-        for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
-            f.write(f"{v / s * 100:6.2f}%  {v:10.1f} us  n={cnt[k]:4d}  avg {v / cnt[k]:8.1f} us  {k}\n")
+        rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+        hdr = rows[0]
+        ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        tot, cnt = collections.defaultdict(float), collections.Counter()
+        for r in rows[1:]:
+            try:
+                v = float(r[vi].replace(",", ""))
+            except ValueError:
+                continue
+            v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v
+            name = re.sub(r"\(.*", "", r[ki])[:100]
+            tot[name] += v
+            cnt[name] += 1
+        s = sum(tot.values())
+        with open(os.path.join(OUT, f"{tag}_{suffix}.txt"), "w") as f:
+            f.write(f"# {what}\n")
+            f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
+            f.write(f"# total {s:.1f} us over {sum(cnt.values())} profiled launches\n")
+            for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
+                f.write(f"{v / s * 100:6.2f}%  {v:10.1f} us  n={cnt[k]:4d}  avg {v / cnt[k]:8.1f} us  {k}\n")
 
 
 def full_set(tag):
-    rep = os.path.join(GP, "prof_conv.ncu-rep")
-    if not os.path.exists(rep):
-        return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    with open(os.path.join(OUT, f"{tag}_conv_kernels_ncu_full.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc (one launch of each conv kernel)\n")
-        for r in rows[2:]:
-            f.write(f"\n== {r[hdr.index('Kernel Name')]}\n")
-            for i, h in enumerate(hdr):
-                if any(h.endswith(k) for k in KEYS) and r[i] not in ("",):
-                    f.write(f"  {h:95s} {units[i]:16s} {r[i]}\n")
+    for fname, suffix, what in REPORTS:
+        rep = os.path.join(GP, fname)
+        if not os.path.exists(rep):
+            continue
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        with open(os.path.join(OUT, f"{tag}_{suffix}.txt"), "w") as f:
+            f.write(f"# ncu --set full --clock-control none --import-source on: {what} (one launch each)\n")
+            for r in rows[2:]:
+                f.write(f"\n== {r[hdr.index('Kernel Name')]}\n")
+                for i, h in enumerate(hdr):
+                    if any(h.endswith(k) for k in KEYS) and r[i] not in ("",):
+                        f.write(f"  {h:95s} {units[i]:16s} {r[i]}\n")
 
 
 if __name__ == "__main__":
@@ -67,4 +85,4 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     launch_share(tag)
     full_set(tag)
-    print(os.listdir(OUT))
+    print(sorted(os.listdir(OUT)))
