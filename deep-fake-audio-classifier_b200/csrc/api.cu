@@ -35,7 +35,7 @@ extern "C" int64_t dfs_launch_count(void) { return (int64_t)g_launches.load(); }
 // ------------------------------------------------------------------------------------------
 // model handle
 // ------------------------------------------------------------------------------------------
-enum { KIND_CNN2D = 0, KIND_CNN1D = 1, KIND_CAE = 2 };
+enum { KIND_CNN2D = 0, KIND_CNN1D = 1, KIND_CAE = 2, KIND_DLQ = 3 };
 
 struct dfs_model {
   int kind = -1;
@@ -64,6 +64,7 @@ struct dfs_model {
   // ---- CAE / 1D-CNN on the tcgen05 template (cae_tc.cu, cnn1d_tc.cu) ----
   CaeTcState* cae = nullptr;
   Cnn1dTcState* c1d = nullptr;
+  DlqState* dlq = nullptr;
   // ---- CNN1D / CAE (CUDA-core path; for the CAE it is the conv_impl = 1 cross-check) ----
   SimtConv sc[8];
   float* work = nullptr;
@@ -202,6 +203,7 @@ extern "C" int dfs_model_destroy(dfs_model* m) {
   for (void* p : m->allocs) cudaFree(p);
   delete m->cae;
   delete m->c1d;
+  delete m->dlq;
   for (int b = 0; b < 2; ++b) {
     if (m->ev_in[b]) cudaEventDestroy(m->ev_in[b]);
     if (m->ev_done[b]) cudaEventDestroy(m->ev_done[b]);
@@ -521,6 +523,94 @@ extern "C" int dfs_cnn1d_score(dfs_model* m, const dfs_features* feats, float* o
     else
       DFS_PROPAGATE(launch_cnn1d_simt(feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->sc, m->fcw_dev,
                                       m->fcb, apply_sigmoid, m->work, out_dev + i0, stream));
+  }
+  return DFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// StatsPool detector (src/dlqueen_model.py:132-173)
+// ------------------------------------------------------------------------------------------
+// Conv1d (Co,Ci,K) -> [group][tap][ci_pad/8][64][8], output channels in groups of 64, BN folded
+static std::vector<uint16_t> pack_conv1d_groups(const dfs_conv_bn& c, int co, int ci, int ci_pad, int ktaps, float* bias_out) {
+  std::vector<double> scale, shift;
+  bn_fold(c, co, scale, shift);
+  for (int o = 0; o < co; ++o) bias_out[o] = (float)shift[o];
+  std::vector<uint16_t> out((size_t)ktaps * ci_pad * co, 0);
+  for (int o = 0; o < co; ++o)
+    for (int i = 0; i < ci; ++i)
+      for (int k = 0; k < ktaps; ++k) {
+        const double w = (double)c.weight[((size_t)o * ci + i) * ktaps + k] * scale[o];
+        const size_t g = o / 64, ol = o % 64;
+        out[((((size_t)g * ktaps + k) * (ci_pad / 8) + (i >> 3)) * 64 + ol) * 8 + (i & 7)] = f32_to_act_bits((float)w);
+      }
+  return out;
+}
+
+extern "C" int dfs_dlq_create(dfs_model** out, int device, const dfs_dlq_weights* w, int max_chunk) {
+  DFS_REQUIRE(out && w, DFS_ERR_INVALID, "dfs_dlq_create: NULL argument");
+  *out = nullptr;
+  DFS_REQUIRE(w->in_ch == kF && w->hidden == 256, DFS_ERR_UNSUPPORTED, "StatsPool detector kernels are built for in_ch=180, hidden=256 (got %d, %d)",
+              w->in_ch, w->hidden);
+  for (int i = 0; i < 3; ++i) DFS_REQUIRE(conv_ok(w->conv[i], true), DFS_ERR_INVALID, "dfs_dlq_create: conv[%d] has NULL tensors", i);
+  DFS_REQUIRE(w->fc1_weight && w->fc1_bias && w->fc2_weight && w->fc2_bias, DFS_ERR_INVALID, "dfs_dlq_create: head tensors are NULL");
+  dfs_model* m = new (std::nothrow) dfs_model();
+  DFS_REQUIRE(m, DFS_ERR_NOMEM, "out of host memory");
+  m->kind = KIND_DLQ;
+  int st = model_common_init(m, device);
+  if (st != DFS_OK) { delete m; return st; }
+  // 4 output-channel groups share the SMs: 1184 utterances = 74 column tiles = 2 per CTA at 37 CTAs per group
+  m->chunk = max_chunk > 0 ? max_chunk : 1184;
+  auto fail = [&](int s) { dfs_model_destroy(m); return s; };
+  DlqState* s = new (std::nothrow) DlqState();
+  if (!s) return fail(DFS_ERR_NOMEM);
+  m->dlq = s;
+  memset(s->bias, 0, sizeof(s->bias));
+  std::vector<uint16_t> packs[3];
+  packs[0] = pack_conv1d_groups(w->conv[0], 256, kF, 192, 5, s->bias[0]);
+  packs[1] = pack_conv1d_groups(w->conv[1], 256, 256, 256, 3, s->bias[1]);
+  packs[2] = pack_conv1d_groups(w->conv[2], 256, 256, 256, 3, s->bias[2]);
+  for (int i = 0; i < 3; ++i) {
+    uint16_t* d = nullptr;
+    if ((st = dev_upload(m, &d, packs[i])) != DFS_OK) return fail(st);
+    s->w[i] = d;
+  }
+  std::vector<float> w1t((size_t)512 * 256), b1(w->fc1_bias, w->fc1_bias + 256), w2(w->fc2_weight, w->fc2_weight + 256);
+  for (int j = 0; j < 256; ++j)
+    for (int k = 0; k < 512; ++k) w1t[(size_t)k * 256 + j] = w->fc1_weight[(size_t)j * 512 + k];
+  float *d1 = nullptr, *d2 = nullptr, *d3 = nullptr;
+  if ((st = dev_upload(m, &d1, w1t)) != DFS_OK) return fail(st);
+  if ((st = dev_upload(m, &d2, b1)) != DFS_OK) return fail(st);
+  if ((st = dev_upload(m, &d3, w2)) != DFS_OK) return fail(st);
+  s->fc1_wt = d1;
+  s->fc1_b = d2;
+  s->fc2_w = d3;
+  s->fc2_b = w->fc2_bias[0];
+  ActBuf* bufs[3] = {&s->act0, &s->actA, &s->actB};
+  for (int b = 0; b < 3; ++b) {
+    int planes, rs;
+    dlq_geometry(b, &planes, &rs);
+    *bufs[b] = ActBuf{nullptr, planes, rs, (int64_t)m->chunk + 1 + 32};
+    if ((st = dev_alloc(m, reinterpret_cast<void**>(&bufs[b]->ptr), bufs[b]->bytes(), true)) != DFS_OK) return fail(st);
+  }
+  if ((st = dlq_make_maps(s)) != DFS_OK) return fail(st);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    dfs_set_error("dfs_dlq_create: device synchronize failed");
+    return fail(DFS_ERR_CUDA);
+  }
+  *out = m;
+  return DFS_OK;
+}
+
+extern "C" int dfs_dlq_score(dfs_model* m, const dfs_features* feats, const int32_t* lengths_dev, float* out_dev, int apply_sigmoid, void* stream_) {
+  DFS_REQUIRE(m && m->kind == KIND_DLQ, DFS_ERR_INVALID, "dfs_dlq_score: not a StatsPool-detector handle");
+  DFS_PROPAGATE(check_feats(feats, "dfs_dlq_score"));
+  DFS_REQUIRE(feats->n == 0 || out_dev, DFS_ERR_INVALID, "dfs_dlq_score: out_dev is NULL");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DFS_CUDA_CHECK(cudaSetDevice(m->device));
+  for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk) {
+    const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
+    DFS_PROPAGATE(launch_dlq(m->dlq, feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk,
+                             lengths_dev ? lengths_dev + i0 : nullptr, apply_sigmoid, out_dev + i0, m->num_sms, stream));
   }
   return DFS_OK;
 }

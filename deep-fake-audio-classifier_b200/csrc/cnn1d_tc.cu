@@ -106,4 +106,99 @@ int launch_cnn1d_tc(const Cnn1dTcState* s, const float* x, int64_t sn, int64_t s
   return DFS_OK;
 }
 
+// ==========================================================================================================
+// StatsPool detector: /root/reference/src/dlqueen_model.py:115-173  (DeepfakeDetector, eval mode)
+//   ConvEncoder  Conv1d(180,256,k5,p2)+BN+GELU -> Conv1d(256,256,k3,p1)+BN+GELU -> Conv1d(256,256,k3,p1)+BN+GELU
+//   StatsPool    masked mean and std over time (two passes, var clamped at 1e-6)           -> (B, 512)
+//   head         Linear(512,256) + GELU + Linear(256,1)
+// The conv layers are the conv1d template with 4 output-channel groups of N = 64 (the 256-wide weights of one layer are
+// 295-480 KB, one group 98-123 KB), K pieces of 8 channel planes, exact (erf) GELU in the epilogue.  Same input copy as
+// the 1D-CNN (cnn1d_prep_kernel); the k = 5 halo rows beyond the stored pad row are the TMA's out-of-bounds zeros.
+// Pooling + head are one block per utterance (256 threads = 256 channels / hidden units), fp32, fixed order.
+using DlqL1 = ConvCfg<MODE_5X1, 192, 64, 64, kC1dRows, 1, 3, 4, 3, EPI_GELU>;
+using DlqL2 = ConvCfg<MODE_3X1, 256, 64, 64, kC1dRows, 1, 3, 4, 4, EPI_GELU>;
+
+void dlq_geometry(int buf, int* planes, int* rs) {
+  *planes = buf == 0 ? 24 : 32;
+  *rs = kC1dRS;
+}
+
+int dlq_make_maps(DlqState* s) {
+  DFS_PROPAGATE(make_act_tensor_map(&s->tmap[0], s->act0, DlqL1::WROWS, DlqL1::WCOLS, DlqL1::PPL));
+  DFS_PROPAGATE(make_act_tensor_map(&s->tmap[1], s->actA, DlqL2::WROWS, DlqL2::WCOLS, DlqL2::PPL));
+  DFS_PROPAGATE(make_act_tensor_map(&s->tmap[2], s->actB, DlqL2::WROWS, DlqL2::WCOLS, DlqL2::PPL));
+  return DFS_OK;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// one block per utterance, thread c = encoder channel c / hidden unit c
+__global__ void __launch_bounds__(256) dlq_stats_head_kernel(ActBuf h, const int32_t* __restrict__ lengths, const float* __restrict__ w1t /*[512][256]*/,
+                                                              const float* __restrict__ b1, const float* __restrict__ w2, float b2, int apply_sigmoid,
+                                                              float* __restrict__ out) {
+  const int n = blockIdx.x, c = threadIdx.x;
+  int len = lengths != nullptr ? lengths[n] : kT;
+  len = len < 0 ? 0 : (len > kT ? kT : len);
+  const uint16_t* col = h.ptr + (long long)(c >> 3) * h.plane_elems() + ((long long)(n + 1) * h.RS + 1) * 8 + (c & 7);
+  const float denom = fmaxf((float)len, 1.0f);                      // mask.sum(dim=2).clamp(min=1.0)
+  float s = 0.0f;
+  for (int t = 0; t < len; ++t) s += act_bits_to_float(col[(long long)t * 8]);
+  const float mean = s / denom;
+  float v = 0.0f;
+  for (int t = 0; t < len; ++t) {
+    const float d = act_bits_to_float(col[(long long)t * 8]) - mean;
+    v = fmaf(d, d, v);
+  }
+  const float sd = sqrtf(fmaxf(v / denom, 1e-6f));                  // torch.sqrt(var.clamp(min=1e-6))
+  __shared__ float z[512];
+  __shared__ float part[8];
+  z[c] = mean;
+  z[256 + c] = sd;
+  __syncthreads();
+  float a = b1[c];
+#pragma unroll 8
+  for (int k = 0; k < 512; ++k) a = fmaf(w1t[k * 256 + c], z[k], a);
+  float contrib = gelu_erf(a) * w2[c];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+  if ((c & 31) == 0) part[c >> 5] = contrib;
+  __syncthreads();
+  if (c == 0) {
+    float zl = b2;
+    for (int k = 0; k < 8; ++k) zl += part[k];
+    out[n] = apply_sigmoid ? 1.0f / (1.0f + expf(-zl)) : zl;
+  }
+}
+
+static ConvParams dlq_params(const DlqState* s, int layer, int n_utts, const ActBuf& outbuf) {
+  ConvParams p{};
+  p.wpack = s->w[layer];
+  for (int i = 0; i < 256; ++i) p.bias[i] = s->bias[layer][i];
+  p.n_units = (n_utts + kColTile - 1) / kColTile;
+  p.n_utts = n_utts;
+  p.cols = 1;
+  p.feats = 1;
+  p.rows_valid = kT;
+  p.out = outbuf.ptr;
+  p.out_ncols = outbuf.ncols;
+  p.out_rs = outbuf.RS;
+  p.out_cols = 1;
+  p.out_feats = 1;
+  return p;
+}
+
+int launch_dlq(const DlqState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const int32_t* lengths_dev, int apply_sigmoid,
+               float* out, int num_sms, cudaStream_t stream) {
+  if (n_utts <= 0) return DFS_OK;
+  const long long total = (long long)n_utts * kT * 24;
+  cnn1d_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, s->act0);
+  DFS_LAUNCH_CHECK();
+  DFS_PROPAGATE(launch_conv_tc<DlqL1>(s->tmap[0], dlq_params(s, 0, n_utts, s->actA), 4, num_sms, stream));
+  DFS_PROPAGATE(launch_conv_tc<DlqL2>(s->tmap[1], dlq_params(s, 1, n_utts, s->actB), 4, num_sms, stream));
+  DFS_PROPAGATE(launch_conv_tc<DlqL2>(s->tmap[2], dlq_params(s, 2, n_utts, s->actA), 4, num_sms, stream));
+  dlq_stats_head_kernel<<<n_utts, 256, 0, stream>>>(s->actA, lengths_dev, s->fc1_wt, s->fc1_b, s->fc2_w, s->fc2_b, apply_sigmoid, out);
+  DFS_LAUNCH_CHECK();
+  return DFS_OK;
+}
+
 }  // namespace dfs

@@ -22,6 +22,8 @@
 //             8 consecutive columns and the [n][f][c] store is 128 contiguous bytes per warp.
 // MODE_3X1  : three taps along the row (time) axis only, no column halo: the Conv1d(k=3) layers of the 1D-CNN with one
 //             "feature column" per utterance (cols = 1: a tile is 16 utterances x 8 time steps).
+// MODE_5X1  : the same with five taps (Conv1d(k=5, p=2) of the StatsPool detector); the two halo rows per side that the
+//             padded layout does not store come from the TMA's out-of-bounds zero fill.
 // KSPLIT    : the CIN/8 channel planes of a window are loaded as KSPLIT separate pipeline stages ("pieces"),
 //             which bounds shared memory for CIN >= 128.
 // blockIdx.y: output-channel / quadrant group (weights, bias and output placement are offset per group).
@@ -36,7 +38,7 @@
 
 namespace dfs {
 
-enum { MODE_3X3 = 0, MODE_PAIR = 1, MODE_1X1 = 2, MODE_3X1 = 3, MODE_3X3S = 4 };
+enum { MODE_3X3 = 0, MODE_PAIR = 1, MODE_1X1 = 2, MODE_3X1 = 3, MODE_3X3S = 4, MODE_5X1 = 5 };
 enum {
   EPI_PAIR_POOL = 0,    // PAIR: relu both time steps, add (time pool), store FT8                    (CNN2D conv2)
   EPI_MEAN_T = 1,       // 3x3 : relu, sum over all rows of the unit, store [n][F][COUT] fp32         (CNN2D conv3)
@@ -45,8 +47,9 @@ enum {
   EPI_SHUFFLE = 4,      // 1x1 : relu, pixel-shuffle store of the quadrant(s) held in the columns      (CAE dec1-3)
   EPI_RELU = 5,         // any : relu, store FT8 at the same position                                   (CNN1D layers 1, 2)
   EPI_MEAN_T_SWAP = 6,  // 3x3S: lanes = output channels, columns = positions; relu, time sum in-thread   (CNN2D conv3)
-  EPI_SHUFFLE_MSE = 7   // 1x1 : CAE dec3 with the final ConvTranspose2d(32,1) and the squared error against the input fused in:
+  EPI_SHUFFLE_MSE = 7,  // 1x1 : CAE dec3 with the final ConvTranspose2d(32,1) and the squared error against the input fused in:
                         //        neither d3 nor the reconstruction is written; one partial sum per 16-column unit   (CAE dec3+final)
+  EPI_GELU = 8          // any : exact (erf) GELU, store FT8 at the same position, output-channel groups          (StatsPool detector)
 };
 
 template <int MODE_, int CIN_, int COUT_, int NG_, int ROWS_, int MT_, int NSTAGE_, int NACC_, int KSPLIT_, int EPI_>
@@ -56,9 +59,9 @@ struct ConvCfg {
   static constexpr bool PAIR = (MODE == MODE_PAIR);
   static constexpr bool SWAP = (MODE == MODE_3X3S);
   static constexpr int CT = SWAP ? 32 : kColTile;      // feature columns per tile
-  static constexpr int HALO = (MODE == MODE_1X1) ? 0 : 1;                       // row halo
-  static constexpr int HALO_C = (MODE == MODE_1X1 || MODE == MODE_3X1) ? 0 : 1;  // column halo
-  static constexpr int NTAP = PAIR ? 12 : (MODE == MODE_1X1 ? 1 : (MODE == MODE_3X1 ? 3 : 9));
+  static constexpr int HALO = (MODE == MODE_1X1) ? 0 : (MODE == MODE_5X1 ? 2 : 1);   // row halo
+  static constexpr int HALO_C = (MODE == MODE_1X1 || MODE == MODE_3X1 || MODE == MODE_5X1) ? 0 : 1;  // column halo
+  static constexpr int NTAP = PAIR ? 12 : (MODE == MODE_1X1 ? 1 : (MODE == MODE_3X1 ? 3 : (MODE == MODE_5X1 ? 5 : 9)));
   static constexpr int CCH = CIN / 8;                  // 16-byte channel chunks
   static constexpr int KCH = PAIR ? 2 * CCH : CCH;     // planes of the input layout (PAIR: x2 time parities)
   static constexpr int PPL = KCH / KSPLIT;             // planes per piece
@@ -100,7 +103,7 @@ struct ConvCfg {
       return (par * CCH + 2 * kk) * PLANE_B + (kw * WROWS + rowoff) * 16;
     }
     if (MODE == MODE_1X1) return (2 * kk) * PLANE_B;
-    if (MODE == MODE_3X1) return (2 * kk) * PLANE_B + tap * 16;
+    if (MODE == MODE_3X1 || MODE == MODE_5X1) return (2 * kk) * PLANE_B + tap * 16;
     const int kh = tap / 3, kw = tap % 3;
     return (2 * kk) * PLANE_B + (kw * WROWS + kh) * 16;
   }
@@ -462,10 +465,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             store_chunks<Q2 / 8>(dst, plane_elems, pk);
           }
         }
-      } else if constexpr (Cfg::EPI == EPI_RELU) {
+      } else if constexpr (Cfg::EPI == EPI_RELU || Cfg::EPI == EPI_GELU) {
         constexpr int HC = COUT / 2;
-        static_assert(Cfg::EPI != EPI_RELU || HC % 32 == 0, "relu epilogue: 32-column blocks");
+        static_assert((Cfg::EPI != EPI_RELU && Cfg::EPI != EPI_GELU) || HC % 32 == 0, "activation epilogue: 32-column blocks");
         const long long plane_elems = p.out_ncols * p.out_rs * 8;
+        const int cbase = grp * COUT + h * HC;   // first output channel of this thread (grp = blockIdx.y output-channel group)
         for (int tt = 0; tt < Cfg::TILES; ++tt, ++it) {
           const int acc = it % NACC;
           mbar_wait(&tfull[acc], (it / NACC) & 1, 5);
@@ -479,10 +483,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           if (lane == 0) mbar_arrive(&tempty[acc]);
           uint32_t pk[HC / 2];
 #pragma unroll
-          for (int c = 0; c < HC; c += 2) pk[c >> 1] = pack_act2(fmaxf(v[c] + bias[h * HC + c], 0.0f), fmaxf(v[c + 1] + bias[h * HC + c + 1], 0.0f));
+          for (int c = 0; c < HC; c += 2) {
+            float a0 = v[c] + bias[cbase + c], a1 = v[c + 1] + bias[cbase + c + 1];
+            if constexpr (Cfg::EPI == EPI_GELU) {   // nn.GELU() (approximate='none'): 0.5 x (1 + erf(x / sqrt 2))
+              a0 = 0.5f * a0 * (1.0f + erff(a0 * 0.70710678118654752f));
+              a1 = 0.5f * a1 * (1.0f + erff(a1 * 0.70710678118654752f));
+              a0 = fmaxf(a0, -65504.0f);
+              a1 = fmaxf(a1, -65504.0f);
+            } else {
+              a0 = fmaxf(a0, 0.0f);
+              a1 = fmaxf(a1, 0.0f);
+            }
+            pk[c >> 1] = pack_act2(a0, a1);
+          }
           const int tp = 1 + 8 * tt + i;
           if (colvalid && tp <= p.rows_valid) {
-            uint16_t* dst = p.out + ((long long)gc * p.out_rs + tp) * 8 + (long long)(h * HC / 8) * plane_elems;
+            uint16_t* dst = p.out + ((long long)gc * p.out_rs + tp) * 8 + (long long)(cbase / 8) * plane_elems;
             store_chunks<HC / 8>(dst, plane_elems, pk);
           }
         }

@@ -81,6 +81,23 @@ struct Cnn1dTcState {
   float fcb;
   int l1_fused;           // 1 (default) = layer 1 converts the fp32 rows in flight (cnn1d_l1_fused.cu) when the layout allows
 };
+// ---- StatsPool detector (dlqueen_model.py) on the conv1d template, cnn1d_tc.cu ----
+struct DlqState {
+  ActBuf act0;            // fp16 input copy, 24 planes (180 features zero-padded to 192)
+  ActBuf actA, actB;      // 32-plane (256-channel) ping-pong activation buffers
+  CUtensorMap tmap[3];    // inputs of the three conv layers: act0, actA, actB
+  const uint16_t* w[3];   // packed fp16 weights [group 4][tap][ci/8][64][8]
+  float bias[3][256];
+  const float* fc1_wt;    // head.0.weight transposed to [512][256] (device)
+  const float* fc1_b;     // [256]
+  const float* fc2_w;     // head.3.weight [256]
+  float fc2_b;
+};
+void dlq_geometry(int buf, int* planes, int* rs);
+int dlq_make_maps(DlqState* s);
+int launch_dlq(const DlqState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const int32_t* lengths_dev, int apply_sigmoid,
+               float* out, int num_sms, cudaStream_t stream);
+
 // ---- cnn1d_l1_fused.cu ----
 bool cnn1d_l1_fused_supported(const float* x, int64_t sn, int64_t st, int64_t sf);
 int launch_cnn1d_l1_fused(const float* x, int64_t sn, int n_utts, const uint16_t* wpack, const float* bias, ActBuf out, int num_sms, cudaStream_t stream);

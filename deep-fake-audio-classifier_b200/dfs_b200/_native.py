@@ -37,6 +37,12 @@ class CaeWeights(C.Structure):
                 ("norm_mean", C.POINTER(C.c_float)), ("norm_std", C.POINTER(C.c_float))]
 
 
+class DlqWeights(C.Structure):
+    _fields_ = [("in_ch", C.c_int), ("hidden", C.c_int), ("conv", ConvBn * 3),
+                ("fc1_weight", C.POINTER(C.c_float)), ("fc1_bias", C.POINTER(C.c_float)),
+                ("fc2_weight", C.POINTER(C.c_float)), ("fc2_bias", C.POINTER(C.c_float))]
+
+
 class Features(C.Structure):
     _fields_ = [("x", C.c_void_p), ("n", C.c_int64), ("stride_n", C.c_int64), ("stride_t", C.c_int64), ("stride_f", C.c_int64)]
 
@@ -54,6 +60,8 @@ SIGNATURES = {
     "dfs_cnn2d_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Cnn2dWeights), C.c_int]),
     "dfs_cnn1d_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Cnn1dWeights), C.c_int]),
     "dfs_cae_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(CaeWeights), C.c_int]),
+    "dfs_dlq_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(DlqWeights), C.c_int]),
+    "dfs_dlq_score": (C.c_int, [C.c_void_p, C.POINTER(Features), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dfs_model_destroy": (C.c_int, [C.c_void_p]),
     "dfs_model_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "dfs_model_workspace_bytes": (C.c_int64, [C.c_void_p]),

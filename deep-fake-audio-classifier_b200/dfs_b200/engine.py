@@ -184,6 +184,47 @@ class Cnn1dScorer(_Scorer):
         return out
 
 
+class DlqScorer(_Scorer):
+    """StatsPool detector ``DeepfakeDetector`` (src/dlqueen_model.py:132-173): Conv1d k5/k3/k3 + BN + GELU encoder on the
+    conv1d tensor-core template, masked mean+std pooling and the two-layer head."""
+    KIND = "dlq"
+
+    def __init__(self, state_dict, device: int = 0, max_chunk: int = 0):
+        super().__init__()
+        _require_cuda()
+        keep = []
+        w = N.DlqWeights()
+        w0 = _np32(state_dict["enc.net.0.weight"])
+        w.hidden, w.in_ch = int(w0.shape[0]), int(w0.shape[1])
+        for i, (ck, bk) in enumerate((("enc.net.0", "enc.net.1"), ("enc.net.4", "enc.net.5"), ("enc.net.8", "enc.net.9"))):
+            w.conv[i] = _conv_bn(state_dict, ck, bk, keep)
+        arrs = [_np32(state_dict[k]) for k in ("head.0.weight", "head.0.bias", "head.3.weight", "head.3.bias")]
+        keep += arrs
+        w.fc1_weight, w.fc1_bias, w.fc2_weight, w.fc2_bias = (_fptr(a) for a in arrs)
+        self.device_index = int(device)
+        N.check(self._lib.dfs_dlq_create(C.byref(self._h), int(device), C.byref(w), int(max_chunk)), "dfs_dlq_create")
+
+    def score(self, x, lengths=None, apply_sigmoid: bool = False):
+        """x: CUDA fp32 (B,321,180) view (any strides; the reference's (B,180,T) batch is ``x.transpose(1, 2)``); lengths:
+        optional (B,) valid frame counts.  Returns (B,) logits / sigmoid scores."""
+        torch = _require_cuda()
+        f, x = _features_struct(x)
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        lp = None
+        if lengths is not None:
+            lengths = torch.as_tensor(lengths).to(x.device, torch.int32).contiguous()
+            if lengths.numel() != x.shape[0]:
+                raise ValueError("lengths must have one entry per utterance")
+            lp = C.c_void_p(lengths.data_ptr())
+        with torch.cuda.device(x.device):
+            N.check(self._lib.dfs_dlq_score(self._h, C.byref(f), lp, C.c_void_p(out.data_ptr()), int(bool(apply_sigmoid)),
+                                            _stream_ptr(torch, x.device)), "dfs_dlq_score")
+        return out
+
+    def score_host(self, feats, flag: int = 1):
+        raise RuntimeError("DlqScorer has no host-buffer pipeline; move the batch to the device and call score()")
+
+
 class CaeScorer(_Scorer):
     """ConvAutoencoder reconstruction-MSE scorer (src/model_cae.py:23-125 + src/predict_hybrid.py:66-78).
     ``mean``/``std`` are the FeatureNormalizer statistics (src/dataset_cae.py:18-52), optional."""

@@ -79,6 +79,22 @@ def cnn1d_state(seed: int = 0, in_features: int = N_FEATS, base_channels: int = 
     return sd
 
 
+def dlq_state(seed: int = 0, in_ch: int = N_FEATS, hidden: int = 256, logit_scale: float = 1.0) -> "OrderedDict[str, np.ndarray]":
+    """Random-init DeepfakeDetector state dict (/root/reference/src/dlqueen_model.py:132-173): enc.net.{0,4,8} Conv1d
+    (k = 5, 3, 3), enc.net.{1,5,9} BatchNorm1d, head.{0,3} Linear."""
+    rng = _rng(4000 + seed)
+    sd = OrderedDict()
+    for (ci, k), conv_i, bn_i in zip(((in_ch, 5), (hidden, 3), (hidden, 3)), (0, 4, 8), (1, 5, 9)):
+        sd[f"enc.net.{conv_i}.weight"] = _uniform_fan_in(rng, (hidden, ci, k), ci * k)
+        sd[f"enc.net.{conv_i}.bias"] = _uniform_fan_in(rng, (hidden,), ci * k)
+        _bn(rng, sd, f"enc.net.{bn_i}", hidden)
+    sd["head.0.weight"] = _uniform_fan_in(rng, (hidden, 2 * hidden), 2 * hidden)
+    sd["head.0.bias"] = _uniform_fan_in(rng, (hidden,), 2 * hidden)
+    sd["head.3.weight"] = _uniform_fan_in(rng, (1, hidden), hidden) * np.float32(logit_scale)
+    sd["head.3.bias"] = _uniform_fan_in(rng, (1,), hidden)
+    return sd
+
+
 def cae_state(seed: int = 0, base_channels: int = 32) -> "OrderedDict[str, np.ndarray]":
     rng = _rng(3000 + seed)
     bc = base_channels

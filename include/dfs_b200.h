@@ -81,6 +81,19 @@ typedef struct {
   const float* norm_std;  /* (180) or NULL */
 } dfs_cae_weights;
 
+/* src/dlqueen_model.py:132-173  DeepfakeDetector(in_ch=180, hidden=256): ConvEncoder (Conv1d k5 / k3 / k3 + BatchNorm1d +
+ * GELU), masked mean+std StatsPool, head Linear(512,256) + GELU + Linear(256,1).  state_dict keys: enc.net.{0,4,8} convs,
+ * enc.net.{1,5,9} BN, head.{0,3}.                                                                                   */
+typedef struct {
+  int in_ch;              /* must be 180 */
+  int hidden;             /* must be 256 */
+  dfs_conv_bn conv[3];    /* enc.net.{0,4,8} (256,in,5) / (256,256,3) / (256,256,3) + BN enc.net.{1,5,9} */
+  const float* fc1_weight; /* head.0.weight (256, 512) */
+  const float* fc1_bias;   /* head.0.bias (256)        */
+  const float* fc2_weight; /* head.3.weight (1, 256)   */
+  const float* fc2_bias;   /* head.3.bias (1)          */
+} dfs_dlq_weights;
+
 /* Strided view of the feature maps: element (i, t, f) is at x[i*stride_n + t*stride_t + f*stride_f]
  * (strides in ELEMENTS).  The reference hands its models a transposed, non-contiguous
  * (B,321,180) view of (B,180,321) storage (src/predict.py:103-105): stride_t = 1,
@@ -101,6 +114,7 @@ int64_t dfs_launch_count(void);
 int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_weights* w, int max_chunk);
 int dfs_cnn1d_create(dfs_model** out, int device, const dfs_cnn1d_weights* w, int max_chunk);
 int dfs_cae_create(dfs_model** out, int device, const dfs_cae_weights* w, int max_chunk);
+int dfs_dlq_create(dfs_model** out, int device, const dfs_dlq_weights* w, int max_chunk);
 int dfs_model_destroy(dfs_model* m);
 /* options: "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = CUDA-core direct conv (debug
  * cross-check, same layouts); "profile" 0/1 = per-kernel event timing (dfs_model_profile). */
@@ -132,6 +146,12 @@ int dfs_cae_forward(dfs_model* m, const dfs_features* feats, float* recon_dev, f
  * path (impl 0) or the CUDA-core cross-check path (impl 1); n <= the handle's chunk.  Tests only. */
 int dfs_cae_debug_layer(dfs_model* m, const dfs_features* feats, int impl, int layer, int apply_normalizer, float* out_dev,
                         void* stream);
+
+/* DeepfakeDetector.forward(x, lengths) (src/dlqueen_model.py:168-173; the reference stores x as (B, 180, T): pass the
+ * (B, T, 180) view with stride_t = 1, stride_f = T).  T = 321; lengths_dev = NULL (all 321) or [n] int32 valid frame counts
+ * for the masked pooling -- frames beyond an utterance's length must be zero in x, as pad_sequence leaves them
+ * (src/dlqueen_model.py:98-103).  out_dev [n] logits (or sigmoid scores).                                            */
+int dfs_dlq_score(dfs_model* m, const dfs_features* feats, const int32_t* lengths_dev, float* out_dev, int apply_sigmoid, void* stream);
 
 /* ---- scoring (HOST features; copies are pipelined inside) --------------------------- */
 /* The batch loop of src/predict.py:100-111 / src/predict_hybrid.py:52-78 behind one call:

@@ -155,6 +155,45 @@ def cae_mse_scores(sd, x, mean=None, std=None, dtype=np.float64):
     return ((recon - x) ** 2).reshape(x.shape[0], -1).mean(axis=1)
 
 
+# --------------------------------------------------------------------------------------
+# DeepfakeDetector / StatsPool  (/root/reference/src/dlqueen_model.py:115-173)
+# --------------------------------------------------------------------------------------
+def _conv1d_same(x, w, b):
+    """nn.Conv1d(kernel_size=K, padding=K//2): x (B,Ci,L), w (Co,Ci,K) -> (B,Co,L)."""
+    B, Ci, L = x.shape
+    K = w.shape[2]
+    xp = np.zeros((B, Ci, L + K - 1), dtype=x.dtype)
+    xp[:, :, K // 2:K // 2 + L] = x
+    out = np.zeros((B, w.shape[0], L), dtype=x.dtype)
+    for k in range(K):
+        out += np.einsum("bcl,oc->bol", xp[:, :, k:k + L], w[:, :, k], optimize=True)
+    return out + b.reshape(1, -1, 1)
+
+
+def _gelu(x):
+    """nn.GELU() (approximate='none'): 0.5 x (1 + erf(x / sqrt 2))."""
+    from math import erf
+    return 0.5 * x * (1.0 + np.vectorize(erf, otypes=[x.dtype])(x / np.sqrt(x.dtype.type(2.0))))
+
+
+def dlq_forward(sd, x, lengths=None, dtype=np.float64):
+    """x (B,321,180) as every scorer here takes it (the reference holds (B,180,T), dlqueen_model.py:102); lengths (B,)
+    valid frame counts (None = all T; frames beyond a length must be zero in x, as pad_sequence leaves them) -> logits (B,)."""
+    h = np.asarray(x, dtype=dtype).transpose(0, 2, 1)                                # (B, C, T)
+    B, _, T = h.shape
+    for conv_i, bn_i in ((0, 1), (4, 5), (8, 9)):                                    # ConvEncoder :135-150 (Dropout = identity)
+        h = _conv1d_same(h, sd[f"enc.net.{conv_i}.weight"].astype(dtype), sd[f"enc.net.{conv_i}.bias"].astype(dtype))
+        h = _gelu(_bn_eval(h, sd, f"enc.net.{bn_i}", np.dtype(dtype).type))
+    lengths = np.full(B, T) if lengths is None else np.asarray(lengths)
+    mask = (np.arange(T)[None, :] < lengths[:, None]).astype(dtype)[:, None, :]      # StatsPool :121-122
+    denom = np.maximum(mask.sum(axis=2), 1.0)                                        # :124
+    mean = (h * mask).sum(axis=2) / denom                                            # :125
+    var = (mask * (h - mean[:, :, None]) ** 2).sum(axis=2) / denom                   # :127
+    z = np.concatenate([mean, np.sqrt(np.maximum(var, 1e-6))], axis=1)               # :128-129
+    a = _gelu(z @ sd["head.0.weight"].astype(dtype).T + sd["head.0.bias"].astype(dtype))   # head :161-166
+    return (a @ sd["head.3.weight"].astype(dtype).T + sd["head.3.bias"].astype(dtype))[:, 0]
+
+
 def sigmoid(z):
     z = np.asarray(z)
     return 1.0 / (1.0 + np.exp(-z))

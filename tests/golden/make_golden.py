@@ -14,6 +14,7 @@ GPU box, so the tests only ever read the .npz files written here.  What is pinne
 * blend_known_answer.npz -- the one bit-exact known-answer triple the reference ships
                    (results/prediction_{final_test,cae_only_final,hybrid_final}.pkl).
 * prediction_format.json -- dtype/shape facts of examples/prediction.pkl.
+* dlq.npz       -- reference DeepfakeDetector (src/dlqueen_model.py) logits on seeded weights, full-length and ragged batches.
 """
 import importlib.util
 import json
@@ -172,11 +173,44 @@ def make_blend():
     print("blend_known_answer.npz, prediction_format.json:", facts)
 
 
+def make_dlq():
+    """DeepfakeDetector (src/dlqueen_model.py:156-173, imported unmodified) on seeded weights / inputs: full-length batch and a
+    ragged one (frames beyond the length zeroed, as pad_sequence leaves them)."""
+    spec = importlib.util.spec_from_file_location("ref_dlqueen_model", os.path.join(REF, "src", "dlqueen_model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.set_num_threads(8)
+    n = 12
+    x = syn.features(n, seed=1234)
+    lengths = np.array([321, 300, 321, 123, 64, 321, 1, 200, 321, 319, 8, 250], dtype=np.int64)
+    xz = x.copy()
+    for i, l in enumerate(lengths):
+        xz[i, l:, :] = 0
+    out = {"n": n, "features_sha256": syn.state_digest([x]), "lengths": lengths}
+    for scale, tag in ((1.0, "init"), (300.0, "trained")):
+        sd = syn.dlq_state(0, logit_scale=scale)
+        m = mod.DeepfakeDetector(in_ch=180, hidden=256, dropout=0.3)
+        assert list(m.state_dict().keys()) == list(sd.keys())
+        m.load_state_dict(_to_torch(sd))
+        m.eval()
+        with torch.no_grad():
+            full = m(torch.from_numpy(x).transpose(1, 2).contiguous(), torch.full((n,), 321, dtype=torch.long))
+            ragged = m(torch.from_numpy(xz).transpose(1, 2).contiguous(), torch.from_numpy(lengths))
+        out[f"dlq_{tag}_sha256"] = syn.state_digest(sd)
+        out[f"dlq_{tag}_logits_full"] = full.numpy()
+        out[f"dlq_{tag}_logits_ragged"] = ragged.numpy()
+    out["state_dict_keys"] = np.array(list(sd.keys()))
+    np.savez_compressed(os.path.join(HERE, "dlq.npz"), **out)
+    print("dlq.npz:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["models", "eer", "blend"]
+    which = sys.argv[1:] or ["models", "eer", "blend", "dlq"]
     if "models" in which:
         make_models()
     if "eer" in which:
         make_eer()
     if "blend" in which:
         make_blend()
+    if "dlq" in which:
+        make_dlq()

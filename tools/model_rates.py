@@ -28,9 +28,11 @@ mean, std = syn.normalizer_stats(1)
 c2 = D.Cnn2dScorer(syn.cnn2d_state(0))
 c1 = D.Cnn1dScorer(syn.cnn1d_state(0))
 ca = D.CaeScorer(syn.cae_state(0), mean, std)
+dq = D.DlqScorer(syn.dlq_state(0))
 print(f"cnn2d  {rate(lambda: c2.score(x, True), n):12.0f} utt/s")
 print(f"cnn1d  {rate(lambda: c1.score(x, True), n):12.0f} utt/s")
 print(f"cae    {rate(lambda: ca.score(x), n):12.0f} utt/s")
+print(f"dlq    {rate(lambda: dq.score(x, apply_sigmoid=True), n):12.0f} utt/s")
 s2, s1, m = c2.score(x, True), c1.score(x, True), ca.score(x)
 print(f"hybrid blend+eer on {n}: {rate(lambda: D.calculate_eer(D.hybrid_blend(D.ensemble_mean([s2, s1], as_numpy=False), m, 0.8, as_numpy=False), syn.labels(n)), n):12.0f} scores/s")
 for big in (1_000_000, 100_000_000):
