@@ -348,9 +348,24 @@ __device__ __forceinline__ bool better(double d, long long i, double bd, long lo
 
 // The curve points evaluated are k = k_base .. k_base + n, where the first k_base sorted scores (c1_base of them bonafide)
 // precede pay[0] (k_base = c1_base = 0 for the full sweep; the radix-select path sweeps one tie group only).
+// FAR - FRR is strictly decreasing in k, so the arg-min of |FAR - FRR| is the last non-negative or the first negative point:
+// only the ONE tile whose first point is >= 0 and whose last point is < 0 can hold it (both computed from the tile's label
+// counts); every other tile returns at once without reading its payloads or doing fp64 divisions.
 __global__ void __launch_bounds__(256) sweep_min_kernel(const uint32_t* __restrict__ pay, long long n, long long n_bona, long long n_spoof,
-                                                         const unsigned long long* __restrict__ block_excl, SweepBest* __restrict__ block_best,
-                                                         long long k_base, long long c1_base) {
+                                                         const unsigned long long* __restrict__ block_excl, const uint32_t* __restrict__ block_ones,
+                                                         SweepBest* __restrict__ block_best, long long k_base, long long c1_base) {
+  {
+    const long long t0 = (long long)blockIdx.x * kSortTile;
+    const long long len = (n - t0) < kSortTile ? (n - t0) : kSortTile;
+    const long long ks = k_base + t0, c1s = c1_base + (long long)block_excl[blockIdx.x];
+    const long long ke = ks + len, c1e = c1s + (long long)block_ones[blockIdx.x];
+    const double ds = __dsub_rn(__ddiv_rn((double)(n_spoof - (ks - c1s)), (double)n_spoof), __ddiv_rn((double)c1s, (double)n_bona));
+    const double de = __dsub_rn(__ddiv_rn((double)(n_spoof - (ke - c1e)), (double)n_spoof), __ddiv_rn((double)c1e, (double)n_bona));
+    if (!(ds >= 0.0 && de < 0.0)) {   // block-uniform
+      if (threadIdx.x == 0) block_best[blockIdx.x] = SweepBest{1.0e300, 0x7fffffffffffffffll, 0};
+      return;
+    }
+  }
   // blocked arrangement: thread t owns sorted positions base + 16 t .. + 15
   const long long base = (long long)blockIdx.x * kSortTile + (long long)threadIdx.x * kSortItems;
   uint32_t lab[kSortItems];
@@ -387,12 +402,13 @@ __global__ void __launch_bounds__(256) sweep_min_kernel(const uint32_t* __restri
   const double dspoof = (double)n_spoof, dbona = (double)n_bona;
   double bd = 1.0e300;
   long long bi = 0x7fffffffffffffffll, bc1 = 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // first curve point (k = 0: FAR = 1, FRR = 0)
-    const double far0 = __ddiv_rn((double)(n_spoof - (k_base - c1_base)), dspoof);
-    const double frr0 = __ddiv_rn((double)c1_base, dbona);
+  if (threadIdx.x == 0) {  // the point just before this tile's first score (k = 0 for the first tile: FAR = 1, FRR = 0)
+    const long long ks = k_base + (long long)blockIdx.x * kSortTile;
+    const double far0 = __ddiv_rn((double)(n_spoof - (ks - c1)), dspoof);
+    const double frr0 = __ddiv_rn((double)c1, dbona);
     bd = fabs(__dsub_rn(far0, frr0));
-    bi = k_base;
-    bc1 = c1_base;
+    bi = ks;
+    bc1 = c1;
   }
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
@@ -587,7 +603,7 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   DFS_LAUNCH_CHECK();
   sweep_scan_kernel<<<1, 1024, 0, stream>>>(bones, tiles, bexcl);
   DFS_LAUNCH_CHECK();
-  sweep_min_kernel<<<(unsigned)tiles, 256, 0, stream>>>(pay[cur], n, n_bona, n_spoof, bexcl, bbest, 0, 0);
+  sweep_min_kernel<<<(unsigned)tiles, 256, 0, stream>>>(pay[cur], n, n_bona, n_spoof, bexcl, bones, bbest, 0, 0);
   DFS_LAUNCH_CHECK();
   sweep_final_kernel<K><<<1, 256, 0, stream>>>(bbest, tiles, keys[cur], n, n_bona, n_spoof, res_dev);
   DFS_LAUNCH_CHECK();
@@ -1224,7 +1240,7 @@ static int eer_select_impl(const void* scores_v, const uint8_t* labels, int64_t 
     DFS_LAUNCH_CHECK();
     sweep_scan_kernel<<<1, 1024, 0, stream>>>(bones, tiles_m, bexcl);
     DFS_LAUNCH_CHECK();
-    sweep_min_kernel<<<(unsigned)tiles_m, 256, 0, stream>>>(gpay, m, (long long)host.n_bona, (long long)host.n_spoof, bexcl, bbest, start,
+    sweep_min_kernel<<<(unsigned)tiles_m, 256, 0, stream>>>(gpay, m, (long long)host.n_bona, (long long)host.n_spoof, bexcl, bones, bbest, start,
                                                            (long long)host.c1_below);
     DFS_LAUNCH_CHECK();
     select_reduce_best_kernel<<<1, 256, 0, stream>>>(bbest, tiles_m, sc.state);
