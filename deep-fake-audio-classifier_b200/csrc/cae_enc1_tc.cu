@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "layout.cuh"
+#include "xt_prep.cuh"
 
 namespace dfs {
 
@@ -230,8 +231,12 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
 int launch_cae_enc1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const float* norm_mean, const float* norm_std, uint16_t* xt,
                        const uint16_t* wpack, const float* bias_quarter, ActBuf out, int out_cols, int num_sms, cudaStream_t stream) {
   if (n_utts <= 0) return DFS_OK;
-  const long long total = (long long)n_utts * kF * kE1Blocks;
-  cae_enc1_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, norm_mean, norm_std, xt);
+  if (sf == 1) {   // feature-contiguous storage: transpose through shared memory (xt_prep.cuh)
+    xt_prep_transpose_kernel<<<dim3((kF + 31) / 32, n_utts), 256, 0, stream>>>(x, sn, st, kE1Cols, 2, kE1Lead, norm_mean, norm_std, xt);
+  } else {
+    const long long total = (long long)n_utts * kF * kE1Blocks;
+    cae_enc1_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, norm_mean, norm_std, xt);
+  }
   DFS_LAUNCH_CHECK();
   static bool configured[32] = {false};
   if (dfs_first_use_on_device(configured))

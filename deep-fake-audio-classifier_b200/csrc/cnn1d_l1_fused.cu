@@ -37,7 +37,6 @@ constexpr int kL1ProdWarps = 12;                         // enough loads in flig
 constexpr int kL1Prod = 32 * kL1ProdWarps;
 constexpr int kL1MmaWarp = 4 + kL1ProdWarps;
 constexpr int kL1Threads = 32 * (kL1MmaWarp + 2);        // warps 0-3 epilogue, 4-15 producers, 16 MMA issuer, 17 TMEM allocator
-constexpr int kL1Items = kColTile * kL1Rows * 23;        // 16-byte output chunks per stage (features 0..183; chunk 23 stays zero)
 
 struct L1FusedParams {
   const float* x;          // dense [n][321][180] fp32
