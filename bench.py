@@ -377,6 +377,18 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_value = Pe * world * args.e2e_steps / float(e2e_dt.item())
+    # the same call on an fp16 pinned slab (dfs_score_host_f16): the 2D-CNN's scores are bit-identical, the PCIe bytes halve
+    host16 = host_pool.half().pin_memory()
+    same16 = bool((scorer.score_host(host16, 1) == e2e_scores).all())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        D.eer_details(scorer.score_host(host16, 1), labels_global[:Pe])
+    torch.cuda.synchronize()
+    e2e16_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e16_dt, op=dist.ReduceOp.MAX)
+    e2e16_value = Pe * world * args.e2e_steps / float(e2e16_dt.item())
 
     if rank != 0:
         if world > 1:
@@ -415,7 +427,11 @@ def main():
            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
            "e2e": {"value": e2e_value, "unit": "utterances/s", "h2d_bytes_per_step": Pe * BYTES_PER_UTT, "d2h_bytes_per_step": Pe * 4,
                    "utterances_per_step_per_gpu": Pe, "steps": args.e2e_steps,
-                   "note": "dfs_score_host: pinned host features -> double-buffered H2D -> kernels -> D2H scores, + EER"}}
+                   "note": "dfs_score_host: pinned host features -> double-buffered H2D -> kernels -> D2H scores, + EER"},
+           "e2e_f16_slab": {"value": e2e16_value, "unit": "utterances/s", "h2d_bytes_per_step": Pe * BYTES_PER_UTT // 2,
+                            "scores_identical_to_fp32_slab": same16,
+                            "note": "same call on an fp16 pinned slab (dfs_score_host_f16); informational: `e2e` above is the fp32 format "
+                                    "the reference stores"}}
 
     if world == 1 and not args.no_cpu_baseline:
         n_cpu = 2048

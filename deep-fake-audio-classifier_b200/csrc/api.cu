@@ -78,6 +78,7 @@ struct dfs_model {
   size_t prof_used = 0;               // pairs in use since the last reset
   // ---- host-buffer pipeline ----
   float* stage_in[2] = {nullptr, nullptr};
+  uint16_t* stage_in16[2] = {nullptr, nullptr};   // fp16 slabs (dfs_score_host_f16), allocated on first use
   float* stage_out[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -853,6 +854,63 @@ extern "C" int dfs_score_host(dfs_model* m, const dfs_features* feats, int flag,
     else if (m->kind == KIND_CNN1D) st = dfs_cnn1d_score(m, &dv, m->stage_out[b], flag, stream);
     else st = dfs_cae_score(m, &dv, flag, m->stage_out[b], stream);
     DFS_PROPAGATE(st);
+    DFS_CUDA_CHECK(cudaMemcpyAsync(out_host + i0, m->stage_out[b], (size_t)nk * 4, cudaMemcpyDeviceToHost, stream));
+    DFS_CUDA_CHECK(cudaEventRecord(m->ev_done[b], stream));
+  }
+  DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return DFS_OK;
+}
+
+// fp16 host slabs: half the PCIe bytes of the fp32 path.  The engine quantises the features to fp16 before the first GEMM
+// anyway, so for the 2D-CNN and the 1D-CNN a slab that holds the fp16 image of the fp32 features gives the same bits.
+__global__ void __launch_bounds__(256) widen_f16_kernel(const uint16_t* __restrict__ in, long long n8, long long n_total, float* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x < 8) {   // an odd number of utterances leaves 4 halfs after the last 16-byte group
+    const long long i = 8 * n8 + threadIdx.x;
+    if (i < n_total) out[i] = __half2float(*reinterpret_cast<const __half*>(in + i));
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[e]);
+      f[2 * e] = __low2float(h);
+      f[2 * e + 1] = __high2float(h);
+    }
+    reinterpret_cast<float4*>(out)[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
+extern "C" int dfs_score_host_f16(dfs_model* m, const uint16_t* x_host, int64_t n, int time_major, int flag, float* out_host, void* stream_) {
+  DFS_REQUIRE(m && (m->kind == KIND_CNN2D || m->kind == KIND_CNN1D || m->kind == KIND_CAE), DFS_ERR_INVALID, "dfs_score_host_f16: bad model handle");
+  DFS_REQUIRE(n >= 0 && n < (1ll << 31) && (n == 0 || (x_host && out_host)), DFS_ERR_INVALID, "dfs_score_host_f16: bad argument");
+  const int64_t per_utt = (int64_t)kT * kF;   // 57,780 halfs = 115,560 B (a multiple of 16)
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DFS_CUDA_CHECK(cudaSetDevice(m->device));
+  DFS_PROPAGATE(model_stage_init(m));
+  for (int b = 0; b < 2; ++b)
+    if (!m->stage_in16[b]) DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&m->stage_in16[b]), (size_t)m->chunk * per_utt * 2, false));
+  const int64_t st = time_major ? 1 : kF, sf = time_major ? kT : 1;   // [n][180][321] storage (the reference's rows) or [n][321][180]
+  int k = 0;
+  for (int64_t i0 = 0; i0 < n; i0 += m->chunk, ++k) {
+    const int b = k & 1;
+    const int nk = (int)std::min<int64_t>(m->chunk, n - i0);
+    if (k >= 2) DFS_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_done[b], 0));
+    DFS_CUDA_CHECK(cudaMemcpyAsync(m->stage_in16[b], x_host + i0 * per_utt, (size_t)nk * per_utt * 2, cudaMemcpyHostToDevice, m->copy_stream));
+    DFS_CUDA_CHECK(cudaEventRecord(m->ev_in[b], m->copy_stream));
+    DFS_CUDA_CHECK(cudaStreamWaitEvent(stream, m->ev_in[b], 0));
+    const long long n8 = (long long)nk * per_utt / 8;
+    widen_f16_kernel<<<(unsigned)std::max<long long>(1, std::min<long long>(ceil_div64(n8, 256), (long long)m->num_sms * 8)), 256, 0, stream>>>(
+        m->stage_in16[b], n8, (long long)nk * per_utt, m->stage_in[b]);
+    DFS_LAUNCH_CHECK();
+    dfs_features dv{m->stage_in[b], nk, per_utt, st, sf};
+    int rc;
+    if (m->kind == KIND_CNN2D) rc = dfs_cnn2d_score(m, &dv, m->stage_out[b], nullptr, flag, stream);
+    else if (m->kind == KIND_CNN1D) rc = dfs_cnn1d_score(m, &dv, m->stage_out[b], flag, stream);
+    else rc = dfs_cae_score(m, &dv, flag, m->stage_out[b], stream);
+    DFS_PROPAGATE(rc);
     DFS_CUDA_CHECK(cudaMemcpyAsync(out_host + i0, m->stage_out[b], (size_t)nk * 4, cudaMemcpyDeviceToHost, stream));
     DFS_CUDA_CHECK(cudaEventRecord(m->ev_done[b], stream));
   }

@@ -72,6 +72,7 @@ SIGNATURES = {
     "dfs_cae_forward": (C.c_int, [C.c_void_p, C.POINTER(Features), C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfs_cae_debug_layer": (C.c_int, [C.c_void_p, C.POINTER(Features), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dfs_score_host": (C.c_int, [C.c_void_p, C.POINTER(Features), C.c_int, C.c_void_p, C.c_void_p]),
+    "dfs_score_host_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dfs_blend_f64": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_double,
                                 C.c_int64, C.c_void_p, C.c_void_p]),
     "dfs_widen_f32_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

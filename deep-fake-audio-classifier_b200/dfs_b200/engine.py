@@ -103,8 +103,11 @@ class _Scorer:
 
     # -- host buffers: H2D / D2H inside (the e2e path of bench.py) --
     def score_host(self, feats, flag: int = 1):
-        """feats: pinned torch CPU tensor or numpy array (B,321,180) fp32, dense. Returns numpy fp32 (B,)."""
+        """feats: pinned torch CPU tensor or numpy array (B,321,180) fp32, dense (or fp16: dfs_score_host_f16, half the
+        PCIe bytes; the engine quantises to fp16 anyway). Returns numpy fp32 (B,)."""
         torch = _require_cuda()
+        if (hasattr(feats, "dtype") and str(feats.dtype) in ("torch.float16", "float16")):
+            return self._score_host_f16(feats, flag)
         if hasattr(feats, "numpy") and not isinstance(feats, np.ndarray):
             t = feats
             ptr, shape, strides = t.data_ptr(), tuple(t.shape), t.stride()
@@ -120,6 +123,32 @@ class _Scorer:
             N.check(self._lib.dfs_score_host(self._h, C.byref(f), int(flag), C.c_void_p(out.data_ptr()),
                                              _stream_ptr(torch, self._device(torch))), "dfs_score_host")
         del t
+        return out.numpy()
+
+
+    def _score_host_f16(self, feats, flag):
+        torch = _require_cuda()
+        if isinstance(feats, np.ndarray):
+            a = feats
+            ptr, shape, strides, keep = a.ctypes.data, a.shape, tuple(s // 2 for s in a.strides), a
+        else:
+            ptr, shape, strides, keep = feats.data_ptr(), tuple(feats.shape), feats.stride(), feats
+        if len(shape) != 3 or shape[1] != T_FRAMES or shape[2] != N_FEATS:
+            raise ValueError(f"expected features of shape (B, {T_FRAMES}, {N_FEATS}), got {shape}")
+        per = T_FRAMES * N_FEATS
+        if shape[0] > 1 and strides[0] != per:
+            raise ValueError("fp16 slab: utterances must be dense and back to back")
+        if (strides[1], strides[2]) == (N_FEATS, 1):
+            time_major = 0
+        elif (strides[1], strides[2]) == (1, T_FRAMES):
+            time_major = 1                                  # the (B,321,180) view of [B,180,321] rows
+        else:
+            raise ValueError("fp16 slab: each utterance must be one dense 321x180 (or 180x321) block")
+        out = torch.empty(shape[0], dtype=torch.float32, pin_memory=True)
+        with torch.cuda.device(self.device_index):
+            N.check(self._lib.dfs_score_host_f16(self._h, C.c_void_p(ptr), shape[0], time_major, int(flag), C.c_void_p(out.data_ptr()),
+                                                 _stream_ptr(torch, self._device(torch))), "dfs_score_host_f16")
+        del keep
         return out.numpy()
 
 

@@ -159,6 +159,11 @@ int dfs_dlq_score(dfs_model* m, const dfs_features* feats, const int32_t* length
  * chunk k; returns after the scores are in out_host.  `kind`: 0 cnn2d, 1 cnn1d, 2 cae-mse.
  * `flag` = apply_sigmoid (cnn) / apply_normalizer (cae).                                   */
 int dfs_score_host(dfs_model* m, const dfs_features* feats, int flag, float* out_host, void* stream);
+/* Same pipeline for a HOST slab of IEEE fp16 features, [n][321][180] (time_major = 0) or the reference's row shape
+ * [n][180][321] (time_major = 1), dense: half the PCIe bytes.  The kernels quantise the features to fp16 before the first
+ * GEMM anyway, so for the 2D-CNN and the 1D-CNN a slab holding the fp16 image of the fp32 features scores bit-identically;
+ * the CAE additionally reads the input in its fp32 residual, so its MSE moves by the input rounding (~1e-4 relative). */
+int dfs_score_host_f16(dfs_model* m, const uint16_t* x_host, int64_t n, int time_major, int flag, float* out_host, void* stream);
 
 /* ---- ensemble blend (float64, like numpy) ------------------------------------------- */
 /* out[i] = (sum_m weights[m] * (minmax_flags[m] ? normalise_01(scores[m])[i] : scores[m][i])) / divisor

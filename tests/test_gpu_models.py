@@ -188,3 +188,23 @@ def test_cnn2d_baseline_config0_2048_utterances_vs_cpu_reference_path():
     eer_dev = D.calculate_eer(got, lab)[0]
     assert abs(eer_ref - eer_dev) <= 2e-3        # reported: score ranks 3e-6 apart; see DESIGN.md "Precision"
     assert D.calculate_eer(ref, lab) == oeer.calculate_eer(ref, lab)   # identical scores -> bit-exact EER and threshold
+
+
+def test_fp16_host_slab_scores_like_the_fp32_slab():
+    """dfs_score_host_f16: a pinned fp16 slab (half the PCIe bytes).  The engine quantises the features to fp16 before the
+    first GEMM, so for the 2D-CNN and the 1D-CNN the fp16 image of an fp32 slab gives the very same bits; the CAE also
+    reads the input in its fp32 residual, so there the fp32 slab must hold the fp16-rounded values for equality."""
+    x = torch.from_numpy(syn.features(21, seed=3))
+    x16 = x.half().pin_memory()
+    xr = x16.float().pin_memory()
+    c2 = Cnn2dScorer(syn.cnn2d_state(0), max_chunk=8)
+    np.testing.assert_array_equal(c2.score_host(x16, 1), c2.score_host(x.pin_memory(), 1))
+    c1 = Cnn1dScorer(syn.cnn1d_state(0), max_chunk=16)
+    np.testing.assert_array_equal(c1.score_host(x16, 1), c1.score_host(x.pin_memory(), 1))
+    mean, std = syn.normalizer_stats(1)
+    ca = CaeScorer(syn.cae_state(0), mean, std, max_chunk=8)
+    np.testing.assert_array_equal(ca.score_host(x16), ca.score_host(xr))
+    assert _rel(ca.score_host(x16), ca.score_host(x.pin_memory())) <= 1e-3
+    # the reference's row shape [B,180,321] as an fp16 slab, read through the transposed view
+    rows16 = x.transpose(1, 2).contiguous().half().pin_memory()
+    np.testing.assert_array_equal(c2.score_host(rows16.transpose(1, 2), 1), c2.score_host(x16, 1))
