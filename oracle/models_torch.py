@@ -70,6 +70,23 @@ def cae_forward(sd, x):
 
 
 @torch.no_grad()
+def dlq_forward(sd, x, lengths=None):
+    """src/dlqueen_model.py:115-173 (DeepfakeDetector, eval): x (B,321,180) -> logits (B,)."""
+    h = x.transpose(1, 2)                                                              # (B, C, T)
+    for conv_i, bn_i, pad in ((0, 1, 2), (4, 5, 1), (8, 9, 1)):
+        h = F.gelu(_bn(F.conv1d(h, _t(sd, f"enc.net.{conv_i}.weight"), _t(sd, f"enc.net.{conv_i}.bias"), padding=pad), sd, f"enc.net.{bn_i}"))
+    B, _, T = h.shape
+    lengths = torch.full((B,), T, dtype=torch.long) if lengths is None else torch.as_tensor(lengths)
+    mask = (torch.arange(T).unsqueeze(0) < lengths.unsqueeze(1)).unsqueeze(1).float()
+    denom = mask.sum(dim=2).clamp(min=1.0)
+    mean = (h * mask).sum(dim=2) / denom
+    var = (mask * (h - mean.unsqueeze(-1)) ** 2).sum(dim=2) / denom
+    z = torch.cat([mean, torch.sqrt(var.clamp(min=1e-6))], dim=1)
+    a = F.gelu(F.linear(z, _t(sd, "head.0.weight"), _t(sd, "head.0.bias")))
+    return F.linear(a, _t(sd, "head.3.weight"), _t(sd, "head.3.bias")).squeeze(1)
+
+
+@torch.no_grad()
 def reference_loop_supervised(forward, sd, feats, batch_size=32, apply_sigmoid=True):
     """predict.py:100-111 / predict_hybrid.py:52-63 on an in-memory (N,321,180) fp32 tensor."""
     out = []

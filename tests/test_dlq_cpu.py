@@ -37,6 +37,14 @@ def test_oracle_matches_reference_golden(tag, scale):
     np.testing.assert_allclose(onp.dlq_forward(sd, xz, lengths), G[f"dlq_{tag}_logits_ragged"], rtol=2e-4, atol=2e-6 * scale)
 
 
+def test_torch_oracle_matches_reference_golden():
+    from oracle import models_torch as ot
+    x, xz, lengths = _inputs()
+    sd = syn.dlq_state(0)
+    np.testing.assert_allclose(ot.dlq_forward(sd, torch.from_numpy(x)).numpy(), G["dlq_init_logits_full"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ot.dlq_forward(sd, torch.from_numpy(xz), lengths).numpy(), G["dlq_init_logits_ragged"], rtol=1e-5, atol=1e-7)
+
+
 def test_dropin_contract_and_train_mode_forward():
     sd = syn.dlq_state(0)
     model = dq.DeepfakeDetector(in_ch=180, hidden=256, dropout=0.3)                # dlqueen_model.py:340,417

@@ -208,3 +208,20 @@ def test_fp16_host_slab_scores_like_the_fp32_slab():
     # the reference's row shape [B,180,321] as an fp16 slab, read through the transposed view
     rows16 = x.transpose(1, 2).contiguous().half().pin_memory()
     np.testing.assert_array_equal(c2.score_host(rows16.transpose(1, 2), 1), c2.score_host(x16, 1))
+
+
+def test_large_batches_across_default_pass_sizes_vs_torch_oracle():
+    """300 utterances through the DEFAULT internal pass sizes (CAE 256, 1D-CNN 4736, StatsPool 1184: partial column tiles,
+    second passes) against the torch-CPU oracle of the reference's loops."""
+    from dfs_b200 import DlqScorer
+    from oracle import models_torch as ot
+    n = 300
+    xh = torch.from_numpy(syn.features(n, seed=2024))
+    x = xh.cuda()
+    mean, std = syn.normalizer_stats(1)
+    ref = ot.reference_loop_cae(syn.cae_state(0), xh, torch.from_numpy(mean), torch.from_numpy(std))
+    assert _rel(CaeScorer(syn.cae_state(0), mean, std).score(x).cpu().numpy(), ref) <= REL
+    ref = ot.reference_loop_supervised(ot.cnn1d_forward, syn.cnn1d_state(0), xh)
+    assert _rel(Cnn1dScorer(syn.cnn1d_state(0)).score(x, apply_sigmoid=True).cpu().numpy(), ref) <= REL
+    ref = torch.sigmoid(ot.dlq_forward(syn.dlq_state(0), xh)).numpy()
+    assert _rel(DlqScorer(syn.dlq_state(0)).score(x, apply_sigmoid=True).cpu().numpy(), ref) <= REL
