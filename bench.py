@@ -43,8 +43,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool", type=int, default=16640, help="utterances resident per GPU and scored per step")
     ap.add_argument("--chunk", type=int, default=0, help="utterances per internal pass (0 = library default 416)")
-    ap.add_argument("--e2e-pool", type=int, default=4160, help="utterances in pinned host memory for the e2e leg")
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-pool", type=int, default=16640, help="utterances in pinned host memory for the e2e leg (one step = one call over all of them)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="cnn2d", choices=["cnn2d", "cae", "cnn1d", "hybrid", "eer"],
@@ -363,7 +363,7 @@ def main():
     value = P * world * args.steps / (ms_max * 1e-3)
 
     # ---- e2e: the same metric through the public host-buffer call (pinned host -> H2D -> kernels -> D2H) ----
-    Pe = args.e2e_pool
+    Pe = min(args.e2e_pool, P)
     host_pool = torch.empty((Pe, 321, 180), dtype=torch.float32, pin_memory=True)
     host_pool.copy_(pool[:Pe])
     scorer.score_host(host_pool, 1)
