@@ -34,7 +34,7 @@ N_FEATS, T_FRAMES = 180, 321
 @dataclass
 class FeatureTable:
     uttids: np.ndarray            # object array, file order
-    slab: "torch.Tensor"          # [N, 180, 321] fp32, pinned when a CUDA device is present
+    slab: "torch.Tensor"          # [N, 180, 321] fp32 (or fp16), pinned when a CUDA device is present
 
     def __len__(self):
         return int(self.slab.shape[0])
@@ -46,20 +46,21 @@ class FeatureTable:
     def take(self, index):
         """Sub-table in the given row order (rows are copied into a fresh pinned slab)."""
         index = np.asarray(index, dtype=np.int64)
-        out = _alloc(len(index))
+        out = _alloc(len(index), self.slab.dtype)
         if len(index):
             torch.index_select(self.slab, 0, torch.from_numpy(index), out=out)
         return FeatureTable(self.uttids[index], out)
 
 
-def _alloc(n):
-    return torch.empty((n, N_FEATS, T_FRAMES), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+def _alloc(n, dtype=torch.float32):
+    return torch.empty((n, N_FEATS, T_FRAMES), dtype=dtype, pin_memory=torch.cuda.is_available())
 
 
-def pack_features(rows) -> "torch.Tensor":
-    """list / Series of per-utterance tensors (or arrays) [180, 321] of any float dtype -> one pinned fp32 slab.
+def pack_features(rows, dtype=torch.float32) -> "torch.Tensor":
+    """list / Series of per-utterance tensors (or arrays) [180, 321] of any float dtype -> one pinned slab.
     fp32 rows are stacked by a single multi-threaded ``torch.stack(out=)``; other dtypes are cast like the
-    reference's ``.float()`` (src/predict.py:63)."""
+    reference's ``.float()`` (src/predict.py:63).  ``dtype=torch.float16`` packs the half-width slab of
+    ``dfs_score_host_f16`` (same 2D-CNN / 1D-CNN scores, half the PCIe bytes)."""
     rows = list(rows)
     n = len(rows)
     if n == 0:
@@ -72,13 +73,20 @@ def pack_features(rows) -> "torch.Tensor":
         if t.dtype != torch.float32 or t.device.type != "cpu":
             t = t.detach().to("cpu").float()
         fixed.append(t.detach())
-    slab = _alloc(n)
-    torch.stack(fixed, out=slab)
+    if dtype == torch.float32:
+        slab = _alloc(n)
+        torch.stack(fixed, out=slab)
+        return slab
+    if dtype != torch.float16:
+        raise ValueError("slab dtype must be torch.float32 or torch.float16")
+    slab = _alloc(n, torch.float16)
+    for i, t in enumerate(fixed):
+        slab[i].copy_(t)                      # fp32 -> fp16, round to nearest even (what the first kernel would do)
     return slab
 
 
-def load_feature_table(source) -> FeatureTable:
-    """``source``: path of a features.pkl or the DataFrame itself ({uttid, features})."""
+def load_feature_table(source, dtype=torch.float32) -> FeatureTable:
+    """``source``: path of a features.pkl or the DataFrame itself ({uttid, features}); ``dtype``: slab dtype (fp32 | fp16)."""
     import pandas as pd
     df = pd.read_pickle(source) if isinstance(source, (str, os.PathLike)) else source
     if "uttid" not in df.columns:
@@ -86,7 +94,7 @@ def load_feature_table(source) -> FeatureTable:
     if "features" not in df.columns:
         raise ValueError("features.pkl must contain 'features'")
     uttids = np.asarray(df["uttid"].values, dtype=object)
-    return FeatureTable(uttids, pack_features(df["features"].reset_index(drop=True)))
+    return FeatureTable(uttids, pack_features(df["features"].reset_index(drop=True), dtype))
 
 
 def merge_labels(table: FeatureTable, labels_df):

@@ -38,6 +38,8 @@ def test_pack_features_matches_row_by_row_float_cast(tmp_path):
     mixed = [df["features"].iloc[0].double(), df["features"].iloc[1].half(), df["features"].iloc[2].numpy()]
     slab = ingest.pack_features(mixed)
     assert torch.equal(slab[0], mixed[0].float()) and torch.equal(slab[1], mixed[1].float()) and torch.equal(slab[2], df["features"].iloc[2])
+    t16 = ingest.load_feature_table(paths["features"], dtype=torch.float16)        # half-width slab for dfs_score_host_f16
+    assert t16.slab.dtype == torch.float16 and torch.equal(t16.slab, table.slab.half()) and t16.take([2]).slab.dtype == torch.float16
     sub = table.take([3, 1])
     assert list(sub.uttids) == [fx.uttids()[3], fx.uttids()[1]] and torch.equal(sub.slab[0], table.slab[3])
 

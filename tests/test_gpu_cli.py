@@ -116,3 +116,12 @@ def test_evaluate_with_fused_bce_matches_reference_evaluate(files):
     assert abs(D.bce_with_logits_mean(x, y) - want) <= 1e-6 * want
     # EER on 12 random-init scores a few 1e-6 apart is rank-sensitive (DESIGN.md "Tolerances"): check it on the reference's scores
     assert D.calculate_eer(CLI["evaluate_scores"], CLI["evaluate_labels"]) == (ref_eer, ref_thr)
+
+
+def test_fp16_ingestion_scores_like_fp32_ingestion(files):
+    """features.pkl -> fp16 pinned slab -> dfs_score_host_f16 gives the same 2D-CNN scores as the fp32 slab."""
+    model = dpredict.load_checkpoint_into(m2.CNN2D(in_features=180, dropout=0.2).cuda(), files["cnn2d"], "cuda")
+    model.eval()
+    a = dpredict.score_table(model, ingest.load_feature_table(files["features"]), "cuda")
+    b = dpredict.score_table(model, ingest.load_feature_table(files["features"], dtype=torch.float16), "cuda")
+    assert np.array_equal(a, b)
