@@ -164,7 +164,7 @@ struct ProfScope {
   cudaStream_t s;
   cudaEvent_t stop = nullptr;
   ProfScope(dfs_model* m_, int kid, cudaStream_t s_) : m(m_), s(s_) {
-    if (!m->profile) return;
+    if (!m->profile || !((m->profile >> kid) & 1)) return;   // option "profile" = bit mask of kernel ids (1 = all)
     if (m->prof_used * 2 + 2 > m->prof_ev.size()) {
       cudaEvent_t a, b;
       if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
@@ -237,8 +237,8 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     m->c1d->l1_fused = (int)value;
     return DFS_OK;
   }
-  if (strcmp(key, "profile") == 0) {
-    m->profile = value != 0;
+  if (strcmp(key, "profile") == 0) {   // 0 = off, 1 = every kernel id, otherwise a bit mask of kernel ids (bit k = id k)
+    m->profile = value == 1 ? 0x7fffffff : (int)value;
     m->prof_used = 0;
     return DFS_OK;
   }
