@@ -58,8 +58,10 @@ struct dfs_model {
   float* emb = nullptr;
   CUtensorMap tmap1{}, tmap2{};
   int conv1_impl = 0;          // 0 = tensor-core Toeplitz GEMM, 1 = CUDA-core cross-check
+  int conv12_fused = 0;        // 1 = conv1 + conv2 in one kernel (conv12_fused.cu), act1 never written
   uint16_t* xt = nullptr;      // fp16 time-major copy of the features (conv1_tc A operand)
   uint16_t* w1pack = nullptr;  // Toeplitz weights [kw][2][256][8]
+  uint16_t* w1pack_fused = nullptr;  // the same, split into two 16-channel passes [pass][kw][2][128][8] (conv12_fused.cu)
   float b1h[32] = {0};         // 0.5 * folded conv1 bias
   // ---- CAE / 1D-CNN on the tcgen05 template (cae_tc.cu, cnn1d_tc.cu) ----
   CaeTcState* cae = nullptr;
@@ -227,6 +229,11 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     if (m->cae != nullptr) m->cae->enc1_impl = (int)value;
     return DFS_OK;
   }
+  if (strcmp(key, "conv12_fused") == 0) {
+    DFS_REQUIRE(m->kind == KIND_CNN2D && (value == 0 || value == 1), DFS_ERR_INVALID, "conv12_fused is a CNN2D option (0 | 1)");
+    m->conv12_fused = (int)value;
+    return DFS_OK;
+  }
   if (strcmp(key, "final_fused") == 0) {
     DFS_REQUIRE(m->cae != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "final_fused is a CAE option (0 | 1)");
     m->cae->final_fused = (int)value;
@@ -341,6 +348,17 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
           }
     for (int c = 0; c < 32; ++c) m->b1h[c] = 0.5f * m->c1.b[c];
     if ((st = dev_upload(m, &m->w1pack, p1)) != DFS_OK) return fail(st);
+    // the same weights for conv12_fused.cu, which runs conv1 as two N = 128 passes of 16 output channels each (its
+    // accumulator gets 128 TMEM columns): [pass][kw][K chunk][n' = jj*16 + c'][8], channel c = 16*pass + c'
+    std::vector<uint16_t> p1f((size_t)2 * 3 * 2 * 128 * 8, 0);
+    for (int ps = 0; ps < 2; ++ps)
+      for (int kw = 0; kw < 3; ++kw)
+        for (int ch = 0; ch < 2; ++ch)
+          for (int jj = 0; jj < 8; ++jj)
+            for (int cp = 0; cp < 16; ++cp)
+              for (int e = 0; e < 8; ++e)
+                p1f[(((((size_t)ps * 3 + kw) * 2 + ch) * 128) + jj * 16 + cp) * 8 + e] = p1[(((size_t)kw * 2 + ch) * 256 + jj * 32 + 16 * ps + cp) * 8 + e];
+    if ((st = dev_upload(m, &m->w1pack_fused, p1f)) != DFS_OK) return fail(st);
     if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->xt), (size_t)conv1_xt_rows(m->chunk) * 16, true)) != DFS_OK) return fail(st);
   }
 
@@ -377,6 +395,16 @@ extern "C" int dfs_cnn2d_score(dfs_model* m, const dfs_features* feats, float* o
   for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk) {
     const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
     const float* x = feats->x + i0 * feats->stride_n;
+    if (m->conv12_fused && m->conv_impl == 0 && m->conv1_impl == 0) {
+      {
+        ProfScope ps(m, 0, stream);
+        DFS_PROPAGATE(launch_conv1_prep(x, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->xt, stream));
+      }
+      {
+        ProfScope ps(m, 1, stream);
+        DFS_PROPAGATE(launch_cnn2d_conv12_fused(m->xt, m->w1pack_fused, m->b1h, m->w2pack, m->b2, nk, m->act2, m->num_sms, stream));
+      }
+    } else {
     {
       ProfScope ps(m, 0, stream);
       if (m->conv1_impl == 0)
@@ -389,6 +417,7 @@ extern "C" int dfs_cnn2d_score(dfs_model* m, const dfs_features* feats, float* o
       ProfScope ps(m, 1, stream);
       if (m->conv_impl == 0) DFS_PROPAGATE(launch_cnn2d_conv2_tc(m->tmap1, m->w2pack, m->b2, nk, m->act2, m->num_sms, stream));
       else DFS_PROPAGATE(launch_cnn2d_conv2_simt(m->act1, m->w2pack, m->b2_dev, nk, m->act2, stream));
+    }
     }
     {
       ProfScope ps(m, 2, stream);

@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
   }
 }
 
-int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, const uint16_t* wpack, const float* bias_half,
-                    ActBuf out, int num_sms, cudaStream_t stream) {
+// fp32 strided features -> xT (the A operand image of conv1_tc_kernel and of conv12_fused_kernel)
+int launch_conv1_prep(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, cudaStream_t stream) {
   if (n_utts <= 0) return DFS_OK;
   if (sf == 1) {   // feature-contiguous storage: transpose through shared memory (xt_prep.cuh)
     xt_prep_transpose_kernel<<<dim3((kF + 31) / 32, n_utts), 256, 0, stream>>>(x, sn, st, kCols, 1, kXtLead, nullptr, nullptr, xt);
@@ -241,6 +241,13 @@ int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_ut
     conv1_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, xt);
   }
   DFS_LAUNCH_CHECK();
+  return DFS_OK;
+}
+
+int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, const uint16_t* wpack, const float* bias_half,
+                    ActBuf out, int num_sms, cudaStream_t stream) {
+  if (n_utts <= 0) return DFS_OK;
+  DFS_PROPAGATE(launch_conv1_prep(x, sn, st, sf, n_utts, xt, stream));
   static bool configured[32] = {false};
   if (dfs_first_use_on_device(configured))
     DFS_CUDA_CHECK(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1SmemB));
