@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) cnn1d_l1_fused_kernel(const __g
   uint8_t* wsm = smem;
   uint8_t* stage0 = smem + kL1StageOff;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kL1BarOff);
-  uint64_t* full = bars;                   // [stages]  producers -> MMA (one arrival per producer thread)
+  uint64_t* full = bars;                   // [stages]  producers -> MMA (one arrival per producer warp)
   uint64_t* empty = bars + kL1Stages;      // [stages]  MMA -> producers
   uint64_t* tfull = empty + kL1Stages;     // [acc]     MMA -> epilogue
   uint64_t* tempty = tfull + kL1Acc;       // [acc]     epilogue -> MMA (4 warps)
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) cnn1d_l1_fused_kernel(const __g
   for (int i = threadIdx.x; i < kL1Stages * kL1StageB / 16; i += kL1Threads) reinterpret_cast<uint4*>(stage0)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   if (warp == kL1MmaWarp && lane == 0) {
-    for (int i = 0; i < kL1Stages; ++i) { mbar_init(&full[i], kL1Prod); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kL1Stages; ++i) { mbar_init(&full[i], kL1ProdWarps); mbar_init(&empty[i], 1); }
     for (int i = 0; i < kL1Acc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     mbar_init(wbar, 1);
     fence_mbar_init();
@@ -145,8 +145,9 @@ __global__ void __launch_bounds__(kL1Threads, 1) cnn1d_l1_fused_kernel(const __g
             }
           }
         }
-        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        mbar_arrive(&full[stage]);
+        fence_proxy_async_smem();   // every lane: generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();               // then ONE arrival per warp (hundreds of single-thread arrivals on one mbarrier serialise: ~4 cycles each)
+        if (lane == 0) mbar_arrive(&full[stage]);
       }
     }
   } else if (warp == kL1MmaWarp) {
