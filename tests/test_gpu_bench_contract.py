@@ -1,0 +1,47 @@
+"""GPU: bench.py prints ONE JSON line carrying every key of the measurement contract, for the headline
+workload (with the CPU baseline / parity leg) and for a side workload."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from conftest import ROOT  # noqa: E402
+
+
+def _run(*args):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    return json.loads(lines[0])
+
+
+def test_headline_line_has_every_contract_key():
+    d = _run("--pool", "832", "--steps", "2", "--warmup", "3", "--e2e-steps", "1", "--cpu-seconds", "3")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "utterances/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"] and "l2" in d["config"]
+    assert d["value"] > 1e4 and d["gpu_launches"] > 0
+    e = d["e2e"]
+    assert e["value"] > 1e3 and e["h2d_bytes_per_step"] == 832 * 321 * 180 * 4 and e["d2h_bytes_per_step"] == 832 * 4
+    assert e["value"] != d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    assert d["parity"]["max_rel_err_scores_vs_cpu_reference"] <= d["parity"]["tolerance"] == 1e-3
+    assert d["e2e_f16_slab"]["scores_identical_to_fp32_slab"] is True
+
+
+def test_eer_workload_reports_both_paths():
+    d = _run("--workload", "eer", "--eer-n", "3000000", "--steps", "2", "--warmup", "3")
+    assert d["unit"] == "scores/s" and d["roofline"]["bound"] == "hbm" and d["scaling"] == "replicas only"
+    assert d["eer_select"]["identical_result"] is True and d["eer_select"]["value"] > d["value"]

@@ -33,7 +33,10 @@ LISTS = (("launches.csv", "launch_share", "bench.py (2D-CNN headline workload)")
          ("eer_launches.csv", "eer_launch_share", "bench.py --workload eer (100 M scores: sort path, then select path)"))
 REPORTS = (("prof_conv.ncu-rep", "conv_kernels_ncu_full", "2D-CNN conv kernels"),
            ("prof_hybrid.ncu-rep", "hybrid_kernels_ncu_full", "CAE enc1 / final and 1D-CNN fused layer 1"),
-           ("prof_eer.ncu-rep", "eer_kernels_ncu_full", "EER: select histogram, radix count and scatter passes"))
+           ("prof_eer.ncu-rep", "eer_kernels_ncu_full", "EER sort path: radix count and scatter passes"),
+           ("prof_sel.ncu-rep", "eer_select_kernels_ncu_full", "EER select path: TMA-fed (digit, label) histogram, first and later levels"),
+           ("prof_c1d.ncu-rep", "cnn1d_fused_and_prep_ncu_full", "1D-CNN fused layer 1, transposing input prep, CAE score finish"),
+           ("prof_cae.ncu-rep", "cae_layers_ncu_full", "CAE: dec3 with fused final layer + MSE, enc4 (4 groups of N = 64), enc2 (PAIR)"))
 
 
 def launch_share(tag):
