@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool", type=int, default=16640, help="utterances resident per GPU and scored per step")
     ap.add_argument("--chunk", type=int, default=0, help="utterances per internal pass (0 = library default 416)")
-    ap.add_argument("--e2e-pool", type=int, default=16640, help="utterances in pinned host memory for the e2e leg (one step = one call over all of them)")
+    ap.add_argument("--e2e-pool", type=int, default=8320, help="utterances in pinned host memory for the e2e leg (one step = one call over all of them)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
