@@ -29,7 +29,7 @@ using Enc4Cfg = ConvCfg<MODE_3X3, 128, 64, 64, 40, 1, 3, 4, 2, EPI_POOL_TF>;
 using Dec1Cfg = ConvCfg<MODE_1X1, 256, 128, 128, 24, 1, 3, 2, 4, EPI_SHUFFLE>;
 using Dec2Cfg = ConvCfg<MODE_1X1, 128, 64, 128, 40, 1, 3, 2, 2, EPI_SHUFFLE>;
 using Dec3Cfg = ConvCfg<MODE_1X1, 64, 32, 128, 80, 2, 3, 4, 1, EPI_SHUFFLE>;
-using Dec3MseCfg = ConvCfg<MODE_1X1, 64, 32, 128, 80, 2, 3, 4, 1, EPI_SHUFFLE_MSE>;   // dec3 + final ConvT + squared error, nothing written but partial sums
+using Dec3MseCfg = ConvCfg<MODE_1X1, 64, 32, 128, 80, 2, 3, 2, 1, EPI_SHUFFLE_MSE>;   // dec3 + final ConvT + squared error, nothing written but partial sums
 
 // geometry of the seven activation buffers: planes, padded cols per utterance, rows per column
 static const int kCaePlanes[7] = {8, 8, 16, 32, 16, 8, 4};
