@@ -285,9 +285,8 @@ def run_other_workload(args, rank, world, local):
 
 def main():
     args = parse()
-    # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it; an explicit INFO / TRACE is left alone
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 prints ONE JSON line on stdout: NCCL's banner / debug lines (NCCL_DEBUG=VERSION|WARN|INFO on the box) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
