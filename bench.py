@@ -285,7 +285,10 @@ def run_other_workload(args, rank, world, local):
 
 def main():
     args = parse()
-    # rank 0 prints ONE JSON line on stdout: NCCL's banner / debug lines (NCCL_DEBUG=VERSION|WARN|INFO on the box) go to stderr
+    # rank 0 prints ONE JSON line on stdout.  With NCCL_DEBUG=VERSION|WARN NCCL printf()s its version banner straight to
+    # stdout: drop those two levels (errors still surface as exceptions); INFO / TRACE output goes to stderr
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
