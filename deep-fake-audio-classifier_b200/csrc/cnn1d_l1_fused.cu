@@ -34,7 +34,6 @@ constexpr int kL1StageOff = (kL1WgtB + 127) & ~127;
 constexpr int kL1BarOff = kL1StageOff + kL1Stages * kL1StageB;
 constexpr int kL1SmemB = kL1BarOff + 256;
 constexpr int kL1ProdWarps = 12;                         // enough loads in flight to cover the L2 / HBM latency of the fp32 rows
-constexpr int kL1Prod = 32 * kL1ProdWarps;
 constexpr int kL1MmaWarp = 4 + kL1ProdWarps;
 constexpr int kL1Threads = 32 * (kL1MmaWarp + 2);        // warps 0-3 epilogue, 4-15 producers, 16 MMA issuer, 17 TMEM allocator
 

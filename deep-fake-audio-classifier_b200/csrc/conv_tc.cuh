@@ -147,7 +147,7 @@ __device__ __forceinline__ void store_chunks(uint16_t* dst, long long plane_elem
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::OCC)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvParams p) {
-  constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, MT = Cfg::MT, NSTAGE = Cfg::NSTAGE, NACC = Cfg::NACC, NG = Cfg::NG;
+  constexpr int COUT = Cfg::COUT, MT = Cfg::MT, NSTAGE = Cfg::NSTAGE, NACC = Cfg::NACC, NG = Cfg::NG;
   constexpr int WROWS = Cfg::WROWS, PLANE_B = Cfg::PLANE_B, KSPLIT = Cfg::KSPLIT, HALO = Cfg::HALO, HALO_C = Cfg::HALO_C;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* wsm = smem;
