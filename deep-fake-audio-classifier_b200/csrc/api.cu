@@ -560,8 +560,8 @@ extern "C" int dfs_cnn1d_score(dfs_model* m, const dfs_features* feats, float* o
 // ------------------------------------------------------------------------------------------
 // StatsPool detector (src/dlqueen_model.py:132-173)
 // ------------------------------------------------------------------------------------------
-// Conv1d (Co,Ci,K) -> [group][tap][ci_pad/8][64][8], output channels in groups of 64, BN folded
-static std::vector<uint16_t> pack_conv1d_groups(const dfs_conv_bn& c, int co, int ci, int ci_pad, int ktaps, float* bias_out) {
+// Conv1d (Co,Ci,K) -> [group][tap][ci_pad/8][gco][8], output channels in groups of gco, BN folded
+static std::vector<uint16_t> pack_conv1d_groups(const dfs_conv_bn& c, int co, int ci, int ci_pad, int ktaps, int gco, float* bias_out) {
   std::vector<double> scale, shift;
   bn_fold(c, co, scale, shift);
   for (int o = 0; o < co; ++o) bias_out[o] = (float)shift[o];
@@ -570,8 +570,8 @@ static std::vector<uint16_t> pack_conv1d_groups(const dfs_conv_bn& c, int co, in
     for (int i = 0; i < ci; ++i)
       for (int k = 0; k < ktaps; ++k) {
         const double w = (double)c.weight[((size_t)o * ci + i) * ktaps + k] * scale[o];
-        const size_t g = o / 64, ol = o % 64;
-        out[((((size_t)g * ktaps + k) * (ci_pad / 8) + (i >> 3)) * 64 + ol) * 8 + (i & 7)] = f32_to_act_bits((float)w);
+        const size_t g = o / gco, ol = o % gco;
+        out[((((size_t)g * ktaps + k) * (ci_pad / 8) + (i >> 3)) * gco + ol) * 8 + (i & 7)] = f32_to_act_bits((float)w);
       }
   return out;
 }
@@ -588,7 +588,7 @@ extern "C" int dfs_dlq_create(dfs_model** out, int device, const dfs_dlq_weights
   m->kind = KIND_DLQ;
   int st = model_common_init(m, device);
   if (st != DFS_OK) { delete m; return st; }
-  // 4 output-channel groups share the SMs: 1184 utterances = 74 column tiles = 2 per CTA at 37 CTAs per group
+  // the output-channel groups share the SMs: 1184 utterances = 74 column tiles = 2 (layer 1, 37 CTAs per group) or 1 (layers 2-3) per CTA
   m->chunk = max_chunk > 0 ? max_chunk : 1184;
   auto fail = [&](int s) { dfs_model_destroy(m); return s; };
   DlqState* s = new (std::nothrow) DlqState();
@@ -596,9 +596,9 @@ extern "C" int dfs_dlq_create(dfs_model** out, int device, const dfs_dlq_weights
   m->dlq = s;
   memset(s->bias, 0, sizeof(s->bias));
   std::vector<uint16_t> packs[3];
-  packs[0] = pack_conv1d_groups(w->conv[0], 256, kF, 192, 5, s->bias[0]);
-  packs[1] = pack_conv1d_groups(w->conv[1], 256, 256, 256, 3, s->bias[1]);
-  packs[2] = pack_conv1d_groups(w->conv[2], 256, 256, 256, 3, s->bias[2]);
+  packs[0] = pack_conv1d_groups(w->conv[0], 256, kF, 192, 5, 64, s->bias[0]);
+  packs[1] = pack_conv1d_groups(w->conv[1], 256, 256, 256, 3, 128, s->bias[1]);
+  packs[2] = pack_conv1d_groups(w->conv[2], 256, 256, 256, 3, 128, s->bias[2]);
   for (int i = 0; i < 3; ++i) {
     uint16_t* d = nullptr;
     if ((st = dev_upload(m, &d, packs[i])) != DFS_OK) return fail(st);

@@ -111,12 +111,15 @@ int launch_cnn1d_tc(const Cnn1dTcState* s, const float* x, int64_t sn, int64_t s
 //   ConvEncoder  Conv1d(180,256,k5,p2)+BN+GELU -> Conv1d(256,256,k3,p1)+BN+GELU -> Conv1d(256,256,k3,p1)+BN+GELU
 //   StatsPool    masked mean and std over time (two passes, var clamped at 1e-6)           -> (B, 512)
 //   head         Linear(512,256) + GELU + Linear(256,1)
-// The conv layers are the conv1d template with 4 output-channel groups of N = 64 (the 256-wide weights of one layer are
-// 295-480 KB, one group 98-123 KB), K pieces of 8 channel planes, exact (erf) GELU in the epilogue.  Same input copy as
+// The conv layers are the conv1d template with output-channel groups (the 256-wide weights of one layer are 390-480 KB):
+// layer 1 (k = 5) as 4 groups of N = 64 (123 KB each), layers 2 and 3 as 2 groups of N = 128 (196 KB each), exact (erf)
+// GELU in the epilogue.  Same input copy as
 // the 1D-CNN (cnn1d_prep_kernel); the k = 5 halo rows beyond the stored pad row are the TMA's out-of-bounds zeros.
 // Pooling + head are one block per utterance (256 threads = 256 channels / hidden units), fp32, fixed order.
 using DlqL1 = ConvCfg<MODE_5X1, 192, 64, 64, kC1dRows, 1, 3, 4, 3, EPI_GELU>;
-using DlqL2 = ConvCfg<MODE_3X1, 256, 64, 64, kC1dRows, 1, 3, 4, 4, EPI_GELU>;
+// layers 2 and 3: two groups of N = 128 (196 KB of resident weights; the activation window is cut into 8 pieces of 4 channel
+// planes = 10 KB so that three stages still fit): an N = 128 MMA costs the same 88-100 cycles as an N = 64 one
+using DlqL2 = ConvCfg<MODE_3X1, 256, 128, 128, kC1dRows, 1, 3, 4, 8, EPI_GELU>;
 
 void dlq_geometry(int buf, int* planes, int* rs) {
   *planes = buf == 0 ? 24 : 32;
@@ -194,8 +197,8 @@ int launch_dlq(const DlqState* s, const float* x, int64_t sn, int64_t st, int64_
   cnn1d_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, s->act0);
   DFS_LAUNCH_CHECK();
   DFS_PROPAGATE(launch_conv_tc<DlqL1>(s->tmap[0], dlq_params(s, 0, n_utts, s->actA), 4, num_sms, stream));
-  DFS_PROPAGATE(launch_conv_tc<DlqL2>(s->tmap[1], dlq_params(s, 1, n_utts, s->actB), 4, num_sms, stream));
-  DFS_PROPAGATE(launch_conv_tc<DlqL2>(s->tmap[2], dlq_params(s, 2, n_utts, s->actA), 4, num_sms, stream));
+  DFS_PROPAGATE(launch_conv_tc<DlqL2>(s->tmap[1], dlq_params(s, 1, n_utts, s->actB), 2, num_sms, stream));
+  DFS_PROPAGATE(launch_conv_tc<DlqL2>(s->tmap[2], dlq_params(s, 2, n_utts, s->actA), 2, num_sms, stream));
   dlq_stats_head_kernel<<<n_utts, 256, 0, stream>>>(s->actA, lengths_dev, s->fc1_wt, s->fc1_b, s->fc2_w, s->fc2_b, apply_sigmoid, out);
   DFS_LAUNCH_CHECK();
   return DFS_OK;

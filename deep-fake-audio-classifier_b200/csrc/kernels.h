@@ -90,7 +90,7 @@ struct DlqState {
   ActBuf act0;            // fp16 input copy, 24 planes (180 features zero-padded to 192)
   ActBuf actA, actB;      // 32-plane (256-channel) ping-pong activation buffers
   CUtensorMap tmap[3];    // inputs of the three conv layers: act0, actA, actB
-  const uint16_t* w[3];   // packed fp16 weights [group 4][tap][ci/8][64][8]
+  const uint16_t* w[3];   // packed fp16 weights [group][tap][ci/8][gco][8], gco = 64 (layer 1) / 128 (layers 2, 3)
   float bias[3][256];
   const float* fc1_wt;    // head.0.weight transposed to [512][256] (device)
   const float* fc1_b;     // [256]
