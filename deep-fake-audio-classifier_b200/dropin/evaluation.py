@@ -54,3 +54,34 @@ def evaluate(model, dataloader, criterion=None, device="cpu", apply_sigmoid=Fals
     if scores and labels:
         eer, threshold = calculate_eer(scores, labels)
     return {"avg_loss": (total_loss / total_count) if total_count > 0 else None, "eer": eer, "threshold": threshold}, scores, labels
+
+
+def main(argv=None):
+    """``python evaluation.py <prediction.pkl> <labels.pkl>`` -- the reference's scoring CLI (scripts/evaluation.py:59-95):
+    same validation errors, same printout, EER and confusion counts on the device."""
+    import pandas as pd
+    argv = sys.argv[1:] if argv is None else list(argv)
+    if len(argv) != 2:
+        raise ValueError("Usage: python evaluation.py <prediction.pkl> <labels.pkl>")
+    prediction_df = pd.read_pickle(argv[0])
+    labels_df = pd.read_pickle(argv[1])
+    if "uttid" not in prediction_df.columns or "predictions" not in prediction_df.columns:
+        raise ValueError("prediction.pkl must have 'uttid' and 'predictions' columns")
+    if "uttid" not in labels_df.columns or "label" not in labels_df.columns:
+        raise ValueError("labels.pkl must have 'uttid' and 'label' columns")
+    merged = pd.merge(prediction_df, labels_df, on="uttid", how="inner")
+    if len(merged) != len(prediction_df) or len(merged) != len(labels_df):
+        raise ValueError("uttid mismatch between prediction and labels")
+    scores = merged["predictions"].values
+    labels = merged["label"].values
+    eer, threshold = calculate_eer(scores, labels)
+    tp, fp, tn, fn, far, frr = confusion_at_threshold(scores, labels, threshold)
+    print(f"EER: {eer:.6f}")
+    print(f"Threshold: {threshold:.6f}")
+    print(f"TP: {tp}  FP: {fp}  TN: {tn}  FN: {fn}")
+    print(f"FAR: {far:.6f}  FRR: {frr:.6f}")
+    return eer, threshold, (tp, fp, tn, fn, far, frr)
+
+
+if __name__ == "__main__":
+    main()

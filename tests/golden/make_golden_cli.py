@@ -6,6 +6,7 @@ build container on CPU:
 * src/predict.py --model cnn2d|cnn1d [--no-apply-sigmoid]     (prediction.pkl: uttid order, dtypes, values)
 * src/predict_hybrid.py --alpha 0.8                            (hybrid prediction.pkl)
 * scripts/evaluation.py prediction.pkl labels.pkl              (printed EER / threshold / confusion)
+* src/ensemble.py --checkpoints cnn2d:... cnn1d:...            (per-model and ensemble EER printout)
 * src/hybrid_ensemble.py's alpha sweep loop (lines 139-151)    (EER per alpha on the dev scores)
 * src/evaluation.py::evaluate with nn.BCEWithLogitsLoss        (avg_loss, eer, threshold on logits)
 
@@ -63,6 +64,10 @@ def main():
         # scripts/evaluation.py on the cnn2d sigmoid predictions
         text = run([os.path.join(REF, "scripts", "evaluation.py"), os.path.join(tmp, "pred_cnn2d_sigmoid.pkl"), paths["labels"]], tmp)
         out["evaluation_stdout"] = np.array(text)
+        # src/ensemble.py on the two supervised checkpoints (per-model and ensemble EER printout)
+        text = run([os.path.join(REF, "src", "ensemble.py"), "--checkpoints", "cnn2d:" + paths["cnn2d"], "cnn1d:" + paths["cnn1d"],
+                    "--dev-features", paths["features"], "--dev-labels", paths["labels"], "--device", "cpu"], os.path.join(REF, "src"))
+        out["ensemble_stdout"] = np.array(text)
         # the alpha sweep of src/hybrid_ensemble.py:131-151 on (sup, cae) score vectors of the reference itself
         spec = importlib.util.spec_from_file_location("ref_scripts_evaluation", os.path.join(REF, "scripts", "evaluation.py"))
         ev = importlib.util.module_from_spec(spec)

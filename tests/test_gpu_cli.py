@@ -125,3 +125,40 @@ def test_fp16_ingestion_scores_like_fp32_ingestion(files):
     a = dpredict.score_table(model, ingest.load_feature_table(files["features"]), "cuda")
     b = dpredict.score_table(model, ingest.load_feature_table(files["features"], dtype=torch.float16), "cuda")
     assert np.array_equal(a, b)
+
+
+def _parse_ensemble(text):
+    import re
+    eers = [float(x) for x in re.findall(r"EER\s*=\s*([0-9.]+)", text)]
+    thrs = [float(x) for x in re.findall(r"threshold\s*=\s*([0-9.]+)", text)]
+    return eers, thrs
+
+
+def test_ensemble_cli_matches_reference_cli(files, capsys):
+    """src/ensemble.py's printout (per-model EER / threshold, ensemble EER / threshold) on the same files."""
+    import ensemble as dens
+    res = dens.main(["--checkpoints", "cnn2d:" + files["cnn2d"], "cnn1d:" + files["cnn1d"], "--dev-features", files["features"],
+                     "--dev-labels", files["labels"], "--device", "cuda"])
+    got_e, got_t = _parse_ensemble(capsys.readouterr().out)
+    ref_e, ref_t = _parse_ensemble(str(CLI["ensemble_stdout"]))
+    assert len(got_e) == len(ref_e) == 3
+    assert got_e == ref_e                                            # rank-based: equal as long as the score order is preserved
+    assert np.max(np.abs(np.array(got_t) - np.array(ref_t))) <= 1e-4
+    from oracle import eer as oeer
+    ref_mean = oeer.ensemble_mean([CLI["predict_cnn2d_sigmoid"], CLI["predict_cnn1d_sigmoid"]])
+    assert np.max(np.abs(res["ensemble_scores"] - ref_mean) / ref_mean) <= TOL
+
+
+def test_evaluation_cli_printout_is_the_reference_printout(files, tmp_path, capsys):
+    """scripts/evaluation.py <prediction.pkl> <labels.pkl>: identical inputs -> identical text."""
+    from scoring import write_predictions
+    pred = str(tmp_path / "prediction.pkl")
+    write_predictions(fx.uttids(), CLI["predict_cnn2d_sigmoid"], pred)
+    dev_eval.main([pred, files["labels"]])
+    assert capsys.readouterr().out == str(CLI["evaluation_stdout"])
+    with pytest.raises(ValueError, match="Usage"):
+        dev_eval.main([pred])
+    bad = str(tmp_path / "bad.pkl")
+    pd.DataFrame({"uttid": fx.uttids()}).to_pickle(bad)
+    with pytest.raises(ValueError, match="must have 'uttid' and 'predictions'"):
+        dev_eval.main([bad, files["labels"]])
