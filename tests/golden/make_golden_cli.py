@@ -68,6 +68,14 @@ def main():
         text = run([os.path.join(REF, "src", "ensemble.py"), "--checkpoints", "cnn2d:" + paths["cnn2d"], "cnn1d:" + paths["cnn1d"],
                     "--dev-features", paths["features"], "--dev-labels", paths["labels"], "--device", "cpu"], os.path.join(REF, "src"))
         out["ensemble_stdout"] = np.array(text)
+        # src/hybrid_ensemble.py and src/evaluation_cae.py CLIs (printouts)
+        out["hybrid_ensemble_stdout"] = np.array(run([os.path.join(REF, "src", "hybrid_ensemble.py"), "--sup-checkpoint", paths["cnn2d"],
+                                                      "--cae-checkpoint", paths["cae"], "--cae-normalizer", paths["normalizer"],
+                                                      "--dev-features", paths["features"], "--dev-labels", paths["labels"], "--device", "cpu"],
+                                                     os.path.join(REF, "src")))
+        out["evaluation_cae_stdout"] = np.array(run([os.path.join(REF, "src", "evaluation_cae.py"), "--features", paths["features"], "--labels",
+                                                     paths["labels"], "--checkpoint", paths["cae"], "--normalizer", paths["normalizer"], "--device", "cpu"],
+                                                    os.path.join(REF, "src")))
         # the alpha sweep of src/hybrid_ensemble.py:131-151 on (sup, cae) score vectors of the reference itself
         spec = importlib.util.spec_from_file_location("ref_scripts_evaluation", os.path.join(REF, "scripts", "evaluation.py"))
         ev = importlib.util.module_from_spec(spec)

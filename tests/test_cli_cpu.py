@@ -81,6 +81,15 @@ def test_cli_flag_surface_matches_the_reference():
         dpredict.parse_args(["--features", "f", "--checkpoint", "c", "--model", "cae", "--out", "o"])
     h = dhybrid.parse_args(["--sup-checkpoint", "s", "--cae-checkpoint", "c", "--cae-normalizer", "n", "--test-features", "t"])
     assert (h.alpha, h.out, h.batch_size, h.device, h.existing_submission) == (0.80, "prediction_hybrid.pkl", 32, None, None)
+    import evaluation_cae as dcae
+    import hybrid_ensemble as dhe
+    e = dhe.parse_args(["--sup-checkpoint", "s", "--cae-checkpoint", "c", "--cae-normalizer", "n"])   # hybrid_ensemble.py:96-109
+    assert (e.sup_arch, e.dev_features, e.dev_labels, e.batch_size, e.device, e.alpha_steps) == \
+           ("cnn2d", "data/dev/features.pkl", "data/dev/labels.pkl", 32, None, 21)
+    with pytest.raises(SystemExit):
+        dhe.parse_args(["--sup-checkpoint", "s", "--cae-checkpoint", "c", "--cae-normalizer", "n", "--sup-arch", "cnn1d"])
+    c = dcae.parse_args(["--features", "f", "--labels", "l", "--checkpoint", "c", "--normalizer", "n"])  # evaluation_cae.py:94-104
+    assert (c.batch_size, c.base_channels, c.device) == (32, 32, None)
 
 
 def test_cli_refuses_to_run_without_cuda(tmp_path):
@@ -134,3 +143,21 @@ def test_cli_goldens_are_consistent_with_the_oracle():
     eer, thr = oeer.calculate_eer(CLI["predict_cnn2d_sigmoid"], fx.labels())
     text = str(CLI["evaluation_stdout"])
     assert f"EER: {eer:.6f}" in text and f"Threshold: {thr:.6f}" in text
+
+
+def test_cae_metrics_follow_the_reference_report():
+    """evaluation_cae.py:58-88 on the reference's own CAE scores: the printed numbers of the reference CLI, recomputed with
+    the oracle EER (the drop-in's cae_metrics needs the device; its arithmetic outside the two EERs is this)."""
+    text = str(CLI["evaluation_cae_stdout"])
+    mse, lab = CLI["cae_scores"], fx.labels()
+    e_neg, t_neg = oeer.calculate_eer((-mse).tolist(), lab.tolist())
+    e_pos, t_pos = oeer.calculate_eer(mse.tolist(), lab.tolist())
+    assert f"Avg MSE (all):      {np.mean(mse):.6f}" in text
+    assert f"Avg MSE (bonafide): {np.mean(mse[lab == 1]):.6f}" in text and f"Avg MSE (spoof):    {np.mean(mse[lab == 0]):.6f}" in text
+    assert f"EER (-MSE):         {e_neg:.6f}" in text and f"EER (+MSE):         {e_pos:.6f}" in text
+    thr = -t_neg if e_neg <= e_pos else t_pos
+    assert f"Threshold (MSE):    {thr:.6f}" in text
+    # hybrid_ensemble.py's printout: the sweep table is the pinned sweep
+    htext = str(CLI["hybrid_ensemble_stdout"])
+    for a, (eer, _) in zip(CLI["alpha_sweep_alphas"], CLI["alpha_sweep_eer_thr"]):
+        assert f"  {a:.2f}    {eer:.6f}" in htext

@@ -162,3 +162,62 @@ def test_evaluation_cli_printout_is_the_reference_printout(files, tmp_path, caps
     pd.DataFrame({"uttid": fx.uttids()}).to_pickle(bad)
     with pytest.raises(ValueError, match="must have 'uttid' and 'predictions'"):
         dev_eval.main([bad, files["labels"]])
+
+
+def _numbers(text):
+    import re
+    return [float(x) for x in re.findall(r"-?\d+\.\d+", text)]
+
+
+def _shape(text):
+    """The printout with every number and temp path blanked: the line structure a downstream parser sees."""
+    import re
+    text = re.sub(r"(Loaded \w+ from ).*", r"\1<path>", text)
+    return re.sub(r"-?\d+\.\d+", "#", text).replace(" *", "")
+
+
+def test_evaluation_cae_cli_matches_reference_cli(files, capsys):
+    """src/evaluation_cae.py's report: same lines, MSE statistics within the score tolerance, both EERs equal."""
+    import evaluation_cae as dcae
+    metrics, mse, labels = dcae.main(["--features", files["features"], "--labels", files["labels"], "--checkpoint", files["cae"],
+                                      "--normalizer", files["normalizer"], "--device", "cuda"])
+    got, ref = capsys.readouterr().out, str(CLI["evaluation_cae_stdout"])
+    assert _shape(got) == _shape(ref)
+    g, r = np.array(_numbers(_shape_keep(got))), np.array(_numbers(_shape_keep(ref)))
+    assert g.shape == r.shape and np.max(np.abs(g - r)) <= 2e-6 + TOL * 1e-2 * np.max(np.abs(r))     # printed to 6 decimals
+    assert _rel(np.asarray(mse), CLI["cae_scores"]) <= TOL
+    assert (metrics["eer_neg"], metrics["eer_pos"]) == (0.5, 0.5) and metrics["convention"].startswith("standard")
+    from oracle import eer as oeer
+    assert metrics["eer_neg"] == oeer.calculate_eer((-np.asarray(mse)).tolist(), labels.tolist(), kind="stable")[0]
+
+
+def _shape_keep(text):
+    import re
+    return re.sub(r"(Loaded \w+ from ).*", r"\1<path>", text)
+
+
+def test_hybrid_ensemble_cli_matches_reference_cli(files, capsys):
+    """src/hybrid_ensemble.py's report.  The 12 random-init supervised scores lie a few 1e-6 apart, so their rank (and with it
+    every EER that involves them) is not determined at the 1e-3 score tolerance: the line structure is the reference's, the
+    CAE-only EER (well separated scores) is the reference's, and every printed EER is the oracle's on the scores this run
+    produced; the bit-exact sweep on identical scores is test_alpha_sweep_on_reference_scores_is_bit_exact."""
+    from oracle import eer as oeer
+    from dataset_cae import FeatureNormalizer
+    from model_cae import ConvAutoencoder
+    from scoring import get_cae_scores, get_supervised_scores
+    res = dhe.main(["--sup-checkpoint", files["cnn2d"], "--cae-checkpoint", files["cae"], "--cae-normalizer", files["normalizer"],
+                    "--dev-features", files["features"], "--dev-labels", files["labels"], "--device", "cuda"])
+    got, ref = capsys.readouterr().out, str(CLI["hybrid_ensemble_stdout"])
+    assert _shape(got) == _shape(ref)
+    assert f"CAE-only         EER = {res['cae_eer']:.6f}" in ref
+    table = ingest.load_feature_table(files["features"])
+    sup = get_supervised_scores(dpredict.load_checkpoint_into(m2.CNN2D(in_features=180, dropout=0.2).cuda(), files["cnn2d"], "cuda"), table, "cuda")
+    cae = get_cae_scores(dpredict.load_checkpoint_into(ConvAutoencoder().cuda(), files["cae"], "cuda"), table,
+                         FeatureNormalizer.load(files["normalizer"]), "cuda")
+    lab = fx.labels().astype(np.float64)
+    assert res["sup_eer"] == oeer.calculate_eer(sup.tolist(), lab.tolist(), kind="stable")[0]
+    assert len(res["sweep"]) == 21
+    for a, e, t in res["sweep"]:
+        comb = a * oeer.normalise_01(sup) + (1 - a) * oeer.normalise_01(cae)
+        assert (e, t) == oeer.calculate_eer(comb.tolist(), lab.tolist(), kind="stable")
+    assert res["best_eer"] == min(e for _, e, _ in res["sweep"])
