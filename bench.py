@@ -460,6 +460,18 @@ def main():
         out["parity"] = {"max_rel_err_scores_vs_cpu_reference": rel, "n": n_used, "tolerance": 1e-3,
                          "eer_cpu": eer_cpu, "eer_gpu": eer_gpu, "eer_delta_pp": 100.0 * abs(eer_cpu - eer_gpu),
                          "labels": "Bernoulli(sigmoid(6*(reference rank/n - 0.5))), seed 7"}
+        # the same utterances through the full-fp32 CUDA-core kernels (Cnn2dScorer(precision="fp32"), csrc/cnn2d_fp32.cu): the
+        # option for evaluations where the rank order of scores a few 1e-6 apart matters (random-init scores are)
+        exact = D.Cnn2dScorer(sd, device=local, precision="fp32")
+        exact.score(pool[:16], apply_sigmoid=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s32 = exact.score(pool[:n_used], apply_sigmoid=True).cpu().numpy()
+        dt = time.perf_counter() - t0
+        eer32 = D.calculate_eer(s32, lab)[0]
+        out["parity"]["fp32_mode"] = {"max_rel_err_scores_vs_cpu_reference": float(np.max(np.abs(s32 - ref_scores) / np.abs(ref_scores))),
+                                      "eer_gpu": eer32, "eer_delta_pp": 100.0 * abs(eer_cpu - eer32), "utterances_per_s": n_used / dt,
+                                      "note": "precision=\"fp32\": fp32 operands and accumulation on the CUDA cores, explicit option"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -63,6 +63,11 @@ struct dfs_model {
   uint16_t* w1pack = nullptr;  // Toeplitz weights [kw][2][256][8]
   uint16_t* w1pack_fused = nullptr;  // the same, split into two 16-channel passes [pass][kw][2][128][8] (conv12_fused.cu)
   float b1h[32] = {0};         // 0.5 * folded conv1 bias
+  int precision = 0;           // 0 = fp16 tensor-core operands / fp32 accumulate, 1 = full fp32 on the CUDA cores (cnn2d_fp32.cu)
+  float* w32[3] = {nullptr, nullptr, nullptr};   // folded fp32 weights [(kh*3+kw)*ci + i][co] of the three conv blocks
+  float* b32[3] = {nullptr, nullptr, nullptr};
+  float* work32 = nullptr;     // fp32 activations of one sub-chunk, allocated when the option is first set
+  int chunk32 = 0;
   // ---- CAE / 1D-CNN on the tcgen05 template (cae_tc.cu, cnn1d_tc.cu) ----
   CaeTcState* cae = nullptr;
   Cnn1dTcState* c1d = nullptr;
@@ -229,6 +234,17 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     if (m->cae != nullptr) m->cae->enc1_impl = (int)value;
     return DFS_OK;
   }
+  if (strcmp(key, "precision") == 0) {
+    DFS_REQUIRE(m->kind == KIND_CNN2D && (value == 0 || value == 1), DFS_ERR_INVALID,
+                "precision is a CNN2D option: 0 (fp16 tensor-core operands, fp32 accumulate) | 1 (full fp32, CUDA cores)");
+    if (value == 1 && m->work32 == nullptr) {
+      DFS_CUDA_CHECK(cudaSetDevice(m->device));
+      m->chunk32 = std::min(m->chunk, 16);
+      DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&m->work32), cnn2d_fp32_work_floats(m->chunk32) * sizeof(float), false));
+    }
+    m->precision = (int)value;
+    return DFS_OK;
+  }
   if (strcmp(key, "conv12_fused") == 0) {
     DFS_REQUIRE(m->kind == KIND_CNN2D && (value == 0 || value == 1), DFS_ERR_INVALID, "conv12_fused is a CNN2D option (0 | 1)");
     m->conv12_fused = (int)value;
@@ -335,6 +351,23 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
     for (int c = 0; c < 128; ++c) fcw[(size_t)f * 128 + c] = (float)((double)w->fc_weight[(size_t)c * kF + f] / 80.0);
   if ((st = dev_upload(m, &m->fcw_dev, fcw)) != DFS_OK) return fail(st);
   m->fcb = w->fc_bias[0];
+  // the same three blocks folded for the full-fp32 path (option "precision" = 1, cnn2d_fp32.cu): [(kh*3+kw)*ci + i][co]
+  {
+    const int cis[3] = {1, 32, 64}, cos[3] = {32, 64, 128};
+    for (int l = 0; l < 3; ++l) {
+      std::vector<double> scale, shift;
+      bn_fold(w->conv[l], cos[l], scale, shift);
+      std::vector<float> wf((size_t)9 * cis[l] * cos[l]), bf(cos[l]);
+      for (int o = 0; o < cos[l]; ++o) {
+        bf[o] = (float)shift[o];
+        for (int i = 0; i < cis[l]; ++i)
+          for (int tap = 0; tap < 9; ++tap)
+            wf[((size_t)tap * cis[l] + i) * cos[l] + o] = (float)((double)w->conv[l].weight[((size_t)o * cis[l] + i) * 9 + tap] * scale[o]);
+      }
+      if ((st = dev_upload(m, &m->w32[l], wf)) != DFS_OK) return fail(st);
+      if ((st = dev_upload(m, &m->b32[l], bf)) != DFS_OK) return fail(st);
+    }
+  }
   // conv1 as a Toeplitz-in-time GEMM (conv1_tc.cu): B_kw[n = jj*32 + c][o] = 0.5 * w'[c][o - jj][kw] for 0 <= o-jj <= 2,
   // stored [kw][K chunk o/8][n][o%8]; 0.5 = the (2,1) average pool folded through the ReLU (positively homogeneous)
   {
@@ -392,6 +425,15 @@ extern "C" int dfs_cnn2d_score(dfs_model* m, const dfs_features* feats, float* o
   DFS_REQUIRE(feats->n == 0 || out_dev, DFS_ERR_INVALID, "dfs_cnn2d_score: out_dev is NULL");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DFS_CUDA_CHECK(cudaSetDevice(m->device));
+  if (m->precision == 1) {   // full fp32 on the CUDA cores, sub-chunks of chunk32 utterances
+    for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk32) {
+      const int nk = (int)std::min<int64_t>(m->chunk32, feats->n - i0);
+      DFS_PROPAGATE(launch_cnn2d_fp32(feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->w32, m->b32,
+                                      m->fcw_dev, m->fcb, apply_sigmoid, m->work32, m->emb, out_dev + i0, stream));
+      if (embedding_dev) DFS_PROPAGATE(launch_cnn2d_embedding_export(m->emb, nk, embedding_dev + i0 * (int64_t)kF * 128, stream));
+    }
+    return DFS_OK;
+  }
   for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk) {
     const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
     const float* x = feats->x + i0 * feats->stride_n;

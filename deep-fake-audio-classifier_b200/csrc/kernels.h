@@ -43,6 +43,11 @@ int launch_cnn2d_head(const float* emb, const float* wfc, float fcb, int n_utts,
 // embedding[n][c*180+f] = emb[n][f][c] / 80   (src/model.py:37-38 flatten order)
 int launch_cnn2d_embedding_export(const float* emb, int n_utts, float* embedding, cudaStream_t stream);
 
+// ---- cnn2d_fp32.cu (option "precision" = 1: the whole 2D-CNN in fp32 on the CUDA cores) ----
+size_t cnn2d_fp32_work_floats(int n_utts);
+int launch_cnn2d_fp32(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const float* const w[3], const float* const b[3],
+                      const float* wfc, float fcb, int apply_sigmoid, float* work, float* emb, float* out, cudaStream_t stream);
+
 // ---- cae_tc.cu (convolutional autoencoder on the tcgen05 template) ----
 struct CaeTcState {
   Conv1Weights c1;        // folded encoder block 1 (fp32, CUDA cores)

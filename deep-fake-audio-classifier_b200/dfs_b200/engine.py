@@ -153,11 +153,14 @@ class _Scorer:
 
 
 class Cnn2dScorer(_Scorer):
-    """CNN2D (src/model.py:12-42) on the tcgen05 path."""
+    """CNN2D (src/model.py:12-42) on the tcgen05 path.  ``precision="fp32"`` selects the full-fp32 CUDA-core kernels
+    (csrc/cnn2d_fp32.cu; ~35x slower) for evaluations where the rank order of near-equal scores matters."""
     KIND = "cnn2d"
 
-    def __init__(self, state_dict, device: int = 0, max_chunk: int = 0):
+    def __init__(self, state_dict, device: int = 0, max_chunk: int = 0, precision: str = "fp16"):
         super().__init__()
+        if precision not in ("fp16", "fp32"):
+            raise ValueError(f"precision must be 'fp16' or 'fp32', got {precision!r}")
         _require_cuda()
         keep = []
         w = N.Cnn2dWeights()
@@ -170,6 +173,8 @@ class Cnn2dScorer(_Scorer):
         w.fc_weight, w.fc_bias = _fptr(fcw), _fptr(fcb)
         self.device_index = int(device)
         N.check(self._lib.dfs_cnn2d_create(C.byref(self._h), int(device), C.byref(w), int(max_chunk)), "dfs_cnn2d_create")
+        if precision == "fp32":
+            self.set_option("precision", 1)
 
     def score(self, x, apply_sigmoid: bool = False, return_embedding: bool = False):
         """x: CUDA fp32 (B,321,180), any strides.  Returns (B,) logits/scores [, (B,23040) embedding]."""

@@ -248,3 +248,34 @@ def test_cnn2d_fused_conv1_conv2_equals_separate_kernels():
     sc = Cnn2dScorer(syn.cnn2d_state(0))
     sc.set_option("conv12_fused", 1)
     assert _rel(sc.score(x[:4], apply_sigmoid=True).cpu().numpy(), ref) <= REL
+
+
+def test_cnn2d_fp32_precision_mode_tracks_the_reference_ranks(feats):
+    """Option "precision" = 1 (csrc/cnn2d_fp32.cu): fp32 operands and accumulation like the reference's CPU path.  Logits
+    agree with the reference to fp32 round-off (the tcgen05 path: ~5e-5 absolute), and on 256 utterances of the bench's data
+    set the score ORDER is the reference's up to fp32 near-ties, which the fp16-operand path cannot promise."""
+    from oracle import eer as oeer
+    from oracle import models_torch as ot
+    import dfs_b200 as D
+    sd = syn.cnn2d_state(0)
+    exact = Cnn2dScorer(sd, precision="fp32")
+    logits, emb = exact.score(feats, return_embedding=True)
+    np.testing.assert_allclose(logits.cpu().numpy(), G["cnn2d_init_logits"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(emb[:, :512].cpu().numpy(), G["cnn2d_init_embedding_head"], rtol=2e-5, atol=2e-6)
+    xt = feats.transpose(1, 2).contiguous().transpose(1, 2)          # the reference's strided view, ragged sub-chunks
+    np.testing.assert_array_equal(Cnn2dScorer(sd, max_chunk=5, precision="fp32").score(xt).cpu().numpy(), logits.cpu().numpy())
+    n = 256
+    x = fill_features(n, first_utt=0, seed=1234)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = ot.reference_loop_supervised(ot.cnn2d_forward, sd, x.cpu())
+    got32 = exact.score(x, apply_sigmoid=True).cpu().numpy()
+    got16 = Cnn2dScorer(sd).score(x, apply_sigmoid=True).cpu().numpy()
+    assert _rel(got32, ref) <= 2e-6 and _rel(got16, ref) <= REL
+    rank = lambda v: np.argsort(np.argsort(v, kind="stable"), kind="stable")  # noqa: E731
+    moved32, moved16 = int(np.sum(rank(got32) != rank(ref))), int(np.sum(rank(got16) != rank(ref)))
+    print(f"utterances whose rank differs from the reference's: fp32 mode {moved32}, fp16 operands {moved16} of {n}")
+    assert moved32 <= 8 and moved32 <= moved16
+    lab = (np.random.Generator(np.random.PCG64(7)).random(n) < 1 / (1 + np.exp(-6.0 * (rank(ref) / n - 0.5)))).astype(np.uint8)
+    assert abs(D.calculate_eer(got32, lab)[0] - oeer.calculate_eer(ref, lab)[0]) <= 1e-4     # north_star: EER within 0.01 pp
+    exact.set_option("precision", 0)                                  # back on the tensor-core path: the default bits
+    assert np.array_equal(exact.score(x, apply_sigmoid=True).cpu().numpy(), got16)
