@@ -740,6 +740,24 @@ static std::vector<uint16_t> pack_convT(const dfs_conv_bn& c, int ci, int co, in
   return out;
 }
 
+// The same GEMMs for EPI_SHUFFLE_ROWS (conv_tc.cuh): 4*co columns = groups of 128; thread set ts = b*(co/32) + o/32 lives in group
+// ts/2, column half ts%2, and holds both row offsets a: column n = (ts%2)*64 + a*32 + o%32
+static std::vector<uint16_t> pack_convT_rows(const dfs_conv_bn& c, int ci, int co, float* bias_out) {
+  std::vector<double> scale, shift;
+  bn_fold(c, co, scale, shift);
+  for (int o = 0; o < co; ++o) bias_out[o] = (float)shift[o];
+  std::vector<uint16_t> out((size_t)4 * ci * co);
+  for (int q = 0; q < 4; ++q)
+    for (int i = 0; i < ci; ++i)
+      for (int o = 0; o < co; ++o) {
+        const double w = (double)c.weight[((size_t)i * co + o) * 4 + q] * scale[o];
+        const int a = q >> 1, b = q & 1, ts = b * (co / 32) + o / 32;
+        const size_t g = ts / 2, nn = (size_t)(ts % 2) * 64 + a * 32 + (o % 32);
+        out[(((size_t)g * (ci / 8) + (i >> 3)) * 128 + nn) * 8 + (i & 7)] = f32_to_act_bits((float)w);
+      }
+  return out;
+}
+
 static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
   CaeTcState* s = new (std::nothrow) CaeTcState();
   DFS_REQUIRE(s, DFS_ERR_NOMEM, "out of host memory");
@@ -769,8 +787,8 @@ static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
   packs[0] = pack_pair(w->enc[1], 64, 32, 0.25, s->bias[0]);             // enc2: 2x2 average folded (4 ReLU outputs are summed)
   packs[1] = pack_3x3_groups(w->enc[2], 128, 64, 128, 0.25, s->bias[1]);  // enc3
   packs[2] = pack_3x3_groups(w->enc[3], 256, 128, 64, 0.25, s->bias[2]);  // enc4: 4 groups of 64 output channels
-  packs[3] = pack_convT(w->dec[0], 256, 128, 4, s->bias[3]);              // dec1: one quadrant per group
-  packs[4] = pack_convT(w->dec[1], 128, 64, 2, s->bias[4]);               // dec2: group = a, columns (b, co)
+  packs[3] = pack_convT_rows(w->dec[0], 256, 128, s->bias[3]);            // dec1: 4 groups (b, channel half), both a per thread
+  packs[4] = pack_convT_rows(w->dec[1], 128, 64, s->bias[4]);             // dec2: group = b, both a per thread
   packs[5] = pack_convT(w->dec[2], 64, 32, 1, s->bias[5]);                // dec3: columns (a, b, co)
   for (int i = 0; i < 6; ++i) {
     uint16_t* d = nullptr;

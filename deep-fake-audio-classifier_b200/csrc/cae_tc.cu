@@ -8,8 +8,8 @@
 //   enc2   32 x 160 x 90       PAIR GEMM  N=128, K=384, time pool in-thread + lane^8 e2 FT8  ( 8, 48,  82)
 //   enc3   64 x 80 x 45        3x3 GEMM   N=128, K=576, 2x2 pool lane^1 / lane^8     e3 FT8  (16, 24,  42)
 //   enc4   128 x 40 x 22       3x3 GEMM   4 groups of N=64, K=1152 in 2 pieces       e4 FT8  (32, 14,  26)   = latent
-//   dec1   256 x 20 x 11       1x1 GEMM   4 quadrant groups of N=128, K=256          d1 FT8  (16, 24,  42)
-//   dec2   128 x 40 x 22       1x1 GEMM   2 groups (a) of N=(b,64), K=128            d2 FT8  ( 8, 48,  82)   col 45 = relu(bias)
+//   dec1   256 x 20 x 11       1x1 GEMM   4 groups (b, channel half) of N=(32-ch block, a, 32), K=256   d1 FT8  (16, 24,  42)
+//   dec2   128 x 40 x 22       1x1 GEMM   2 groups (b) of N=(32-ch block, a, 32), K=128   d2 FT8  ( 8, 48,  82)   col 45 = relu(bias)
 //   dec3   64 x 80 x 45        1x1 GEMM   N=(a,b,32), K=64                           d3 FT8  ( 4, 92, 162)
 //   final  32 x 160 x 90       fused into dec3's epilogue on the scoring path (EPI_SHUFFLE_MSE: 4 outputs x 32 MACs per d3 vector,
 //                              residual vs the (normalised) input, one partial sum per 16-column unit; neither d3 nor the
@@ -26,8 +26,8 @@ namespace dfs {
 using Enc2Cfg = ConvCfg<MODE_PAIR, 32, 64, 128, 80, 2, 3, 4, 1, EPI_PAIR_POOL_F>;
 using Enc3Cfg = ConvCfg<MODE_3X3, 64, 128, 128, 80, 2, 2, 4, 1, EPI_POOL_TF>;
 using Enc4Cfg = ConvCfg<MODE_3X3, 128, 64, 64, 40, 1, 3, 4, 2, EPI_POOL_TF>;
-using Dec1Cfg = ConvCfg<MODE_1X1, 256, 128, 128, 24, 1, 3, 2, 4, EPI_SHUFFLE>;
-using Dec2Cfg = ConvCfg<MODE_1X1, 128, 64, 128, 40, 1, 3, 2, 2, EPI_SHUFFLE>;
+using Dec1Cfg = ConvCfg<MODE_1X1, 256, 128, 128, 24, 1, 3, 2, 4, EPI_SHUFFLE_ROWS>;
+using Dec2Cfg = ConvCfg<MODE_1X1, 128, 64, 128, 40, 1, 3, 2, 2, EPI_SHUFFLE_ROWS>;
 using Dec3Cfg = ConvCfg<MODE_1X1, 64, 32, 128, 80, 2, 3, 4, 1, EPI_SHUFFLE>;
 using Dec3MseCfg = ConvCfg<MODE_1X1, 64, 32, 128, 80, 2, 3, 2, 1, EPI_SHUFFLE_MSE>;   // dec3 + final ConvT + squared error, nothing written but partial sums
 

@@ -253,4 +253,11 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// 256-bit store (sm_100: STG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* lo, const uint32_t* hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(hi[0]),
+               "r"(hi[1]), "r"(hi[2]), "r"(hi[3])
+               : "memory");
+}
+
 #endif  // __CUDACC__

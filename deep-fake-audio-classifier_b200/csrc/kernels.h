@@ -31,7 +31,7 @@ struct Conv1Weights {
   float w[32 * 9];  // folded, [co][kh][kw]
   float b[32];
 };
-// conv1 + BN + ReLU + AvgPool (2,1) [or (2,2) for the CAE encoder] -> FT8 bf16.
+// conv1 + BN + ReLU + AvgPool (2,1) [or (2,2) for the CAE encoder] -> FT8 fp16.
 // x element (i,t,f) at x[i*sn + t*st + f*sf]; optional per-feature normaliser (mean, 1/std) applied first.
 int launch_conv1(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const Conv1Weights& w, const float* norm_mean,
                  const float* norm_std, bool pool_f, ActBuf out, cudaStream_t stream);

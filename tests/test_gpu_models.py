@@ -39,7 +39,7 @@ def test_cnn2d_matches_reference_golden(feats, impl):
     logits, emb, scores = logits.cpu().numpy(), emb.cpu().numpy(), scores.cpu().numpy()
     assert _rel(scores, G["cnn2d_init_sigmoid"]) <= REL
     np.testing.assert_allclose(logits, G["cnn2d_init_logits"], atol=1e-3)
-    # embedding = mean over time of the conv stack, flatten order c*180+f (model.py:37-38); bf16 operands
+    # embedding = mean over time of the conv stack, flatten order c*180+f (model.py:37-38); fp16 operands
     np.testing.assert_allclose(emb[:, :512], G["cnn2d_init_embedding_head"], rtol=3e-2, atol=3e-3)
     np.testing.assert_allclose(emb.sum(1), G["cnn2d_init_embedding_sum"], rtol=2e-3)
 
@@ -50,7 +50,7 @@ def test_cnn2d_tcgen05_equals_cuda_core_crosscheck(feats):
     sc.set_option("conv_impl", 1)
     b, eb = sc.score(feats, return_embedding=True)
     torch.cuda.synchronize()
-    # same bf16 operands, fp32 accumulation: only summation order differs
+    # same fp16 operands, fp32 accumulation: only summation order differs
     np.testing.assert_allclose(ea.cpu().numpy(), eb.cpu().numpy(), rtol=1e-3, atol=2e-4)
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=2e-5)
 
