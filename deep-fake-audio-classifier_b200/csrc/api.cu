@@ -255,6 +255,11 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     m->cae->final_fused = (int)value;
     return DFS_OK;
   }
+  if (strcmp(key, "dec_wide") == 0) {
+    DFS_REQUIRE(m->cae != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "dec_wide is a CAE option (0 | 1)");
+    m->cae->dec_wide = (int)value;
+    return DFS_OK;
+  }
   if (strcmp(key, "l1_fused") == 0) {
     DFS_REQUIRE(m->c1d != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "l1_fused is a CNN1D option (0 | 1)");
     m->c1d->l1_fused = (int)value;
@@ -740,9 +745,10 @@ static std::vector<uint16_t> pack_convT(const dfs_conv_bn& c, int ci, int co, in
   return out;
 }
 
-// The same GEMMs for EPI_SHUFFLE_ROWS (conv_tc.cuh): 4*co columns = groups of 128; thread set ts = b*(co/32) + o/32 lives in group
-// ts/2, column half ts%2, and holds both row offsets a: column n = (ts%2)*64 + a*32 + o%32
-static std::vector<uint16_t> pack_convT_rows(const dfs_conv_bn& c, int ci, int co, float* bias_out) {
+// The same GEMMs for EPI_SHUFFLE_ROWS (conv_tc.cuh): 4*co columns = groups of ng = 128*sub_n; thread set ts = b*(co/32) + o/32
+// lives in 128-column block ts/2 (group (ts/2)/sub_n, sub-group (ts/2)%sub_n), column half ts%2, and holds both row offsets a:
+// column n = ((ts/2)%sub_n)*128 + (ts%2)*64 + a*32 + o%32
+static std::vector<uint16_t> pack_convT_rows(const dfs_conv_bn& c, int ci, int co, float* bias_out, int sub_n = 1) {
   std::vector<double> scale, shift;
   bn_fold(c, co, scale, shift);
   for (int o = 0; o < co; ++o) bias_out[o] = (float)shift[o];
@@ -752,8 +758,8 @@ static std::vector<uint16_t> pack_convT_rows(const dfs_conv_bn& c, int ci, int c
       for (int o = 0; o < co; ++o) {
         const double w = (double)c.weight[((size_t)i * co + o) * 4 + q] * scale[o];
         const int a = q >> 1, b = q & 1, ts = b * (co / 32) + o / 32;
-        const size_t g = ts / 2, nn = (size_t)(ts % 2) * 64 + a * 32 + (o % 32);
-        out[(((size_t)g * (ci / 8) + (i >> 3)) * 128 + nn) * 8 + (i & 7)] = f32_to_act_bits((float)w);
+        const size_t g = (ts / 2) / sub_n, nn = (size_t)((ts / 2) % sub_n) * 128 + (ts % 2) * 64 + a * 32 + (o % 32);
+        out[(((size_t)g * (ci / 8) + (i >> 3)) * (128 * sub_n) + nn) * 8 + (i & 7)] = f32_to_act_bits((float)w);
       }
   return out;
 }
@@ -794,6 +800,15 @@ static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
     uint16_t* d = nullptr;
     DFS_PROPAGATE(dev_upload(m, &d, packs[i]));
     s->w[i] = d;
+  }
+  {
+    float scratch[256];
+    uint16_t* d = nullptr;
+    DFS_PROPAGATE(dev_upload(m, &d, pack_convT_rows(w->dec[0], 256, 128, scratch, 2)));
+    s->w_wide[0] = d;
+    DFS_PROPAGATE(dev_upload(m, &d, pack_convT_rows(w->dec[1], 128, 64, scratch, 2)));
+    s->w_wide[1] = d;
+    s->dec_wide = 1;
   }
   std::vector<float> wf(128);
   for (int q = 0; q < 4; ++q)

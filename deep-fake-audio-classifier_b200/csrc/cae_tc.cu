@@ -8,8 +8,9 @@
 //   enc2   32 x 160 x 90       PAIR GEMM  N=128, K=384, time pool in-thread + lane^8 e2 FT8  ( 8, 48,  82)
 //   enc3   64 x 80 x 45        3x3 GEMM   N=128, K=576, 2x2 pool lane^1 / lane^8     e3 FT8  (16, 24,  42)
 //   enc4   128 x 40 x 22       3x3 GEMM   4 groups of N=64, K=1152 in 2 pieces       e4 FT8  (32, 14,  26)   = latent
-//   dec1   256 x 20 x 11       1x1 GEMM   4 groups (b, channel half) of N=(32-ch block, a, 32), K=256   d1 FT8  (16, 24,  42)
-//   dec2   128 x 40 x 22       1x1 GEMM   2 groups (b) of N=(32-ch block, a, 32), K=128   d2 FT8  ( 8, 48,  82)   col 45 = relu(bias)
+//   dec1   256 x 20 x 11       1x1 GEMM   2 groups (b) of N=256=(32-ch block, a, 32), K=256    d1 FT8  (16, 24,  42)
+//   dec2   128 x 40 x 22       1x1 GEMM   1 group of N=256=(b, 32-ch block, a, 32), K=128      d2 FT8  ( 8, 48,  82)   col 45 = relu(bias)
+//          (option "dec_wide" = 0: the N = 128 variants with 4 / 2 groups, bit-identical, 1.3-1.5x slower: each group re-reads the input)
 //   dec3   64 x 80 x 45        1x1 GEMM   N=(a,b,32), K=64                           d3 FT8  ( 4, 92, 162)
 //   final  32 x 160 x 90       fused into dec3's epilogue on the scoring path (EPI_SHUFFLE_MSE: 4 outputs x 32 MACs per d3 vector,
 //                              residual vs the (normalised) input, one partial sum per 16-column unit; neither d3 nor the
@@ -28,6 +29,9 @@ using Enc3Cfg = ConvCfg<MODE_3X3, 64, 128, 128, 80, 2, 2, 4, 1, EPI_POOL_TF>;
 using Enc4Cfg = ConvCfg<MODE_3X3, 128, 64, 64, 40, 1, 3, 4, 2, EPI_POOL_TF>;
 using Dec1Cfg = ConvCfg<MODE_1X1, 256, 128, 128, 24, 1, 3, 2, 4, EPI_SHUFFLE_ROWS>;
 using Dec2Cfg = ConvCfg<MODE_1X1, 128, 64, 128, 40, 1, 3, 2, 2, EPI_SHUFFLE_ROWS>;
+using Dec1WideCfg = ConvCfg<MODE_1X1, 256, 128, 256, 24, 1, 5, 2, 4, EPI_SHUFFLE_ROWS>;   // option "dec_wide": N = 256, 2 groups
+using Dec2WideCfg = ConvCfg<MODE_1X1, 128, 64, 256, 40, 1, 6, 2, 2, EPI_SHUFFLE_ROWS>;    //                    N = 256, 1 group
+static_assert(Dec1WideCfg::PPL == Dec1Cfg::PPL && Dec2WideCfg::PPL == Dec2Cfg::PPL && Dec1WideCfg::WROWS == Dec1Cfg::WROWS, "the wide variants share the tensor maps");
 using Dec3Cfg = ConvCfg<MODE_1X1, 64, 32, 128, 80, 2, 3, 4, 1, EPI_SHUFFLE>;
 using Dec3MseCfg = ConvCfg<MODE_1X1, 64, 32, 128, 80, 2, 3, 2, 1, EPI_SHUFFLE_MSE>;   // dec3 + final ConvT + squared error, nothing written but partial sums
 
@@ -271,9 +275,21 @@ int launch_cae_tc(const CaeTcState* s, const float* x, int64_t sn, int64_t st, i
     DFS_LAUNCH_CHECK();
   }
   if (stop_after_layer == 3) return DFS_OK;
-  DFS_PROPAGATE(launch_conv_tc<Dec1Cfg>(s->tmap[3], base_params(s, 3, 3, 4, n_utts, 11, 20, 22), 4, num_sms, stream));
+  if (s->dec_wide) {
+    ConvParams p1 = base_params(s, 3, 3, 4, n_utts, 11, 20, 22);
+    p1.wpack = s->w_wide[0];
+    DFS_PROPAGATE(launch_conv_tc<Dec1WideCfg>(s->tmap[3], p1, 2, num_sms, stream));
+  } else {
+    DFS_PROPAGATE(launch_conv_tc<Dec1Cfg>(s->tmap[3], base_params(s, 3, 3, 4, n_utts, 11, 20, 22), 4, num_sms, stream));
+  }
   if (stop_after_layer == 4) return DFS_OK;
-  DFS_PROPAGATE(launch_conv_tc<Dec2Cfg>(s->tmap[4], base_params(s, 4, 4, 5, n_utts, 22, 40, 44), 2, num_sms, stream));
+  if (s->dec_wide) {
+    ConvParams p2 = base_params(s, 4, 4, 5, n_utts, 22, 40, 44);
+    p2.wpack = s->w_wide[1];
+    DFS_PROPAGATE(launch_conv_tc<Dec2WideCfg>(s->tmap[4], p2, 1, num_sms, stream));
+  } else {
+    DFS_PROPAGATE(launch_conv_tc<Dec2Cfg>(s->tmap[4], base_params(s, 4, 4, 5, n_utts, 22, 40, 44), 2, num_sms, stream));
+  }
   if (stop_after_layer == 5) return DFS_OK;
   if (s->final_fused && stop_after_layer == 7 && mse_out != nullptr && recon_out == nullptr) {
     // scoring path: dec3's epilogue applies the final layer and accumulates the squared error; d3 never reaches HBM

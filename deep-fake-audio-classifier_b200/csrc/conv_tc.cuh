@@ -592,49 +592,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         // sectors with one 256-bit store per channel chunk; lane 0 writes its a = 0 half, lane 7 also its a = 1 half.  The
         // first version (EPI_SHUFFLE, one (a, b) per thread) wrote 16-byte pieces 32 bytes apart: ncu showed 29 sectors per
         // store request, twice the sector writes the data needs, and the kernels ran 3-4x over their HBM time.
-        static_assert(Cfg::EPI != EPI_SHUFFLE_ROWS || (NG == 128 && COUT % 32 == 0 && Cfg::MODE == MODE_1X1), "shuffle-rows shape");
-        constexpr int CB = COUT / 32;
-        const int ts = 2 * grp + h, bq = ts / CB, cblk = ts % CB;
-        const float* bs = bias + 32 * cblk;
+        // NG = 256 holds two such 128-column sub-groups (sub), i.e. twice the columns per read of the input window.
+        static_assert(Cfg::EPI != EPI_SHUFFLE_ROWS || (NG % 128 == 0 && COUT % 32 == 0 && Cfg::MODE == MODE_1X1), "shuffle-rows shape");
+        constexpr int CB = COUT / 32, SUB = NG / 128;
         const long long plane_elems = p.out_ncols * p.out_rs * 8;
-        const int fo = 2 * (fp - 1) + bq;
-        uint16_t* colbase = p.out + ((long long)n * p.out_cols + fo + 1) * p.out_rs * 8 + (long long)(4 * cblk) * plane_elems;
+        const float* bs[SUB];
+        uint16_t* colbase[SUB];
+#pragma unroll
+        for (int sub = 0; sub < SUB; ++sub) {
+          const int ts = 2 * (grp * SUB + sub) + h, bq = ts / CB, cblk = ts % CB;
+          bs[sub] = bias + 32 * cblk;
+          colbase[sub] = p.out + ((long long)n * p.out_cols + 2 * (fp - 1) + bq + 1) * p.out_rs * 8 + (long long)(4 * cblk) * plane_elems;
+        }
         for (int tt = 0; tt < Cfg::TILES; ++tt, ++it) {
           const int acc = it % NACC;
           mbar_wait(&tfull[acc], (it / NACC) & 1, 5);
           tc_fence_after();
-          float v[64];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * 64, v);
-          tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * 64 + 32, v + 32);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-          uint32_t p0[16], up[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            p0[c >> 1] = pack_act2(fmaxf(v[c] + bs[c], 0.0f), fmaxf(v[c + 1] + bs[c + 1], 0.0f));
-            up[c >> 1] = pack_act2(fmaxf(v[32 + c] + bs[c], 0.0f), fmaxf(v[33 + c] + bs[c + 1], 0.0f));
-          }
           const int tp = 1 + 8 * tt + i;
-          if (i == 7 && colvalid && tp <= p.rows_valid) {   // the a = 1 half of the tile's last row: the next tile owns the other half
 #pragma unroll
-            for (int k = 0; k < 4; ++k) st_global_v4(colbase + (long long)k * plane_elems + (2 * tp) * 8, up[4 * k], up[4 * k + 1], up[4 * k + 2], up[4 * k + 3]);
-          }
+          for (int sub = 0; sub < SUB; ++sub) {
+            float v[64];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + sub * 128 + h * 64, v);
+            tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + sub * 128 + h * 64 + 32, v + 32);
+            tmem_ld_wait();
+            if (sub == SUB - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            uint32_t p0[16], up[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) up[k] = __shfl_up_sync(0xffffffffu, up[k], 1);   // lane i now holds a = 1 of row tp-1 (i > 0)
-          if (colvalid) {
-            if (i > 0 && tp <= p.rows_valid) {
+            for (int c = 0; c < 32; c += 2) {
+              p0[c >> 1] = pack_act2(fmaxf(v[c] + bs[sub][c], 0.0f), fmaxf(v[c + 1] + bs[sub][c + 1], 0.0f));
+              up[c >> 1] = pack_act2(fmaxf(v[32 + c] + bs[sub][c], 0.0f), fmaxf(v[33 + c] + bs[sub][c + 1], 0.0f));
+            }
+            uint16_t* cb = colbase[sub];
+            if (i == 7 && colvalid && tp <= p.rows_valid) {   // the a = 1 half of the tile's last row: the next tile owns the other half
 #pragma unroll
-              for (int k = 0; k < 4; ++k) st_global_v8(colbase + (long long)k * plane_elems + (2 * tp - 2) * 8, up + 4 * k, p0 + 4 * k);
-            } else if (i > 0 && tp - 1 <= p.rows_valid) {   // tp-1 is the last valid row
+              for (int k = 0; k < 4; ++k) st_global_v4(cb + (long long)k * plane_elems + (2 * tp) * 8, up[4 * k], up[4 * k + 1], up[4 * k + 2], up[4 * k + 3]);
+            }
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                st_global_v4(colbase + (long long)k * plane_elems + (2 * tp - 2) * 8, up[4 * k], up[4 * k + 1], up[4 * k + 2], up[4 * k + 3]);
-            } else if (i == 0 && tp <= p.rows_valid) {
+            for (int k = 0; k < 16; ++k) up[k] = __shfl_up_sync(0xffffffffu, up[k], 1);   // lane i now holds a = 1 of row tp-1 (i > 0)
+            if (colvalid) {
+              if (i > 0 && tp <= p.rows_valid) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                st_global_v4(colbase + (long long)k * plane_elems + (2 * tp - 1) * 8, p0[4 * k], p0[4 * k + 1], p0[4 * k + 2], p0[4 * k + 3]);
+                for (int k = 0; k < 4; ++k) st_global_v8(cb + (long long)k * plane_elems + (2 * tp - 2) * 8, up + 4 * k, p0 + 4 * k);
+              } else if (i > 0 && tp - 1 <= p.rows_valid) {   // tp-1 is the last valid row
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  st_global_v4(cb + (long long)k * plane_elems + (2 * tp - 2) * 8, up[4 * k], up[4 * k + 1], up[4 * k + 2], up[4 * k + 3]);
+              } else if (i == 0 && tp <= p.rows_valid) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  st_global_v4(cb + (long long)k * plane_elems + (2 * tp - 1) * 8, p0[4 * k], p0[4 * k + 1], p0[4 * k + 2], p0[4 * k + 3]);
+              }
             }
           }
         }

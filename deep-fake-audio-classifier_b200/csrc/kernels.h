@@ -62,6 +62,8 @@ struct CaeTcState {
   const uint16_t* w1pack; // enc1 Toeplitz weights [kw][K chunk][n 256][8] fp16, 0.25 folded
   float b1q[32];          // 0.25 * folded enc1 bias
   int enc1_impl;          // 0 = tensor-core Toeplitz GEMM, 1 = fp32 CUDA-core conv1_kernel<POOLF> (cross-check)
+  const uint16_t* w_wide[2]; // dec1 / dec2 weights for the N = 256 variants (option "dec_wide")
+  int dec_wide;           // 1 = dec1 / dec2 as N = 256 GEMMs (half the TMA re-reads of the input, one CTA per SM), 0 = N = 128
   int final_fused;        // 1 (default) = final layer + squared error in dec3's epilogue, 0 = separate cae_final_tc_kernel over d3
   float* mse_partial;     // [chunk][kCaeFinalSplit] partial squared-error sums of the fused final layer
   unsigned int* mse_done; // [chunk] arrival counters (self-resetting)

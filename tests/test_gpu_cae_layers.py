@@ -99,3 +99,19 @@ def test_cae_fused_final_layer_equals_separate_final_kernel():
     ref = onp.cae_mse_scores(syn.cae_state(0), x.cpu().numpy(), mean, std)
     got = CaeScorer(syn.cae_state(0), mean, std).score(x).cpu().numpy()
     assert np.max(np.abs(got - ref) / ref) <= 1e-3
+
+
+def test_cae_wide_decoder_variant_is_bit_identical():
+    """Option "dec_wide" (default 1): dec1 / dec2 as N = 256 GEMMs (two 128-column sub-groups per CTA, half the re-reads of the
+    input window) against the N = 128 variants.  Same K order per output column, so d1, d2 and the scores must not differ by
+    a bit; 13 utterances through passes of 5."""
+    mean, std = syn.normalizer_stats(1)
+    x = torch.from_numpy(syn.features(13, seed=21)).cuda()
+    sc = CaeScorer(syn.cae_state(1), mean, std, max_chunk=5)
+    sc.set_option("dec_wide", 0)
+    base = sc.score(x).cpu().numpy()
+    d1, d2 = sc.debug_layer(x[:5], 4, impl=0).cpu().numpy(), sc.debug_layer(x[:5], 5, impl=0).cpu().numpy()
+    sc.set_option("dec_wide", 1)
+    np.testing.assert_array_equal(sc.debug_layer(x[:5], 4, impl=0).cpu().numpy(), d1)
+    np.testing.assert_array_equal(sc.debug_layer(x[:5], 5, impl=0).cpu().numpy(), d2)
+    np.testing.assert_array_equal(sc.score(x).cpu().numpy(), base)
