@@ -65,8 +65,7 @@ __global__ void __launch_bounds__(256) cae_enc1_prep_kernel(const float* __restr
     float val = 0.0f;                               // zero padding is applied AFTER the normalisation
     if (t >= 0 && t < kT) {
       val = src[(long long)t * st];
-      if (mean != nullptr) val = (val - m) / s;
-      val = fmaxf(val, -65504.0f);
+      if (mean != nullptr) val = (val - m) / s;      // pack_act2 saturates to +-65504
     }
     v[e] = val;
   }

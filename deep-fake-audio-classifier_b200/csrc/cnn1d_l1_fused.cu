@@ -137,9 +137,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) cnn1d_l1_fused_kernel(const __g
             }
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-              const float lim = -65504.0f;
-              const uint4 v = make_uint4(pack_act2(fmaxf(lo[k].x, lim), fmaxf(lo[k].y, lim)), pack_act2(fmaxf(lo[k].z, lim), fmaxf(lo[k].w, lim)),
-                                         pack_act2(fmaxf(hi[k].x, lim), fmaxf(hi[k].y, lim)), pack_act2(fmaxf(hi[k].z, lim), fmaxf(hi[k].w, lim)));
+              // pack_act2 saturates both ways (F2FP.SATFINITE): no separate clamp instructions in this issue-sensitive loop
+              const uint4 v = make_uint4(pack_act2(lo[k].x, lo[k].y), pack_act2(lo[k].z, lo[k].w), pack_act2(hi[k].x, hi[k].y), pack_act2(hi[k].z, hi[k].w));
               *reinterpret_cast<uint4*>(dst + (r0 + k) * 16) = v;
             }
           }

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) cnn1d_prep_kernel(const float* __restrict
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int f = 8 * c8 + e;
-    v[e] = f < kF ? fmaxf(src[(long long)f * sf], -65504.0f) : 0.0f;
+    v[e] = f < kF ? src[(long long)f * sf] : 0.0f;   // pack_act2 saturates to +-65504
   }
   uint16_t* dst = out.ptr + (long long)c8 * out.plane_elems() + ((n + 1) * out.RS + t + 1) * 8;
   st_global_v4(dst, pack_act2(v[0], v[1]), pack_act2(v[2], v[3]), pack_act2(v[4], v[5]), pack_act2(v[6], v[7]));

@@ -76,8 +76,10 @@ __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_
 // the same rate; fp16's 11-bit significand keeps the score error ~8x below bf16, DESIGN.md
 // "Precision").  Values are clamped to the fp16 range (post-ReLU activations are >= 0).
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
-  const __half2 v = __floats2half2_rn(fminf(lo, 65504.0f), fminf(hi, 65504.0f));
-  return *reinterpret_cast<const uint32_t*>(&v);
+  // one F2FP.SATFINITE.F16.F32.PACK_AB: round to nearest even, |x| > 65504 (and +-inf) -> +-65504 (was: two FMNMX + F2FP)
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ float act_bits_to_float(uint16_t b) {
   return __half2float(*reinterpret_cast<const __half*>(&b));

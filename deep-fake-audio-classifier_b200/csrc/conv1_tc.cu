@@ -66,9 +66,7 @@ __global__ void __launch_bounds__(256) conv1_prep_kernel(const float* __restrict
     v[e] = (t >= 0 && t < kT) ? src[(long long)t * st] : 0.0f;
   }
   uint16_t* dst = xt + ((long long)kXtLead + (n * kCols + f + 1) * kXtBlocks + blk) * 8;
-  const float lim = 65504.0f;
-  st_global_v4(dst, pack_act2(fmaxf(v[0], -lim), fmaxf(v[1], -lim)), pack_act2(fmaxf(v[2], -lim), fmaxf(v[3], -lim)),
-               pack_act2(fmaxf(v[4], -lim), fmaxf(v[5], -lim)), pack_act2(fmaxf(v[6], -lim), fmaxf(v[7], -lim)));
+  st_global_v4(dst, pack_act2(v[0], v[1]), pack_act2(v[2], v[3]), pack_act2(v[4], v[5]), pack_act2(v[6], v[7]));   // saturating
 }
 
 // ------------------------------------------------------------------------------------------

@@ -490,8 +490,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             if constexpr (Cfg::EPI == EPI_GELU) {   // nn.GELU() (approximate='none'): 0.5 x (1 + erf(x / sqrt 2))
               a0 = 0.5f * a0 * (1.0f + erff(a0 * 0.70710678118654752f));
               a1 = 0.5f * a1 * (1.0f + erff(a1 * 0.70710678118654752f));
-              a0 = fmaxf(a0, -65504.0f);
-              a1 = fmaxf(a1, -65504.0f);
             } else {
               a0 = fmaxf(a0, 0.0f);
               a1 = fmaxf(a1, 0.0f);
@@ -531,7 +529,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             for (int b = 0; b < 2; ++b) {
               float d[32];
 #pragma unroll
-              for (int c = 0; c < 32; ++c) d[c] = __half2float(__float2half_rn(fminf(fmaxf(v[b * 32 + c] + bias[c], 0.0f), 65504.0f)));
+              for (int c = 0; c < 32; c += 2) {   // d3 rounded to fp16 like the stored layer (pack_act2), then widened again
+                const uint32_t pk = pack_act2(fmaxf(v[b * 32 + c] + bias[c], 0.0f), fmaxf(v[b * 32 + c + 1] + bias[c + 1], 0.0f));
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+                d[c] = f2.x;
+                d[c + 1] = f2.y;
+              }
 #pragma unroll
               for (int a2 = 0; a2 < 2; ++a2)
 #pragma unroll
