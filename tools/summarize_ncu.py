@@ -36,7 +36,7 @@ REPORTS = (("prof_conv.ncu-rep", "conv_kernels_ncu_full", "2D-CNN conv kernels")
            ("prof_eer.ncu-rep", "eer_kernels_ncu_full", "EER sort path: radix count and scatter passes"),
            ("prof_sel.ncu-rep", "eer_select_kernels_ncu_full", "EER select path: TMA-fed (digit, label) histogram, first and later levels"),
            ("prof_c1d.ncu-rep", "cnn1d_fused_and_prep_ncu_full", "1D-CNN fused layer 1, transposing input prep, CAE score finish"),
-           ("prof_cae.ncu-rep", "cae_layers_ncu_full", "CAE: dec3 with fused final layer + MSE, enc4 (4 groups of N = 64), enc2 (PAIR)"))
+           ("prof_cae.ncu-rep", "cae_layers_ncu_full", "CAE layers of one pass (prep, enc1, enc2 PAIR, enc3, enc4 as 4 groups of N = 64, dec1 / dec2 wide, dec3 + final + MSE)"))
 
 
 def launch_share(tag):
