@@ -255,6 +255,11 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     m->cae->final_fused = (int)value;
     return DFS_OK;
   }
+  if (strcmp(key, "pair_mma") == 0) {
+    DFS_REQUIRE(m->cae != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "pair_mma is a CAE option (0 | 1)");
+    m->cae->pair_mma = (int)value;
+    return DFS_OK;
+  }
   if (strcmp(key, "dec_wide") == 0) {
     DFS_REQUIRE(m->cae != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "dec_wide is a CAE option (0 | 1)");
     m->cae->dec_wide = (int)value;
@@ -818,6 +823,7 @@ static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
     DFS_PROPAGATE(dev_upload(m, &d, pack_convT_rows(w->dec[1], 128, 64, scratch, 2)));
     s->w_wide[1] = d;
     s->dec_wide = 1;
+    s->pair_mma = 0;
   }
   std::vector<float> wf(128);
   for (int q = 0; q < 4; ++q)

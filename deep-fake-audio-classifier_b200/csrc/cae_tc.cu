@@ -27,6 +27,8 @@ namespace dfs {
 using Enc2Cfg = ConvCfg<MODE_PAIR, 32, 64, 128, 80, 2, 3, 4, 1, EPI_PAIR_POOL_F>;
 using Enc3Cfg = ConvCfg<MODE_3X3, 64, 128, 128, 80, 2, 2, 4, 1, EPI_POOL_TF>;
 using Enc4Cfg = ConvCfg<MODE_3X3, 128, 64, 64, 40, 1, 3, 4, 2, EPI_POOL_TF>;
+using Enc4PairCfg = ConvCfg<MODE_3X3, 128, 128, 128, 40, 1, 3, 4, 2, EPI_POOL_TF, 1>;   // option "pair_mma": CTA pairs, 2 groups of N = 128 (64 weight rows per CTA)
+static_assert(Enc4PairCfg::PPL == Enc4Cfg::PPL && Enc4PairCfg::WROWS == Enc4Cfg::WROWS && Enc4PairCfg::WGT_B == Enc4Cfg::WGT_B, "enc4 pair variant shares map and weights");
 using Dec1Cfg = ConvCfg<MODE_1X1, 256, 128, 128, 24, 1, 3, 2, 4, EPI_SHUFFLE_ROWS>;
 using Dec2Cfg = ConvCfg<MODE_1X1, 128, 64, 128, 40, 1, 3, 2, 2, EPI_SHUFFLE_ROWS>;
 using Dec1WideCfg = ConvCfg<MODE_1X1, 256, 128, 256, 24, 1, 5, 2, 4, EPI_SHUFFLE_ROWS>;   // option "dec_wide": N = 256, 2 groups
@@ -268,7 +270,10 @@ int launch_cae_tc(const CaeTcState* s, const float* x, int64_t sn, int64_t st, i
   if (stop_after_layer == 1) return DFS_OK;
   DFS_PROPAGATE(launch_conv_tc<Enc3Cfg>(s->tmap[1], base_params(s, 1, 1, 2, n_utts, 45, 80, 22), 1, num_sms, stream));
   if (stop_after_layer == 2) return DFS_OK;
-  DFS_PROPAGATE(launch_conv_tc<Enc4Cfg>(s->tmap[2], base_params(s, 2, 2, 3, n_utts, 22, 40, 11), 4, num_sms, stream));
+  if (s->pair_mma)
+    DFS_PROPAGATE(launch_conv_tc<Enc4PairCfg>(s->tmap[2], base_params(s, 2, 2, 3, n_utts, 22, 40, 11), 2, num_sms, stream));
+  else
+    DFS_PROPAGATE(launch_conv_tc<Enc4Cfg>(s->tmap[2], base_params(s, 2, 2, 3, n_utts, 22, 40, 11), 4, num_sms, stream));
   if (latent_out != nullptr) {
     const long long total = (long long)n_utts * 256 * 220;
     cae_latent_nchw_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(s->act[3], kCaeCols[3], total, latent_out);

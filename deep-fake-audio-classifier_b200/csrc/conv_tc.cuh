@@ -54,10 +54,13 @@ enum {
                         //        one lane up so that every thread writes whole 32-byte sectors (256-bit stores)        (CAE dec1, dec2)
 };
 
-template <int MODE_, int CIN_, int COUT_, int NG_, int ROWS_, int MT_, int NSTAGE_, int NACC_, int KSPLIT_, int EPI_>
+// CTA2 = 1: the kernel runs as CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA covers the two units of a pair (M = 256) and
+//           each CTA keeps only NG/2 of the NG weight rows, so the operand bytes read from shared memory per CTA and MMA fall from
+//           (128 + NG) to (128 + NG/2) rows -- the SS-mode MMAs of these convolutions are paced by exactly that stream.
+template <int MODE_, int CIN_, int COUT_, int NG_, int ROWS_, int MT_, int NSTAGE_, int NACC_, int KSPLIT_, int EPI_, int CTA2_ = 0>
 struct ConvCfg {
   static constexpr int MODE = MODE_, CIN = CIN_, COUT = COUT_, NG = NG_, ROWS = ROWS_, MT = MT_, NSTAGE = NSTAGE_, NACC = NACC_,
-                       KSPLIT = KSPLIT_, EPI = EPI_;
+                       KSPLIT = KSPLIT_, EPI = EPI_, CTA2 = CTA2_;
   static constexpr bool PAIR = (MODE == MODE_PAIR);
   static constexpr bool SWAP = (MODE == MODE_3X3S);
   static constexpr int CT = SWAP ? 32 : kColTile;      // feature columns per tile
@@ -73,7 +76,7 @@ struct ConvCfg {
   static constexpr int PLANE_B = WCOLS * WROWS * 16;   // bytes of one plane of the window
   static constexpr int WIN_B = PPL * PLANE_B;          // TMA transaction bytes per piece
   static constexpr int WIN_B_AL = (WIN_B + 1023) & ~1023;
-  static constexpr int WROWS_OUT = SWAP ? COUT : NG;   // rows of the weight operand image
+  static constexpr int WROWS_OUT = SWAP ? COUT : (CTA2 ? NG / 2 : NG);   // rows of the weight operand image (per CTA)
   static constexpr int WGT_B = NTAP * CIN * WROWS_OUT * 2;  // per output group
   static constexpr int WGT_B_AL = (WGT_B + 1023) & ~1023;
   static constexpr int ST = ROWS / (8 * MT);           // windows (super-tiles) per unit
@@ -83,7 +86,8 @@ struct ConvCfg {
   static constexpr int SMEM_B = WGT_B_AL + NSTAGE * WIN_B_AL + BAR_B;
   static constexpr int THREADS = 352;
   // two CTAs per SM when shared memory and TMEM allow
-  static constexpr int OCC = (SMEM_B <= 113 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
+  static constexpr int OCC = (!CTA2 && SMEM_B <= 113 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
+  static_assert(!CTA2 || (!SWAP && NG % 32 == 0), "CTA pairs: the activation window is the A operand");
   static_assert(ROWS % (8 * MT) == 0, "rows must be a multiple of the super-tile height");
   static_assert(NACC % MT == 0, "the accumulators of one window must be consecutive");
   static_assert(WROWS * 8 <= 256, "TMA box inner dimension limit");
@@ -140,6 +144,12 @@ struct ConvParams {
 };
 
 // ---- epilogue helpers -----------------------------------------------------------------------------
+// accumulator drained: tell the MMA issuer (CTA pairs: the leader's barrier counts the 8 epilogue warps of both CTAs)
+template <int CTA2>
+__device__ __forceinline__ void acc_release(uint64_t* tempty_bar) {
+  if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar), 0));
+  else mbar_arrive(tempty_bar);
+}
 template <int NCH>
 __device__ __forceinline__ void store_chunks(uint16_t* dst, long long plane_elems, const uint32_t* pk) {
 #pragma unroll
@@ -160,24 +170,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   uint64_t* tfull = bars + 2 * NSTAGE;      // [NACC]    MMA -> epilogue
   uint64_t* tempty = tfull + NACC;          // [NACC]    epilogue -> MMA
   uint64_t* wbar = tempty + NACC;           // weights resident
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  uint64_t* pwbar = wbar + 1;               // CTA pairs: the peer's weights are resident (leader's copy is the one waited on)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pwbar + 1);
+  static_assert((2 * NSTAGE + 2 * NACC + 2) * 8 + 4 <= 160, "barrier page");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = blockIdx.y;               // output-channel / quadrant group
+  // CTA pairs: rank 0 (leader) and rank 1 work on the units 2j and 2j+1 in lockstep; a unit index past n_units is all padding
+  const int rank = Cfg::CTA2 ? (int)cluster_ctarank() : 0;
+  const int u_first = Cfg::CTA2 ? (int)(blockIdx.x & ~1u) + rank : (int)blockIdx.x;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap);
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], Cfg::CTA2 ? 16 : 8); }
     mbar_init(wbar, 1);
+    mbar_init(pwbar, 1);
     fence_mbar_init();
   }
   if (warp == 10) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (Cfg::CTA2) {
+      tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (Cfg::CTA2) cluster_sync_all();   // the peer's barriers must be initialised before anything is signalled across
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -186,29 +208,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     if (lane == 0) {
       mbar_arrive_expect_tx(wbar, Cfg::WGT_B);
       constexpr int PIECE = 16384;
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)grp * Cfg::WGT_B;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)(Cfg::CTA2 ? 2 * grp + rank : grp) * Cfg::WGT_B;
       for (int off = 0; off < Cfg::WGT_B; off += PIECE) {
         const int bytes = (Cfg::WGT_B - off) < PIECE ? (Cfg::WGT_B - off) : PIECE;
         bulk_g2s(wsm + off, wsrc + off, bytes, wbar);
       }
       uint32_t ws = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (int u = u_first; u - rank < p.n_units; u += gridDim.x) {
         for (int st = 0; st < Cfg::ST; ++st) {
 #pragma unroll 1
           for (int pc = 0; pc < KSPLIT; ++pc, ++ws) {
             const int stage = ws % NSTAGE;
             mbar_wait(&empty[stage], ((ws / NSTAGE) & 1) ^ 1, 1);
-            mbar_arrive_expect_tx(&full[stage], Cfg::WIN_B);
-            tma_load_3d(win0 + stage * Cfg::WIN_B_AL, &tmap, (1 + 8 * MT * st - HALO) * 8, 1 + u * Cfg::CT - HALO_C, pc * Cfg::PPL,
-                        &full[stage]);
+            if constexpr (Cfg::CTA2) {   // both windows of the pair are counted on the leader's barrier
+              if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::WIN_B);
+              tma_load_3d_pair(win0 + stage * Cfg::WIN_B_AL, &tmap, (1 + 8 * MT * st - HALO) * 8, 1 + u * Cfg::CT - HALO_C, pc * Cfg::PPL,
+                               mapa_u32(smem_u32(&full[stage]), 0));
+            } else {
+              mbar_arrive_expect_tx(&full[stage], Cfg::WIN_B);
+              tma_load_3d(win0 + stage * Cfg::WIN_B_AL, &tmap, (1 + 8 * MT * st - HALO) * 8, 1 + u * Cfg::CT - HALO_C, pc * Cfg::PPL,
+                          &full[stage]);
+            }
           }
         }
       }
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(128, NG);
+    if (Cfg::CTA2 && rank == 1) {
+      if (lane == 0) {   // the peer only reports its weights
+        mbar_wait(wbar, 0, 2);
+        mbar_arrive_cluster(mapa_u32(smem_u32(pwbar), 0));
+      }
+    } else if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(Cfg::CTA2 ? 256 : 128, NG);
       // descriptor = (low word: start address >> 4 | LBO >> 4 << 16, high word: SBO >> 4 | version); taps and
       // K steps only move the start address, i.e. add a compile-time constant to the low word
       const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), Cfg::WROWS_OUT * 16, 128);
@@ -216,8 +249,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const uint64_t a_desc0 = umma_smem_desc(smem_u32(win0), PLANE_B, WROWS * 16);
       const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
       mbar_wait(wbar, 0, 2);
+      if constexpr (Cfg::CTA2) mbar_wait(pwbar, 0, 6);
       uint32_t ws = 0, it = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (int u = u_first; u < p.n_units; u += gridDim.x) {
         for (int st = 0; st < Cfg::ST; ++st) {
           const int acc0 = it % NACC;  // NACC % MT == 0: the MT accumulators of a window are consecutive
 #pragma unroll
@@ -241,6 +275,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 for (int m = 0; m < MT; ++m) {  // tile m = rows 8m.. of the window: +8 rows of 16 B
                   if constexpr (Cfg::SWAP)  // weights are the A (M) operand, the activation window is the B (N = 256) operand
                     umma_f16_lohi(tmem_base + (acc0 + m) * NG, b_lo0 + b_off, b_hi, a_lo_stage + a_off, a_hi, idesc, (pc | tap | kk) != 0 ? 1u : 0u);
+                  else if constexpr (Cfg::CTA2)
+                    umma_f16_lohi_pair(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc,
+                                       (pc | tap | kk) != 0 ? 1u : 0u);
                   else
                     umma_f16_lohi(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc,
                                   (pc | tap | kk) != 0 ? 1u : 0u);
@@ -249,9 +286,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             }
             if (pc == KSPLIT - 1) {
 #pragma unroll
-              for (int m = 0; m < MT; ++m) umma_commit(&tfull[acc0 + m]);  // accumulators ready for the epilogue
+              for (int m = 0; m < MT; ++m) {  // accumulators ready for the epilogue
+                if constexpr (Cfg::CTA2) umma_commit_pair(&tfull[acc0 + m]);
+                else umma_commit(&tfull[acc0 + m]);
+              }
             }
-            umma_commit(&empty[stage]);  // window may be overwritten once these MMAs retire
+            // window may be overwritten once these MMAs retire
+            if constexpr (Cfg::CTA2) umma_commit_pair(&empty[stage]);
+            else umma_commit(&empty[stage]);
           }
           it += MT;
         }
@@ -267,7 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const float* bias = p.bias;  // param space: uniform constant-bank reads
     uint32_t it = 0;
     [[maybe_unused]] uint32_t unit_seq = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    for (int u = u_first; u - rank < p.n_units; u += gridDim.x) {
       const int gc = 1 + Cfg::CT * u + g;
       // padded layouts: column gc = n*cols + f' (f' = 0 and cols-1 are zero pads); cols == 1: one column per utterance at gc = 1 + n
       const int n = (p.cols == 1) ? gc - 1 : gc / p.cols;
@@ -288,7 +330,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
           // bias + ReLU on both time steps, sum = time pool (the pool's 1/2 or 1/4 is folded into weights and bias)
           float o[32];
 #pragma unroll
@@ -348,7 +390,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
         }
         // transpose-reduce over the 8 time lanes of a feature column: after the three steps each lane
         // holds the complete sums of HC/8 consecutive channels.
@@ -409,7 +451,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
         }
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -435,7 +477,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
 #pragma unroll
           for (int c = 0; c < HC; ++c) v[c] = fmaxf(v[c] + bias[grp * COUT + h * HC + c], 0.0f);
 #pragma unroll
@@ -482,7 +524,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
           uint32_t pk[HC / 2];
 #pragma unroll
           for (int c = 0; c < HC; c += 2) {
@@ -521,7 +563,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
           const int tp = 1 + 8 * tt + i;
           if (colvalid && tp <= p.rows_valid) {
             float rec[2][4];
@@ -621,7 +663,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             if (sub == SUB - 1) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty[acc]);
+              if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
             }
             uint32_t p0[16], up[16];
 #pragma unroll
@@ -669,7 +711,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
           const int tp = 1 + 8 * tt + i;
           const bool ok = colvalid && (tp <= p.rows_valid);
           constexpr int CPT = (COUT < HN) ? COUT : HN;   // channels of one quadrant held by this thread
@@ -695,10 +737,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (Cfg::CTA2) cluster_sync_all();   // neither CTA may exit (or free TMEM) while the other can still signal it
+  else __syncthreads();
   if (warp == 10) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (Cfg::CTA2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -711,6 +755,37 @@ static int launch_conv_tc(const CUtensorMap& tmap, const ConvParams& p, int grou
   int gx = (num_sms * Cfg::OCC) / groups;
   if (gx < 1) gx = 1;
   if (gx > p.n_units) gx = p.n_units;
+  if constexpr (Cfg::CTA2) {
+    // clusters of 2 along x; the grid is sized from the number of pairs the device can keep resident at once
+    static int max_pairs[32] = {0};
+    int dev = 0;
+    DFS_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_B;
+    cfg.stream = stream;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (max_pairs[dev & 31] == 0) {
+      cfg.gridDim = dim3(2 * num_sms, 1);
+      int n = 0;
+      DFS_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<Cfg>, &cfg));
+      DFS_REQUIRE(n >= 1, DFS_ERR_CUDA, "no CTA pair of this kernel fits the device");
+      max_pairs[dev & 31] = n;
+    }
+    int pairs = max_pairs[dev & 31] / groups;
+    if (pairs < 1) pairs = 1;
+    if (pairs > (p.n_units + 1) / 2) pairs = (p.n_units + 1) / 2;
+    cfg.gridDim = dim3(2 * pairs, groups);
+    DFS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<Cfg>, tmap, p));
+    dfs_count_launch();
+    return DFS_OK;
+  }
   conv_tc_kernel<Cfg><<<dim3(gx, groups), Cfg::THREADS, Cfg::SMEM_B, stream>>>(tmap, p);
   DFS_LAUNCH_CHECK();
   return DFS_OK;

@@ -115,3 +115,20 @@ def test_cae_wide_decoder_variant_is_bit_identical():
     np.testing.assert_array_equal(sc.debug_layer(x[:5], 4, impl=0).cpu().numpy(), d1)
     np.testing.assert_array_equal(sc.debug_layer(x[:5], 5, impl=0).cpu().numpy(), d2)
     np.testing.assert_array_equal(sc.score(x).cpu().numpy(), base)
+
+
+def test_cae_enc4_on_cta_pairs_is_bit_identical():
+    """Option "pair_mma": enc4 as tcgen05 cta_group::2 MMAs (cluster of 2 CTAs, M = 256 = the two units of a pair, each CTA holding
+    64 of the 128 weight rows of its group) against the single-CTA kernel with 4 groups of N = 64: same K order per output, so
+    the latent and the scores must agree bit for bit.  3 utterances = 5 column tiles (odd: the last pair has a padding unit),
+    then 13 utterances through passes of 5."""
+    mean, std = syn.normalizer_stats(1)
+    x = torch.from_numpy(syn.features(13, seed=23)).cuda()
+    sc = CaeScorer(syn.cae_state(2), mean, std, max_chunk=5)
+    sc.set_option("pair_mma", 0)
+    base = sc.score(x).cpu().numpy()
+    e4_3, e4_5 = sc.debug_layer(x[:3], 3, impl=0).cpu().numpy(), sc.debug_layer(x[5:10], 3, impl=0).cpu().numpy()
+    sc.set_option("pair_mma", 1)
+    np.testing.assert_array_equal(sc.debug_layer(x[:3], 3, impl=0).cpu().numpy(), e4_3)
+    np.testing.assert_array_equal(sc.debug_layer(x[5:10], 3, impl=0).cpu().numpy(), e4_5)
+    np.testing.assert_array_equal(sc.score(x).cpu().numpy(), base)
