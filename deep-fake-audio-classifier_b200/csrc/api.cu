@@ -823,7 +823,7 @@ static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
     DFS_PROPAGATE(dev_upload(m, &d, pack_convT_rows(w->dec[1], 128, 64, scratch, 2)));
     s->w_wide[1] = d;
     s->dec_wide = 1;
-    s->pair_mma = 0;
+    s->pair_mma = 1;
   }
   std::vector<float> wf(128);
   for (int q = 0; q < 4; ++q)

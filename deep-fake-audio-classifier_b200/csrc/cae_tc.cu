@@ -27,6 +27,8 @@ namespace dfs {
 using Enc2Cfg = ConvCfg<MODE_PAIR, 32, 64, 128, 80, 2, 3, 4, 1, EPI_PAIR_POOL_F>;
 using Enc3Cfg = ConvCfg<MODE_3X3, 64, 128, 128, 80, 2, 2, 4, 1, EPI_POOL_TF>;
 using Enc4Cfg = ConvCfg<MODE_3X3, 128, 64, 64, 40, 1, 3, 4, 2, EPI_POOL_TF>;
+// enc4's weights (147 KB per 64 output channels) force N = 64 on one CTA; a CTA pair runs N = 128 with 64 weight rows per CTA.
+// enc2 / enc3 (already N = 128) were also tried on pairs: bit-identical and slower (CAE 351 k vs 362 k utt/s), see conv_tc.cu.
 using Enc4PairCfg = ConvCfg<MODE_3X3, 128, 128, 128, 40, 1, 3, 4, 2, EPI_POOL_TF, 1>;   // option "pair_mma": CTA pairs, 2 groups of N = 128 (64 weight rows per CTA)
 static_assert(Enc4PairCfg::PPL == Enc4Cfg::PPL && Enc4PairCfg::WROWS == Enc4Cfg::WROWS && Enc4PairCfg::WGT_B == Enc4Cfg::WGT_B, "enc4 pair variant shares map and weights");
 using Dec1Cfg = ConvCfg<MODE_1X1, 256, 128, 128, 24, 1, 3, 2, 4, EPI_SHUFFLE_ROWS>;

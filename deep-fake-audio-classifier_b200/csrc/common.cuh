@@ -274,8 +274,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// Default (.release.cta) semantics on purpose: the callers order TMEM reads / TMA-written shared memory, which the tcgen05 fences and
+// the mbarrier phases themselves cover; the .release.cluster form costs a cluster-scope memory barrier per arrival (ncu: 17 % of the
+// epilogue warps' samples sat on it).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // tensor copy into THIS CTA's shared memory whose completion bytes are counted on a barrier given as a shared::cluster address
 // (the leader's barrier for both CTAs of a pair)

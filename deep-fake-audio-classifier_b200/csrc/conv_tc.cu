@@ -41,6 +41,9 @@ int make_act_tensor_map(CUtensorMap* out, const ActBuf& a, int wrows, int wcols,
 
 // CNN2D conv2: 32 -> 64 channels on 160 x 180 as 80 time PAIRS per column, pooled to 80 rows.
 using Conv2Cfg = ConvCfg<MODE_PAIR, 32, 64, 128, 80, 2, 3, 4, 1, EPI_PAIR_POOL>;
+// (A CTA-pair variant of conv2 -- ConvCfg<..., CTA2 = 1>, M = 256, 64 weight rows per CTA -- was measured and removed: bit-identical, but
+// 616 vs 985 TFLOP/s.  A cta_group::2 MMA costs the cycles of a single-CTA MMA of the same N (profiles/r01f_umma_bench_pairs.txt):
+// each SM still streams its own 128 rows of A and consumes all N rows of B, so pairs only pay where shared memory forces N < 128.)
 // CNN2D conv3: 64 -> 128 channels on 80 x 180, summed over time.
 using Conv3Cfg = ConvCfg<MODE_3X3S, 64, 128, 256, 80, 1, 3, 2, 2, EPI_MEAN_T_SWAP>;   // weights as A, 256 positions as N
 using Conv3PlainCfg = ConvCfg<MODE_3X3, 64, 128, 128, 80, 2, 2, 4, 1, EPI_MEAN_T>;   // positions as A (N = 128), kept for comparison

@@ -149,18 +149,82 @@ __global__ void __launch_bounds__(128) probe_umma_bench_kernel(const __grid_cons
   }
 }
 
+// The same loop on a CTA pair (cluster of 2): the leader issues tcgen05.mma.cta_group::2 (M = 256, each CTA supplies its 128 rows of A
+// and n/2 rows of B from the same shared-memory offsets) and commits to the barrier at the same offset in both CTAs.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe_umma_bench_pair_kernel(const __grid_constant__ UmmaBenchParams p,
+                                                                                            long long* __restrict__ cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int A_BYTES = 96 * 1024, B_BYTES = 64 * 1024;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const uint32_t rank = cluster_ctarank();
+  for (int i = threadIdx.x; i < (A_BYTES + B_BYTES) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if ((threadIdx.x >> 5) == 0) {
+    tmem_alloc_pair(tmem_slot, 256);
+    tmem_relinquish_pair();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0 && rank == 0) {
+    const uint32_t idesc = umma_idesc_bf16(256, p.n);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + A_BYTES);
+    uint64_t* ad = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES + 64);
+    uint64_t* bd = ad + 40;
+    for (int i = 0; i < p.nmma; ++i) {
+      const uint32_t aa = a0 + p.a_off[i], bb = b0 + p.b_off[i];
+      ad[i] = umma_smem_desc(aa, p.a_lbo, p.a_sbo) | ((uint64_t)p.layout << 61);
+      bd[i] = umma_smem_desc(bb, p.b_lbo, p.b_sbo) | ((uint64_t)p.layout << 61);
+    }
+    uint32_t phase = 0;
+    for (int i = 0; i < p.nmma; ++i)
+      umma_f16_lohi_pair(tmem_base, (uint32_t)ad[i], (uint32_t)(ad[i] >> 32), (uint32_t)bd[i], (uint32_t)(bd[i] >> 32), idesc, i != 0);
+    umma_commit_pair(bar);
+    mbar_wait(bar, phase, 13);
+    phase ^= 1;
+    const long long t0 = clock64();
+    for (int it = 0; it < p.iters; ++it) {
+#pragma unroll 4
+      for (int i = 0; i < p.nmma; ++i)
+        umma_f16_lohi_pair(tmem_base, (uint32_t)ad[i], (uint32_t)(ad[i] >> 32), (uint32_t)bd[i], (uint32_t)(bd[i] >> 32), idesc, i != 0);
+      umma_commit_pair(bar);
+      mbar_wait(bar, phase, 14);
+      phase ^= 1;
+    }
+    const long long t1 = clock64();
+    cycles_out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if ((threadIdx.x >> 5) == 0) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 256);
+  }
+}
+
 int probe_umma_bench(int n, int nmma, int iters, const uint32_t* a_off, const uint32_t* b_off, uint32_t a_lbo, uint32_t a_sbo,
                      uint32_t b_lbo, uint32_t b_sbo, uint32_t layout, uint32_t use_base_offset, long long* cycles_host, cudaStream_t stream) {
   DFS_REQUIRE(n % 16 == 0 && n >= 16 && n <= 256 && nmma >= 1 && nmma <= 40 && iters >= 1, DFS_ERR_INVALID, "probe_umma_bench: bad argument");
   UmmaBenchParams p{};
   p.n = n; p.nmma = nmma; p.iters = iters;
   for (int i = 0; i < nmma; ++i) { p.a_off[i] = a_off[i]; p.b_off[i] = b_off[i]; }
-  p.a_lbo = a_lbo; p.a_sbo = a_sbo; p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.layout = layout; p.use_base_offset = use_base_offset;
+  p.a_lbo = a_lbo; p.a_sbo = a_sbo; p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.layout = layout; p.use_base_offset = use_base_offset & 1;
   long long* d = nullptr;
   DFS_CUDA_CHECK(cudaMalloc(&d, 8));
   const int smem = 160 * 1024 + 64 + 80 * 8;
   DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  probe_umma_bench_kernel<<<1, 128, smem, stream>>>(p, d);
+  if (use_base_offset & 2) {   // bit 1: run on a CTA pair (cta_group::2); n is the N of the pair's MMA
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_umma_bench_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    probe_umma_bench_pair_kernel<<<2, 128, smem, stream>>>(p, d);
+  } else {
+    probe_umma_bench_kernel<<<1, 128, smem, stream>>>(p, d);
+  }
   dfs_count_launch();
   cudaError_t e = cudaStreamSynchronize(stream);
   if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 8, cudaMemcpyDeviceToHost);

@@ -118,9 +118,9 @@ def test_cae_wide_decoder_variant_is_bit_identical():
 
 
 def test_cae_enc4_on_cta_pairs_is_bit_identical():
-    """Option "pair_mma": enc4 as tcgen05 cta_group::2 MMAs (cluster of 2 CTAs, M = 256 = the two units of a pair, each CTA holding
-    64 of the 128 weight rows of its group) against the single-CTA kernel with 4 groups of N = 64: same K order per output, so
-    the latent and the scores must agree bit for bit.  3 utterances = 5 column tiles (odd: the last pair has a padding unit),
+    """Option "pair_mma" (default 1): enc4 as tcgen05 cta_group::2 MMAs (cluster of 2 CTAs, M = 256 = the two units of a pair, each CTA
+    holding 64 of the 128 weight rows of its group) against the single-CTA kernel with 4 groups of N = 64: same K order per output,
+    so the latent and the scores must agree bit for bit.  3 utterances = 5 column tiles (odd: the last pair has a padding unit),
     then 13 utterances through passes of 5."""
     mean, std = syn.normalizer_stats(1)
     x = torch.from_numpy(syn.features(13, seed=23)).cuda()

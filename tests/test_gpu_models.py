@@ -279,3 +279,4 @@ def test_cnn2d_fp32_precision_mode_tracks_the_reference_ranks(feats):
     assert abs(D.calculate_eer(got32, lab)[0] - oeer.calculate_eer(ref, lab)[0]) <= 1e-4     # north_star: EER within 0.01 pp
     exact.set_option("precision", 0)                                  # back on the tensor-core path: the default bits
     assert np.array_equal(exact.score(x, apply_sigmoid=True).cpu().numpy(), got16)
+

@@ -56,3 +56,11 @@ sw64 = [(kw * 18 + kh) * 64 + kk * 32 for kh in range(3) for kw in range(3) for 
 b64 = [(t * 4096 + kk * 32) for t in range(9) for kk in range(2)]
 run("SW64  conv2 taps: row shifts of 64 B, SBO=18*64, N=64", 64, sw64, b64, 16, 18 * 64, 16, 512, layout=4)
 run("SW64  aligned (SBO=512), N=64", 64, [kk * 32 for _ in range(9) for kk in range(2)], b64, 16, 512, 16, 512, layout=4)
+
+# --- CTA pairs (cta_group::2, M = 256): bit 1 of the last flag.  B strides are those of the per-CTA half image (n/2 rows).
+print("# cta_group::2 (M = 256 per MMA; 'ideal' is per CTA pair = 128 * n / 256 cycles)")
+for n in (64, 128, 256):
+    run(f"pair  none aligned, N={n} (B half = {n // 2} rows per CTA)", n, [0] * 16, [0] * 16, P3a, 128, (n // 2) * 16, 128, base=2)
+run("pair  none conv3-like taps, N=128", 128, taps3, [((t * 8 + 2 * kk) * 64) * 16 % 65536 for t in range(9) for kk in range(4)], P3, 160, 1024, 128, base=2)
+run("pair  SW128 aligned, N=128", 128, sw_al, [(t * 8192 + kk * 32) % 65536 for t in range(9) for kk in range(4)], 16, 1024, 16, 1024, layout=2, base=2)
+run("pair  SW128 aligned, N=256", 256, sw_al[:16], [(kk * 32) for _ in range(4) for kk in range(4)], 16, 1024, 16, 1024, layout=2, base=2)
