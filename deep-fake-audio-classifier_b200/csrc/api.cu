@@ -256,8 +256,10 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     return DFS_OK;
   }
   if (strcmp(key, "pair_mma") == 0) {
-    DFS_REQUIRE(m->cae != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "pair_mma is a CAE option (0 | 1)");
-    m->cae->pair_mma = (int)value;
+    DFS_REQUIRE((m->cae != nullptr || m->dlq != nullptr) && (value == 0 || value == 1), DFS_ERR_INVALID,
+                "pair_mma is an option of the CAE and the StatsPool detector (0 | 1)");
+    if (m->cae != nullptr) m->cae->pair_mma = (int)value;
+    else m->dlq->pair_mma = (int)value;
     return DFS_OK;
   }
   if (strcmp(key, "dec_wide") == 0) {
@@ -655,6 +657,7 @@ extern "C" int dfs_dlq_create(dfs_model** out, int device, const dfs_dlq_weights
   DlqState* s = new (std::nothrow) DlqState();
   if (!s) return fail(DFS_ERR_NOMEM);
   m->dlq = s;
+  s->pair_mma = 1;
   memset(s->bias, 0, sizeof(s->bias));
   std::vector<uint16_t> packs[3];
   packs[0] = pack_conv1d_groups(w->conv[0], 256, kF, 192, 5, 64, s->bias[0]);

@@ -117,6 +117,10 @@ int launch_cnn1d_tc(const Cnn1dTcState* s, const float* x, int64_t sn, int64_t s
 // the 1D-CNN (cnn1d_prep_kernel); the k = 5 halo rows beyond the stored pad row are the TMA's out-of-bounds zeros.
 // Pooling + head are one block per utterance (256 threads = 256 channels / hidden units), fp32, fixed order.
 using DlqL1 = ConvCfg<MODE_5X1, 192, 64, 64, kC1dRows, 1, 3, 4, 3, EPI_GELU>;
+// the same layer on CTA pairs (option "pair_mma"): M = 256 = the two 16-utterance column tiles of a pair, 2 groups of N = 128 with 64
+// weight rows (the same 123 KB group image) per CTA
+using DlqL1Pair = ConvCfg<MODE_5X1, 192, 128, 128, kC1dRows, 1, 3, 4, 3, EPI_GELU, 1>;
+static_assert(DlqL1Pair::WGT_B == DlqL1::WGT_B && DlqL1Pair::PPL == DlqL1::PPL && DlqL1Pair::WROWS == DlqL1::WROWS, "pair variant shares map and weights");
 // layers 2 and 3: two groups of N = 128 (196 KB of resident weights; the activation window is cut into 8 pieces of 4 channel
 // planes = 10 KB so that three stages still fit): an N = 128 MMA costs the same 88-100 cycles as an N = 64 one
 using DlqL2 = ConvCfg<MODE_3X1, 256, 128, 128, kC1dRows, 1, 3, 4, 8, EPI_GELU>;
@@ -196,7 +200,10 @@ int launch_dlq(const DlqState* s, const float* x, int64_t sn, int64_t st, int64_
   const long long total = (long long)n_utts * kT * 24;
   cnn1d_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, s->act0);
   DFS_LAUNCH_CHECK();
-  DFS_PROPAGATE(launch_conv_tc<DlqL1>(s->tmap[0], dlq_params(s, 0, n_utts, s->actA), 4, num_sms, stream));
+  if (s->pair_mma)
+    DFS_PROPAGATE(launch_conv_tc<DlqL1Pair>(s->tmap[0], dlq_params(s, 0, n_utts, s->actA), 2, num_sms, stream));
+  else
+    DFS_PROPAGATE(launch_conv_tc<DlqL1>(s->tmap[0], dlq_params(s, 0, n_utts, s->actA), 4, num_sms, stream));
   DFS_PROPAGATE(launch_conv_tc<DlqL2>(s->tmap[1], dlq_params(s, 1, n_utts, s->actB), 2, num_sms, stream));
   DFS_PROPAGATE(launch_conv_tc<DlqL2>(s->tmap[2], dlq_params(s, 2, n_utts, s->actA), 2, num_sms, stream));
   dlq_stats_head_kernel<<<n_utts, 256, 0, stream>>>(s->actA, lengths_dev, s->fc1_wt, s->fc1_b, s->fc2_w, s->fc2_b, apply_sigmoid, out);

@@ -104,6 +104,7 @@ struct DlqState {
   const float* fc1_b;     // [256]
   const float* fc2_w;     // head.3.weight [256]
   float fc2_b;
+  int pair_mma;           // 1 (default) = layer 1 on CTA pairs (tcgen05 cta_group::2): 2 groups of N = 128 instead of 4 of N = 64
 };
 void dlq_geometry(int buf, int* planes, int* rs);
 int dlq_make_maps(DlqState* s);

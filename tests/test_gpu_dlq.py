@@ -74,3 +74,17 @@ def test_dlq_dropin_module_forward():
     assert np.max(np.abs(logits.cpu().numpy() - ref)) <= 2e-3
     eer = D.calculate_eer(logits.cpu().numpy(), (np.arange(12) % 2))                  # evaluate_eer, :247-251
     assert 0.0 <= eer[0] <= 1.0
+
+
+def test_dlq_layer1_on_cta_pairs_is_bit_identical():
+    """Option "pair_mma" (default 1): layer 1 as tcgen05 cta_group::2 MMAs (2 groups of N = 128, 64 weight rows per CTA) against 4
+    groups of N = 64 on single CTAs: same K order, so the logits must agree bit for bit.  40 utterances = 3 column tiles (odd: the
+    last pair has a padding unit), ragged lengths, then passes of 16."""
+    x = torch.from_numpy(syn.features(40, seed=78)).cuda()
+    lengths = torch.tensor([321 - (7 * i) % 200 for i in range(40)], dtype=torch.int32).cuda()
+    for chunk in (0, 16):
+        sc = D.DlqScorer(syn.dlq_state(4), max_chunk=chunk)
+        sc.set_option("pair_mma", 0)
+        a, al = sc.score(x), sc.score(x, lengths=lengths)
+        sc.set_option("pair_mma", 1)
+        assert torch.equal(sc.score(x), a) and torch.equal(sc.score(x, lengths=lengths), al)
