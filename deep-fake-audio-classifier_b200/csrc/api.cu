@@ -235,8 +235,12 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     return DFS_OK;
   }
   if (strcmp(key, "precision") == 0) {
-    DFS_REQUIRE(m->kind == KIND_CNN2D && (value == 0 || value == 1), DFS_ERR_INVALID,
-                "precision is a CNN2D option: 0 (fp16 tensor-core operands, fp32 accumulate) | 1 (full fp32, CUDA cores)");
+    DFS_REQUIRE((m->kind == KIND_CNN2D || m->kind == KIND_CNN1D || m->kind == KIND_CAE) && (value == 0 || value == 1), DFS_ERR_INVALID,
+                "precision: 0 (fp16 tensor-core operands, fp32 accumulate) | 1 (full fp32 on the CUDA cores); 2D-CNN, 1D-CNN and CAE handles");
+    if (m->kind != KIND_CNN2D) {   // 1D-CNN / CAE: the fp32 CUDA-core kernels of simt_models.cu (fp32 weights and activations)
+      m->conv_impl = (int)value;
+      return DFS_OK;
+    }
     if (value == 1 && m->work32 == nullptr) {
       DFS_CUDA_CHECK(cudaSetDevice(m->device));
       m->chunk32 = std::min(m->chunk, 16);

@@ -152,6 +152,12 @@ class _Scorer:
         return out.numpy()
 
 
+def _check_precision(precision):
+    """"fp16" = tensor-core path (fp16 operands, fp32 accumulation); "fp32" = full fp32 on the CUDA cores (rank-exact evaluation)."""
+    if precision not in ("fp16", "fp32"):
+        raise ValueError(f"precision must be 'fp16' or 'fp32', got {precision!r}")
+
+
 class Cnn2dScorer(_Scorer):
     """CNN2D (src/model.py:12-42) on the tcgen05 path.  ``precision="fp32"`` selects the full-fp32 CUDA-core kernels
     (csrc/cnn2d_fp32.cu; ~35x slower) for evaluations where the rank order of near-equal scores matters."""
@@ -159,8 +165,7 @@ class Cnn2dScorer(_Scorer):
 
     def __init__(self, state_dict, device: int = 0, max_chunk: int = 0, precision: str = "fp16"):
         super().__init__()
-        if precision not in ("fp16", "fp32"):
-            raise ValueError(f"precision must be 'fp16' or 'fp32', got {precision!r}")
+        _check_precision(precision)
         _require_cuda()
         keep = []
         w = N.Cnn2dWeights()
@@ -193,9 +198,10 @@ class Cnn1dScorer(_Scorer):
     """CNN1D (src/model_cnn1d.py:12-46)."""
     KIND = "cnn1d"
 
-    def __init__(self, state_dict, device: int = 0, max_chunk: int = 0):
+    def __init__(self, state_dict, device: int = 0, max_chunk: int = 0, precision: str = "fp16"):
         super().__init__()
         _require_cuda()
+        _check_precision(precision)
         keep = []
         w = N.Cnn1dWeights()
         w0 = _np32(state_dict["conv.0.weight"])
@@ -207,6 +213,8 @@ class Cnn1dScorer(_Scorer):
         w.fc_weight, w.fc_bias = _fptr(fcw), _fptr(fcb)
         self.device_index = int(device)
         N.check(self._lib.dfs_cnn1d_create(C.byref(self._h), int(device), C.byref(w), int(max_chunk)), "dfs_cnn1d_create")
+        if precision == "fp32":
+            self.set_option("precision", 1)
 
     def score(self, x, apply_sigmoid: bool = False):
         torch = _require_cuda()
@@ -264,9 +272,10 @@ class CaeScorer(_Scorer):
     ``mean``/``std`` are the FeatureNormalizer statistics (src/dataset_cae.py:18-52), optional."""
     KIND = "cae"
 
-    def __init__(self, state_dict, mean=None, std=None, device: int = 0, max_chunk: int = 0):
+    def __init__(self, state_dict, mean=None, std=None, device: int = 0, max_chunk: int = 0, precision: str = "fp16"):
         super().__init__()
         _require_cuda()
+        _check_precision(precision)
         keep = []
         w = N.CaeWeights()
         w.base_channels = int(_np32(state_dict["encoder.0.weight"]).shape[0])
@@ -283,6 +292,8 @@ class CaeScorer(_Scorer):
             w.norm_mean, w.norm_std = _fptr(m), _fptr(s)
         self.device_index = int(device)
         N.check(self._lib.dfs_cae_create(C.byref(self._h), int(device), C.byref(w), int(max_chunk)), "dfs_cae_create")
+        if precision == "fp32":
+            self.set_option("precision", 1)
 
     def score(self, x, apply_normalizer: bool | None = None):
         """Per-utterance MSE between the (normalised) input and its reconstruction; recon never hits HBM."""

@@ -20,10 +20,18 @@ if _PKG not in sys.path:
 
 
 class NativeBackedModule(nn.Module):
+    # "fp16" (default): tensor-core path, fp16 operands / fp32 accumulation.  "fp32": the full-fp32 CUDA-core kernels, for evaluations
+    # where the rank order of near-equal scores matters.  Set it on the instance (or class) before the first CUDA forward, or export
+    # DFS_B200_PRECISION=fp32.
+    precision = None
+
     def __init__(self):
         super().__init__()
         self._native = None
         self._native_key = None
+
+    def _precision(self):
+        return self.precision or os.environ.get("DFS_B200_PRECISION", "fp16")
 
     def _make_scorer(self, state_dict, device_index):  # pragma: no cover - overridden
         raise NotImplementedError
@@ -34,7 +42,7 @@ class NativeBackedModule(nn.Module):
 
     def native(self, device):
         """The native scorer for the current weights on `device` (cached)."""
-        key = self._weights_key(device)
+        key = self._weights_key(device) + (self._precision(),)
         if self._native is None or self._native_key != key:
             if self._native is not None:
                 self._native.close()

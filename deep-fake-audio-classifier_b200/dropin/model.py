@@ -15,11 +15,6 @@ def _block(cin, cout, pool, dropout):
 
 
 class CNN2D(NativeBackedModule):
-    # "fp16" (default): tcgen05 path, fp16 operands / fp32 accumulate.  "fp32": full-fp32 CUDA-core kernels for evaluations
-    # where the rank order of near-equal scores matters; set it on the instance (or class) before the first CUDA forward,
-    # or export DFS_B200_PRECISION=fp32.
-    precision = None
-
     def __init__(self, in_features=180, base_channels=32, num_classes=1, dropout=0.2):
         super().__init__()
         c = base_channels
@@ -27,9 +22,8 @@ class CNN2D(NativeBackedModule):
         self.classifier = nn.Linear(4 * c * in_features, num_classes)
 
     def _make_scorer(self, sd, device_index):
-        import os
         from dfs_b200 import Cnn2dScorer
-        return Cnn2dScorer(sd, device=device_index, precision=self.precision or os.environ.get("DFS_B200_PRECISION", "fp16"))
+        return Cnn2dScorer(sd, device=device_index, precision=self._precision())
 
     def forward(self, x, return_embedding=False):
         if self._use_native(x):

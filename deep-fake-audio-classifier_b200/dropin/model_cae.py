@@ -34,7 +34,7 @@ class ConvAutoencoder(NativeBackedModule):
     def _make_scorer(self, sd, device_index):
         from dfs_b200 import CaeScorer
         mean, std = self._norm if self._norm is not None else (None, None)
-        return CaeScorer(sd, mean, std, device=device_index)
+        return CaeScorer(sd, mean, std, device=device_index, precision=self._precision())
 
     def score_mse(self, x, apply_normalizer=None):
         """Per-utterance reconstruction MSE, reconstruction never materialised (predict_hybrid.py:75-76)."""

@@ -21,7 +21,7 @@ class CNN1D(NativeBackedModule):
 
     def _make_scorer(self, sd, device_index):
         from dfs_b200 import Cnn1dScorer
-        return Cnn1dScorer(sd, device=device_index)
+        return Cnn1dScorer(sd, device=device_index, precision=self._precision())
 
     def forward(self, x):
         if self._use_native(x):

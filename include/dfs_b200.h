@@ -118,7 +118,7 @@ int dfs_dlq_create(dfs_model** out, int device, const dfs_dlq_weights* w, int ma
 int dfs_model_destroy(dfs_model* m);
 /* options: "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = CUDA-core direct conv (debug
  * cross-check, same layouts); "profile" 0/1 = per-kernel event timing (dfs_model_profile);
- * "precision" (CNN2D) 0 = fp16 tensor-core operands with fp32 accumulation (default), 1 = the whole
+ * "precision" (CNN2D, CNN1D, CAE) 0 = fp16 tensor-core operands with fp32 accumulation (default), 1 = the whole
  * network in fp32 on the CUDA cores (same arithmetic class as the reference's CPU path; for evaluations
  * where the rank order of scores a few 1e-6 apart matters, e.g. the EER of a small dev set). */
 int dfs_model_set_option(dfs_model* m, const char* key, int64_t value);

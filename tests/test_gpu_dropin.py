@@ -95,3 +95,31 @@ def test_predict_hybrid_flow(tmp_path):
     assert out["predictions"].dtype == np.float64
     labels = (np.arange(n) % 2).tolist()
     assert dev_eval.calculate_eer(hyb.tolist(), labels) == oeer.calculate_eer(hyb.tolist(), labels, kind="stable")
+
+
+def test_precision_fp32_on_the_dropin_classes_tracks_the_reference():
+    """`model.precision = "fp32"` (or DFS_B200_PRECISION=fp32) routes the drop-in CNN2D / CNN1D / ConvAutoencoder through the full-fp32
+    CUDA-core kernels: logits / MSE agree with the unmodified reference (goldens) to fp32 round-off."""
+    x = torch.from_numpy(syn.features(12, seed=1234)).cuda()
+    for cls, state, key in ((m2.CNN2D, syn.cnn2d_state(0), "cnn2d_init_logits"), (m1.CNN1D, syn.cnn1d_state(0), "cnn1d_init_logits")):
+        net = cls(in_features=180, dropout=0.2).cuda().eval()
+        net.load_state_dict(_t(state))
+        net.precision = "fp32"
+        with torch.no_grad():
+            got = net(x).squeeze(-1).cpu().numpy()
+        np.testing.assert_allclose(got, G[key], rtol=0, atol=2e-6)
+        net.precision = None                       # back on the tensor-core path: the fp16-operand result, within the score gate
+        with torch.no_grad():
+            fast = net(x).squeeze(-1).cpu().numpy()
+        assert not np.array_equal(fast, got) and np.max(np.abs(fast - G[key])) <= 1e-3
+    cae = mc.ConvAutoencoder().cuda().eval()
+    cae.load_state_dict(_t(syn.cae_state(0)))
+    cae.precision = "fp32"
+    mean, std = syn.normalizer_stats(1)
+    xn = (x - torch.from_numpy(mean).cuda()) / torch.from_numpy(std).cuda()
+    with torch.no_grad():
+        recon, latent = cae(xn)
+    assert tuple(recon.shape) == (12, 321, 180) and tuple(latent.shape) == (12, 256, 20, 11)
+    mse = torch.nn.MSELoss(reduction="none")(recon, xn).view(12, -1).mean(1).cpu().numpy()
+    assert _rel(mse, G["cae_mse"]) <= 5e-6
+    assert _rel(cae.score_mse(xn, apply_normalizer=False).cpu().numpy(), G["cae_mse"]) <= 5e-6
