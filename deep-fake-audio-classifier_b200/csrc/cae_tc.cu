@@ -301,7 +301,8 @@ int launch_cae_tc(const CaeTcState* s, const float* x, int64_t sn, int64_t st, i
   if (s->final_fused && stop_after_layer == 7 && mse_out != nullptr && recon_out == nullptr) {
     // scoring path: dec3's epilogue applies the final layer and accumulates the squared error; d3 never reaches HBM
     ConvParams p = base_params(s, 5, 5, 6, n_utts, 45, 80, 90);
-    for (int k = 0; k < 128; ++k) p.bias[32 + k] = s->w_final_host[k];
+    for (int q = 0; q < 4; ++q)
+      for (int c = 0; c < 32; ++c) p.bias[32 + 4 * c + q] = s->w_final_host[q * 32 + c];   // channel-major: the pairs of an FFMA2 are adjacent
     p.bias[160] = s->final_bias;
     p.x = x;
     p.xsn = sn;

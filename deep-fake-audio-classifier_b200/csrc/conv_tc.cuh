@@ -134,7 +134,7 @@ struct ConvParams {
   // EPI_MEAN_T: per-utterance time SUMS, [n][F][COUT] fp32 (the head applies 1/T)
   float* emb;
   // EPI_SHUFFLE_MSE: the scorer's input (element (n,t,f) at x[n*xsn + t*xst + f*xsf]), the optional normaliser and the
-  // per-unit partial sums; the final layer's weights ride in bias[32..159] ([(a*2+b)*32 + ci]) and its bias in bias[160]
+  // per-unit partial sums; the final layer's weights ride in bias[32..159] ([ci*4 + a*2+b]) and its bias in bias[160]
   const float* x;
   long long xsn, xst, xsf;
   const float* norm_mean;
@@ -577,15 +577,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 d[c] = f2.x;
                 d[c + 1] = f2.y;
               }
+              // 4 outputs x 32 MACs as 64 packed FFMA2 (fma.rn.f32x2: two IEEE fp32 FMAs per instruction, the d3 value broadcast, the
+              // weight pair (q, q+1) of channel c read as one 64-bit uniform operand): same per-output FMA order as the scalar loop,
+              // half the issue slots of the part that bounds this kernel.  Weights at bias[32 + 4 c + q], q = a2 * 2 + b2.
+              uint64_t r01 = pack_f32x2(fb, fb), r23 = r01;
 #pragma unroll
-              for (int a2 = 0; a2 < 2; ++a2)
-#pragma unroll
-                for (int b2 = 0; b2 < 2; ++b2) {
-                  float r = fb;
-#pragma unroll
-                  for (int c = 0; c < 32; ++c) r = fmaf(d[c], bias[32 + (a2 * 2 + b2) * 32 + c], r);
-                  rec[a2][2 * b + b2] = r;
-                }
+              for (int c = 0; c < 32; ++c) {
+                const uint64_t dd = pack_f32x2(d[c], d[c]);
+                r01 = fma_f32x2(dd, pack_f32x2(bias[32 + 4 * c], bias[33 + 4 * c]), r01);
+                r23 = fma_f32x2(dd, pack_f32x2(bias[34 + 4 * c], bias[35 + 4 * c]), r23);
+              }
+              unpack_f32x2(r01, rec[0][2 * b], rec[0][2 * b + 1]);
+              unpack_f32x2(r23, rec[1][2 * b], rec[1][2 * b + 1]);
             }
             const int t0 = 4 * (tp - 1) + 2 * h, f0 = 4 * (fp - 1);
             float mu[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {1.f, 1.f, 1.f, 1.f};
