@@ -7,7 +7,8 @@
 // counts / batch sizes (tools/experiments/reference_self_consistency.py); this path has the same arithmetic class --
 // fp32 operands, fp32 FMA accumulation, BN folded in double and rounded once -- and exists for evaluations where the rank
 // order of near-equal scores matters (dev-set EER of a few thousand utterances).  It is an explicit option, never a
-// fallback: ~35x slower than the tensor-core path and still ~60x the reference's 16-core CPU loop.
+// fallback: ~35x slower than the tensor-core path and still ~60x the reference's 16-core CPU loop.  The FMAs are packed
+// FFMA2 (fma.rn.f32x2, activation broadcast): 288 instead of 576 FMA instructions per channel step, 7.4 k -> 8.4 k utt/s.
 //
 // Layout: activations channels-last fp32 [n][rows][180][C]; weights [(kh*3+kw)*CI + ci][co] fp32.
 // One thread = 2 rows x 2 feature columns x 4 output channels (the 2 rows are the pair the (2,1) average pool combines):
@@ -32,13 +33,14 @@ __global__ void __launch_bounds__(128) conv3x3_fp32_kernel(const float* __restri
   const int j = (int)(p % HP);
   const long long n = p / HP;
 
-  float acc[2][2][4];   // [row of the pair][column of the pair][channel]
+  // accumulators as packed fp32 pairs: one FFMA2 (fma.rn.f32x2) = two IEEE fp32 FMAs with the activation broadcast
+  uint64_t acc[2][2][2];   // [row of the pair][column of the pair][channel pair]
   {
     const float4 bv = *reinterpret_cast<const float4*>(b + co);
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int c = 0; c < 2; ++c) { acc[a][c][0] = bv.x; acc[a][c][1] = bv.y; acc[a][c][2] = bv.z; acc[a][c][3] = bv.w; }
+      for (int c = 0; c < 2; ++c) { acc[a][c][0] = pack_f32x2(bv.x, bv.y); acc[a][c][1] = pack_f32x2(bv.z, bv.w); }
   }
   constexpr int CS = FIRST ? 1 : 4;   // channels per step
   for (int ci = 0; ci < CI; ci += CS) {
@@ -66,31 +68,39 @@ __global__ void __launch_bounds__(128) conv3x3_fp32_kernel(const float* __restri
 #pragma unroll
         for (int q = 0; q < CS; ++q) {
           const float4 wv = *reinterpret_cast<const float4*>(w + ((long long)((kh * 3 + kw) * CI + ci + q)) * CO + co);
+          const uint64_t w01 = pack_f32x2(wv.x, wv.y), w23 = pack_f32x2(wv.z, wv.w);
 #pragma unroll
           for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               const float x = v[a + kh][c + kw][q];
-              acc[a][c][0] = fmaf(x, wv.x, acc[a][c][0]);
-              acc[a][c][1] = fmaf(x, wv.y, acc[a][c][1]);
-              acc[a][c][2] = fmaf(x, wv.z, acc[a][c][2]);
-              acc[a][c][3] = fmaf(x, wv.w, acc[a][c][3]);
+              const uint64_t xx = pack_f32x2(x, x);
+              acc[a][c][0] = fma_f32x2(xx, w01, acc[a][c][0]);
+              acc[a][c][1] = fma_f32x2(xx, w23, acc[a][c][1]);
             }
         }
   }
+  float accf[2][2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      unpack_f32x2(acc[a][c][0], accf[a][c][0], accf[a][c][1]);
+      unpack_f32x2(acc[a][c][1], accf[a][c][2], accf[a][c][3]);
+    }
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     if constexpr (POOL) {   // relu, then the (2,1) average (model.py:18,24)
       float4 o;
-      o.x = 0.5f * (fmaxf(acc[0][c][0], 0.f) + fmaxf(acc[1][c][0], 0.f));
-      o.y = 0.5f * (fmaxf(acc[0][c][1], 0.f) + fmaxf(acc[1][c][1], 0.f));
-      o.z = 0.5f * (fmaxf(acc[0][c][2], 0.f) + fmaxf(acc[1][c][2], 0.f));
-      o.w = 0.5f * (fmaxf(acc[0][c][3], 0.f) + fmaxf(acc[1][c][3], 0.f));
+      o.x = 0.5f * (fmaxf(accf[0][c][0], 0.f) + fmaxf(accf[1][c][0], 0.f));
+      o.y = 0.5f * (fmaxf(accf[0][c][1], 0.f) + fmaxf(accf[1][c][1], 0.f));
+      o.z = 0.5f * (fmaxf(accf[0][c][2], 0.f) + fmaxf(accf[1][c][2], 0.f));
+      o.w = 0.5f * (fmaxf(accf[0][c][3], 0.f) + fmaxf(accf[1][c][3], 0.f));
       *reinterpret_cast<float4*>(out + ((n * HP + j) * kF + f0 + c) * CO + co) = o;
     } else {
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
-        const float4 o = make_float4(fmaxf(acc[a][c][0], 0.f), fmaxf(acc[a][c][1], 0.f), fmaxf(acc[a][c][2], 0.f), fmaxf(acc[a][c][3], 0.f));
+        const float4 o = make_float4(fmaxf(accf[a][c][0], 0.f), fmaxf(accf[a][c][1], 0.f), fmaxf(accf[a][c][2], 0.f), fmaxf(accf[a][c][3], 0.f));
         *reinterpret_cast<float4*>(out + ((n * H + 2 * j + a) * kF + f0 + c) * CO + co) = o;
       }
     }
