@@ -193,6 +193,8 @@ def run_other_workload(args, rank, world, local):
         cae = D.CaeScorer(syn.cae_state(0), mean, std, device=local, max_chunk=args.chunk)
         if os.environ.get("DFS_BENCH_PAIR_MMA"):        # A/B switch: enc4 on CTA pairs (tcgen05 cta_group::2)
             cae.set_option("pair_mma", int(os.environ["DFS_BENCH_PAIR_MMA"]))
+        if os.environ.get("DFS_BENCH_ENC3_SWAP"):       # A/B switch: enc3 with swapped operand roles (N = 256)
+            cae.set_option("enc3_swap", int(os.environ["DFS_BENCH_ENC3_SWAP"]))
         if os.environ.get("DFS_BENCH_DEC_WIDE"):        # A/B switch for the decoder's N = 256 variants
             cae.set_option("dec_wide", int(os.environ["DFS_BENCH_DEC_WIDE"]))
         units, unit_name = P * world, "utterances/s"

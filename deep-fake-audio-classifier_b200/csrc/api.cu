@@ -266,6 +266,11 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     else m->dlq->pair_mma = (int)value;
     return DFS_OK;
   }
+  if (strcmp(key, "enc3_swap") == 0) {
+    DFS_REQUIRE(m->cae != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "enc3_swap is a CAE option (0 | 1)");
+    m->cae->enc3_swap = (int)value;
+    return DFS_OK;
+  }
   if (strcmp(key, "dec_wide") == 0) {
     DFS_REQUIRE(m->cae != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "dec_wide is a CAE option (0 | 1)");
     m->cae->dec_wide = (int)value;
@@ -831,6 +836,7 @@ static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
     s->w_wide[1] = d;
     s->dec_wide = 1;
     s->pair_mma = 1;
+    s->enc3_swap = 1;
   }
   std::vector<float> wf(128);
   for (int q = 0; q < 4; ++q)

@@ -6,7 +6,8 @@
 //   layer  in (C x T x F)      kernel                                              out layout (planes, cols, RS)
 //   enc1   1 x 321 x 180       Toeplitz-in-time GEMM N=256 (cae_enc1_tc.cu; normaliser in the prep) e1 FT8P ( 8, 92,  82)
 //   enc2   32 x 160 x 90       PAIR GEMM  N=128, K=384, time pool in-thread + lane^8 e2 FT8  ( 8, 48,  82)
-//   enc3   64 x 80 x 45        3x3 GEMM   N=128, K=576, 2x2 pool lane^1 / lane^8     e3 FT8  (16, 24,  42)
+//   enc3   64 x 80 x 45        3x3 GEMM   swapped roles: weights = A, N=256 positions, K=576, 2x2 pool in-thread   e3 FT8  (16, 24,  42)
+//          (option "enc3_swap" = 0: positions as M, N=128, pool with lane^1 / lane^8; scores agree to 1e-5)
 //   enc4   128 x 40 x 22       3x3 GEMM   4 groups of N=64, K=1152 in 2 pieces       e4 FT8  (32, 14,  26)   = latent
 //   dec1   256 x 20 x 11       1x1 GEMM   2 groups (b) of N=256=(32-ch block, a, 32), K=256    d1 FT8  (16, 24,  42)
 //   dec2   128 x 40 x 22       1x1 GEMM   1 group of N=256=(b, 32-ch block, a, 32), K=128      d2 FT8  ( 8, 48,  82)   col 45 = relu(bias)
@@ -27,6 +28,9 @@ namespace dfs {
 using Enc2Cfg = ConvCfg<MODE_PAIR, 32, 64, 128, 80, 2, 3, 4, 1, EPI_PAIR_POOL_F>;
 using Enc3Cfg = ConvCfg<MODE_3X3, 64, 128, 128, 80, 2, 2, 4, 1, EPI_POOL_TF>;
 using Enc4Cfg = ConvCfg<MODE_3X3, 128, 64, 64, 40, 1, 3, 4, 2, EPI_POOL_TF>;
+// enc3 with swapped operand roles (the GEMM shape of the 2D-CNN's conv3: weights = A, 256 positions = N, 83 % instead of 73 % of the
+// tensor pipe per MMA); both pool partners are columns of one thread.  Option "enc3_swap".
+using Enc3SwapCfg = ConvCfg<MODE_3X3S, 64, 128, 256, 80, 1, 3, 2, 2, EPI_POOL_TF_SWAP>;
 // enc4's weights (147 KB per 64 output channels) force N = 64 on one CTA; a CTA pair runs N = 128 with 64 weight rows per CTA.
 // enc2 / enc3 (already N = 128) were also tried on pairs: bit-identical and slower (CAE 351 k vs 362 k utt/s), see conv_tc.cu.
 using Enc4PairCfg = ConvCfg<MODE_3X3, 128, 128, 128, 40, 1, 3, 4, 2, EPI_POOL_TF, 1>;   // option "pair_mma": CTA pairs, 2 groups of N = 128 (64 weight rows per CTA)
@@ -54,6 +58,7 @@ int cae_tc_make_maps(CaeTcState* s) {
   DFS_PROPAGATE(make_act_tensor_map(&s->tmap[0], s->act[0], Enc2Cfg::WROWS, Enc2Cfg::WCOLS, Enc2Cfg::PPL));
   DFS_PROPAGATE(make_act_tensor_map(&s->tmap[1], s->act[1], Enc3Cfg::WROWS, Enc3Cfg::WCOLS, Enc3Cfg::PPL));
   DFS_PROPAGATE(make_act_tensor_map(&s->tmap[2], s->act[2], Enc4Cfg::WROWS, Enc4Cfg::WCOLS, Enc4Cfg::PPL));
+  DFS_PROPAGATE(make_act_tensor_map(&s->tmap_enc3_swap, s->act[1], Enc3SwapCfg::WROWS, Enc3SwapCfg::WCOLS, Enc3SwapCfg::PPL));
   DFS_PROPAGATE(make_act_tensor_map(&s->tmap[3], s->act[3], Dec1Cfg::WROWS, Dec1Cfg::WCOLS, Dec1Cfg::PPL));
   DFS_PROPAGATE(make_act_tensor_map(&s->tmap[4], s->act[4], Dec2Cfg::WROWS, Dec2Cfg::WCOLS, Dec2Cfg::PPL));
   DFS_PROPAGATE(make_act_tensor_map(&s->tmap[5], s->act[5], Dec3Cfg::WROWS, Dec3Cfg::WCOLS, Dec3Cfg::PPL));
@@ -270,7 +275,13 @@ int launch_cae_tc(const CaeTcState* s, const float* x, int64_t sn, int64_t st, i
   if (stop_after_layer == 0) return DFS_OK;
   DFS_PROPAGATE(launch_conv_tc<Enc2Cfg>(s->tmap[0], base_params(s, 0, 0, 1, n_utts, 90, 80, 45), 1, num_sms, stream));
   if (stop_after_layer == 1) return DFS_OK;
-  DFS_PROPAGATE(launch_conv_tc<Enc3Cfg>(s->tmap[1], base_params(s, 1, 1, 2, n_utts, 45, 80, 22), 1, num_sms, stream));
+  if (s->enc3_swap) {
+    ConvParams p = base_params(s, 1, 1, 2, n_utts, 45, 80, 22);
+    p.n_units = (int)(((long long)n_utts * kCaeCols[1] - 1 + Enc3SwapCfg::CT - 1) / Enc3SwapCfg::CT);
+    DFS_PROPAGATE(launch_conv_tc<Enc3SwapCfg>(s->tmap_enc3_swap, p, 1, num_sms, stream));
+  } else {
+    DFS_PROPAGATE(launch_conv_tc<Enc3Cfg>(s->tmap[1], base_params(s, 1, 1, 2, n_utts, 45, 80, 22), 1, num_sms, stream));
+  }
   if (stop_after_layer == 2) return DFS_OK;
   if (s->pair_mma)
     DFS_PROPAGATE(launch_conv_tc<Enc4PairCfg>(s->tmap[2], base_params(s, 2, 2, 3, n_utts, 22, 40, 11), 2, num_sms, stream));

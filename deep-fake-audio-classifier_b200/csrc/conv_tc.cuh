@@ -50,6 +50,7 @@ enum {
   EPI_SHUFFLE_MSE = 7,  // 1x1 : CAE dec3 with the final ConvTranspose2d(32,1) and the squared error against the input fused in:
                         //        neither d3 nor the reconstruction is written; one partial sum per 16-column unit   (CAE dec3+final)
   EPI_GELU = 8,         // any : exact (erf) GELU, store FT8 at the same position, output-channel groups          (StatsPool detector)
+  EPI_POOL_TF_SWAP = 10, // 3x3S: lanes = output channels, columns = positions: relu, 2x2 pool entirely in-thread, 2-byte stores    (CAE enc3)
   EPI_SHUFFLE_ROWS = 9  // 1x1 : pixel shuffle with both row offsets (a = 0, 1) of a 32-channel block in one thread; the a = 1 row moves
                         //        one lane up so that every thread writes whole 32-byte sectors (256-bit stores)        (CAE dec1, dec2)
 };
@@ -459,6 +460,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           const int nn = gcc / p.cols;
           const int fpp = gcc - nn * p.cols;
           if (nn < p.n_utts && fpp >= 1 && fpp <= p.feats) p.emb[((long long)nn * p.feats + (fpp - 1)) * COUT + ch] = tsum[c];
+        }
+      } else if constexpr (Cfg::EPI == EPI_POOL_TF_SWAP) {
+        // Swapped roles (weights = A, 256 positions = N): accumulator row (TMEM lane) = output channel, column j = 8 * (feature
+        // column of the 32-column tile) + (row of the 8-row tile).  Both partners of the 2x2 average pool are columns of the same
+        // thread: feature pairs (even tile column, +1) -- the tile starts at an odd padded column and utterances hold an even
+        // number of columns, so a pair never straddles utterances -- and row pairs (even row, +1).  The 1/4 is folded into
+        // weights and bias.  One pooled value = one fp16 of the FT8 chunk of its channel: 2-byte stores, 8 consecutive lanes
+        // fill one 16-byte chunk.
+        static_assert(Cfg::EPI != EPI_POOL_TF_SWAP || (Cfg::SWAP && COUT == 128 && NG == 256), "swapped pool epilogue shape");
+        const int ch = 32 * q + lane;
+        const float bc = bias[ch];
+        const long long plane_elems = p.out_ncols * p.out_rs * 8;
+        uint16_t* chbase = p.out + (long long)(ch >> 3) * plane_elems + (ch & 7);
+        // the 8 feature pairs of this thread's column half: output column offset (elements) or -1 when invalid; fixed per unit
+        long long coloff[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int gcc = 1 + Cfg::CT * u + h * 16 + 2 * k;      // padded input column of the pair's first member (odd f')
+          const int nn = gcc / p.cols;
+          const int fpp = gcc - nn * p.cols;
+          const int fo = (fpp - 1) >> 1;
+          const bool ok = (nn < p.n_utts) && (fpp >= 1) && (fpp + 1 <= p.feats) && (fo < p.out_feats);
+          coloff[k] = ok ? ((long long)nn * p.out_cols + fo + 1) * p.out_rs * 8 : -1;
+        }
+        for (int tt = 0; tt < Cfg::TILES; ++tt, ++it) {
+          const int acc = it % NACC;
+          mbar_wait(&tfull[acc], (it / NACC) & 1, 5);
+          tc_fence_after();
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk) {   // 32 columns = 4 tile columns x 8 rows = 2 feature pairs x 4 row pairs
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * 128 + blk * 32, v);
+            tmem_ld_wait();
+            if (blk == 3) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
+            }
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k] + bc, 0.0f);
+#pragma unroll
+            for (int fpair = 0; fpair < 2; ++fpair) {
+              const long long co = coloff[2 * blk + fpair];
+#pragma unroll
+              for (int rp = 0; rp < 4; ++rp) {
+                const float s = (v[16 * fpair + 2 * rp] + v[16 * fpair + 2 * rp + 1]) + (v[16 * fpair + 8 + 2 * rp] + v[16 * fpair + 8 + 2 * rp + 1]);
+                const int to = 4 * tt + rp;                          // pooled row of input rows 8 tt + 2 rp, +1
+                if (co >= 0 && 8 * tt + 2 * rp + 2 <= p.rows_valid) {
+                  const __half hv = __ushort_as_half((unsigned short)(pack_act2(s, 0.0f) & 0xffffu));
+                  chbase[co + (long long)(to + 1) * 8] = __half_as_ushort(hv);
+                }
+              }
+            }
+          }
         }
       } else if constexpr (Cfg::EPI == EPI_POOL_TF) {
         // relu, then 2x2 average pool: time partner = lane^1, feature partner = lane^8 (1/4 folded into weights/bias).

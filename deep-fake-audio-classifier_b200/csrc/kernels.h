@@ -63,6 +63,8 @@ struct CaeTcState {
   float b1q[32];          // 0.25 * folded enc1 bias
   int enc1_impl;          // 0 = tensor-core Toeplitz GEMM, 1 = fp32 CUDA-core conv1_kernel<POOLF> (cross-check)
   const uint16_t* w_wide[2]; // dec1 / dec2 weights for the N = 256 variants (option "dec_wide")
+  CUtensorMap tmap_enc3_swap; // e2 with the 34-column x 10-row box of the swapped-role enc3
+  int enc3_swap;          // 1 = enc3 with swapped operand roles (N = 256 positions), 0 = positions as M (N = 128)
   int pair_mma;           // 1 (default) = enc4 on CTA pairs (cluster of 2, tcgen05 cta_group::2: M = 256, 64 of the 128 weight rows per CTA)
   int dec_wide;           // 1 = dec1 / dec2 as N = 256 GEMMs (half the TMA re-reads of the input, one CTA per SM), 0 = N = 128
   int final_fused;        // 1 (default) = final layer + squared error in dec3's epilogue, 0 = separate cae_final_tc_kernel over d3

@@ -132,3 +132,25 @@ def test_cae_enc4_on_cta_pairs_is_bit_identical():
     np.testing.assert_array_equal(sc.debug_layer(x[:3], 3, impl=0).cpu().numpy(), e4_3)
     np.testing.assert_array_equal(sc.debug_layer(x[5:10], 3, impl=0).cpu().numpy(), e4_5)
     np.testing.assert_array_equal(sc.score(x).cpu().numpy(), base)
+
+
+def test_cae_enc3_with_swapped_operand_roles_matches():
+    """Option "enc3_swap" (default 1): enc3 as the 2D-CNN's conv3 GEMM (weights = A operand, 256 positions = N) with both 2x2-pool partners in one
+    thread.  Same fp16 operands and fp32 accumulation per conv output; the four ReLU outputs of a pool window are added in a
+    different order than the lane-exchange epilogue adds them, so e3 agrees to fp16 round-off of the pooled value (1 ulp), the
+    scores to 1e-5.  3 and 5 utterances (72 / 120 columns: partial 32-column tiles), then ragged passes."""
+    mean, std = syn.normalizer_stats(1)
+    x = torch.from_numpy(syn.features(13, seed=29)).cuda()
+    sc = CaeScorer(syn.cae_state(3), mean, std, max_chunk=5)
+    sc.set_option("enc3_swap", 0)
+    base = sc.score(x).cpu().numpy()
+    ref3, ref5 = sc.debug_layer(x[:3], 2, impl=0).cpu().numpy(), sc.debug_layer(x[5:10], 2, impl=0).cpu().numpy()
+    sc.set_option("enc3_swap", 1)
+    for xs, want in ((x[:3], ref3), (x[5:10], ref5)):
+        got = sc.debug_layer(xs, 2, impl=0).cpu().numpy()
+        assert got.shape == want.shape and np.array_equal(got == 0, want == 0)
+        assert np.max(np.abs(got - want)) <= 2e-3 * np.abs(want).max() and np.mean(got != want) < 0.2
+    swapped = sc.score(x).cpu().numpy()
+    assert np.max(np.abs(swapped - base) / base) <= 1e-5
+    ref = onp.cae_mse_scores(syn.cae_state(3), x.cpu().numpy(), mean, std)
+    assert np.max(np.abs(swapped - ref) / ref) <= 1e-3
