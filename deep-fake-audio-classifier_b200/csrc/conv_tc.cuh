@@ -43,21 +43,22 @@ enum {
   EPI_PAIR_POOL = 0,    // PAIR: relu both time steps, add (time pool), store FT8                    (CNN2D conv2)
   EPI_MEAN_T = 1,       // 3x3 : relu, sum over all rows of the unit, store [n][F][COUT] fp32         (CNN2D conv3)
   EPI_PAIR_POOL_F = 2,  // PAIR: time pool in-thread + feature pool with lane^8, store FT8            (CAE enc2)
-  EPI_POOL_TF = 3,      // 3x3 : relu, 2x2 pool with lane^1 (time) and lane^8 (feature), store FT8    (CAE enc3, enc4)
+  EPI_POOL_TF = 3,      // 3x3 : relu, 2x2 pool with lane^1 (time) and lane^8 (feature), store FT8    (CAE enc4; enc3 with enc3_swap = 0)
   EPI_SHUFFLE = 4,      // 1x1 : relu, pixel-shuffle store of the quadrant(s) held in the columns      (CAE dec1-3)
   EPI_RELU = 5,         // any : relu, store FT8 at the same position                                   (CNN1D layers 1, 2)
   EPI_MEAN_T_SWAP = 6,  // 3x3S: lanes = output channels, columns = positions; relu, time sum in-thread   (CNN2D conv3)
   EPI_SHUFFLE_MSE = 7,  // 1x1 : CAE dec3 with the final ConvTranspose2d(32,1) and the squared error against the input fused in:
                         //        neither d3 nor the reconstruction is written; one partial sum per 16-column unit   (CAE dec3+final)
   EPI_GELU = 8,         // any : exact (erf) GELU, store FT8 at the same position, output-channel groups          (StatsPool detector)
-  EPI_POOL_TF_SWAP = 10, // 3x3S: lanes = output channels, columns = positions: relu, 2x2 pool entirely in-thread, 2-byte stores    (CAE enc3)
-  EPI_SHUFFLE_ROWS = 9  // 1x1 : pixel shuffle with both row offsets (a = 0, 1) of a 32-channel block in one thread; the a = 1 row moves
+  EPI_SHUFFLE_ROWS = 9, // 1x1 : pixel shuffle with both row offsets (a = 0, 1) of a 32-channel block in one thread; the a = 1 row moves
                         //        one lane up so that every thread writes whole 32-byte sectors (256-bit stores)        (CAE dec1, dec2)
+  EPI_POOL_TF_SWAP = 10 // 3x3S: lanes = output channels, columns = positions: relu, 2x2 pool entirely in-thread, 2-byte stores    (CAE enc3)
 };
 
 // CTA2 = 1: the kernel runs as CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA covers the two units of a pair (M = 256) and
-//           each CTA keeps only NG/2 of the NG weight rows, so the operand bytes read from shared memory per CTA and MMA fall from
-//           (128 + NG) to (128 + NG/2) rows -- the SS-mode MMAs of these convolutions are paced by exactly that stream.
+//           each CTA keeps only NG/2 of the NG weight rows in ITS shared memory.  Measured (profiles/r01f_umma_bench_pairs.txt): a
+//           pair MMA costs the cycles of a single-CTA MMA of the same N, i.e. per SM nothing is gained unless shared memory had
+//           forced N < 128 on one CTA (CAE enc4, StatsPool layer 1: 147 / 123 KB of weights per 64 output channels).
 template <int MODE_, int CIN_, int COUT_, int NG_, int ROWS_, int MT_, int NSTAGE_, int NACC_, int KSPLIT_, int EPI_, int CTA2_ = 0>
 struct ConvCfg {
   static constexpr int MODE = MODE_, CIN = CIN_, COUT = COUT_, NG = NG_, ROWS = ROWS_, MT = MT_, NSTAGE = NSTAGE_, NACC = NACC_,
