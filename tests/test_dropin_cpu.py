@@ -85,3 +85,25 @@ def test_prediction_pickle_format(tmp_path):
     with pytest.raises(ValueError):
         scoring.write_predictions(["a"], [0.1, 0.2], tmp_path / "x.pkl")              # predict.py:113-114
     assert len(df) == 3
+
+
+def test_precision_selection_on_the_dropin_classes(monkeypatch):
+    """`precision` is an instance / class attribute with the DFS_B200_PRECISION environment variable as the default; it is part of
+    the scorer cache key (changing it rebuilds the native handle) and never part of the state dict."""
+    monkeypatch.delenv("DFS_B200_PRECISION", raising=False)
+    for cls in (m2.CNN2D, m1.CNN1D, mc.ConvAutoencoder):
+        net = cls()
+        assert net._precision() == "fp16"
+        dev = torch.device("cuda", 0)
+        k16 = net._weights_key(dev) + (net._precision(),)
+        monkeypatch.setenv("DFS_B200_PRECISION", "fp32")
+        assert net._precision() == "fp32"
+        net.precision = "fp16"                                            # the attribute wins over the environment
+        assert net._precision() == "fp16"
+        net.precision = "fp32"
+        assert net._weights_key(dev) + (net._precision(),) != k16
+        assert not any("precision" in k for k in net.state_dict())
+        monkeypatch.delenv("DFS_B200_PRECISION")
+    from dfs_b200 import engine
+    with pytest.raises(ValueError, match="precision must be"):
+        engine._check_precision("bf16")
