@@ -120,7 +120,15 @@ int dfs_model_destroy(dfs_model* m);
  * cross-check, same layouts); "profile" 0/1 = per-kernel event timing (dfs_model_profile);
  * "precision" (CNN2D, CNN1D, CAE) 0 = fp16 tensor-core operands with fp32 accumulation (default), 1 = the whole
  * network in fp32 on the CUDA cores (same arithmetic class as the reference's CPU path; for evaluations
- * where the rank order of scores a few 1e-6 apart matters, e.g. the EER of a small dev set). */
+ * where the rank order of scores a few 1e-6 apart matters, e.g. the EER of a small dev set).
+ * Kernel-variant switches kept for on-device cross-checks (tests compare the variants; defaults are the product path):
+ *   "conv1_impl"   (CNN2D, CAE) 0 = Toeplitz tcgen05 GEMM for the Cin = 1 layer, 1 = fp32 CUDA-core conv
+ *   "conv12_fused" (CNN2D)      1 = conv1 + conv2 in one kernel (default 0: slower in the power-capped regime)
+ *   "l1_fused"     (CNN1D)      1 (default) = layer 1 converts the fp32 rows in flight, 0 = prep kernel + TMA
+ *   "final_fused"  (CAE)        1 (default) = final ConvTranspose + squared error in dec3's epilogue, 0 = separate kernel over d3
+ *   "dec_wide"     (CAE)        1 (default) = dec1 / dec2 as N = 256 GEMMs, 0 = N = 128 with twice the groups
+ *   "enc3_swap"    (CAE)        1 (default) = enc3 with swapped operand roles (N = 256 positions), 0 = positions as M
+ *   "pair_mma"     (CAE, StatsPool) 1 (default) = enc4 / layer 1 on CTA pairs (tcgen05 cta_group::2), 0 = single CTAs, N = 64 */
 int dfs_model_set_option(dfs_model* m, const char* key, int64_t value);
 int64_t dfs_model_workspace_bytes(const dfs_model* m);
 /* With option "profile" = 1 every kernel launch of the scoring loop is bracketed by a CUDA event

@@ -55,3 +55,15 @@ def test_no_cpu_fallback():
         Cnn2dScorer(synthetic.cnn2d_state(0))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         calculate_eer([0.1, 0.9], [0, 1])
+
+
+def test_every_option_key_is_documented_in_the_header():
+    """Every key dfs_model_set_option / dfs_set_global_option accepts (csrc/api.cu, csrc/eer.cu) is described in include/dfs_b200.h."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    keys = set()
+    for src in ("api.cu", "eer.cu"):
+        text = open(os.path.join(root, "deep-fake-audio-classifier_b200", "csrc", src)).read()
+        keys |= set(re.findall(r'strcmp\(key, "([a-z0-9_]+)"\)', text))
+    header = open(os.path.join(root, "include", "dfs_b200.h")).read()
+    assert keys and all(f'"{k}"' in header for k in keys), sorted(k for k in keys if f'"{k}"' not in header)
