@@ -39,6 +39,8 @@ def test_headline_line_has_every_contract_key():
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
     assert d["parity"]["max_rel_err_scores_vs_cpu_reference"] <= d["parity"]["tolerance"] == 1e-3
     assert d["e2e_f16_slab"]["scores_identical_to_fp32_slab"] is True
+    f32 = d["parity"]["fp32_mode"]                      # the same utterances through the full-fp32 kernels (precision="fp32")
+    assert f32["max_rel_err_scores_vs_cpu_reference"] <= 5e-6 and f32["utterances_per_s"] > 0 and "eer_delta_pp" in f32
 
 
 def test_eer_workload_reports_both_paths():
