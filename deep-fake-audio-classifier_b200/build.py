@@ -13,8 +13,10 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libdfs_b200.so")
+OUT_PROBES = os.path.join(HERE, "lib", "libdfs_b200_probes.so")   # bring-up probes + micro-benchmarks (tests / tools only)
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "conv_tc.cu", "conv1_tc.cu", "conv12_fused.cu", "cae_tc.cu", "cae_enc1_tc.cu", "cnn1d_tc.cu", "cnn1d_l1_fused.cu", "cnn2d.cu", "cnn2d_fp32.cu", "simt_models.cu", "eer.cu", "synth.cu", "probe.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv1_tc.cu", "conv12_fused.cu", "cae_tc.cu", "cae_enc1_tc.cu", "cnn1d_tc.cu", "cnn1d_l1_fused.cu", "cnn2d.cu", "cnn2d_fp32.cu", "simt_models.cu", "eer.cu", "synth.cu"]
+PROBE_SOURCES = ["probe.cu", "conv_tc.cu"]   # probe.cu uses conv_tc.cu's tensor-map helper
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -41,18 +43,30 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     hdr_m = _deps_mtime()
+    all_sources = SOURCES + [s for s in PROBE_SOURCES if s not in SOURCES]
     with ThreadPoolExecutor(max_workers=8) as ex:
-        results = list(ex.map(lambda s: _compile(s, force, hdr_m), SOURCES))
-    objs = [o for o, _ in results]
+        results = list(ex.map(lambda s: _compile(s, force, hdr_m), all_sources))
+    by_src = {s: o for s, (o, _) in zip(all_sources, results)}
+    objs = [by_src[s] for s in SOURCES]
     if verbose:
         for _, log in results:
             if log:
                 print(log)
     if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
-        r = subprocess.run([NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        _link(OUT, objs)
+    pobjs = [by_src[s] for s in PROBE_SOURCES]
+    if force or not os.path.exists(OUT_PROBES) or any(os.path.getmtime(o) > os.path.getmtime(OUT_PROBES) for o in pobjs):
+        _link(OUT_PROBES, pobjs)
     return OUT
+
+
+def _link(out, objs):
+    # --cudart shared: the artefact binds to libcudart.so at load time (torch ships one) instead of carrying a static copy of the
+    # whole runtime, entry points this code never calls included; -Bsymbolic: each library resolves its own helpers internally
+    r = subprocess.run([NVCC, "-shared", "--cudart", "shared", "-Xlinker", "-Bsymbolic", "-o", out, *objs, "-lcuda",
+                        "-gencode", "arch=compute_100a,code=sm_100a"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
 
 
 if __name__ == "__main__":

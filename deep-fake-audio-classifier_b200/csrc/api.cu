@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -1054,7 +1055,247 @@ extern "C" int dfs_score_host_f16(dfs_model* m, const uint16_t* x_host, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------
-// metric / blend / synthetic / probes: thin forwards
+// debug: fp16 saturation census of the activation buffers left by the last pass
+// ------------------------------------------------------------------------------------------
+// The epilogues and prep kernels convert with cvt.rn.satfinite: |v| > 65504 is stored as +-65504 without a trace.  This scan
+// counts the fp16 elements that sit exactly at +-65504 (0x7BFF / 0xFBFF) or are non-finite, so that a caller feeding
+// heavy-tailed features (real LFCC maps reach -61 ... +86) can check that nothing was clipped.
+__global__ void __launch_bounds__(256) count_sat_kernel(const uint4* __restrict__ p, long long n16, unsigned long long* __restrict__ out) {
+  unsigned int sat = 0, nonfin = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 q = __ldg(p + i);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t v = (w[e] >> (16 * h)) & 0x7fffu;
+        sat += v == 0x7bffu;
+        nonfin += v >= 0x7c00u;
+      }
+    }
+  }
+  sat = __reduce_add_sync(0xffffffffu, sat);
+  nonfin = __reduce_add_sync(0xffffffffu, nonfin);
+  if ((threadIdx.x & 31) == 0) {
+    if (sat) atomicAdd(out, (unsigned long long)sat);
+    if (nonfin) atomicAdd(out + 1, (unsigned long long)nonfin);
+  }
+}
+
+extern "C" int dfs_model_saturation_count(dfs_model* m, int64_t* saturated_out, int64_t* nonfinite_out, void* stream_) {
+  DFS_REQUIRE(m && saturated_out && nonfinite_out, DFS_ERR_INVALID, "dfs_model_saturation_count: NULL argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DFS_CUDA_CHECK(cudaSetDevice(m->device));
+  std::vector<std::pair<const void*, size_t>> bufs;   // (pointer, bytes), all 16-byte multiples
+  if (m->kind == KIND_CNN2D) {
+    bufs.push_back({m->xt, (size_t)conv1_xt_rows(m->chunk) * 16});
+    bufs.push_back({m->act1.ptr, (size_t)m->act1.bytes()});
+    bufs.push_back({m->act2.ptr, (size_t)m->act2.bytes()});
+  } else if (m->kind == KIND_CNN1D) {
+    for (int b = 0; b < 3; ++b) bufs.push_back({m->c1d->act[b].ptr, (size_t)m->c1d->act[b].bytes()});
+  } else if (m->kind == KIND_CAE) {
+    bufs.push_back({m->cae->xt1, (size_t)cae_enc1_xt_rows(m->chunk) * 16});
+    for (int l = 0; l < 7; ++l) bufs.push_back({m->cae->act[l].ptr, (size_t)m->cae->act[l].bytes()});
+  } else {
+    bufs.push_back({m->dlq->act0.ptr, (size_t)m->dlq->act0.bytes()});
+    bufs.push_back({m->dlq->actA.ptr, (size_t)m->dlq->actA.bytes()});
+    bufs.push_back({m->dlq->actB.ptr, (size_t)m->dlq->actB.bytes()});
+  }
+  unsigned long long* cnt = nullptr;
+  DFS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&cnt), 16));
+  cudaError_t e = cudaMemsetAsync(cnt, 0, 16, stream);
+  for (size_t i = 0; e == cudaSuccess && i < bufs.size(); ++i) {
+    const long long n16 = (long long)(bufs[i].second / 16);
+    if (n16 == 0 || bufs[i].first == nullptr) continue;
+    count_sat_kernel<<<(unsigned)std::min<long long>(ceil_div64(n16, 256), (long long)m->num_sms * 8), 256, 0, stream>>>(
+        static_cast<const uint4*>(bufs[i].first), n16, cnt);
+    dfs_count_launch();
+    e = cudaGetLastError();
+  }
+  unsigned long long host[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host, cnt, 16, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(cnt);
+  if (e != cudaSuccess) {
+    dfs_set_error("dfs_model_saturation_count: %s", cudaGetErrorString(e));
+    return DFS_ERR_CUDA;
+  }
+  *saturated_out = (int64_t)host[0];
+  *nonfinite_out = (int64_t)host[1];
+  return DFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// scorer groups: every slab of the host table crosses PCIe once and all member models score it
+// (src/ensemble.py:105-122 and src/predict_hybrid.py:142-145 read the table once per model)
+// ------------------------------------------------------------------------------------------
+struct dfs_group {
+  int device = 0;
+  int num_sms = 148;
+  int stage = 0;                       // utterances per staged slab
+  std::vector<dfs_model*> models;
+  float* stage_in[2] = {nullptr, nullptr};
+  uint16_t* stage_in16[2] = {nullptr, nullptr};   // fp16 slabs, allocated on first use
+  float* widened = nullptr;                        // fp32 image of the current fp16 slab (one: the compute stream is serial)
+  std::vector<float*> stage_out[2];                // per model
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  size_t bytes = 0;
+};
+
+extern "C" int dfs_group_destroy(dfs_group* g) {
+  if (!g) return DFS_OK;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(g->stage_in[b]);
+    cudaFree(g->stage_in16[b]);
+    for (float* p : g->stage_out[b]) cudaFree(p);
+    if (g->ev_in[b]) cudaEventDestroy(g->ev_in[b]);
+    if (g->ev_done[b]) cudaEventDestroy(g->ev_done[b]);
+  }
+  cudaFree(g->widened);
+  if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+  delete g;
+  return DFS_OK;
+}
+
+extern "C" int dfs_group_create(dfs_group** out, dfs_model* const* models, int n_models, int stage_utts) {
+  DFS_REQUIRE(out && models && n_models >= 1 && n_models <= 16, DFS_ERR_INVALID, "dfs_group_create: 1..16 models");
+  *out = nullptr;
+  for (int i = 0; i < n_models; ++i) {
+    DFS_REQUIRE(models[i] != nullptr, DFS_ERR_INVALID, "dfs_group_create: model %d is NULL", i);
+    DFS_REQUIRE(models[i]->kind == KIND_CNN2D || models[i]->kind == KIND_CNN1D || models[i]->kind == KIND_CAE || models[i]->kind == KIND_DLQ,
+                DFS_ERR_INVALID, "dfs_group_create: model %d has an unknown kind", i);
+    DFS_REQUIRE(models[i]->device == models[0]->device, DFS_ERR_INVALID, "dfs_group_create: all models of a group live on one device");
+  }
+  DFS_REQUIRE(stage_utts >= 0, DFS_ERR_INVALID, "dfs_group_create: stage_utts < 0");
+  dfs_group* g = new (std::nothrow) dfs_group();
+  DFS_REQUIRE(g, DFS_ERR_NOMEM, "out of host memory");
+  g->device = models[0]->device;
+  g->num_sms = models[0]->num_sms;
+  g->models.assign(models, models + n_models);
+  // default slab: 2,368 utterances = 4 CAE passes of 592 = 5.7 2D-CNN passes of 416 (whole waves on every layer for the
+  // CAE, a 0.1-wave tail for the 2D-CNN); a single model keeps its own pass size (smallest pipeline fill)
+  g->stage = stage_utts > 0 ? stage_utts : (n_models == 1 ? std::min(models[0]->chunk, 2368) : 2368);
+  auto fail = [&](int s) { dfs_group_destroy(g); return s; };
+  auto alloc = [&](void** p, size_t bytes) -> int {
+    DFS_CUDA_CHECK(cudaMalloc(p, bytes));
+    g->bytes += bytes;
+    return DFS_OK;
+  };
+  int st;
+  if (cudaSetDevice(g->device) != cudaSuccess) return fail(DFS_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    dfs_set_error("dfs_group_create: cudaStreamCreate failed");
+    return fail(DFS_ERR_CUDA);
+  }
+  for (int b = 0; b < 2; ++b) {
+    if ((st = alloc(reinterpret_cast<void**>(&g->stage_in[b]), (size_t)g->stage * kT * kF * 4)) != DFS_OK) return fail(st);
+    g->stage_out[b].assign(n_models, nullptr);
+    for (int i = 0; i < n_models; ++i)
+      if ((st = alloc(reinterpret_cast<void**>(&g->stage_out[b][i]), (size_t)g->stage * 4)) != DFS_OK) return fail(st);
+    if (cudaEventCreateWithFlags(&g->ev_in[b], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g->ev_done[b], cudaEventDisableTiming) != cudaSuccess) {
+      dfs_set_error("dfs_group_create: cudaEventCreate failed");
+      return fail(DFS_ERR_CUDA);
+    }
+  }
+  *out = g;
+  return DFS_OK;
+}
+
+extern "C" int64_t dfs_group_stage_utts(const dfs_group* g) { return g ? g->stage : 0; }
+
+static int group_score_member(dfs_model* m, const dfs_features* dv, int flag, float* out_dev, cudaStream_t stream) {
+  switch (m->kind) {
+    case KIND_CNN2D: return dfs_cnn2d_score(m, dv, out_dev, nullptr, flag, stream);
+    case KIND_CNN1D: return dfs_cnn1d_score(m, dv, out_dev, flag, stream);
+    case KIND_CAE: return dfs_cae_score(m, dv, flag, out_dev, stream);
+    default: return dfs_dlq_score(m, dv, nullptr, out_dev, flag, stream);
+  }
+}
+
+// x_host: fp32 (elem_bytes 4) or fp16 (2) dense slab; (st, sf) = element strides of the (321, 180) view of one utterance
+static int group_run(dfs_group* g, const void* x_host, int elem_bytes, int64_t n, int64_t st, int64_t sf, const int* flags,
+                     float* const* out_host, cudaStream_t stream) {
+  const int64_t per_utt = (int64_t)kT * kF;
+  const int nm = (int)g->models.size();
+  DFS_CUDA_CHECK(cudaSetDevice(g->device));
+  if (elem_bytes == 2) {
+    for (int b = 0; b < 2; ++b)
+      if (!g->stage_in16[b]) {
+        DFS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&g->stage_in16[b]), (size_t)g->stage * per_utt * 2));
+        g->bytes += (size_t)g->stage * per_utt * 2;
+      }
+  }
+  // ramp: the first slab is not overlapped with anything, so it is kept short (one CAE pass); the following ones are full
+  int64_t i0 = 0;
+  for (int k = 0; i0 < n; ++k) {
+    const int b = k & 1;
+    const int cap = (k == 0) ? std::min(g->stage, 592) : g->stage;
+    const int nk = (int)std::min<int64_t>(cap, n - i0);
+    if (k >= 2) DFS_CUDA_CHECK(cudaStreamWaitEvent(g->copy_stream, g->ev_done[b], 0));
+    void* dst = elem_bytes == 4 ? static_cast<void*>(g->stage_in[b]) : static_cast<void*>(g->stage_in16[b]);
+    DFS_CUDA_CHECK(cudaMemcpyAsync(dst, static_cast<const char*>(x_host) + (size_t)i0 * per_utt * elem_bytes, (size_t)nk * per_utt * elem_bytes,
+                                   cudaMemcpyHostToDevice, g->copy_stream));
+    DFS_CUDA_CHECK(cudaEventRecord(g->ev_in[b], g->copy_stream));
+    DFS_CUDA_CHECK(cudaStreamWaitEvent(stream, g->ev_in[b], 0));
+    if (elem_bytes == 2) {   // the kernels read fp32: widen on the device (exact), into the slot's fp32 buffer
+      const long long n8 = (long long)nk * per_utt / 8;
+      widen_f16_kernel<<<(unsigned)std::max<long long>(1, std::min<long long>(ceil_div64(n8, 256), (long long)g->num_sms * 8)), 256, 0, stream>>>(
+          g->stage_in16[b], n8, (long long)nk * per_utt, g->stage_in[b]);
+      DFS_LAUNCH_CHECK();
+    }
+    dfs_features dv{g->stage_in[b], nk, per_utt, st, sf};
+    for (int i = 0; i < nm; ++i) {
+      DFS_PROPAGATE(group_score_member(g->models[i], &dv, flags ? flags[i] : 1, g->stage_out[b][i], stream));
+      DFS_CUDA_CHECK(cudaMemcpyAsync(out_host[i] + i0, g->stage_out[b][i], (size_t)nk * 4, cudaMemcpyDeviceToHost, stream));
+    }
+    DFS_CUDA_CHECK(cudaEventRecord(g->ev_done[b], stream));
+    i0 += nk;
+  }
+  DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return DFS_OK;
+}
+
+extern "C" int dfs_group_score_host(dfs_group* g, const dfs_features* feats, const int* flags, float* const* out_host, void* stream_) {
+  DFS_REQUIRE(g, DFS_ERR_INVALID, "dfs_group_score_host: group is NULL");
+  DFS_PROPAGATE(check_feats(feats, "dfs_group_score_host"));
+  DFS_REQUIRE(feats->n == 0 || out_host, DFS_ERR_INVALID, "dfs_group_score_host: out_host is NULL");
+  for (size_t i = 0; feats->n > 0 && i < g->models.size(); ++i)
+    DFS_REQUIRE(out_host[i] != nullptr, DFS_ERR_INVALID, "dfs_group_score_host: out_host[%d] is NULL", (int)i);
+  const int64_t per_utt = (int64_t)kT * kF;
+  const bool dense = (feats->stride_f == 1 && feats->stride_t == kF) || (feats->stride_t == 1 && feats->stride_f == kT);
+  DFS_REQUIRE(dense && (feats->n <= 1 || feats->stride_n == per_utt), DFS_ERR_UNSUPPORTED,
+              "dfs_group_score_host: each utterance must be one dense 321x180 (or 180x321) block, utterances back to back");
+  return group_run(g, feats->x, 4, feats->n, feats->stride_t, feats->stride_f, flags, out_host, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int dfs_group_score_host_f16(dfs_group* g, const uint16_t* x_host, int64_t n, int time_major, const int* flags, float* const* out_host,
+                                        void* stream_) {
+  DFS_REQUIRE(g, DFS_ERR_INVALID, "dfs_group_score_host_f16: group is NULL");
+  DFS_REQUIRE(n >= 0 && n < (1ll << 31) && (n == 0 || (x_host && out_host)), DFS_ERR_INVALID, "dfs_group_score_host_f16: bad argument");
+  for (size_t i = 0; n > 0 && i < g->models.size(); ++i)
+    DFS_REQUIRE(out_host[i] != nullptr, DFS_ERR_INVALID, "dfs_group_score_host_f16: out_host[%d] is NULL", (int)i);
+  return group_run(g, x_host, 2, n, time_major ? 1 : kF, time_major ? kT : 1, flags, out_host, static_cast<cudaStream_t>(stream_));
+}
+
+// pinned (page-locked) host slabs for the *_host entry points, allocated against the calling thread's current device
+extern "C" int dfs_pinned_alloc(void** out_host, size_t bytes, int write_combined) {
+  DFS_REQUIRE(out_host != nullptr && bytes > 0, DFS_ERR_INVALID, "dfs_pinned_alloc: bad argument");
+  *out_host = nullptr;
+  DFS_CUDA_CHECK(cudaHostAlloc(out_host, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  return DFS_OK;
+}
+extern "C" int dfs_pinned_free(void* p) {
+  if (p) DFS_CUDA_CHECK(cudaFreeHost(p));
+  return DFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// metric / blend / synthetic: thin forwards
 // ------------------------------------------------------------------------------------------
 extern "C" int dfs_blend_f64(const double* const* scores, int m, const double* weights, const int* minmax, double divisor, int64_t n,
                              double* out_dev, void* stream) {
@@ -1091,21 +1332,4 @@ extern "C" int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_
 }
 extern "C" int dfs_fill_features(float* out_dev, int64_t n, int64_t first_utt, uint64_t seed, float std_, void* stream) {
   return fill_features_device(out_dev, n, first_utt, seed, std_, static_cast<cudaStream_t>(stream));
-}
-extern "C" int dfs_probe_umma(const uint16_t* a_dev, const uint16_t* b_dev, int rows_a, int n, int k, int row_shift, int group_rows,
-                              float* out_dev, void* stream) {
-  return probe_umma(a_dev, b_dev, rows_a, n, k, row_shift, group_rows, out_dev, static_cast<cudaStream_t>(stream));
-}
-extern "C" int dfs_probe_tma_window(const uint16_t* act_dev, int planes, int rs, int64_t ncols, int wrows, int row0, int col0,
-                                    uint16_t* out_dev, void* stream) {
-  return probe_tma_window(act_dev, planes, rs, ncols, wrows, row0, col0, out_dev, static_cast<cudaStream_t>(stream));
-}
-extern "C" int dfs_probe_umma_bench(int n, int nmma, int iters, const uint32_t* a_off_host, const uint32_t* b_off_host, uint32_t a_lbo,
-                                    uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t layout, uint32_t use_base_offset,
-                                    int64_t* cycles_host, void* stream) {
-  long long c = 0;
-  int st = probe_umma_bench(n, nmma, iters, a_off_host, b_off_host, a_lbo, a_sbo, b_lbo, b_sbo, layout, use_base_offset, &c,
-                            static_cast<cudaStream_t>(stream));
-  if (cycles_host) *cycles_host = c;
-  return st;
 }

@@ -20,13 +20,17 @@ constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096
 
 // ---- order-preserving key transforms (-0.0 is canonicalised to +0.0: numpy treats them as ties) ----
+// NaN of either sign maps to the largest key: np.argsort (scripts/evaluation.py:11) sorts NaN after +inf, whatever its sign
+// bit or payload; from_key() of that key is a (canonical) NaN again.
 __device__ __forceinline__ uint32_t to_key(float s) {
   uint32_t b = __float_as_uint(s);
+  if ((b & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;
   if (b == 0x80000000u) b = 0;
   return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);   // negative: flip all bits, else set the sign bit
 }
 __device__ __forceinline__ uint64_t to_key(double s) {
   uint64_t b = (uint64_t)__double_as_longlong(s);
+  if ((b & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) return ~0ull;
   if (b == 0x8000000000000000ull) b = 0;
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }

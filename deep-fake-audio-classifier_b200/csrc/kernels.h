@@ -150,11 +150,13 @@ int widen_device(const float* in, int64_t n, double* out, cudaStream_t stream);
 // ---- synth.cu ----
 int fill_features_device(float* out, int64_t n, int64_t first_utt, uint64_t seed, float std, cudaStream_t stream);
 
-// ---- probe.cu ----
+// ---- probe.cu (lib/libdfs_b200_probes.so only) ----
 int probe_umma(const uint16_t* a, const uint16_t* b, int rows_a, int n, int k, int row_shift, int group_rows, float* out,
                cudaStream_t stream);
-int probe_umma_bench(int n, int nmma, int iters, const uint32_t* a_off, const uint32_t* b_off, uint32_t a_lbo, uint32_t a_sbo,
+int probe_umma_bench(int n, int nmma, int iters, int n_acc, const uint32_t* a_off, const uint32_t* b_off, uint32_t a_lbo, uint32_t a_sbo,
                      uint32_t b_lbo, uint32_t b_sbo, uint32_t layout, uint32_t use_base_offset, long long* cycles_host, cudaStream_t stream);
+int probe_tmem_ld_bench(int shape, int nwarps, int blocks, int iters, int lds_per_wait, long long* cycles_host, long long* bytes_per_block_host,
+                        cudaStream_t stream);
 int probe_tma_window(const uint16_t* act, int planes, int RS, int64_t ncols, int wrows, int row0, int col0, uint16_t* out,
                      cudaStream_t stream);
 

@@ -4,8 +4,28 @@
 //                     address shifted by an arbitrary number of 16-byte rows and an arbitrary
 //                     8-row-group stride (SBO) -- the addressing the 3x3 taps use.
 //   probe_tma_window  one 3-D TMA box load of an FT8 activation window, dumped back to global.
+//   probe_umma_bench  tcgen05.mma issue / operand-fetch cost for the addressing patterns of the conv kernels
+//   probe_tmem_ld_bench  tcgen05.ld read-out rate per SM for the shapes and warp counts an epilogue can use
+// Built into lib/libdfs_b200_probes.so (test / measurement only; csrc/probes.h), NOT into the product library.
 #include "common.cuh"
 #include "kernels.h"
+#include "probes.h"
+#include "tmem_ld_shapes.cuh"
+
+#include <stdarg.h>
+
+#include <vector>
+
+// the probes library carries its own copies of the error plumbing common.cuh declares
+static thread_local char g_probe_err[1024] = "";
+void dfs_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_probe_err, sizeof(g_probe_err), fmt, ap);
+  va_end(ap);
+}
+void dfs_count_launch(int) {}
+extern "C" const char* dfs_probe_last_error(void) { return g_probe_err; }
 
 namespace dfs {
 
@@ -86,10 +106,12 @@ int probe_umma(const uint16_t* a, const uint16_t* b, int rows_a, int n, int k, i
 // (M=128, N=n, K=16) whose A start addresses walk a caller-given list of byte offsets (e.g. the 9
 // tap offsets of a conv tile), commits once per round and waits; reports SM cycles per MMA.
 // Operand CONTENT is irrelevant (shared memory is zero-filled), only the addressing is timed.
+constexpr int kBenchMaxMma = 96;
 struct UmmaBenchParams {
   int n, nmma, iters;
-  uint32_t a_off[40];      // byte offsets of the A start address per MMA of a round
-  uint32_t b_off[40];      // byte offsets of the B start address per MMA
+  int n_acc;               // accumulators used in rotation (MMA i of a round targets accumulator i % n_acc); 1 = one dependent chain
+  uint32_t a_off[kBenchMaxMma];      // byte offsets of the A start address per MMA of a round
+  uint32_t b_off[kBenchMaxMma];      // byte offsets of the B start address per MMA
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
   uint32_t layout;         // descriptor layout_type field (0 none, 2 SW128, 4 SW64, 6 SW32)
   uint32_t use_base_offset;
@@ -106,7 +128,7 @@ __global__ void __launch_bounds__(128) probe_umma_bench_kernel(const __grid_cons
     fence_mbar_init();
   }
   if ((threadIdx.x >> 5) == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   fence_proxy_async_smem();
@@ -118,7 +140,8 @@ __global__ void __launch_bounds__(128) probe_umma_bench_kernel(const __grid_cons
     const uint32_t idesc = umma_idesc_bf16(128, p.n);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + A_BYTES);
     uint64_t* ad = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES + 64);   // descriptor tables in shared memory
-    uint64_t* bd = ad + 40;
+    uint64_t* bd = ad + kBenchMaxMma;
+    const int nacc = p.n_acc;
     for (int i = 0; i < p.nmma; ++i) {
       const uint32_t aa = a0 + p.a_off[i], bb = b0 + p.b_off[i];
       ad[i] = umma_smem_desc(aa, p.a_lbo, p.a_sbo) | ((uint64_t)p.layout << 61) | (p.use_base_offset ? ((uint64_t)((aa >> 7) & 7) << 49) : 0ull);
@@ -126,14 +149,14 @@ __global__ void __launch_bounds__(128) probe_umma_bench_kernel(const __grid_cons
     }
     uint32_t phase = 0;
     // warm-up round
-    for (int i = 0; i < p.nmma; ++i) umma_bf16(tmem_base, ad[i], bd[i], idesc, i != 0);
+    for (int i = 0; i < p.nmma; ++i) umma_bf16(tmem_base + (uint32_t)((i % nacc) * p.n), ad[i], bd[i], idesc, i >= nacc);
     umma_commit(bar);
     mbar_wait(bar, phase, 11);
     phase ^= 1;
     const long long t0 = clock64();
     for (int it = 0; it < p.iters; ++it) {
 #pragma unroll 4
-      for (int i = 0; i < p.nmma; ++i) umma_bf16(tmem_base, ad[i], bd[i], idesc, i != 0);
+      for (int i = 0; i < p.nmma; ++i) umma_bf16(tmem_base + (uint32_t)((i % nacc) * p.n), ad[i], bd[i], idesc, i >= nacc);
       umma_commit(bar);
       mbar_wait(bar, phase, 12);
       phase ^= 1;
@@ -145,7 +168,7 @@ __global__ void __launch_bounds__(128) probe_umma_bench_kernel(const __grid_cons
   __syncthreads();
   if ((threadIdx.x >> 5) == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -176,7 +199,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe_umma_benc
     const uint32_t idesc = umma_idesc_bf16(256, p.n);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + A_BYTES);
     uint64_t* ad = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES + 64);
-    uint64_t* bd = ad + 40;
+    uint64_t* bd = ad + kBenchMaxMma;
     for (int i = 0; i < p.nmma; ++i) {
       const uint32_t aa = a0 + p.a_off[i], bb = b0 + p.b_off[i];
       ad[i] = umma_smem_desc(aa, p.a_lbo, p.a_sbo) | ((uint64_t)p.layout << 61);
@@ -208,16 +231,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe_umma_benc
   }
 }
 
-int probe_umma_bench(int n, int nmma, int iters, const uint32_t* a_off, const uint32_t* b_off, uint32_t a_lbo, uint32_t a_sbo,
+int probe_umma_bench(int n, int nmma, int iters, int n_acc, const uint32_t* a_off, const uint32_t* b_off, uint32_t a_lbo, uint32_t a_sbo,
                      uint32_t b_lbo, uint32_t b_sbo, uint32_t layout, uint32_t use_base_offset, long long* cycles_host, cudaStream_t stream) {
-  DFS_REQUIRE(n % 16 == 0 && n >= 16 && n <= 256 && nmma >= 1 && nmma <= 40 && iters >= 1, DFS_ERR_INVALID, "probe_umma_bench: bad argument");
+  DFS_REQUIRE(n % 16 == 0 && n >= 16 && n <= 256 && nmma >= 1 && nmma <= kBenchMaxMma && iters >= 1, DFS_ERR_INVALID, "probe_umma_bench: bad argument");
+  DFS_REQUIRE(n_acc >= 1 && n_acc * n <= 512 && (!(use_base_offset & 2) || n_acc == 1), DFS_ERR_INVALID,
+              "probe_umma_bench: n_acc accumulators of n columns must fit the 512 TMEM columns (pairs: n_acc = 1)");
   UmmaBenchParams p{};
-  p.n = n; p.nmma = nmma; p.iters = iters;
+  p.n = n; p.nmma = nmma; p.iters = iters; p.n_acc = n_acc;
   for (int i = 0; i < nmma; ++i) { p.a_off[i] = a_off[i]; p.b_off[i] = b_off[i]; }
   p.a_lbo = a_lbo; p.a_sbo = a_sbo; p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.layout = layout; p.use_base_offset = use_base_offset & 1;
   long long* d = nullptr;
   DFS_CUDA_CHECK(cudaMalloc(&d, 8));
-  const int smem = 160 * 1024 + 64 + 80 * 8;
+  const int smem = 160 * 1024 + 64 + 2 * kBenchMaxMma * 8;
   DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   if (use_base_offset & 2) {   // bit 1: run on a CTA pair (cta_group::2); n is the N of the pair's MMA
     DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_umma_bench_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -264,4 +289,144 @@ int probe_tma_window(const uint16_t* act, int planes, int RS, int64_t ncols, int
   return DFS_OK;
 }
 
+// ---- TMEM read-out rate --------------------------------------------------------------------------------------------
+// `nwarps` warps (4, 8 or 16) of ONE CTA read their lane quadrant (warp % 4) of the 512 allocated columns with one
+// tcgen05.ld shape, `lds_per_wait` loads in flight before each tcgen05.wait::ld, `iters` rounds.  Reported: SM cycles between
+// two block-wide barriers, and the bytes moved (lanes x columns x 4 B per load); content is whatever TMEM holds.
+//   shape ids: 0..4 = 32x32b .x8 .x16 .x32 .x64 .x128 | 5..7 = 16x256b .x4 .x8 .x16 | 8..10 = 16x128b .x8 .x16 .x32
+template <int SHAPE>
+__device__ __forceinline__ uint32_t tmem_ld_shape(uint32_t taddr) {
+  constexpr int NR = SHAPE == 0 ? 8 : SHAPE == 1 ? 16 : SHAPE == 2 ? 32 : SHAPE == 3 ? 64 : SHAPE == 4 ? 128 : SHAPE == 5 ? 16 : SHAPE == 6 ? 32
+                     : SHAPE == 7 ? 64 : SHAPE == 8 ? 16 : SHAPE == 9 ? 32 : 64;
+  uint32_t r[NR];
+  if constexpr (SHAPE == 0) tmem_ld_32x32b_x8(taddr, r);
+  else if constexpr (SHAPE == 1) tmem_ld_32x32b_x16(taddr, r);
+  else if constexpr (SHAPE == 2) tmem_ld_32x32b_x32(taddr, r);
+  else if constexpr (SHAPE == 3) tmem_ld_32x32b_x64(taddr, r);
+  else if constexpr (SHAPE == 4) tmem_ld_32x32b_x128(taddr, r);
+  else if constexpr (SHAPE == 5) tmem_ld_16x256b_x4(taddr, r);
+  else if constexpr (SHAPE == 6) tmem_ld_16x256b_x8(taddr, r);
+  else if constexpr (SHAPE == 7) tmem_ld_16x256b_x16(taddr, r);
+  else if constexpr (SHAPE == 8) tmem_ld_16x128b_x8(taddr, r);
+  else if constexpr (SHAPE == 9) tmem_ld_16x128b_x16(taddr, r);
+  else tmem_ld_16x128b_x32(taddr, r);
+  uint32_t x = 0;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) x ^= r[i];
+  return x;
+}
+// columns one load of the shape spans, lanes it reads
+__host__ __device__ constexpr int tmem_shape_cols(int s) {
+  return s == 0 ? 8 : s == 1 ? 16 : s == 2 ? 32 : s == 3 ? 64 : s == 4 ? 128 : s == 5 ? 32 : s == 6 ? 64 : s == 7 ? 128 : s == 8 ? 32 : s == 9 ? 64 : 128;
+}
+__host__ __device__ constexpr int tmem_shape_lanes(int s) { return s <= 4 ? 32 : 16; }
+
+template <int SHAPE>
+__global__ void __launch_bounds__(SHAPE == 4 ? 256 : 512) probe_tmem_ld_kernel(int iters, int lds_per_wait, long long* __restrict__ cycles_out,
+                                                             uint32_t* __restrict__ sink) {
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16);
+  constexpr int COLS = tmem_shape_cols(SHAPE);
+  uint32_t acc = 0, col = (uint32_t)((warp >> 2) * COLS) & 511u;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    for (int j = 0; j < lds_per_wait; ++j) {
+      acc ^= tmem_ld_shape<SHAPE>(base + col);
+      col = (col + COLS) & 511u;                 // COLS divides 512: a load never runs past the allocation
+    }
+    tmem_ld_wait();
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles_out[blockIdx.x] = t1 - t0;
+  if (acc == 0x9e3779b9u) sink[0] = acc;         // keeps the loaded registers alive
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_slot, 512);
+  }
+}
+
+template <int SHAPE>
+static void launch_tmem_ld(int blocks, int nwarps, int iters, int lpw, long long* cyc, uint32_t* sink, cudaStream_t stream) {
+  probe_tmem_ld_kernel<SHAPE><<<blocks, nwarps * 32, 0, stream>>>(iters, lpw, cyc, sink);
+}
+
+int probe_tmem_ld_bench(int shape, int nwarps, int blocks, int iters, int lds_per_wait, long long* cycles_host, long long* bytes_per_block_host,
+                        cudaStream_t stream) {
+  DFS_REQUIRE(shape >= 0 && shape <= 10 && (nwarps == 4 || nwarps == 8 || nwarps == 16) && blocks >= 1 && blocks <= 148 && iters >= 1 &&
+                  lds_per_wait >= 1 && cycles_host && bytes_per_block_host,
+              DFS_ERR_INVALID, "probe_tmem_ld_bench: bad argument");
+  DFS_REQUIRE(shape != 4 || nwarps <= 8, DFS_ERR_INVALID, "probe_tmem_ld_bench: 32x32b.x128 needs 128+ registers per thread: at most 8 warps");
+  long long* d = nullptr;
+  uint32_t* sink = nullptr;
+  DFS_CUDA_CHECK(cudaMalloc(&d, 8 * (size_t)blocks));
+  DFS_CUDA_CHECK(cudaMalloc(&sink, 4));
+  switch (shape) {
+    case 0: launch_tmem_ld<0>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+    case 1: launch_tmem_ld<1>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+    case 2: launch_tmem_ld<2>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+    case 3: launch_tmem_ld<3>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+    case 4: launch_tmem_ld<4>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+    case 5: launch_tmem_ld<5>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+    case 6: launch_tmem_ld<6>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+    case 7: launch_tmem_ld<7>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+    case 8: launch_tmem_ld<8>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+    case 9: launch_tmem_ld<9>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+    default: launch_tmem_ld<10>(blocks, nwarps, iters, lds_per_wait, d, sink, stream); break;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  long long worst = 0;
+  if (e == cudaSuccess) {
+    std::vector<long long> h(blocks);
+    e = cudaMemcpy(h.data(), d, 8 * (size_t)blocks, cudaMemcpyDeviceToHost);
+    for (long long c : h) worst = c > worst ? c : worst;
+  }
+  cudaFree(d);
+  cudaFree(sink);
+  DFS_REQUIRE(e == cudaSuccess, DFS_ERR_CUDA, "probe_tmem_ld_bench: %s", cudaGetErrorString(e));
+  *cycles_host = worst;
+  *bytes_per_block_host = (long long)nwarps * iters * lds_per_wait * tmem_shape_lanes(shape) * tmem_shape_cols(shape) * 4;
+  return DFS_OK;
+}
+
 }  // namespace dfs
+
+// ---- C exports of the probes library (csrc/probes.h) ------------------------------------------------------------------
+using namespace dfs;
+extern "C" int dfs_probe_umma(const uint16_t* a_dev, const uint16_t* b_dev, int rows_a, int n, int k, int row_shift, int group_rows,
+                              float* out_dev, void* stream) {
+  return probe_umma(a_dev, b_dev, rows_a, n, k, row_shift, group_rows, out_dev, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dfs_probe_tma_window(const uint16_t* act_dev, int planes, int rs, int64_t ncols, int wrows, int row0, int col0,
+                                    uint16_t* out_dev, void* stream) {
+  return probe_tma_window(act_dev, planes, rs, ncols, wrows, row0, col0, out_dev, static_cast<cudaStream_t>(stream));
+}
+extern "C" int dfs_probe_umma_bench(int n, int nmma, int iters, int n_acc, const uint32_t* a_off_host, const uint32_t* b_off_host, uint32_t a_lbo,
+                                    uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t layout, uint32_t use_base_offset,
+                                    int64_t* cycles_host, void* stream) {
+  long long c = 0;
+  int st = probe_umma_bench(n, nmma, iters, n_acc, a_off_host, b_off_host, a_lbo, a_sbo, b_lbo, b_sbo, layout, use_base_offset, &c,
+                            static_cast<cudaStream_t>(stream));
+  if (cycles_host) *cycles_host = c;
+  return st;
+}
+extern "C" int dfs_probe_tmem_ld_bench(int shape, int nwarps, int blocks, int iters, int lds_per_wait, int64_t* cycles_host,
+                                       int64_t* bytes_per_block_host, void* stream) {
+  long long c = 0, b = 0;
+  int st = probe_tmem_ld_bench(shape, nwarps, blocks, iters, lds_per_wait, &c, &b, static_cast<cudaStream_t>(stream));
+  if (cycles_host) *cycles_host = c;
+  if (bytes_per_block_host) *bytes_per_block_host = b;
+  return st;
+}

@@ -66,6 +66,7 @@ SIGNATURES = {
     "dfs_model_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "dfs_model_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "dfs_model_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int, C.c_int]),
+    "dfs_model_saturation_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]),
     "dfs_cnn2d_score": (C.c_int, [C.c_void_p, C.POINTER(Features), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dfs_cnn1d_score": (C.c_int, [C.c_void_p, C.POINTER(Features), C.c_void_p, C.c_int, C.c_void_p]),
     "dfs_cae_score": (C.c_int, [C.c_void_p, C.POINTER(Features), C.c_int, C.c_void_p, C.c_void_p]),
@@ -73,6 +74,13 @@ SIGNATURES = {
     "dfs_cae_debug_layer": (C.c_int, [C.c_void_p, C.POINTER(Features), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dfs_score_host": (C.c_int, [C.c_void_p, C.POINTER(Features), C.c_int, C.c_void_p, C.c_void_p]),
     "dfs_score_host_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dfs_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "dfs_group_destroy": (C.c_int, [C.c_void_p]),
+    "dfs_group_stage_utts": (C.c_int64, [C.c_void_p]),
+    "dfs_group_score_host": (C.c_int, [C.c_void_p, C.POINTER(Features), C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_void_p]),
+    "dfs_group_score_host_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_void_p]),
+    "dfs_pinned_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
+    "dfs_pinned_free": (C.c_int, [C.c_void_p]),
     "dfs_blend_f64": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_double,
                                 C.c_int64, C.c_void_p, C.c_void_p]),
     "dfs_widen_f32_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -82,10 +90,6 @@ SIGNATURES = {
     "dfs_set_global_option": (C.c_int, [C.c_char_p, C.c_int64]),
     "dfs_confusion": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.POINTER(C.c_int64), C.c_void_p]),
     "dfs_fill_features": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_float, C.c_void_p]),
-    "dfs_probe_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "dfs_probe_umma_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32,
-                                       C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int64), C.c_void_p]),
-    "dfs_probe_tma_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

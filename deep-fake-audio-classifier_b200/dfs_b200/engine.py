@@ -7,6 +7,7 @@ batch loops (src/predict.py:100-111, src/predict_hybrid.py:52-78) and ``forward`
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -94,6 +95,16 @@ class _Scorer:
         N.check(self._lib.dfs_model_profile(self._h, ms, cnt, n_ids, int(reset)), "dfs_model_profile")
         return list(ms), list(cnt)
 
+    def saturation_count(self):
+        """(elements at +-65504, non-finite elements) in the fp16 feature image and activation buffers of the LAST pass
+        (dfs_model_saturation_count): a debug census of what the saturating fp16 converts clipped."""
+        torch = _require_cuda()
+        sat, nonfin = C.c_int64(), C.c_int64()
+        with torch.cuda.device(self.device_index):
+            N.check(self._lib.dfs_model_saturation_count(self._h, C.byref(sat), C.byref(nonfin), _stream_ptr(torch, self._device(torch))),
+                    "dfs_model_saturation_count")
+        return int(sat.value), int(nonfin.value)
+
     @property
     def workspace_bytes(self) -> int:
         return int(self._lib.dfs_model_workspace_bytes(self._h))
@@ -103,53 +114,142 @@ class _Scorer:
 
     # -- host buffers: H2D / D2H inside (the e2e path of bench.py) --
     def score_host(self, feats, flag: int = 1):
-        """feats: pinned torch CPU tensor or numpy array (B,321,180) fp32, dense (or fp16: dfs_score_host_f16, half the
-        PCIe bytes; the engine quantises to fp16 anyway). Returns numpy fp32 (B,)."""
+        """feats: pinned torch CPU tensor or numpy array (B,321,180), fp32 (dfs_score_host) or fp16 (dfs_score_host_f16:
+        half the PCIe bytes; the engine quantises to fp16 anyway), each utterance one dense block.  Other dtypes are
+        converted to fp32 first; CUDA tensors are rejected (use score()).  Returns numpy fp32 (B,)."""
         torch = _require_cuda()
-        if (hasattr(feats, "dtype") and str(feats.dtype) in ("torch.float16", "float16")):
-            return self._score_host_f16(feats, flag)
-        if hasattr(feats, "numpy") and not isinstance(feats, np.ndarray):
-            t = feats
-            ptr, shape, strides = t.data_ptr(), tuple(t.shape), t.stride()
-        else:
-            a = np.asarray(feats, dtype=np.float32)
-            ptr, shape, strides = a.ctypes.data, a.shape, tuple(s // 4 for s in a.strides)
-            t = a
-        if len(shape) != 3 or shape[1] != T_FRAMES or shape[2] != N_FEATS:
-            raise ValueError(f"expected features of shape (B, {T_FRAMES}, {N_FEATS}), got {shape}")
-        out = torch.empty(shape[0], dtype=torch.float32, pin_memory=True)
-        f = N.Features(ptr, shape[0], strides[0], strides[1], strides[2])
+        slab = _host_slab(feats)
+        out = torch.empty(slab.n, dtype=torch.float32, pin_memory=True)
         with torch.cuda.device(self.device_index):
-            N.check(self._lib.dfs_score_host(self._h, C.byref(f), int(flag), C.c_void_p(out.data_ptr()),
-                                             _stream_ptr(torch, self._device(torch))), "dfs_score_host")
-        del t
+            stream = _stream_ptr(torch, self._device(torch))
+            if slab.f16:
+                N.check(self._lib.dfs_score_host_f16(self._h, C.c_void_p(slab.ptr), slab.n, slab.time_major, int(flag),
+                                                     C.c_void_p(out.data_ptr()), stream), "dfs_score_host_f16")
+            else:
+                f = N.Features(slab.ptr, slab.n, *slab.strides)
+                N.check(self._lib.dfs_score_host(self._h, C.byref(f), int(flag), C.c_void_p(out.data_ptr()), stream), "dfs_score_host")
+        del slab
         return out.numpy()
 
 
-    def _score_host_f16(self, feats, flag):
+class _HostSlab:
+    """A validated host feature table: pointer, utterance count, element strides, fp16 flag (+ the object that owns the bytes)."""
+    __slots__ = ("ptr", "n", "strides", "f16", "time_major", "keep")
+
+
+def _host_slab(feats) -> "_HostSlab":
+    """numpy array or torch CPU tensor (B,321,180) -> _HostSlab.  fp32 and fp16 are passed through in place (any other dtype
+    is converted to fp32: reading float64 / bfloat16 bytes as fp32 would return garbage scores without an error); a CUDA
+    tensor raises.  Each utterance must be one dense 321x180 or 180x321 block, utterances back to back."""
+    import torch
+    if isinstance(feats, torch.Tensor):
+        if feats.device.type != "cpu":
+            raise RuntimeError(f"score_host takes HOST features (got a tensor on {feats.device}); use score() for device tensors")
+        if feats.dtype not in (torch.float32, torch.float16):
+            feats = feats.float()
+        f16 = feats.dtype == torch.float16
+        ptr, shape, strides, keep = feats.data_ptr(), tuple(feats.shape), tuple(feats.stride()), feats
+    else:
+        a = np.asarray(feats)
+        if a.dtype not in (np.float32, np.float16):
+            a = a.astype(np.float32)
+        f16 = a.dtype == np.float16
+        ptr, shape, strides, keep = a.ctypes.data, a.shape, tuple(s // a.itemsize for s in a.strides), a
+    if len(shape) != 3 or shape[1] != T_FRAMES or shape[2] != N_FEATS:
+        raise ValueError(f"expected features of shape (B, {T_FRAMES}, {N_FEATS}), got {tuple(shape)}")
+    per = T_FRAMES * N_FEATS
+    if shape[0] > 1 and strides[0] != per:
+        raise ValueError("host features: utterances must be dense and back to back")
+    if (strides[1], strides[2]) == (N_FEATS, 1):
+        time_major = 0
+    elif (strides[1], strides[2]) == (1, T_FRAMES):
+        time_major = 1                                  # the (B,321,180) view of [B,180,321] rows (src/predict.py:103-105)
+    else:
+        raise ValueError("host features: each utterance must be one dense 321x180 (or 180x321) block")
+    s = _HostSlab()
+    s.ptr, s.n, s.strides, s.f16, s.time_major, s.keep = ptr, int(shape[0]), (per, strides[1], strides[2]), f16, time_major, keep
+    return s
+
+
+class ScorerGroup:
+    """Several scorers over ONE upload of a host feature table (dfs_group_*): every slab crosses PCIe once and all
+    members score it.  The reference reads the table once per model (src/ensemble.py:105-122, src/predict_hybrid.py:142-145).
+
+        group = ScorerGroup([cnn2d, cnn1d, cae])
+        s2, s1, mse = group.score_host(pinned_table)        # flags default: sigmoid on, CAE normaliser if it has one
+    """
+
+    def __init__(self, scorers, stage_utts: int = 0):
+        scorers = list(scorers)
+        if not scorers:
+            raise ValueError("ScorerGroup needs at least one scorer")
+        if len({s.device_index for s in scorers}) != 1:
+            raise ValueError("all scorers of a group must live on one device")
+        _require_cuda()
+        self.scorers = scorers
+        self.device_index = scorers[0].device_index
+        self._lib = N.load()
+        self._h = C.c_void_p()
+        handles = (C.c_void_p * len(scorers))(*[s._h.value for s in scorers])
+        N.check(self._lib.dfs_group_create(C.byref(self._h), handles, len(scorers), int(stage_utts)), "dfs_group_create")
+
+    @property
+    def stage_utts(self) -> int:
+        return int(self._lib.dfs_group_stage_utts(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.dfs_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def default_flags(self):
+        return [int(getattr(s, "has_normalizer", True)) for s in self.scorers]
+
+    def score_host(self, feats, flags=None):
+        """feats as in ``_Scorer.score_host``; flags[i] = apply_sigmoid / apply_normalizer of member i.
+        Returns a list of numpy fp32 (B,) score vectors, one per member."""
         torch = _require_cuda()
-        if isinstance(feats, np.ndarray):
-            a = feats
-            ptr, shape, strides, keep = a.ctypes.data, a.shape, tuple(s // 2 for s in a.strides), a
-        else:
-            ptr, shape, strides, keep = feats.data_ptr(), tuple(feats.shape), feats.stride(), feats
-        if len(shape) != 3 or shape[1] != T_FRAMES or shape[2] != N_FEATS:
-            raise ValueError(f"expected features of shape (B, {T_FRAMES}, {N_FEATS}), got {shape}")
-        per = T_FRAMES * N_FEATS
-        if shape[0] > 1 and strides[0] != per:
-            raise ValueError("fp16 slab: utterances must be dense and back to back")
-        if (strides[1], strides[2]) == (N_FEATS, 1):
-            time_major = 0
-        elif (strides[1], strides[2]) == (1, T_FRAMES):
-            time_major = 1                                  # the (B,321,180) view of [B,180,321] rows
-        else:
-            raise ValueError("fp16 slab: each utterance must be one dense 321x180 (or 180x321) block")
-        out = torch.empty(shape[0], dtype=torch.float32, pin_memory=True)
-        with torch.cuda.device(self.device_index):
-            N.check(self._lib.dfs_score_host_f16(self._h, C.c_void_p(ptr), shape[0], time_major, int(flag), C.c_void_p(out.data_ptr()),
-                                                 _stream_ptr(torch, self._device(torch))), "dfs_score_host_f16")
-        del keep
-        return out.numpy()
+        slab = _host_slab(feats)
+        flags = self.default_flags() if flags is None else [int(f) for f in flags]
+        if len(flags) != len(self.scorers):
+            raise ValueError("one flag per scorer")
+        m = len(self.scorers)
+        outs = [torch.empty(slab.n, dtype=torch.float32, pin_memory=True) for _ in range(m)]
+        optr = (C.c_void_p * m)(*[o.data_ptr() for o in outs])
+        fl = (C.c_int * m)(*flags)
+        dev = torch.device("cuda", self.device_index)
+        with torch.cuda.device(dev):
+            stream = _stream_ptr(torch, dev)
+            if slab.f16:
+                N.check(self._lib.dfs_group_score_host_f16(self._h, C.c_void_p(slab.ptr), slab.n, slab.time_major, fl, optr, stream),
+                        "dfs_group_score_host_f16")
+            else:
+                f = N.Features(slab.ptr, slab.n, *slab.strides)
+                N.check(self._lib.dfs_group_score_host(self._h, C.byref(f), fl, optr, stream), "dfs_group_score_host")
+        del slab
+        return [o.numpy() for o in outs]
+
+
+def pinned_empty(shape, dtype="float32", write_combined: bool = False):
+    """Page-locked host array from dfs_pinned_alloc (cudaHostAlloc against the current device; optionally write-combined).
+    Returns a numpy array that frees the allocation when it is garbage-collected."""
+    _require_cuda()
+    dt = np.dtype(dtype)
+    count = int(np.prod(shape))
+    nbytes = max(count * dt.itemsize, 1)
+    lib = N.load()
+    p = C.c_void_p()
+    N.check(lib.dfs_pinned_alloc(C.byref(p), nbytes, int(write_combined)), "dfs_pinned_alloc")
+
+    buf = (C.c_char * nbytes).from_address(p.value)
+    weakref.finalize(buf, lib.dfs_pinned_free, C.c_void_p(p.value))     # the array (and every view of it) keeps `buf` alive as its base
+    return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
 
 
 def _check_precision(precision):

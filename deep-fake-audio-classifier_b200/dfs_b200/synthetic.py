@@ -47,9 +47,10 @@ def _bn(rng, sd, prefix, c):
 
 
 def cnn2d_state(seed: int = 0, in_features: int = N_FEATS, base_channels: int = 32,
-                logit_scale: float = 1.0) -> "OrderedDict[str, np.ndarray]":
-    """Random-init CNN2D state dict. ``logit_scale`` rescales the classifier weights
-    ("trained-like" regime of SURVEY.md §7.2 #5: logits spanning +-20 instead of +-0.01)."""
+                logit_scale: float = 1.0, classifier_bias: float | None = None) -> "OrderedDict[str, np.ndarray]":
+    """Random-init CNN2D state dict. ``logit_scale`` rescales the classifier weights and ``classifier_bias`` replaces the
+    bias ("trained-like" regime of SURVEY.md §7.2 #5: logits centred on 0 and spanning +-20 instead of 0.06 +- 0.01; the
+    pair is calibrated against the unmodified reference by tests/golden/make_golden.py and stored in trained.npz)."""
     rng = _rng(1000 + seed)
     bc = base_channels
     sd = OrderedDict()
@@ -61,11 +62,13 @@ def cnn2d_state(seed: int = 0, in_features: int = N_FEATS, base_channels: int = 
     fan = 4 * bc * in_features
     sd["classifier.weight"] = _uniform_fan_in(rng, (1, fan), fan) * np.float32(logit_scale)
     sd["classifier.bias"] = _uniform_fan_in(rng, (1,), fan)
+    if classifier_bias is not None:
+        sd["classifier.bias"] = np.array([classifier_bias], dtype=np.float32)
     return sd
 
 
 def cnn1d_state(seed: int = 0, in_features: int = N_FEATS, base_channels: int = 32,
-                logit_scale: float = 1.0) -> "OrderedDict[str, np.ndarray]":
+                logit_scale: float = 1.0, classifier_bias: float | None = None) -> "OrderedDict[str, np.ndarray]":
     rng = _rng(2000 + seed)
     bc = base_channels
     sd = OrderedDict()
@@ -76,6 +79,8 @@ def cnn1d_state(seed: int = 0, in_features: int = N_FEATS, base_channels: int = 
         _bn(rng, sd, f"conv.{bn_i}", co)
     sd["classifier.weight"] = _uniform_fan_in(rng, (1, 4 * bc), 4 * bc) * np.float32(logit_scale)
     sd["classifier.bias"] = _uniform_fan_in(rng, (1,), 4 * bc)
+    if classifier_bias is not None:
+        sd["classifier.bias"] = np.array([classifier_bias], dtype=np.float32)
     return sd
 
 
@@ -128,6 +133,32 @@ def features(n: int, seed: int = 1234, start: int = 0) -> np.ndarray:
     for i in range(n):
         rng = np.random.Generator(np.random.PCG64([seed, start + i]))
         out[i] = (FEATURE_STD * rng.standard_normal((T_FRAMES, N_FEATS), dtype=np.float32))
+    return out
+
+
+def features_structured(n: int, seed: int = 4321, start: int = 0, heavy_tail: bool = True) -> np.ndarray:
+    """``[n, 321, 180]`` fp32 utterances that DIFFER from one another the way real LFCC maps do -- unlike ``features()``,
+    whose i.i.d. noise gives every utterance nearly the same embedding.  Per utterance (seeded by (seed, start+i)):
+    a gain (lognormal around the real std 3.19), a spectral tilt over the 180 features, a slow temporal envelope, a
+    per-feature offset pattern, and (``heavy_tail``) a dozen outliers reaching the real data's range -61 ... +86
+    (results/archive/20260206_final_prep/model_prediction_report.md:24-29)."""
+    out = np.empty((n, T_FRAMES, N_FEATS), dtype=np.float32)
+    f = np.arange(N_FEATS, dtype=np.float32) / np.float32(N_FEATS - 1)
+    t = np.arange(T_FRAMES, dtype=np.float32) / np.float32(T_FRAMES)
+    for i in range(n):
+        rng = np.random.Generator(np.random.PCG64([seed, start + i]))
+        gain = np.float32(np.clip(FEATURE_STD * np.exp(0.5 * rng.standard_normal()), 1.0, 8.0))
+        tilt = (1.0 + rng.uniform(-1.0, 1.0) * (f - 0.5)).astype(np.float32)
+        env = (1.0 + 0.5 * np.sin(2.0 * np.pi * (rng.uniform(0.5, 3.0) * t + rng.random()))).astype(np.float32)
+        offs = (rng.standard_normal() * np.cos(2.0 * np.pi * rng.uniform(1.0, 6.0) * f)).astype(np.float32)
+        x = gain * rng.standard_normal((T_FRAMES, N_FEATS), dtype=np.float32) * tilt[None, :] * env[:, None] + offs[None, :]
+        if heavy_tail:
+            k = 12
+            tt, ff = rng.integers(0, T_FRAMES, k), rng.integers(0, N_FEATS, k)
+            mag = rng.uniform(30.0, 86.0, k)
+            sign = np.where(rng.random(k) < 0.5, -1.0, 1.0)
+            x[tt, ff] = np.where(sign < 0, -np.minimum(mag, 61.0), mag).astype(np.float32)
+        out[i] = x
     return out
 
 

@@ -1,6 +1,6 @@
 """Drop-in for ``src/ensemble.py``: ensemble-average the sigmoid scores of several checkpoints on a labelled set and
 report the per-model and ensemble EER, with the reference's flags and printout (/root/reference/src/ensemble.py:66-128).
-The features are ingested once into a pinned slab, every model scores that slab through the native pipeline, the mean
+The features are ingested once into a pinned slab, every slab is uploaded ONCE and scored by all checkpoints (dfs_group_score_host), the mean
 (``np.mean(all_scores, axis=0)``, :121) and the EERs are computed on the device."""
 import argparse
 import os
@@ -19,7 +19,7 @@ from ingest import load_feature_table, merge_labels  # noqa: E402
 from model import CNN2D  # noqa: E402
 from model_cnn1d import CNN1D  # noqa: E402
 from predict import load_checkpoint_into, resolve_device, score_table  # noqa: E402
-from scoring import collect_scores  # noqa: E402,F401  (per-batch variant, same name as the reference helper)
+from scoring import collect_scores, score_models_once  # noqa: E402,F401  (collect_scores: per-batch variant, same name as the reference helper)
 
 
 def parse_args(argv=None):
@@ -54,12 +54,14 @@ def main(argv=None):
     if len(idx) != len(table):
         table = table.take(idx)
     labels = labels.astype(np.float64).tolist()                             # the loader yields float labels (dataset.py:54)
-    all_scores, results = [], []
-    for spec in args.checkpoints:
-        arch, path = spec.split(":", 1)
-        model = load_model(arch, path, device, in_features=args.in_features, dropout=args.dropout)
-        scores = score_table(model, table, device, apply_sigmoid=True, swap_tf=args.swap_tf)
-        all_scores.append(scores)
+    if not args.swap_tf:
+        raise ValueError("--no-swap-tf: stored features are [180,321]; the models take (B,321,180)")
+    specs = [spec.split(":", 1) for spec in args.checkpoints]
+    models = [load_model(arch, path, device, in_features=args.in_features, dropout=args.dropout) for arch, path in specs]
+    # ensemble.py:105-122 scores the dev set once per checkpoint; here all of them score every slab of ONE upload
+    all_scores = score_models_once(models, table, device, apply_sigmoid=True)
+    results = []
+    for (arch, path), scores in zip(specs, all_scores):
         eer, thr = calculate_eer(scores.tolist(), labels)
         results.append((arch, path, eer, thr))
         print(f"  {arch:6s}  {path}")

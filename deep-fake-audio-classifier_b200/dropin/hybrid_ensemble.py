@@ -60,7 +60,7 @@ def main(argv=None):
     from model import CNN2D
     from model_cae import ConvAutoencoder
     from predict import load_checkpoint_into, resolve_device
-    from scoring import get_cae_scores, get_supervised_scores
+    from scoring import score_models_once
 
     args = parse_args(argv)
     device = resolve_device(args.device)
@@ -72,10 +72,9 @@ def main(argv=None):
     if len(idx) != len(table):
         table = table.take(idx)
     labels = labels.astype(np.float64)
-    sup_scores = get_supervised_scores(sup_model, table, device, args.batch_size)
+    sup_scores, cae_scores = score_models_once([sup_model, cae_model], table, device, [None, cae_normalizer])   # one upload (hybrid_ensemble.py:119-130 makes two passes)
     sup_eer, _ = calculate_eer(sup_scores.tolist(), labels.tolist())
     print(f"Supervised-only  EER = {sup_eer:.6f}")
-    cae_scores = get_cae_scores(cae_model, table, cae_normalizer, device, args.batch_size)
     cae_eer, _ = calculate_eer(cae_scores.tolist(), labels.tolist())
     print(f"CAE-only         EER = {cae_eer:.6f}")
     best_alpha, best_eer, table_rows = alpha_sweep(sup_scores, cae_scores, labels, alpha_steps=args.alpha_steps, verbose=True)

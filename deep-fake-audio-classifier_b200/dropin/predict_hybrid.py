@@ -1,6 +1,6 @@
 """Drop-in for ``src/predict_hybrid.py``: hybrid (2D-CNN + CAE reconstruction error) predictions with the
-reference's flags and output (/root/reference/src/predict_hybrid.py:100-196).  Both models score the same pinned
-slab; min-max normalisation and the alpha blend run in float64 on the device (``dfs_blend_f64``), bit-identical to
+reference's flags and output (/root/reference/src/predict_hybrid.py:100-207).  Both models score the same pinned
+slab through ONE upload (scoring.score_models_once -> dfs_group_score_host); min-max normalisation and the alpha blend run in float64 on the device (``dfs_blend_f64``), bit-identical to
 ``alpha * normalise_01(sup) + (1 - alpha) * normalise_01(cae)`` in numpy.
 """
 import argparse
@@ -21,7 +21,8 @@ from ingest import load_feature_table  # noqa: E402
 from model import CNN2D  # noqa: E402
 from model_cae import ConvAutoencoder  # noqa: E402
 from predict import load_checkpoint_into, resolve_device  # noqa: E402
-from scoring import get_cae_scores, get_supervised_scores, hybrid_blend, normalise_01, write_predictions  # noqa: E402,F401
+from scoring import (get_cae_scores, get_supervised_scores, hybrid_blend, normalise_01, score_models_once,  # noqa: E402,F401
+                     write_predictions)
 
 
 def parse_args(argv=None):
@@ -46,6 +47,34 @@ def print_distribution(name, scores):
     print(f"    est real (>0.5): {(scores > 0.5).sum()}  est fake (<=0.5): {(scores <= 0.5).sum()}")
 
 
+def compare_with_existing(pred_df, existing, out=print):
+    """The --existing-submission report of predict_hybrid.py:166-207: the new HYBRID predictions against an older
+    prediction file (a bare DataFrame or a submission dict holding one under "predictions"), rows aligned by uttid.
+    Returns dict(n, diff, agree, disagreements) for tests."""
+    import pandas as pd
+    old_df = existing["predictions"] if isinstance(existing, dict) and "predictions" in existing else existing
+    print_distribution("Existing submission", old_df["predictions"].values)
+    both = pd.merge(pred_df, old_df, on="uttid", suffixes=("_new", "_old"))
+    new, old = both["predictions_new"].values, both["predictions_old"].values
+    diff = new - old
+    out("\n  Per-sample diff (new - old):")
+    out(f"    mean={diff.mean():.6f}  std={diff.std():.6f}")
+    out(f"    min={diff.min():.6f}  max={diff.max():.6f}")
+    new_cls, old_cls = (new > 0.5).astype(int), (old > 0.5).astype(int)
+    agree = int((new_cls == old_cls).sum())
+    out(f"    class agreement: {agree}/{len(both)} ({100 * agree / len(both):.1f}%)")
+    where = np.where(new_cls != old_cls)[0]
+    shown = where if len(where) <= 20 else where[:10]
+    if 0 < len(where) <= 20:
+        out("    disagreements:")
+    elif len(where) > 20:
+        out(f"    {len(where)} disagreements (showing first 10):")
+    for i in shown:
+        row = both.iloc[i]
+        out(f"      {row['uttid']}: old={row['predictions_old']:.4f} new={row['predictions_new']:.4f}")
+    return dict(n=len(both), diff=diff, agree=agree, disagreements=[both.iloc[i]["uttid"] for i in where])
+
+
 def main(argv=None):
     args = parse_args(argv)
     device = resolve_device(args.device)
@@ -54,22 +83,21 @@ def main(argv=None):
     sup_model = load_checkpoint_into(CNN2D(in_features=180, dropout=0.2).to(device), args.sup_checkpoint, device)
     cae_norm = FeatureNormalizer.load(args.cae_normalizer)
     cae_model = load_checkpoint_into(ConvAutoencoder().to(device), args.cae_checkpoint, device)
-    print("Running supervised inference...")
-    sup_scores = get_supervised_scores(sup_model, table, device, args.batch_size)
-    print("Running CAE inference...")
-    cae_scores = get_cae_scores(cae_model, table, cae_norm, device, args.batch_size)
+    # predict_hybrid.py:142-145 runs the two models over the table one after the other; here both score every slab of ONE upload
+    print("Running supervised + CAE inference (one upload)...")
+    sup_scores, cae_scores = score_models_once([sup_model, cae_model], table, device, [None, cae_norm])
     hybrid = hybrid_blend(sup_scores, cae_scores, args.alpha)            # predict_hybrid.py:149-151, float64 on the device
     pred_df = write_predictions(table.uttids, hybrid, args.out)
     print(f"\nSaved hybrid predictions to {args.out}")
-    print_distribution("Supervised (sigmoid)", sup_scores)
-    print_distribution("CAE MSE", cae_scores)
+    print(f"\n{'=' * 60}")
+    print("Distribution Comparison")
+    print_distribution("Supervised-only (sigmoid)", sup_scores)
+    print_distribution("CAE-only (raw MSE, higher=real)", cae_scores)
     print_distribution(f"Hybrid (alpha={args.alpha})", hybrid)
-    if args.existing_submission:                                          # predict_hybrid.py:166-192
+    if args.existing_submission:                                          # predict_hybrid.py:166-207
         with open(args.existing_submission, "rb") as f:
-            old = pickle.load(f)
-        old_preds = old["predictions"]["predictions"].values if isinstance(old, dict) else old["predictions"].values
-        flips = int(((old_preds > 0.5) != (sup_scores > 0.5)).sum())
-        print(f"\n  decisions changed vs existing submission: {flips}")
+            compare_with_existing(pred_df, pickle.load(f))
+    print(f"\n{'=' * 60}")
     return pred_df
 
 

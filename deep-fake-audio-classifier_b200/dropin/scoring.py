@@ -4,6 +4,7 @@ through one pinned slab and the engine's chunked host pipeline instead of a bs-3
 
     get_supervised_scores(model, features_df, device, batch_size=32)           predict_hybrid.py:52-63
     get_cae_scores(model, features_df, normalizer, device, batch_size=32)      predict_hybrid.py:66-78
+    score_models_once(models, features_df, device, normalizers)               both of the above (and ensemble.py:105-122) over ONE upload
     normalise_01(scores)                                                      predict_hybrid.py:81-85
     write_predictions(uttids, scores, path)                                   predict.py:116-122
 """
@@ -60,6 +61,35 @@ def get_cae_scores(model, features_df, normalizer, device, batch_size=32):
     scorer = model.native(torch.device("cuda", _device_index(device)))
     mse = scorer.score_host(slab.transpose(1, 2), int(normalizer is not None))
     return np.array(mse.tolist())
+
+
+@torch.no_grad()
+def score_models_once(models, features_df, device, normalizers=None, apply_sigmoid=True):
+    """Several models over ONE upload of the feature table (dfs_group_score_host): the reference makes one DataLoader pass
+    per model (src/ensemble.py:105-122, src/predict_hybrid.py:142-145); here every staged slab crosses PCIe once and all
+    models score it.  ``models``: drop-in CNN2D / CNN1D / ConvAutoencoder instances; ``normalizers[i]``: FeatureNormalizer
+    (or None) for autoencoder i.  Returns one float64 numpy vector per model, in row order -- sigmoid scores
+    (``apply_sigmoid``) for the classifiers, reconstruction MSE for autoencoders -- equal bit for bit to
+    get_supervised_scores / get_cae_scores run one after the other."""
+    from dfs_b200 import ScorerGroup
+    dev = torch.device("cuda", _device_index(device))
+    normalizers = list(normalizers) if normalizers is not None else [None] * len(models)
+    scorers, flags = [], []
+    for model, norm in zip(models, normalizers):
+        model.eval()
+        model.to(device)
+        is_cae = hasattr(model, "set_normalizer")
+        if is_cae and norm is not None:
+            model.set_normalizer(norm.mean, norm.std)
+        scorers.append(model.native(dev))
+        flags.append(int(norm is not None) if is_cae else int(bool(apply_sigmoid)))
+    slab = features_slab(features_df)
+    group = ScorerGroup(scorers)
+    try:
+        outs = group.score_host(slab.transpose(1, 2), flags)
+    finally:
+        group.close()
+    return [np.array(o.tolist()) for o in outs]
 
 
 def collect_scores(model, dataloader, device, swap_tf=True):

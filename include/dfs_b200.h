@@ -137,6 +137,13 @@ int64_t dfs_model_workspace_bytes(const dfs_model* m);
  * since the last reset.  Used by bench.py for the live roofline figure.                     */
 int dfs_model_profile(dfs_model* m, double* ms_out, int64_t* launches_out, int n_ids, int reset);
 
+/* Debug census of fp16 saturation.  Activations and the fp16 image of the features are stored with a saturating convert
+ * (|v| > 65504 becomes +-65504 silently).  This scans the fp16 buffers the LAST pass (<= chunk utterances) of `m` left
+ * behind -- feature image and every inter-layer activation -- and returns how many elements sit exactly at +-65504 and how
+ * many are non-finite.  0 / 0 on real LFCC maps (range -61 ... +86, model_prediction_report.md:24-29); tests feed
+ * heavy-tailed inputs and check it.  Synchronises `stream`.                                                          */
+int dfs_model_saturation_count(dfs_model* m, int64_t* saturated_out, int64_t* nonfinite_out, void* stream);
+
 /* ---- scoring (device-resident features) --------------------------------------------- */
 /* CNN2D.forward + squeeze(-1) [+ torch.sigmoid]  (src/model.py:33-42, src/predict.py:106-108).
  * out_dev: [n] fp32 logits (apply_sigmoid=0) or scores.  embedding_dev: NULL or [n,23040] fp32
@@ -175,6 +182,29 @@ int dfs_score_host(dfs_model* m, const dfs_features* feats, int flag, float* out
  * GEMM anyway, so for the 2D-CNN and the 1D-CNN a slab holding the fp16 image of the fp32 features scores bit-identically;
  * the CAE additionally reads the input in its fp32 residual, so its MSE moves by the input rounding (~1e-4 relative). */
 int dfs_score_host_f16(dfs_model* m, const uint16_t* x_host, int64_t n, int time_major, int flag, float* out_host, void* stream);
+
+/* ---- scorer groups: ONE upload of the host table, every member model scores it --------- */
+/* src/ensemble.py:105-122 and src/predict_hybrid.py:142-145 run one DataLoader pass over the feature table per model.
+ * A group stages each slab of `stage_utts` utterances (0 = default 2,368; a single-model group keeps that model's pass
+ * size) of the HOST table on the device once -- H2D of slab k+1 overlaps the kernels of slab k -- and every member
+ * scores the staged slab before the buffer is re-used, so the PCIe bytes do not grow with the number of models.
+ * The group borrows the model handles (they must outlive it and live on one device; not thread-safe, like the handles).
+ * flags[i] = apply_sigmoid (2D-CNN, 1D-CNN, StatsPool detector) / apply_normalizer (CAE) of member i (NULL = all 1);
+ * out_host[i] = HOST pointer to [n] fp32 scores of member i.  Returns after all scores are in host memory.            */
+typedef struct dfs_group dfs_group; /* opaque */
+int dfs_group_create(dfs_group** out, dfs_model* const* models, int n_models, int stage_utts);
+int dfs_group_destroy(dfs_group* g);
+int64_t dfs_group_stage_utts(const dfs_group* g);
+int dfs_group_score_host(dfs_group* g, const dfs_features* feats_host, const int* flags, float* const* out_host, void* stream);
+/* same for a dense HOST slab of IEEE fp16 features (layout as dfs_score_host_f16) */
+int dfs_group_score_host_f16(dfs_group* g, const uint16_t* x_host, int64_t n, int time_major, const int* flags, float* const* out_host,
+                             void* stream);
+
+/* Page-locked host memory for the *_host entry points (cudaHostAlloc, portable; write_combined != 0 adds
+ * cudaHostAllocWriteCombined: faster for the device to read over PCIe on some hosts, slow for the CPU to read back).
+ * Stands where src/dataloaders.py:44-50 sets pin_memory=True on its DataLoaders.  Allocate after selecting the device.  */
+int dfs_pinned_alloc(void** out_host, size_t bytes, int write_combined);
+int dfs_pinned_free(void* p);
 
 /* ---- ensemble blend (float64, like numpy) ------------------------------------------- */
 /* out[i] = (sum_m weights[m] * (minmax_flags[m] ? normalise_01(scores[m])[i] : scores[m][i])) / divisor
@@ -223,27 +253,6 @@ int dfs_bce_with_logits(const float* logits_dev, const float* labels_dev, int64_
 /* Fill [n,321,180] fp32 with N(0, std^2) from a counter-based generator keyed by
  * (seed, first_utt + i, element) so every rank / GPU count sees the same global data set. */
 int dfs_fill_features(float* out_dev, int64_t n, int64_t first_utt, uint64_t seed, float std, void* stream);
-
-/* ---- bring-up probes (tests only) --------------------------------------------------- */
-/* One tcgen05.mma tile D[128,N] = A'[128,K] * B[N,K]^T.  A [rows_a,K] and B [N,K] are row-major
- * bf16 bit patterns in device memory; they are staged in shared memory in the layout the conv
- * kernels use and read through the same SWIZZLE_NONE K-major descriptors.  D row r = 8g+i reads
- * staged A row (row_shift + g*group_rows + i) -- the addressing of a 3x3 tap on a 16x8 tile.
- * out_dev [128*N] fp32.                                                                     */
-int dfs_probe_umma(const uint16_t* a_dev, const uint16_t* b_dev, int rows_a, int n, int k, int row_shift, int group_rows,
-                   float* out_dev, void* stream);
-/* One 3-D TMA box load (wrows rows x 18 columns x all planes) from an FT8 activation buffer
- * (planes, rs rows per column, ncols columns) at (row0, col0); the shared-memory image is
- * copied to out_dev [planes*18*wrows*8] bf16 bits.                                          */
-int dfs_probe_tma_window(const uint16_t* act_dev, int planes, int rs, int64_t ncols, int wrows, int row0, int col0,
-                         uint16_t* out_dev, void* stream);
-
-/* Issue-rate / operand-fetch micro-benchmark of tcgen05.mma (M=128, N=n, K=16): `iters` rounds of
- * `nmma` MMAs whose A/B descriptor start addresses are smem_base + a_off[i] / b_off[i] (bytes);
- * cycles_host receives the SM cycles of the timed rounds.  Data content is zero.           */
-int dfs_probe_umma_bench(int n, int nmma, int iters, const uint32_t* a_off_host, const uint32_t* b_off_host, uint32_t a_lbo,
-                         uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t layout, uint32_t use_base_offset,
-                         int64_t* cycles_host, void* stream);
 
 #ifdef __cplusplus
 }

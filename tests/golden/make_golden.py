@@ -14,6 +14,9 @@ GPU box, so the tests only ever read the .npz files written here.  What is pinne
 * blend_known_answer.npz -- the one bit-exact known-answer triple the reference ships
                    (results/prediction_{final_test,cae_only_final,hybrid_final}.pkl).
 * prediction_format.json -- dtype/shape facts of examples/prediction.pkl.
+* trained.npz   -- trained-like regime: classifier scale / bias calibrated so that the REFERENCE's logits are centred and span
+                   +-20 on 2,048 heterogeneous utterances (dfs_b200.synthetic.features_structured, heavy tails to -61 / +86);
+                   reference logits, sigmoids, labels and the reference's own EER on them.
 * dlq.npz       -- reference DeepfakeDetector (src/dlqueen_model.py) logits on seeded weights, full-length and ragged batches.
 """
 import importlib.util
@@ -103,6 +106,54 @@ def make_models():
     out["cae_latent_shape"] = np.array(latent.shape)
     np.savez_compressed(os.path.join(HERE, "models.npz"), **out)
     print("models.npz:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
+def make_trained():
+    """Trained-like regime on heterogeneous inputs (trained.npz).  The random-init classifiers put every logit near one value
+    (2D-CNN: 0.06 +- 0.016), so sigmoids never leave 0.51-0.52 and a x2000 classifier only moves all of them to +130 (sigmoid
+    exactly 1).  Here the classifier is CALIBRATED against the unmodified reference: scale and bias are chosen on the first 256
+    structured utterances so that the reference's logits are centred on 0 and span +-20, then the reference scores all 2,048
+    utterances.  Pins: the calibration constants, the reference logits / sigmoids, labels drawn from the reference logits,
+    and the reference's own calculate_eer on its scores and on its logits."""
+    from model import CNN2D
+    from model_cnn1d import CNN1D
+    ev = _load_ref_eval()
+    torch.set_num_threads(os.cpu_count() or 8)
+    n, n_cal, seed = 2048, 256, 4321
+    x_np = syn.features_structured(n, seed=seed)
+    out = {"n": n, "n_cal": n_cal, "seed": seed, "features_sha256_first64": syn.state_digest([x_np[:64]])}
+
+    def run(model, xs):
+        outs = []
+        with torch.no_grad():
+            for i in range(0, len(xs), 32):                                   # predict.py:100-111 batch loop, bs 32
+                b = torch.from_numpy(xs[i:i + 32])
+                b = b.transpose(1, 2).contiguous().transpose(1, 2)            # the reference's non-contiguous view (predict.py:103-105)
+                outs.append(model(b).squeeze(-1))
+        return torch.cat(outs).numpy()
+
+    for tag, cls, factory in (("cnn2d", CNN2D, syn.cnn2d_state), ("cnn1d", CNN1D, syn.cnn1d_state)):
+        m = cls(in_features=180, dropout=0.2)
+        m.load_state_dict(_to_torch(factory(0)))
+        m.eval()
+        cal = run(m, x_np[:n_cal]).astype(np.float64)
+        scale = 20.0 / float(np.max(np.abs(cal - cal.mean())))
+        b0 = float(factory(0)["classifier.bias"][0])
+        bias = scale * (b0 - float(cal.mean()))
+        sd = factory(0, logit_scale=scale, classifier_bias=bias)
+        m.load_state_dict(_to_torch(sd))
+        logits = run(m, x_np)
+        sig = torch.sigmoid(torch.from_numpy(logits)).numpy()
+        rng = np.random.Generator(np.random.PCG64(99))
+        lab = (rng.random(n) < 1.0 / (1.0 + np.exp(-logits.astype(np.float64) / 4.0))).astype(np.int64)
+        out[f"{tag}_scale"], out[f"{tag}_bias"] = np.float64(scale), np.float64(bias)
+        out[f"{tag}_sha256"] = syn.state_digest(sd)
+        out[f"{tag}_logits"], out[f"{tag}_sigmoid"], out[f"{tag}_labels"] = logits, sig, lab
+        out[f"{tag}_eer_thr_scores"] = np.array(ev.calculate_eer(np.array(sig.tolist()), lab), dtype=np.float64)   # float64 column like .tolist()
+        out[f"{tag}_eer_thr_logits"] = np.array(ev.calculate_eer(np.array(logits.tolist()), lab), dtype=np.float64)
+        print(tag, "scale", scale, "bias", bias, "logit range", logits.min(), logits.max(), "EER", out[f"{tag}_eer_thr_scores"],
+              "unsaturated", int(((sig > 1e-6) & (sig < 1 - 1e-6)).sum()))
+    np.savez_compressed(os.path.join(HERE, "trained.npz"), **out)
 
 
 def make_eer():
@@ -205,7 +256,7 @@ def make_dlq():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["models", "eer", "blend", "dlq"]
+    which = sys.argv[1:] or ["models", "eer", "blend", "dlq", "trained"]
     if "models" in which:
         make_models()
     if "eer" in which:
@@ -214,3 +265,5 @@ if __name__ == "__main__":
         make_blend()
     if "dlq" in which:
         make_dlq()
+    if "trained" in which:
+        make_trained()

@@ -107,3 +107,51 @@ def test_precision_selection_on_the_dropin_classes(monkeypatch):
     from dfs_b200 import engine
     with pytest.raises(ValueError, match="precision must be"):
         engine._check_precision("bf16")
+
+
+def test_host_slab_validates_dtype_device_and_layout():
+    """engine._host_slab is the gate in front of dfs_score_host / dfs_group_score_host: fp32 and fp16 pass through in place, every
+    other dtype is converted to fp32 (its bytes must never be read as fp32), non-dense layouts and wrong shapes raise."""
+    from dfs_b200 import engine as E
+    x = torch.randn(3, 321, 180)
+    s = E._host_slab(x)
+    assert (s.n, s.f16, s.time_major, s.strides, s.ptr) == (3, False, 0, (57780, 180, 1), x.data_ptr())
+    s64 = E._host_slab(x.double())                                         # float64 -> converted copy, not reinterpreted
+    assert not s64.f16 and s64.keep.dtype == torch.float32 and torch.equal(s64.keep, x)
+    sbf = E._host_slab(x.bfloat16())
+    assert sbf.keep.dtype == torch.float32 and not sbf.f16
+    assert E._host_slab(np.zeros((2, 321, 180), np.float64)).keep.dtype == np.float32
+    rows = torch.randn(2, 180, 321)                                        # the reference's storage, viewed as (B,321,180)
+    sv = E._host_slab(rows.transpose(1, 2))
+    assert (sv.time_major, sv.strides) == (1, (57780, 1, 321))
+    s16 = E._host_slab(np.zeros((2, 321, 180), np.float16))
+    assert s16.f16 and s16.strides == (57780, 180, 1)
+    with pytest.raises(ValueError, match="shape"):
+        E._host_slab(torch.zeros(3, 180, 321))
+    with pytest.raises(ValueError, match="dense"):
+        E._host_slab(torch.zeros(6, 321, 180)[::2])
+    with pytest.raises(ValueError, match="dense"):
+        E._host_slab(torch.zeros(2, 321, 360)[:, :, ::2])
+    if torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="HOST features"):
+            E._host_slab(torch.zeros(1, 321, 180, device="cuda"))
+    else:
+        with pytest.raises(RuntimeError, match="HOST features"):
+            E._host_slab(torch.zeros(1, 321, 180, device="meta"))
+
+
+def test_compare_with_existing_aligns_rows_by_uttid():
+    """predict_hybrid.py:166-207: the report compares the new HYBRID predictions with an older file, rows matched by uttid
+    (a re-ordered or shorter old file must not shift the comparison); both a bare DataFrame and a submission dict are accepted."""
+    import pandas as pd
+    import predict_hybrid as ph
+    new = pd.DataFrame({"uttid": ["a", "b", "c", "d"], "predictions": [0.9, 0.2, 0.6, 0.4]})
+    old = pd.DataFrame({"uttid": ["d", "c", "a"], "predictions": [0.7, 0.1, 0.8]})
+    lines = []
+    for existing in (old, {"student_id": 1, "predictions": old}):
+        lines.clear()
+        r = ph.compare_with_existing(new, existing, out=lines.append)
+        assert r["n"] == 3 and r["agree"] == 1 and sorted(r["disagreements"]) == ["c", "d"]
+        np.testing.assert_allclose(sorted(r["diff"]), sorted([0.9 - 0.8, 0.6 - 0.1, 0.4 - 0.7]))
+        assert any("class agreement: 1/3 (33.3%)" in ln for ln in lines)
+        assert any("c: old=0.1000 new=0.6000" in ln for ln in lines)

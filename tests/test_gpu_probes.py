@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-from dfs_b200 import _native as N  # noqa: E402
+from dfs_b200 import _probes as N  # noqa: E402   (lib/libdfs_b200_probes.so: not part of the product library)
 
 
 def _bf16_bits(a):
@@ -52,3 +52,18 @@ def test_tma_window_layout(planes, rs, wrows, row0, col0):
     got = out.cpu().numpy().view(np.uint16).reshape(planes, 18, wrows, 8)
     ref = act[:, col0:col0 + 18, row0:row0 + wrows, :]
     assert np.array_equal(got, ref)
+
+
+def test_micro_benchmarks_run():
+    """The tcgen05.mma and tcgen05.ld micro-benchmarks (tools/umma_bench.py, tools/micro/tmem_ld_bench.py) return plausible cycle
+    counts: an N = 128 MMA costs more than its 64-cycle floor and less than 4x that; a TMEM read moves more than 16 B/clk/SM."""
+    lib = N.load()
+    cyc, byt = C.c_int64(), C.c_int64()
+    off = (C.c_uint32 * 32)(*([0] * 32))
+    for n_acc in (1, 2):
+        N.check(lib.dfs_probe_umma_bench(128, 32, 50, n_acc, off, off, 2304, 128, 2048, 128, 0, 0, C.byref(cyc), None), "umma_bench")
+        per = cyc.value / (50 * 32)
+        assert 60 <= per <= 256, per
+    for shape, nwarps in ((2, 4), (3, 8), (6, 4)):
+        N.check(lib.dfs_probe_tmem_ld_bench(shape, nwarps, 1, 200, 4, C.byref(cyc), C.byref(byt), None), "tmem_ld_bench")
+        assert byt.value / cyc.value >= 16.0, (shape, nwarps, byt.value / cyc.value)

@@ -1,0 +1,218 @@
+"""GPU parity, round 2: scorer groups (one upload, several models), the trained-like regime pinned by the unmodified
+reference (tests/golden/trained.npz: centred logits spanning +-20 on heterogeneous, heavy-tailed utterances), the fp16
+saturation census, NaN scores in the EER.  Everything goes through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from conftest import GOLDEN, ROOT  # noqa: E402
+import dfs_b200 as D  # noqa: E402
+from dfs_b200 import CaeScorer, Cnn1dScorer, Cnn2dScorer, DlqScorer, ScorerGroup, synthetic as syn  # noqa: E402
+from oracle import eer as oeer  # noqa: E402
+
+T = np.load(os.path.join(GOLDEN, "trained.npz"))
+REL = 1e-3      # north_star: per-utterance scores within 1e-3 relative
+EER_ABS = 1e-4  # north_star: EER within 0.01 percentage points end to end
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30)))
+
+
+def _record(name, payload):
+    """Measured parity figures next to the assertions (gpurun_out/ is brought back from the GPU box)."""
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, "parity_round2.json")
+    data = {}
+    if os.path.exists(path):
+        with open(path) as f:
+            data = json.load(f)
+    data[name] = payload
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# scorer groups
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def trio():
+    mean, std = syn.normalizer_stats(1)
+    return (Cnn2dScorer(syn.cnn2d_state(0), max_chunk=8), Cnn1dScorer(syn.cnn1d_state(0), max_chunk=16),
+            CaeScorer(syn.cae_state(0), mean, std, max_chunk=8))
+
+
+@pytest.mark.parametrize("stage", [0, 7, 16])
+def test_group_scores_equal_the_single_model_host_calls(trio, stage):
+    """dfs_group_score_host: one upload per slab, every member scores it -- the very bits of three dfs_score_host calls
+    (src/predict_hybrid.py:142-145 / src/ensemble.py:105-122 make one pass over the table per model).  37 utterances through
+    slabs of 7 / 16 (ragged last slab, ragged internal passes) and the default slab."""
+    c2, c1, ca = trio
+    x = torch.from_numpy(syn.features(37, seed=11)).pin_memory()
+    want = [c2.score_host(x, 1), c1.score_host(x, 1), ca.score_host(x)]
+    g = ScorerGroup([c2, c1, ca], stage_utts=stage)
+    assert g.stage_utts == (stage or 2368)
+    got = g.score_host(x)                                   # default flags: sigmoid, sigmoid, normaliser
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    logits = g.score_host(x, [0, 0, 1])                     # per-member flags
+    np.testing.assert_array_equal(logits[0], c2.score_host(x, 0))
+    np.testing.assert_array_equal(logits[1], c1.score_host(x, 0))
+    # the reference's row storage [B,180,321] read through the transposed view
+    rows = x.transpose(1, 2).contiguous().pin_memory()
+    for a, b in zip(g.score_host(rows.transpose(1, 2)), want):
+        np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-7)
+    # empty table
+    assert all(v.shape == (0,) for v in g.score_host(x[:0]))
+    g.close()
+
+
+def test_group_fp16_slab_and_fourth_scorer(trio):
+    c2, c1, ca = trio
+    dq = DlqScorer(syn.dlq_state(0), max_chunk=16)
+    x = torch.from_numpy(syn.features(21, seed=3))
+    x16 = x.half().pin_memory()
+    g = ScorerGroup([c2, c1, dq], stage_utts=8)
+    got = g.score_host(x16)
+    np.testing.assert_array_equal(got[0], c2.score_host(x16, 1))
+    np.testing.assert_array_equal(got[1], c1.score_host(x16, 1))
+    np.testing.assert_array_equal(got[2], dq.score(x16.float().cuda(), apply_sigmoid=True).cpu().numpy())
+    g.close()
+    with pytest.raises(ValueError):
+        ScorerGroup([])
+
+
+def test_group_rejects_bad_inputs(trio):
+    g = ScorerGroup(list(trio))
+    with pytest.raises(RuntimeError, match="HOST features"):
+        g.score_host(torch.zeros(2, 321, 180, device="cuda"))
+    with pytest.raises(ValueError):
+        g.score_host(torch.zeros(2, 321, 180), [1, 1])      # one flag per member
+    # float64 host features are converted, not reinterpreted (garbage scores without an error)
+    x = torch.from_numpy(syn.features(3, seed=5))
+    np.testing.assert_array_equal(g.score_host(x.double())[0], g.score_host(x)[0])
+    np.testing.assert_array_equal(trio[0].score_host(x.double().numpy(), 1), trio[0].score_host(x, 1))
+    g.close()
+
+
+def test_pinned_empty_roundtrip(trio):
+    a = D.pinned_empty((5, 321, 180), "float32")
+    a[...] = syn.features(5, seed=8)
+    np.testing.assert_array_equal(trio[0].score_host(a, 1), trio[0].score_host(torch.from_numpy(a.copy()).pin_memory(), 1))
+    wc = D.pinned_empty((5, 321, 180), "float32", write_combined=True)
+    wc[...] = a
+    np.testing.assert_array_equal(trio[0].score_host(wc, 1), trio[0].score_host(a, 1))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# trained-like regime, pinned by the unmodified reference (make_golden.py::make_trained)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def structured():
+    n = int(T["n"])
+    x = syn.features_structured(n, seed=int(T["seed"]))
+    assert syn.state_digest([x[:64]]) == str(T["features_sha256_first64"])
+    return torch.from_numpy(x).pin_memory()
+
+
+def _trained_case(tag, precision, structured):
+    factory, cls = (syn.cnn2d_state, Cnn2dScorer) if tag == "cnn2d" else (syn.cnn1d_state, Cnn1dScorer)
+    sd = factory(0, logit_scale=float(T[f"{tag}_scale"]), classifier_bias=float(T[f"{tag}_bias"]))
+    assert syn.state_digest(sd) == str(T[f"{tag}_sha256"])
+    sc = cls(sd, precision=precision)
+    n = structured.shape[0] if precision == "fp16" or tag == "cnn1d" else 512       # the fp32 CUDA-core 2D-CNN runs ~8 k utt/s
+    x = structured[:n].cuda()
+    logits = sc.score(x, apply_sigmoid=False).cpu().numpy()
+    scores = sc.score(x, apply_sigmoid=True).cpu().numpy()
+    sat = sc.saturation_count()
+    ref_l, ref_s, lab = T[f"{tag}_logits"][:n], T[f"{tag}_sigmoid"][:n], T[f"{tag}_labels"][:n]
+    open_ = (ref_s > 1e-6) & (ref_s < 1 - 1e-6)                     # sigmoids that fp32 has not rounded to 0 / 1
+    rec = dict(n=int(n), n_unsaturated=int(open_.sum()), logit_range=[float(ref_l.min()), float(ref_l.max())],
+               max_abs_logit_err=float(np.max(np.abs(logits - ref_l))), max_rel_sigmoid_err_unsaturated=_rel(scores[open_], ref_s[open_]),
+               max_rel_sigmoid_err_all=_rel(scores, ref_s), fp16_saturated=sat[0], fp16_nonfinite=sat[1])
+    eer_ref_s = oeer.calculate_eer(np.array(ref_s.tolist()), lab)
+    eer_ref_l = oeer.calculate_eer(np.array(ref_l.tolist()), lab)
+    if n == int(T["n"]):                                            # the oracle restatement agrees with the reference's own numbers
+        assert tuple(T[f"{tag}_eer_thr_scores"]) == eer_ref_s and tuple(T[f"{tag}_eer_thr_logits"]) == eer_ref_l
+    eer_s = D.calculate_eer(np.array(scores.tolist()), lab)
+    eer_l = D.calculate_eer(np.array(logits.tolist()), lab)
+    rec.update(eer_ref=eer_ref_s[0], eer_dev=eer_s[0], eer_delta_pp=100 * abs(eer_s[0] - eer_ref_s[0]),
+               eer_logits_ref=eer_ref_l[0], eer_logits_dev=eer_l[0], eer_logits_delta_pp=100 * abs(eer_l[0] - eer_ref_l[0]),
+               rank_changes=int((np.argsort(logits, kind="stable") != np.argsort(ref_l, kind="stable")).sum()))
+    _record(f"trained_like/{tag}/{precision}", rec)
+    return rec
+
+
+@pytest.mark.parametrize("tag", ["cnn2d", "cnn1d"])
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_trained_like_regime_against_the_reference(tag, precision, structured):
+    """The regime where operand rounding matters: reference logits centred on 0 and spanning about +-20 over
+    2,048 heterogeneous utterances with outliers to -61 / +86.  Gates (north_star): every sigmoid that fp32 has not saturated
+    within 1e-3 relative; EER on the scores and on the logits within 0.01 pp of the reference's; no fp16 saturation."""
+    r = _trained_case(tag, precision, structured)
+    assert r["fp16_saturated"] == 0 and r["fp16_nonfinite"] == 0
+    assert r["n_unsaturated"] >= 0.9 * r["n"]
+    assert r["max_rel_sigmoid_err_unsaturated"] <= REL, r
+    assert abs(r["eer_dev"] - r["eer_ref"]) <= EER_ABS, r
+    assert abs(r["eer_logits_dev"] - r["eer_logits_ref"]) <= EER_ABS, r
+
+
+def test_trained_like_scores_through_the_group_host_path(structured):
+    """End to end from host memory: the group upload of the structured table reproduces the device-resident scores."""
+    sd2 = syn.cnn2d_state(0, logit_scale=float(T["cnn2d_scale"]), classifier_bias=float(T["cnn2d_bias"]))
+    sd1 = syn.cnn1d_state(0, logit_scale=float(T["cnn1d_scale"]), classifier_bias=float(T["cnn1d_bias"]))
+    c2, c1 = Cnn2dScorer(sd2), Cnn1dScorer(sd1)
+    n = 1000                                                         # 592 (ramp slab) + 408: two slabs, ragged passes
+    g = ScorerGroup([c2, c1])
+    s2, s1 = g.score_host(structured[:n])
+    np.testing.assert_array_equal(s2, c2.score(structured[:n].cuda(), apply_sigmoid=True).cpu().numpy())
+    np.testing.assert_array_equal(s1, c1.score(structured[:n].cuda(), apply_sigmoid=True).cpu().numpy())
+    open_ = (T["cnn2d_sigmoid"][:n] > 1e-6) & (T["cnn2d_sigmoid"][:n] < 1 - 1e-6)
+    assert _rel(s2[open_], T["cnn2d_sigmoid"][:n][open_]) <= REL
+    g.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# heavy tails and the saturation census
+# ---------------------------------------------------------------------------------------------------------------------
+def test_saturation_census_counts_clipped_values():
+    """Real features reach -61 / +86 (model_prediction_report.md:24-29): nothing may clip there.  Features blown up by 1e4 do
+    exceed fp16's 65504 and the census must say so instead of the clipping staying silent."""
+    x = torch.from_numpy(syn.features_structured(6, seed=77)).cuda()
+    assert float(x.abs().max()) >= 60.0
+    mean, std = syn.normalizer_stats(1)
+    for sc in (Cnn2dScorer(syn.cnn2d_state(0), max_chunk=8), Cnn1dScorer(syn.cnn1d_state(0), max_chunk=16),
+               CaeScorer(syn.cae_state(0), mean, std, max_chunk=8)):
+        sc.score(x)
+        assert sc.saturation_count() == (0, 0), type(sc).__name__
+        sc.score(x * 1e4)
+        sat, nonfin = sc.saturation_count()
+        assert sat > 0 and nonfin == 0, (type(sc).__name__, sat, nonfin)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# EER edge semantics: NaN scores (np.argsort puts them last, scripts/evaluation.py:11)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_eer_with_nan_scores_follows_numpy(dtype):
+    rng = np.random.Generator(np.random.PCG64(5))
+    n = 5000
+    s = rng.random(n).astype(dtype)
+    lab = (rng.random(n) < 0.3 + 0.4 * s).astype(np.int64)
+    s[rng.integers(0, n, 40)] = np.nan
+    s[7] = -np.nan                                            # sign bit set: still sorted last by numpy
+    want = oeer.calculate_eer(s, lab, kind="stable")
+    for method in ("sort", "select"):
+        got = D.calculate_eer(s, lab, method=method)
+        assert got[0] == want[0], method
+        assert got[1] == want[1] or (np.isnan(got[1]) and np.isnan(want[1])), method
+    d = D.eer_details(s, lab, want_perm=True, want_sorted=True)
+    perm = d["perm"].cpu().numpy().astype(np.int64) & 0x7fffffff
+    np.testing.assert_array_equal(perm, np.argsort(s, kind="stable"))
+    assert np.isnan(d["sorted"].cpu().numpy()[-41:]).all()

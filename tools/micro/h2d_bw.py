@@ -1,25 +1,133 @@
-import torch, time
-n = 2 * 1024**3 // 4
-h = torch.empty(n, dtype=torch.float32, pin_memory=True); h.fill_(1.0)
-d = torch.empty(n, dtype=torch.float32, device="cuda")
-for size_mb in (96, 512, 2048):
-    m = size_mb * 1024**2 // 4
-    for _ in range(2):
-        d[:m].copy_(h[:m], non_blocking=True)
+"""Pinned-host -> device copy ceiling of this host with 1 ... N GPUs copying AT ONCE (one process per GPU).
+
+    python tools/micro/h2d_bw.py                                              # one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29517 tools/micro/h2d_bw.py
+
+Why: the end-to-end scoring number (bench.py `e2e`) is bound by how fast the host can feed fp32 features (231 KB per
+utterance), and on the 8-GPU boxes of this pool that rate does not scale with the GPU count (round 1: 53 GB/s for one GPU,
+112 GB/s for four, 184 GB/s for eight).  This prints, per allocation / affinity variant, the AGGREGATE GB/s of all ranks copying
+concurrently -- the ceiling `e2e` is reported against -- so that what a builder can change (how the slab is allocated, which
+cores the rank runs on, how many copies are in flight) is measured rather than guessed.
+
+Variants: torch pin_memory | cudaHostAlloc portable (dfs_pinned_alloc) | + write-combined | rank pinned to its own share of the
+cores before allocating and touching the slab (first-touch placement) | two copy streams per rank | 24 MB vs 96 MB vs 547 MB pieces.
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "deep-fake-audio-classifier_b200"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import dfs_b200 as D  # noqa: E402
+
+rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+UTT = 321 * 180 * 4
+N_UTT = 4096                                   # 947 MB slab per rank
+dst = torch.empty(2 * 2368 * UTT // 4, dtype=torch.float32, device=dev)
+streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+
+
+def barrier():
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
+
+
+def measure(host, piece_utts, n_streams=1, seconds=0.6):
+    """host: 1-D fp32 torch tensor over pinned memory.  Aggregate GB/s of all ranks, timed with CUDA events, max over ranks."""
+    piece = piece_utts * UTT // 4
+    n = host.numel()
+
+    def sweep():
+        k = 0
+        for i in range(0, n, piece):
+            m = min(piece, n - i)
+            with torch.cuda.stream(streams[k % n_streams]):
+                dst[(k & 1) * piece:(k & 1) * piece + m].copy_(host[i:i + m], non_blocking=True)
+            k += 1
+
+    sweep()
+    barrier()
     t0 = time.perf_counter()
-    reps = max(2, 4096 // size_mb)
-    for _ in range(reps):
-        d[:m].copy_(h[:m], non_blocking=True)
+    sweep()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    print(f"H2D {size_mb} MB x{reps}: {reps * m * 4 / dt / 1e9:.1f} GB/s")
-# two streams concurrently
-s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-m = 512 * 1024**2 // 4
-torch.cuda.synchronize(); t0 = time.perf_counter()
-for _ in range(4):
-    with torch.cuda.stream(s1): d[:m].copy_(h[:m], non_blocking=True)
-    with torch.cuda.stream(s2): d[m:2*m].copy_(h[m:2*m], non_blocking=True)
-torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print(f"H2D 2 streams: {8 * m * 4 / dt / 1e9:.1f} GB/s")
+    reps = max(2, int(seconds / max(time.perf_counter() - t0, 1e-4)))
+    t = torch.tensor([float(reps)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    reps = int(t.item())
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(reps):
+        sweep()
+    for s in streams[:n_streams]:
+        torch.cuda.current_stream().wait_stream(s)
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return n * 4 * reps * world / (float(ms.item()) * 1e-3) / 1e9
+
+
+def torch_view(arr):
+    return torch.from_numpy(arr.reshape(-1))
+
+
+results = {}
+
+
+def report(name, gbs):
+    results[name] = gbs
+    if rank == 0:
+        print(f"{name:64s} {gbs:8.1f} GB/s aggregate  {gbs / world:7.1f} per GPU  = {gbs * 1e9 / UTT / 1e3:8.1f} k utt/s", flush=True)
+
+
+if rank == 0:
+    print(f"# pinned host -> device, {world} rank(s) copying at once; {os.cpu_count()} host cores; slab {N_UTT * UTT / 1e6:.0f} MB per rank", flush=True)
+host_t = torch.empty(N_UTT * UTT // 4, dtype=torch.float32, pin_memory=True)
+host_t.fill_(1.0)
+for piece in (104, 416, 2368):
+    report(f"torch pin_memory, pieces of {piece} utterances ({piece * UTT / 1e6:.0f} MB)", measure(host_t, piece))
+report("torch pin_memory, 416-utterance pieces, 2 copy streams", measure(host_t, 416, n_streams=2))
+del host_t
+a = D.pinned_empty((N_UTT * UTT // 4,), "float32")
+a[...] = 1.0
+report("cudaHostAlloc portable (dfs_pinned_alloc), 416-utterance pieces", measure(torch_view(a), 416))
+del a
+wc = D.pinned_empty((N_UTT * UTT // 4,), "float32", write_combined=True)
+wc[...] = 1.0
+report("cudaHostAlloc write-combined, 416-utterance pieces", measure(torch_view(wc), 416))
+del wc
+# rank pinned to its own share of the host cores BEFORE the slab is allocated and first touched
+cores = sorted(os.sched_getaffinity(0))
+share = max(1, len(cores) // world)
+mine = cores[rank * share:(rank + 1) * share] or cores
+try:
+    os.sched_setaffinity(0, mine)
+    b = D.pinned_empty((N_UTT * UTT // 4,), "float32")
+    b[...] = 1.0
+    report(f"rank pinned to {len(mine)} core(s) before alloc + first touch, 416-utterance pieces", measure(torch_view(b), 416))
+    del b
+    os.sched_setaffinity(0, cores)
+except OSError as e:
+    if rank == 0:
+        print("# sched_setaffinity not permitted:", e)
+if rank == 0:
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, f"h2d_bw_n{world}.json"), "w") as f:
+        json.dump({"world": world, "cores": os.cpu_count(), "gbs_aggregate": results}, f, indent=1)
+if world > 1:
+    dist.destroy_process_group()

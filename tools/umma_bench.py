@@ -8,20 +8,43 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "deep-fake-audio-classifier_b200"))
 import torch  # noqa: E402
 
-from dfs_b200 import _native as N  # noqa: E402
+from dfs_b200 import _probes as N  # noqa: E402
 
 torch.zeros(1, device="cuda")
 lib = N.load()
 
 
-def run(name, n, a_off, b_off, a_lbo, a_sbo, b_lbo, b_sbo, layout=0, base=0, iters=200):
+def cycles(n, a_off, b_off, a_lbo, a_sbo, b_lbo, b_sbo, layout=0, base=0, iters=200, n_acc=1):
     nm = len(a_off)
     A = (C.c_uint32 * nm)(*a_off)
     B = (C.c_uint32 * nm)(*b_off)
     cyc = C.c_int64()
-    N.check(lib.dfs_probe_umma_bench(n, nm, iters, A, B, a_lbo, a_sbo, b_lbo, b_sbo, layout, base, C.byref(cyc), None), name)
-    per = cyc.value / (iters * nm)
-    print(f"{name:58s} N={n:3d} nmma={nm:2d}  {per:7.1f} cyc/MMA   ideal {128 * n / 256:5.1f}")
+    N.check(lib.dfs_probe_umma_bench(n, nm, iters, n_acc, A, B, a_lbo, a_sbo, b_lbo, b_sbo, layout, base, C.byref(cyc), None), "umma_bench")
+    return cyc.value / iters
+
+
+def run(name, n, a_off, b_off, a_lbo, a_sbo, b_lbo, b_sbo, layout=0, base=0, iters=200, n_acc=1):
+    per = cycles(n, a_off, b_off, a_lbo, a_sbo, b_lbo, b_sbo, layout, base, iters, n_acc) / len(a_off)
+    print(f"{name:58s} N={n:3d} nmma={len(a_off):2d} acc={n_acc}  {per:7.1f} cyc/MMA   ideal {128 * n / 256:5.1f}")
+
+
+def sweep(name, n, b_lbo, accs=(1, 2), nmmas=(8, 16, 32, 64, 96)):
+    """Rounds of nmma MMAs with one commit + wait per round: cycles(round) = fixed + nmma * per_mma.  The slope between the two
+    longest rounds is the steady-state cost of one MMA, the intercept the commit / wait / pipeline-fill latency that a
+    per-round average (what round 1 reported) smears over the MMAs."""
+    for n_acc in accs:
+        if n_acc * n > 512:
+            continue
+        pts = [(m, cycles(n, [0] * m, [0] * m, 18 * 8 * 16, 128, b_lbo, 128, n_acc=n_acc)) for m in nmmas]
+        (m0, c0), (m1, c1) = pts[-2], pts[-1]
+        slope = (c1 - c0) / (m1 - m0)
+        print(f"{name:40s} N={n:3d} acc={n_acc}  " + "  ".join(f"{m}:{c / m:6.1f}" for m, c in pts) +
+              f"   slope {slope:6.1f} cyc/MMA  fixed {c1 - slope * m1:6.0f} cyc   floor {128 * n / 256:5.1f}")
+
+
+print("# nmma sweep (cycles per MMA averaged over a round of nmma; slope = steady-state cost, fixed = per-round latency)")
+for n_, lbo_ in ((64, 1024), (128, 2048), (256, 4096)):
+    sweep("none aligned, fixed A/B address", n_, lbo_)
 
 
 # --- no swizzle, conv3-like: CIN=64 (4 k-steps), WROWS=10, plane = 18*10*16 = 2880 B
