@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool", type=int, default=50000, help="utterances resident per GPU and scored per step (x 20 steps = 1 M)")
     ap.add_argument("--chunk", type=int, default=0, help="utterances per internal pass (0 = library default 416)")
-    ap.add_argument("--e2e-pool", type=int, default=8320, help="utterances in pinned host memory for the e2e legs (one step = one call over all of them)")
+    ap.add_argument("--e2e-pool", type=int, default=16640, help="utterances in pinned host memory for the e2e legs (one step = one call over all of them)")
     ap.add_argument("--e2e-seconds", type=float, default=1.2, help="minimum timed duration of the e2e leg (and >= 10 steps)")
     ap.add_argument("--leg-seconds", type=float, default=1.2, help="minimum timed duration of each side-workload leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libdfs_b200.so")
 OUT_PROBES = os.path.join(HERE, "lib", "libdfs_b200_probes.so")   # bring-up probes + micro-benchmarks (tests / tools only)
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "conv_tc.cu", "conv1_tc.cu", "conv12_fused.cu", "cae_tc.cu", "cae_enc1_tc.cu", "cnn1d_tc.cu", "cnn1d_l1_fused.cu", "cnn2d.cu", "cnn2d_fp32.cu", "simt_models.cu", "eer.cu", "synth.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv1_tc.cu", "cae_tc.cu", "cae_enc1_tc.cu", "cnn1d_tc.cu", "cnn1d_l1_fused.cu", "cnn1d_fused.cu", "cnn2d.cu", "cnn2d_fp32.cu", "simt_models.cu", "eer.cu", "synth.cu"]
 PROBE_SOURCES = ["probe.cu", "conv_tc.cu"]   # probe.cu uses conv_tc.cu's tensor-map helper
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
@@ -63,10 +63,12 @@ def build(force=False, verbose=False):
 def _link(out, objs):
     # --cudart shared: the artefact binds to libcudart.so at load time (torch ships one) instead of carrying a static copy of the
     # whole runtime, entry points this code never calls included; -Bsymbolic: each library resolves its own helpers internally
-    r = subprocess.run([NVCC, "-shared", "--cudart", "shared", "-Xlinker", "-Bsymbolic", "-o", out, *objs, "-lcuda",
+    tmp = out + ".tmp"
+    r = subprocess.run([NVCC, "-shared", "--cudart", "shared", "-Xlinker", "-Bsymbolic", "-o", tmp, *objs, "-lcuda",
                         "-gencode", "arch=compute_100a,code=sm_100a"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, out)    # atomic: a reader (or a snapshot of the tree) never sees a half-written library
 
 
 if __name__ == "__main__":

@@ -91,6 +91,9 @@ static ConvParams c1d_params(const Cnn1dTcState* s, int layer, int n_utts) {
 int launch_cnn1d_tc(const Cnn1dTcState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, int apply_sigmoid, float* out, int num_sms,
                     cudaStream_t stream) {
   if (n_utts <= 0) return DFS_OK;
+  if (s->fused && cnn1d_l1_fused_supported(x, sn, st, sf))   // the whole network in one kernel: HBM traffic = the fp32 input read
+    return launch_cnn1d_fused(x, sn, n_utts, s->w1_fused, s->w[1], s->w[2], s->bias[0], s->bias[1], s->bias[2], s->fcw_host, s->fcb, apply_sigmoid,
+                              out, num_sms, stream);
   if (s->l1_fused && cnn1d_l1_fused_supported(x, sn, st, sf)) {
     DFS_PROPAGATE(launch_cnn1d_l1_fused(x, sn, n_utts, s->w[0], s->bias[0], s->act[1], num_sms, stream));
   } else {

@@ -11,7 +11,7 @@
 // R's two 16-byte K chunks are xT rows R and R+1, i.e. the SWIZZLE_NONE K-major descriptor has
 // LBO = 16 B, SBO = 128 B, and the feature tap kw is a +-41-row shift of the start address.  One
 // 1-D bulk copy of 212 rows x 16 B (3.4 KB) feeds a 128-row tile: 3 tcgen05.mma (M=128, N=256, K=16)
-// produce 1024 conv outputs x 32 channels.  Epilogue: +bias, ReLU, add the two time steps of a pool
+// (x 2: every weight enters as fp16 value + fp16 residual, see api.cu) produce 1024 conv outputs x 32 channels.  Epilogue: +bias, ReLU, add the two time steps of a pool
 // window (columns n and n+32 of the same thread -- no shuffles), fp16, FT8 stores.
 // Issued MACs are 3.5x the useful ones (Toeplitz zeros) but run ~30x faster than CUDA-core FMAs.
 //
@@ -29,7 +29,8 @@ constexpr int kC1WinRows = 128 + 2 * kXtBlocks + 2;   // 212
 constexpr int kC1WinB = kC1WinRows * 16;               // 3392
 constexpr int kC1WinBAl = 3456;
 constexpr int kC1Stages = 4;
-constexpr int kC1WgtB = 3 * 256 * 16 * 2;              // 24576
+constexpr int kC1WgtImgB = 3 * 256 * 16 * 2;           // 24576: one image [kw][chunk 2][256][8]
+constexpr int kC1WgtB = 2 * kC1WgtImgB;                // value image + residual image (w = hi + lo)
 constexpr int kC1EpiWarps = 16;
 constexpr int kC1Threads = (kC1EpiWarps + 3) * 32;     // 608
 constexpr int kC1StageWarpB = 2 * 128 * 16;              // epilogue staging per warp: 2 planes x 128 chunks x 16 B
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) conv1_prep_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------
 struct Conv1TcParams {
   const uint16_t* xt;      // xT rows (16 B each)
-  const uint16_t* wpack;   // [kw][chunk 2][n 256][8] fp16 Toeplitz weights
+  const uint16_t* wpack;   // [hi | lo][kw][chunk 2][n 256][8] fp16 Toeplitz weights: value and rounding residual
   float bias[32];          // 0.5 * folded bias
   int n_tiles;
   int n_utts;
@@ -143,9 +144,12 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (kC1WinBAl >> 4));
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-          umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kw * kXtBlocks), a_hi, b_lo0 + (uint32_t)(kw * (8192 >> 4)), b_hi, idesc,
-                        kw != 0 ? 1u : 0u);
+        for (int part = 0; part < 2; ++part) {   // weight value, then weight residual
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+            umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kw * kXtBlocks), a_hi,
+                          b_lo0 + (uint32_t)((part * kC1WgtImgB + kw * 8192) >> 4), b_hi, idesc, (part | kw) != 0 ? 1u : 0u);
+        }
         umma_commit(&tfull[acc]);
         umma_commit(&empty[stage]);
       }
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
   }
 }
 
-// fp32 strided features -> xT (the A operand image of conv1_tc_kernel and of conv12_fused_kernel)
+// fp32 strided features -> xT (the A operand image of conv1_tc_kernel)
 int launch_conv1_prep(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, cudaStream_t stream) {
   if (n_utts <= 0) return DFS_OK;
   if (sf == 1) {   // feature-contiguous storage: transpose through shared memory (xt_prep.cuh)

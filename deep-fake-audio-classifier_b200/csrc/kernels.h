@@ -20,9 +20,6 @@ int launch_cnn2d_conv3_tc(const CUtensorMap& tmap_act2, const uint16_t* wpack, c
 // ---- conv1_tc.cu (CNN2D block 1 as a Toeplitz-in-time tcgen05 GEMM) ----
 int64_t conv1_xt_rows(int64_t n_utts);   // 16-byte rows of the fp16 time-major feature copy for n utterances
 int launch_conv1_prep(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, cudaStream_t stream);
-// conv12_fused.cu: conv1 + conv2 in one kernel (act1 stays in shared memory); inputs as launch_conv1_tc / launch_cnn2d_conv2_tc
-int launch_cnn2d_conv12_fused(const uint16_t* xt, const uint16_t* w1pack, const float* b1_half, const uint16_t* w2pack, const float* b2_half, int n_utts,
-                              ActBuf act2, int num_sms, cudaStream_t stream);
 int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, const uint16_t* wpack, const float* bias_half,
                     ActBuf out, int num_sms, cudaStream_t stream);
 
@@ -94,6 +91,9 @@ struct Cnn1dTcState {
   const float* fcw;       // classifier weight (128) on the device
   float fcb;
   int l1_fused;           // 1 (default) = layer 1 converts the fp32 rows in flight (cnn1d_l1_fused.cu) when the layout allows
+  int fused;              // 1 = the whole network in ONE kernel (cnn1d_fused.cu) when the layout allows; 0 = one kernel per layer
+  const uint16_t* w1_fused;  // layer-1 weights with 32 rows per K chunk, [tap][24][32][8] (the template's image pads them to 64)
+  float fcw_host[128];    // classifier weight on the host: rides in the fused kernel's parameter space
 };
 // ---- StatsPool detector (dlqueen_model.py) on the conv1d template, cnn1d_tc.cu ----
 struct DlqState {
@@ -113,6 +113,10 @@ int dlq_make_maps(DlqState* s);
 int launch_dlq(const DlqState* s, const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, const int32_t* lengths_dev, int apply_sigmoid,
                float* out, int num_sms, cudaStream_t stream);
 
+// ---- cnn1d_fused.cu: the three conv layers, the time mean and the classifier in one kernel (dense fp32 input, as cnn1d_l1_fused) ----
+int launch_cnn1d_fused(const float* x, int64_t sn, int n_utts, const uint16_t* w1, const uint16_t* w2, const uint16_t* w3, const float* b1,
+                       const float* b2, const float* b3, const float* fcw_host, float fcb, int apply_sigmoid, float* out, int num_sms,
+                       cudaStream_t stream);
 // ---- cnn1d_l1_fused.cu ----
 bool cnn1d_l1_fused_supported(const float* x, int64_t sn, int64_t st, int64_t sf);
 int launch_cnn1d_l1_fused(const float* x, int64_t sn, int n_utts, const uint16_t* wpack, const float* bias, ActBuf out, int num_sms, cudaStream_t stream);

@@ -141,6 +141,10 @@ __global__ void __launch_bounds__(128) probe_umma_bench_kernel(const __grid_cons
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + A_BYTES);
     uint64_t* ad = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES + 64);   // descriptor tables in shared memory
     uint64_t* bd = ad + kBenchMaxMma;
+    // accumulator of MMA i = i mod n_acc (n_acc is 1, 2 or 4): a mask and a shift, so that the issue loop stays as short as the conv
+    // kernels' (an integer division per MMA made the ISSUING THREAD the bottleneck: 148 cycles per MMA for every N)
+    const uint32_t accmask = (uint32_t)p.n_acc - 1u;
+    const uint32_t nshift = (uint32_t)__ffs(p.n) - 1u;
     const int nacc = p.n_acc;
     for (int i = 0; i < p.nmma; ++i) {
       const uint32_t aa = a0 + p.a_off[i], bb = b0 + p.b_off[i];
@@ -149,20 +153,74 @@ __global__ void __launch_bounds__(128) probe_umma_bench_kernel(const __grid_cons
     }
     uint32_t phase = 0;
     // warm-up round
-    for (int i = 0; i < p.nmma; ++i) umma_bf16(tmem_base + (uint32_t)((i % nacc) * p.n), ad[i], bd[i], idesc, i >= nacc);
+    for (int i = 0; i < p.nmma; ++i) umma_bf16(tmem_base + (((uint32_t)i & accmask) << nshift), ad[i], bd[i], idesc, i >= nacc);
     umma_commit(bar);
     mbar_wait(bar, phase, 11);
     phase ^= 1;
     const long long t0 = clock64();
     for (int it = 0; it < p.iters; ++it) {
 #pragma unroll 4
-      for (int i = 0; i < p.nmma; ++i) umma_bf16(tmem_base + (uint32_t)((i % nacc) * p.n), ad[i], bd[i], idesc, i >= nacc);
+      for (int i = 0; i < p.nmma; ++i) umma_bf16(tmem_base + (((uint32_t)i & accmask) << nshift), ad[i], bd[i], idesc, i >= nacc);
       umma_commit(bar);
       mbar_wait(bar, phase, 12);
       phase ^= 1;
     }
     const long long t1 = clock64();
     cycles_out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Lean issue loop: ONE fixed A / B descriptor pair held in registers, the MMAs of a round unrolled by four with compile-time
+// accumulator offsets -- no shared-memory table loads, no index arithmetic between two tcgen05.mma.  What remains is the tensor
+// pipe's own cost per MMA (the table-driven loop above spends ~10 dependent instructions of the issuing thread per MMA, which is
+// of the same order as an N <= 128 MMA itself).
+template <int NACC>
+__global__ void __launch_bounds__(128) probe_umma_lean_kernel(const __grid_constant__ UmmaBenchParams p, long long* __restrict__ cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int A_BYTES = 96 * 1024, B_BYTES = 64 * 1024;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < (A_BYTES + B_BYTES) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if ((threadIdx.x >> 5) == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, p.n);
+    const uint64_t ad = umma_smem_desc(smem_u32(smem) + p.a_off[0], p.a_lbo, p.a_sbo) | ((uint64_t)p.layout << 61);
+    const uint64_t bd = umma_smem_desc(smem_u32(smem + A_BYTES) + p.b_off[0], p.b_lbo, p.b_sbo) | ((uint64_t)p.layout << 61);
+    const uint32_t n = (uint32_t)p.n;
+    const int groups = p.nmma / 4;
+    uint32_t phase = 0;
+    long long t0 = 0;
+    for (int it = -1; it < p.iters; ++it) {     // round -1 = warm-up
+      if (it == 0) t0 = clock64();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) umma_bf16(tmem_base + (uint32_t)(u % NACC) * n, ad, bd, idesc, u >= NACC ? 1u : 0u);
+      for (int g = 1; g < groups; ++g) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) umma_bf16(tmem_base + (uint32_t)(u % NACC) * n, ad, bd, idesc, 1u);
+      }
+      umma_commit(bar);
+      mbar_wait(bar, phase, 15);
+      phase ^= 1;
+    }
+    cycles_out[0] = clock64() - t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -234,8 +292,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe_umma_benc
 int probe_umma_bench(int n, int nmma, int iters, int n_acc, const uint32_t* a_off, const uint32_t* b_off, uint32_t a_lbo, uint32_t a_sbo,
                      uint32_t b_lbo, uint32_t b_sbo, uint32_t layout, uint32_t use_base_offset, long long* cycles_host, cudaStream_t stream) {
   DFS_REQUIRE(n % 16 == 0 && n >= 16 && n <= 256 && nmma >= 1 && nmma <= kBenchMaxMma && iters >= 1, DFS_ERR_INVALID, "probe_umma_bench: bad argument");
-  DFS_REQUIRE(n_acc >= 1 && n_acc * n <= 512 && (!(use_base_offset & 2) || n_acc == 1), DFS_ERR_INVALID,
-              "probe_umma_bench: n_acc accumulators of n columns must fit the 512 TMEM columns (pairs: n_acc = 1)");
+  DFS_REQUIRE((n_acc == 1 || n_acc == 2 || n_acc == 4) && n_acc * n <= 512 && (n & (n - 1)) == 0 && (!(use_base_offset & 2) || n_acc == 1),
+              DFS_ERR_INVALID, "probe_umma_bench: n a power of two, n_acc in {1, 2, 4} accumulators of n columns within the 512 TMEM columns (pairs: n_acc = 1)");
   UmmaBenchParams p{};
   p.n = n; p.nmma = nmma; p.iters = iters; p.n_acc = n_acc;
   for (int i = 0; i < nmma; ++i) { p.a_off[i] = a_off[i]; p.b_off[i] = b_off[i]; }
@@ -244,7 +302,19 @@ int probe_umma_bench(int n, int nmma, int iters, int n_acc, const uint32_t* a_of
   DFS_CUDA_CHECK(cudaMalloc(&d, 8));
   const int smem = 160 * 1024 + 64 + 2 * kBenchMaxMma * 8;
   DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  if (use_base_offset & 2) {   // bit 1: run on a CTA pair (cta_group::2); n is the N of the pair's MMA
+  if (use_base_offset & 4) {   // bit 2: lean issue loop (fixed descriptors in registers, nmma a multiple of 4)
+    DFS_REQUIRE(nmma % 4 == 0, DFS_ERR_INVALID, "probe_umma_bench: the lean loop issues the MMAs in groups of four");
+    if (n_acc == 1) {
+      DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_umma_lean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      probe_umma_lean_kernel<1><<<1, 128, smem, stream>>>(p, d);
+    } else if (n_acc == 2) {
+      DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_umma_lean_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      probe_umma_lean_kernel<2><<<1, 128, smem, stream>>>(p, d);
+    } else {
+      DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_umma_lean_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      probe_umma_lean_kernel<4><<<1, 128, smem, stream>>>(p, d);
+    }
+  } else if (use_base_offset & 2) {   // bit 1: run on a CTA pair (cta_group::2); n is the N of the pair's MMA
     DFS_CUDA_CHECK(cudaFuncSetAttribute(probe_umma_bench_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     probe_umma_bench_pair_kernel<<<2, 128, smem, stream>>>(p, d);
   } else {

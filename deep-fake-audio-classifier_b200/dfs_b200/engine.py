@@ -119,7 +119,7 @@ class _Scorer:
         converted to fp32 first; CUDA tensors are rejected (use score()).  Returns numpy fp32 (B,)."""
         torch = _require_cuda()
         slab = _host_slab(feats)
-        out = torch.empty(slab.n, dtype=torch.float32, pin_memory=True)
+        out = _pinned_result(self, slab.n, 1)[0]
         with torch.cuda.device(self.device_index):
             stream = _stream_ptr(torch, self._device(torch))
             if slab.f16:
@@ -129,7 +129,18 @@ class _Scorer:
                 f = N.Features(slab.ptr, slab.n, *slab.strides)
                 N.check(self._lib.dfs_score_host(self._h, C.byref(f), int(flag), C.c_void_p(out.data_ptr()), stream), "dfs_score_host")
         del slab
-        return out.numpy()
+        return out.numpy().copy()
+
+
+def _pinned_result(owner, n, m):
+    """m pinned fp32 result vectors of n scores, kept on `owner` between calls: cudaHostAlloc costs ~1 ms per call, more than the
+    D2H copy it serves.  Callers hand out copies, never these buffers."""
+    import torch
+    cache = getattr(owner, "_result_cache", None)
+    if cache is None or cache[0].numel() < n or len(cache) < m:
+        cache = [torch.empty(max(n, 1), dtype=torch.float32, pin_memory=True) for _ in range(m)]
+        owner._result_cache = cache
+    return [c[:n] for c in cache[:m]]
 
 
 class _HostSlab:
@@ -220,7 +231,7 @@ class ScorerGroup:
         if len(flags) != len(self.scorers):
             raise ValueError("one flag per scorer")
         m = len(self.scorers)
-        outs = [torch.empty(slab.n, dtype=torch.float32, pin_memory=True) for _ in range(m)]
+        outs = _pinned_result(self, slab.n, m)
         optr = (C.c_void_p * m)(*[o.data_ptr() for o in outs])
         fl = (C.c_int * m)(*flags)
         dev = torch.device("cuda", self.device_index)
@@ -233,7 +244,7 @@ class ScorerGroup:
                 f = N.Features(slab.ptr, slab.n, *slab.strides)
                 N.check(self._lib.dfs_group_score_host(self._h, C.byref(f), fl, optr, stream), "dfs_group_score_host")
         del slab
-        return [o.numpy() for o in outs]
+        return [o.numpy().copy() for o in outs]
 
 
 def pinned_empty(shape, dtype="float32", write_combined: bool = False):

@@ -227,29 +227,6 @@ def test_large_batches_across_default_pass_sizes_vs_torch_oracle():
     assert _rel(DlqScorer(syn.dlq_state(0)).score(x, apply_sigmoid=True).cpu().numpy(), ref) <= REL
 
 
-def test_cnn2d_fused_conv1_conv2_equals_separate_kernels():
-    """conv12_fused.cu (act1 stays in shared memory) against conv1_tc + conv_tc<PAIR> through HBM: same operands, same
-    MMA order, same epilogue formulas => the very same bits, for contiguous and transposed storage and ragged passes."""
-    x = torch.from_numpy(syn.features(23, seed=17)).cuda()
-    xt = x.transpose(1, 2).contiguous().transpose(1, 2)
-    for chunk in (8, 32):
-        sc = Cnn2dScorer(syn.cnn2d_state(0), max_chunk=chunk)
-        for feats in (x, xt):
-            sc.set_option("conv12_fused", 0)
-            plain, emb0 = sc.score(feats, return_embedding=True)
-            sc.set_option("conv12_fused", 1)
-            fused, emb1 = sc.score(feats, return_embedding=True)
-            torch.cuda.synchronize()
-            np.testing.assert_array_equal(fused.cpu().numpy(), plain.cpu().numpy())
-            np.testing.assert_array_equal(emb1.cpu().numpy(), emb0.cpu().numpy())
-            again = sc.score(feats)
-            np.testing.assert_array_equal(again.cpu().numpy(), fused.cpu().numpy())
-    ref = onp.sigmoid(onp.cnn2d_forward(syn.cnn2d_state(0), x[:4].cpu().numpy())[:, 0])
-    sc = Cnn2dScorer(syn.cnn2d_state(0))
-    sc.set_option("conv12_fused", 1)
-    assert _rel(sc.score(x[:4], apply_sigmoid=True).cpu().numpy(), ref) <= REL
-
-
 def test_cnn2d_fp32_precision_mode_tracks_the_reference_ranks(feats):
     """Option "precision" = 1 (csrc/cnn2d_fp32.cu): fp32 operands and accumulation like the reference's CPU path.  Logits
     agree with the reference to fp32 round-off (the tcgen05 path: ~5e-5 absolute), and on 256 utterances of the bench's data

@@ -28,14 +28,14 @@ def run(name, n, a_off, b_off, a_lbo, a_sbo, b_lbo, b_sbo, layout=0, base=0, ite
     print(f"{name:58s} N={n:3d} nmma={len(a_off):2d} acc={n_acc}  {per:7.1f} cyc/MMA   ideal {128 * n / 256:5.1f}")
 
 
-def sweep(name, n, b_lbo, accs=(1, 2), nmmas=(8, 16, 32, 64, 96)):
+def sweep(name, n, b_lbo, accs=(1, 2, 4), nmmas=(8, 16, 32, 64, 96), base=0):
     """Rounds of nmma MMAs with one commit + wait per round: cycles(round) = fixed + nmma * per_mma.  The slope between the two
     longest rounds is the steady-state cost of one MMA, the intercept the commit / wait / pipeline-fill latency that a
     per-round average (what round 1 reported) smears over the MMAs."""
     for n_acc in accs:
         if n_acc * n > 512:
             continue
-        pts = [(m, cycles(n, [0] * m, [0] * m, 18 * 8 * 16, 128, b_lbo, 128, n_acc=n_acc)) for m in nmmas]
+        pts = [(m, cycles(n, [0] * m, [0] * m, 18 * 8 * 16, 128, b_lbo, 128, n_acc=n_acc, base=base)) for m in nmmas]
         (m0, c0), (m1, c1) = pts[-2], pts[-1]
         slope = (c1 - c0) / (m1 - m0)
         print(f"{name:40s} N={n:3d} acc={n_acc}  " + "  ".join(f"{m}:{c / m:6.1f}" for m, c in pts) +
@@ -43,8 +43,12 @@ def sweep(name, n, b_lbo, accs=(1, 2), nmmas=(8, 16, 32, 64, 96)):
 
 
 print("# nmma sweep (cycles per MMA averaged over a round of nmma; slope = steady-state cost, fixed = per-round latency)")
+print("# lean issue loop: fixed descriptors in registers, nothing between two tcgen05.mma")
+for n_, lbo_ in ((32, 512), (64, 1024), (128, 2048), (256, 4096)):
+    sweep("lean  none aligned, fixed A/B", n_, lbo_, base=4)
+print("# table-driven issue loop (descriptors loaded from shared memory per MMA, as in round 1)")
 for n_, lbo_ in ((64, 1024), (128, 2048), (256, 4096)):
-    sweep("none aligned, fixed A/B address", n_, lbo_)
+    sweep("table none aligned, fixed A/B", n_, lbo_)
 
 
 # --- no swizzle, conv3-like: CIN=64 (4 k-steps), WROWS=10, plane = 18*10*16 = 2880 B
