@@ -391,7 +391,7 @@ def leg_hybrid(ctx, side, seconds):
     def combine(s2, s1, mse):
         g2, g1, gm = (gather_scores(v, n_total=v.numel() * W) for v in (s2, s1, mse))
         sup = D.ensemble_mean([g2, g1], as_numpy=False)
-        return D.eer_details(D.hybrid_blend(sup, gm, 0.8, as_numpy=False), lab[:g2.numel()])
+        return D.eer_details(D.hybrid_blend(sup, gm, 0.8, as_numpy=False), side.labels_global[:g2.numel()])
 
     def step():
         return combine(c2.score(x, apply_sigmoid=True), c1.score(x, apply_sigmoid=True), cae.score(x))
@@ -406,7 +406,6 @@ def leg_hybrid(ctx, side, seconds):
         hp = side.host_pool
         ne = hp.shape[0]
         group = D.ScorerGroup([c2, c1, cae])
-        lab_e = side.labels_global[:ne * W]
 
         def as_dev(v):
             return torch.from_numpy(v).to(ctx.dev)

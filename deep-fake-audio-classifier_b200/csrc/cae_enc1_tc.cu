@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
 
   if (warp == kE1EpiWarps) {
     // ===================== producer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(wbar, kE1WgtB);
       for (int off = 0; off < kE1WgtB; off += 8192) bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, 8192, wbar);
       uint32_t ws = 0;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
     }
   } else if (warp == kE1EpiWarps + 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {   // not `lane == 0`: see conv_tc.cuh
       constexpr uint32_t idesc = umma_idesc_f16(128, 256);
       const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 256 * 16, 128);
       const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) cnn1d_fused_kernel(const __grid
     }
   } else if (warp == kFuMmaWarp) {
     // ===================== MMA issuer: layer 1 of tile k, layer 2 of tile k-1, layer 3 of tile k-2 =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {   // not `lane == 0`: see conv_tc.cuh
       constexpr uint32_t idesc1 = umma_idesc_f16(128, 32), idesc2 = umma_idesc_f16(128, 64), idesc3 = umma_idesc_f16(128, 128);
       const uint64_t a1d = umma_smem_desc(smem_u32(stage), kFuPlaneB, kFuRows * 16);
       const uint64_t a2d = umma_smem_desc(smem_u32(win1), kFuPlaneB, kFuRows * 16);

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) cnn1d_l1_fused_kernel(const __g
     }
   } else if (warp == kL1MmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {   // not `lane == 0`: see conv_tc.cuh
       constexpr uint32_t idesc = umma_idesc_f16(128, kL1N);
       const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 64 * 16, 128);        // K chunk stride = 64 rows of 16 B
       const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);

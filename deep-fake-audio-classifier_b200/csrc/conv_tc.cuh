@@ -207,7 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
   if (warp == 8) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(wbar, Cfg::WGT_B);
       constexpr int PIECE = 16384;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)(Cfg::CTA2 ? 2 * grp + rank : grp) * Cfg::WGT_B;
@@ -238,11 +238,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (Cfg::CTA2 && rank == 1) {
-      if (lane == 0) {   // the peer only reports its weights
+      if (elect_one_sync()) {   // the peer only reports its weights
         mbar_wait(wbar, 0, 2);
         mbar_arrive_cluster(mapa_u32(smem_u32(pwbar), 0));
       }
-    } else if (lane == 0) {
+    } else if (elect_one_sync()) {   // elect_one_sync(), not `lane == 0`: under a lane test the compiler cannot tell that a single thread is active and wraps EVERY tcgen05.mma / TMA issue in an ELECT + BRA.U.ANY serialisation loop (measured: ~100 instead of 64 cycles per N = 128 MMA)
       constexpr uint32_t idesc = umma_idesc_f16(Cfg::CTA2 ? 256 : 128, NG);
       // descriptor = (low word: start address >> 4 | LBO >> 4 << 16, high word: SBO >> 4 | version); taps and
       // K steps only move the start address, i.e. add a compile-time constant to the low word

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128) probe_umma_lean_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32 && elect_one_sync()) {   // elect, not `threadIdx.x == 0`: no per-MMA ELECT / BRA.U.ANY loop in the SASS
     const uint32_t idesc = umma_idesc_bf16(128, p.n);
     const uint64_t ad = umma_smem_desc(smem_u32(smem) + p.a_off[0], p.a_lbo, p.a_sbo) | ((uint64_t)p.layout << 61);
     const uint64_t bd = umma_smem_desc(smem_u32(smem + A_BYTES) + p.b_off[0], p.b_lbo, p.b_sbo) | ((uint64_t)p.layout << 61);
