@@ -181,20 +181,26 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * h;
         uint32_t pk[4][4];
+        // TMEM reads are software-pipelined: the loads of step k+1 are in flight while step k is converted
+        float a[2][16], b[2][16];
+        tmem_ld_32x16(taddr, a[0]);
+        tmem_ld_32x16(taddr + 32, b[0]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // pooled time step within the block: conv time offsets jj = 2k, 2k+1
-          float a[16], b[16];
-          tmem_ld_32x16(taddr + (2 * k) * 32, a);
-          tmem_ld_32x16(taddr + (2 * k + 1) * 32, b);
           tmem_ld_wait();
-          if (k == 3) {  // all TMEM reads of this warp are done: release the accumulator early
+          if (k < 3) {
+            tmem_ld_32x16(taddr + (2 * k + 2) * 32, a[(k + 1) & 1]);
+            tmem_ld_32x16(taddr + (2 * k + 3) * 32, b[(k + 1) & 1]);
+          } else {  // all TMEM reads of this warp are done: release the accumulator early
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
+          const float* av = a[k & 1];
+          const float* bv = b[k & 1];
           float o[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) o[c] = fmaxf(a[c] + p.bias[16 * h + c], 0.0f) + fmaxf(b[c] + p.bias[16 * h + c], 0.0f);
+          for (int c = 0; c < 16; ++c) o[c] = fmaxf(av[c] + p.bias[16 * h + c], 0.0f) + fmaxf(bv[c] + p.bias[16 * h + c], 0.0f);
           float v[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {

@@ -236,29 +236,36 @@ __global__ void __launch_bounds__(kFuThreads, 1) cnn1d_fused_kernel(const __grid
       for (int tt = 0; tt < kFuTiles; ++tt, ++k) {
         if (tt + 1 < kFuTiles) prefetch_rows(u, tt + 1);
         else prefetch_rows(u + gridDim.x, 0);
-        mbar_wait(&emptyh[half], (k & 1) ^ 1, 61);
-        if (active) {
-          constexpr int U = 5;
+        // The half-stage is ONE tile deep: it may be overwritten only after the MMAs of the previous tile have read it.  The global
+        // loads do not touch it, so the first five rows are requested BEFORE that wait and fly while the previous tile's MMAs run.
+        constexpr int U = 5;
+        float4 lo[U], hi[U];
+        auto load_rows = [&](int r0) {
 #pragma unroll
-          for (int r0 = 0; r0 < kFuRows; r0 += U) {
-            float4 lo[U], hi[U];
-#pragma unroll
-            for (int e = 0; e < U; ++e) {
-              const int t = 8 * tt - 1 + r0 + e;
-              lo[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-              hi[e] = lo[e];
-              if (uvalid && t >= 0 && t < kT) {
-                const float4* src = reinterpret_cast<const float4*>(base + (long long)t * kF);
-                lo[e] = __ldg(src);
-                if (c8 < 22) hi[e] = __ldg(src + 1);   // chunk 22 = features 176..179 + zero padding
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < U; ++e) {
-              const uint4 v = make_uint4(pack_act2(lo[e].x, lo[e].y), pack_act2(lo[e].z, lo[e].w), pack_act2(hi[e].x, hi[e].y), pack_act2(hi[e].z, hi[e].w));
-              *reinterpret_cast<uint4*>(dst + (r0 + e) * 16) = v;
+          for (int e = 0; e < U; ++e) {
+            const int t = 8 * tt - 1 + r0 + e;
+            lo[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            hi[e] = lo[e];
+            if (uvalid && t >= 0 && t < kT) {
+              const float4* src = reinterpret_cast<const float4*>(base + (long long)t * kF);
+              lo[e] = __ldg(src);
+              if (c8 < 22) hi[e] = __ldg(src + 1);   // chunk 22 = features 176..179 + zero padding
             }
           }
+        };
+        auto store_rows = [&](int r0) {
+#pragma unroll
+          for (int e = 0; e < U; ++e) {
+            const uint4 v = make_uint4(pack_act2(lo[e].x, lo[e].y), pack_act2(lo[e].z, lo[e].w), pack_act2(hi[e].x, hi[e].y), pack_act2(hi[e].z, hi[e].w));
+            *reinterpret_cast<uint4*>(dst + (r0 + e) * 16) = v;
+          }
+        };
+        if (active) load_rows(0);
+        mbar_wait(&emptyh[half], (k & 1) ^ 1, 61);
+        if (active) {
+          store_rows(0);
+          load_rows(U);
+          store_rows(U);
         }
         fence_proxy_async_smem();   // every lane: generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();

@@ -183,22 +183,29 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * h;
       const int sw = (lane >> 2) & 1;
+      // TMEM reads are software-pipelined: the loads of step k+1 are in flight while step k is converted (tcgen05.wait::ld waits for
+      // ALL outstanding loads of the thread, so the next pair is issued right after each wait)
+      float a[2][16], b[2][16];
+      tmem_ld_32x16(taddr, a[0]);
+      tmem_ld_32x16(taddr + 32, b[0]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {  // pooled row within the block: conv time offsets jj = 2k, 2k+1
-        float a[16], b[16];
-        tmem_ld_32x16(taddr + (2 * k) * 32, a);
-        tmem_ld_32x16(taddr + (2 * k + 1) * 32, b);
         tmem_ld_wait();
-        if (k == 3) {  // all TMEM reads of this warp are done: release the accumulator early
+        if (k < 3) {
+          tmem_ld_32x16(taddr + (2 * k + 2) * 32, a[(k + 1) & 1]);
+          tmem_ld_32x16(taddr + (2 * k + 3) * 32, b[(k + 1) & 1]);
+        } else {  // all TMEM reads of this warp are done: release the accumulator early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
+        const float* av = a[k & 1];
+        const float* bv = b[k & 1];
         uint32_t pk[8];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
-          const float o0 = fmaxf(a[c] + p.bias[16 * h + c], 0.0f) + fmaxf(b[c] + p.bias[16 * h + c], 0.0f);
-          const float o1 = fmaxf(a[c + 1] + p.bias[16 * h + c + 1], 0.0f) + fmaxf(b[c + 1] + p.bias[16 * h + c + 1], 0.0f);
+          const float o0 = fmaxf(av[c] + p.bias[16 * h + c], 0.0f) + fmaxf(bv[c] + p.bias[16 * h + c], 0.0f);
+          const float o1 = fmaxf(av[c + 1] + p.bias[16 * h + c + 1], 0.0f) + fmaxf(bv[c + 1] + p.bias[16 * h + c + 1], 0.0f);
           pk[c >> 1] = pack_act2(o0, o1);
         }
         // pooled step j = 4tb + k: parity k&1, row offset k>>1 within the lane's two rows of that parity plane

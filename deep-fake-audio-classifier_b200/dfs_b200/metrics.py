@@ -145,23 +145,35 @@ def _f64_device(x, dev=None):
 
 
 def blend(score_list, weights, minmax_flags, divisor=1.0, as_numpy=True):
-    """out = (sum_m weights[m] * (minmax? normalise_01(s_m) : s_m)) / divisor in float64 on the device."""
+    """out = (sum_m weights[m] * (minmax? normalise_01(s_m) : s_m)) / divisor in float64 on the device, summed left to right like
+    numpy.  dfs_blend_f64 takes up to 8 vectors per call; longer lists (src/ensemble.py accepts any number of checkpoints) are
+    folded eight at a time with the running sum as the first operand of the next call (weight 1, no min-max, divisor 1: exact),
+    which keeps the very same left-to-right order."""
     torch = _torch()
-    if not (len(score_list) == len(weights) == len(minmax_flags)) or not 1 <= len(score_list) <= 8:
-        raise ValueError("blend takes 1..8 score vectors with one weight and one min-max flag each")
+    if not (len(score_list) == len(weights) == len(minmax_flags)) or len(score_list) < 1:
+        raise ValueError("blend takes one weight and one min-max flag per score vector (at least one)")
     ts = [_f64_device(score_list[0])]
     ts += [_f64_device(s, ts[0].device) for s in score_list[1:]]
     n = ts[0].numel()
     if any(t.numel() != n for t in ts):
         raise ValueError("all score vectors must have the same length")
-    out = torch.empty(n, dtype=torch.float64, device=ts[0].device)
-    m = len(ts)
-    ptrs = (C.c_void_p * m)(*[t.data_ptr() for t in ts])
-    w = (C.c_double * m)(*[float(v) for v in weights])
-    f = (C.c_int * m)(*[int(bool(v)) for v in minmax_flags])
-    with torch.cuda.device(out.device):
-        N.check(N.load().dfs_blend_f64(ptrs, m, w, f, float(divisor), n, C.c_void_p(out.data_ptr()), _stream(torch, out.device)),
-                "dfs_blend_f64")
+    weights, flags = [float(v) for v in weights], [int(bool(v)) for v in minmax_flags]
+    out = None
+    while ts:
+        take = 8 if out is None else 7
+        part, pw, pf = ts[:take], weights[:take], flags[:take]
+        ts, weights, flags = ts[take:], weights[take:], flags[take:]
+        if out is not None:
+            part, pw, pf = [out] + part, [1.0] + pw, [0] + pf
+        nxt = torch.empty(n, dtype=torch.float64, device=part[0].device)
+        m = len(part)
+        ptrs = (C.c_void_p * m)(*[t.data_ptr() for t in part])
+        w = (C.c_double * m)(*pw)
+        f = (C.c_int * m)(*pf)
+        with torch.cuda.device(nxt.device):
+            N.check(N.load().dfs_blend_f64(ptrs, m, w, f, float(divisor) if not ts else 1.0, n, C.c_void_p(nxt.data_ptr()),
+                                           _stream(torch, nxt.device)), "dfs_blend_f64")
+        out = nxt
     return out.cpu().numpy() if as_numpy else out
 
 

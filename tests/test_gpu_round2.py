@@ -269,3 +269,16 @@ def test_cnn1d_fused_kernel_equals_the_layer_kernels():
     t = Cnn1dScorer(sd_t)
     t.set_option("fused", 1)
     np.testing.assert_allclose(t.score(xs).cpu().numpy(), T["cnn1d_logits"][:64], atol=2e-2)
+
+
+def test_ensemble_mean_of_more_than_eight_models_is_numpy_exact():
+    """src/ensemble.py:121 takes any number of checkpoints: np.mean(all_scores, axis=0).  dfs_blend_f64 folds eight vectors per call;
+    longer lists are chained in the same left-to-right order, so the float64 result stays bit-identical to numpy."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    vecs = [rng.random(5000).astype(np.float32).astype(np.float64) for _ in range(19)]
+    np.testing.assert_array_equal(D.ensemble_mean(vecs), np.mean(vecs, axis=0))
+    w = rng.random(19)
+    want = np.zeros(5000)
+    for v, wi in zip(vecs, w):
+        want = want + wi * v
+    np.testing.assert_array_equal(D.blend(vecs, w, [0] * 19, 3.0), want / 3.0)
