@@ -595,7 +595,7 @@ static int cnn1d_tc_create(dfs_model* m, const dfs_cnn1d_weights* w) {
   s->fcw = m->fcw_dev;
   s->fcb = m->fcb;
   s->l1_fused = 1;
-  s->fused = 0;
+  s->fused = 1;
   DFS_CUDA_CHECK(cudaDeviceSynchronize());
   return DFS_OK;
 }

@@ -91,7 +91,7 @@ struct Cnn1dTcState {
   const float* fcw;       // classifier weight (128) on the device
   float fcb;
   int l1_fused;           // 1 (default) = layer 1 converts the fp32 rows in flight (cnn1d_l1_fused.cu) when the layout allows
-  int fused;              // 1 = the whole network in ONE kernel (cnn1d_fused.cu) when the layout allows; 0 = one kernel per layer
+  int fused;              // 1 (default) = the whole network in ONE kernel (cnn1d_fused.cu) when the layout allows; 0 = one kernel per layer
   const uint16_t* w1_fused;  // layer-1 weights with 32 rows per K chunk, [tap][24][32][8] (the template's image pads them to 64)
   float fcw_host[128];    // classifier weight on the host: rides in the fused kernel's parameter space
 };

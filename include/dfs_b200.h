@@ -123,8 +123,8 @@ int dfs_model_destroy(dfs_model* m);
  * where the rank order of scores a few 1e-6 apart matters, e.g. the EER of a small dev set).
  * Kernel-variant switches kept for on-device cross-checks (tests compare the variants; defaults are the product path):
  *   "conv1_impl"   (CNN2D, CAE) 0 = Toeplitz tcgen05 GEMM for the Cin = 1 layer, 1 = fp32 CUDA-core conv
- *   "fused"        (CNN1D)      1 = the three conv layers, the time mean and the classifier in ONE kernel (activations never leave the
- *                               SM; dense feature-contiguous input), 0 (default) = one kernel per layer
+ *   "fused"        (CNN1D)      1 (default) = the three conv layers, the time mean and the classifier in ONE kernel (activations never
+ *                               leave the SM; dense feature-contiguous input), 0 = one kernel per layer
  *   "l1_fused"     (CNN1D)      1 (default) = layer 1 converts the fp32 rows in flight, 0 = prep kernel + TMA
  *   "final_fused"  (CAE)        1 (default) = final ConvTranspose + squared error in dec3's epilogue, 0 = separate kernel over d3
  *   "dec_wide"     (CAE)        1 (default) = dec1 / dec2 as N = 256 GEMMs, 0 = N = 128 with twice the groups

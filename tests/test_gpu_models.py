@@ -121,7 +121,9 @@ def test_cnn1d_matches_reference_golden(feats, impl):
     xt = feats.transpose(1, 2).contiguous().transpose(1, 2)
     small = Cnn1dScorer(syn.cnn1d_state(0), max_chunk=7)          # 12 utterances through ragged chunks of 7, strided input
     small.set_option("conv_impl", impl)
-    np.testing.assert_allclose(small.score(xt).cpu().numpy(), logits, rtol=1e-6, atol=1e-7)
+    # the strided view takes the per-layer kernels, the contiguous tensor above the one-kernel path: same operands, the time mean is summed
+    # in another order
+    np.testing.assert_allclose(small.score(xt).cpu().numpy(), logits, rtol=1e-6, atol=2e-6)
 
 
 def test_cnn1d_fused_first_layer_equals_prep_plus_template_path():
@@ -129,6 +131,7 @@ def test_cnn1d_fused_first_layer_equals_prep_plus_template_path():
     same fp16 operands, same MMA order.  37 utterances through passes of 20 (ragged 16-utterance column tiles)."""
     x = torch.from_numpy(syn.features(37, seed=31)).cuda()
     sc = Cnn1dScorer(syn.cnn1d_state(0), max_chunk=20)
+    sc.set_option("fused", 0)                                   # the per-layer kernels (the one-kernel path has its own test)
     fused = sc.score(x).cpu().numpy()
     sc.set_option("l1_fused", 0)
     plain = sc.score(x).cpu().numpy()

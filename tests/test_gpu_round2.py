@@ -242,6 +242,7 @@ def test_cnn1d_fused_kernel_equals_the_layer_kernels():
     sd = syn.cnn1d_state(0)
     x = torch.from_numpy(syn.features(37, seed=31)).cuda()
     sc = Cnn1dScorer(sd, max_chunk=20)
+    sc.set_option("fused", 0)
     plain = sc.score(x).cpu().numpy()
     sc.set_option("fused", 1)
     fused = sc.score(x).cpu().numpy()
@@ -257,6 +258,7 @@ def test_cnn1d_fused_kernel_equals_the_layer_kernels():
     # several units per CTA, default pass size
     big = D.fill_features(2500, first_utt=0, seed=1234)
     a = Cnn1dScorer(sd)
+    a.set_option("fused", 0)
     ref = a.score(big).cpu().numpy()
     a.set_option("fused", 1)
     np.testing.assert_allclose(a.score(big).cpu().numpy(), ref, rtol=0, atol=2e-6)
