@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <mutex>
 #include <new>
 #include <utility>
 #include <vector>
@@ -1108,6 +1109,8 @@ extern "C" int dfs_model_saturation_count(dfs_model* m, int64_t* saturated_out, 
     bufs.push_back({m->act1.ptr, (size_t)m->act1.bytes()});
     bufs.push_back({m->act2.ptr, (size_t)m->act2.bytes()});
   } else if (m->kind == KIND_CNN1D) {
+    DFS_REQUIRE(m->c1d->fused == 0, DFS_ERR_UNSUPPORTED,
+                "dfs_model_saturation_count: the one-kernel 1D-CNN keeps its activations on the SM; set option \"fused\" = 0 and score again");
     for (int b = 0; b < 3; ++b) bufs.push_back({m->c1d->act[b].ptr, (size_t)m->c1d->act[b].bytes()});
   } else if (m->kind == KIND_CAE) {
     bufs.push_back({m->cae->xt1, (size_t)cae_enc1_xt_rows(m->chunk) * 16});
@@ -1312,9 +1315,21 @@ extern "C" int dfs_pinned_free(void* p) {
 // ------------------------------------------------------------------------------------------
 // metric / blend / synthetic: thin forwards
 // ------------------------------------------------------------------------------------------
+// The metric kernels share one grow-only scratch workspace per device (eer.cu): calls on the same device are serialised here for their
+// whole duration, so that two host threads cannot interleave inside it.  (dfs_blend_f64 and dfs_widen_f32_f64 return with their kernels
+// still in flight: a following metric call on that device must use the same stream, or synchronise it first -- see dfs_b200.h.)
+static std::mutex g_metric_mutex[16];
+static std::mutex& metric_mutex() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_metric_mutex[(dev >= 0 && dev < 16) ? dev : 0];
+}
+#define DFS_METRIC_LOCK() std::lock_guard<std::mutex> metric_guard(metric_mutex())
+
 extern "C" int dfs_blend_f64(const double* const* scores, int m, const double* weights, const int* minmax, double divisor, int64_t n,
                              double* out_dev, void* stream) {
   DFS_REQUIRE(divisor != 0.0, DFS_ERR_INVALID, "dfs_blend_f64: divisor is 0");
+  DFS_METRIC_LOCK();
   return blend_device(scores, m, weights, minmax, divisor, n, out_dev, static_cast<cudaStream_t>(stream));
 }
 extern "C" int dfs_widen_f32_f64(const float* in_dev, int64_t n, double* out_dev, void* stream) {
@@ -1322,13 +1337,16 @@ extern "C" int dfs_widen_f32_f64(const float* in_dev, int64_t n, double* out_dev
 }
 extern "C" int dfs_eer(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, dfs_eer_result* result_host,
                        uint32_t* perm_dev, void* sorted_dev, void* stream) {
+  DFS_METRIC_LOCK();
   return eer_device(scores_dev, key_bytes, labels_dev, n, result_host, perm_dev, sorted_dev, static_cast<cudaStream_t>(stream));
 }
 extern "C" int dfs_eer_select(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, dfs_eer_result* result_host,
                               void* stream) {
+  DFS_METRIC_LOCK();
   return eer_select_device(scores_dev, key_bytes, labels_dev, n, result_host, static_cast<cudaStream_t>(stream));
 }
 extern "C" int dfs_bce_with_logits(const float* logits_dev, const float* labels_dev, int64_t n, double* mean_host, void* stream) {
+  DFS_METRIC_LOCK();
   return bce_with_logits_device(logits_dev, labels_dev, n, mean_host, static_cast<cudaStream_t>(stream));
 }
 namespace dfs { extern int g_select_use_tma; }
@@ -1343,6 +1361,7 @@ extern "C" int dfs_set_global_option(const char* key, int64_t value) {
 }
 extern "C" int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,
                              int64_t* out4_host, void* stream) {
+  DFS_METRIC_LOCK();
   return confusion_device(scores_dev, key_bytes, labels_dev, n, threshold, out4_host, static_cast<cudaStream_t>(stream));
 }
 extern "C" int dfs_fill_features(float* out_dev, int64_t n, int64_t first_utt, uint64_t seed, float std_, void* stream) {

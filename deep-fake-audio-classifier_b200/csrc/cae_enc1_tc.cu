@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
           const float* bv = b[k & 1];
           float o[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) o[c] = fmaxf(av[c] + p.bias[16 * h + c], 0.0f) + fmaxf(bv[c] + p.bias[16 * h + c], 0.0f);
+          for (int c = 0; c < 16; ++c) o[c] = relu_nan(av[c] + p.bias[16 * h + c]) + relu_nan(bv[c] + p.bias[16 * h + c]);
           float v[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {

@@ -73,7 +73,7 @@ __global__ void cae_fill_bias_column_kernel(ActBuf d2, int cols, int n_utts, con
   const int c = (int)(idx % 64);
   const int t = (int)((idx / 64) % 80);
   const long long n = idx / (64 * 80);
-  const __half v = __float2half_rn(fmaxf(bias[c], 0.0f));
+  const __half v = __float2half_rn(relu_nan(bias[c]));
   d2.ptr[(c >> 3) * d2.plane_elems() + ((n * cols + 45) * d2.RS + t + 1) * 8 + (c & 7)] = *reinterpret_cast<const uint16_t*>(&v);
 }
 

@@ -125,7 +125,7 @@ __device__ __forceinline__ void fused_epi_relu(const FusedParams& p, uint8_t* sm
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
         const float b0 = second ? p.b2[blk * 32 + c] : p.b1[c], b1 = second ? p.b2[blk * 32 + c + 1] : p.b1[c + 1];
-        pk[c >> 1] = pack_act2(tvalid ? fmaxf(v[c] + b0, 0.0f) : 0.0f, tvalid ? fmaxf(v[c + 1] + b1, 0.0f) : 0.0f);
+        pk[c >> 1] = pack_act2(tvalid ? relu_nan(v[c] + b0) : 0.0f, tvalid ? relu_nan(v[c + 1] + b1) : 0.0f);
       }
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
@@ -203,13 +203,17 @@ __global__ void __launch_bounds__(kFuThreads, 1) cnn1d_fused_kernel(const __grid
 
   if (warp >= kFuProdWarp0 && warp < kFuMmaWarp) {
     // ===================== producers: fp32 rows -> fp16 K-major stage, one K half per 6 warps =====================
+    // A 720-byte feature row is 45 pieces of 16 B (4 features).  Thread q of a half owns ONE piece index and the two utterance columns
+    // cg, cg + 8, and walks their 10 rows: consecutive lanes read consecutive 16-byte pieces, so a warp's load instruction covers whole
+    // contiguous sectors (the first mapping gave a lane 32 bytes as two 16-byte loads 32 B apart: every sector was fetched by two
+    // instructions, L1 throughput 77 %, 30 sectors per request).  A piece converts to 8 bytes = half of a 16-byte K chunk: st.shared.v2.
     const int pt = threadIdx.x - 32 * kFuProdWarp0;      // 0 .. 383
     const int half = pt >= 192;
     const int q = half ? pt - 192 : pt;
-    const int per = half ? 11 : 12;                      // feature chunks of this half: planes 0..11 / 12..22 (plane 23 stays zero)
-    const bool active = q < kColTile * per;
-    const int col = active ? q / per : 0;
-    const int c8 = (half ? 12 : 0) + (active ? q - col * per : 0);
+    const int piece = q % 24, cg = q / 24;               // cg 0..7
+    const bool active = half ? piece < 21 : true;        // half 1 = pieces 24 .. 44 (features 96 .. 179); plane 22's upper half and plane 23 stay zero
+    const int gp = (half ? 24 : 0) + piece;              // piece index within the row
+    const int c8 = gp >> 1, sub = gp & 1;
     if (pt == 0) {
       mbar_arrive_expect_tx(wbar, kFuW1B + kFuW2B + kFuW3B);
       for (int off = 0; off < kFuW1B; off += 12288) bulk_g2s(w1s + off, reinterpret_cast<const uint8_t*>(p.w1) + off, 12288, wbar);
@@ -229,35 +233,36 @@ __global__ void __launch_bounds__(kFuThreads, 1) cnn1d_fused_kernel(const __grid
     prefetch_rows(blockIdx.x, 0);
     uint32_t k = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const long long gn = (long long)kColTile * u + col;
-      const bool uvalid = active && gn < p.n_utts;
-      const float* base = p.x + (uvalid ? gn : 0) * p.sn + 8 * c8;
-      uint8_t* dst = stage + c8 * kFuPlaneB + col * (kFuRows * 16);
+      const long long gn0 = (long long)kColTile * u + cg, gn1 = gn0 + 8;
+      const bool v0 = active && gn0 < p.n_utts, v1 = active && gn1 < p.n_utts;
+      const float* base0 = p.x + (v0 ? gn0 : 0) * p.sn + 4 * gp;
+      const float* base1 = p.x + (v1 ? gn1 : 0) * p.sn + 4 * gp;
+      uint8_t* dst0 = stage + c8 * kFuPlaneB + cg * (kFuRows * 16) + 8 * sub;
+      uint8_t* dst1 = dst0 + 8 * (kFuRows * 16);
       for (int tt = 0; tt < kFuTiles; ++tt, ++k) {
         if (tt + 1 < kFuTiles) prefetch_rows(u, tt + 1);
         else prefetch_rows(u + gridDim.x, 0);
         // The half-stage is ONE tile deep: it may be overwritten only after the MMAs of the previous tile have read it.  The global
         // loads do not touch it, so the first five rows are requested BEFORE that wait and fly while the previous tile's MMAs run.
         constexpr int U = 5;
-        float4 lo[U], hi[U];
+        float4 ra[U], rb[U];
         auto load_rows = [&](int r0) {
 #pragma unroll
           for (int e = 0; e < U; ++e) {
             const int t = 8 * tt - 1 + r0 + e;
-            lo[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-            hi[e] = lo[e];
-            if (uvalid && t >= 0 && t < kT) {
-              const float4* src = reinterpret_cast<const float4*>(base + (long long)t * kF);
-              lo[e] = __ldg(src);
-              if (c8 < 22) hi[e] = __ldg(src + 1);   // chunk 22 = features 176..179 + zero padding
+            ra[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[e] = ra[e];
+            if (t >= 0 && t < kT) {
+              if (v0) ra[e] = __ldg(reinterpret_cast<const float4*>(base0 + (long long)t * kF));
+              if (v1) rb[e] = __ldg(reinterpret_cast<const float4*>(base1 + (long long)t * kF));
             }
           }
         };
         auto store_rows = [&](int r0) {
 #pragma unroll
           for (int e = 0; e < U; ++e) {
-            const uint4 v = make_uint4(pack_act2(lo[e].x, lo[e].y), pack_act2(lo[e].z, lo[e].w), pack_act2(hi[e].x, hi[e].y), pack_act2(hi[e].z, hi[e].w));
-            *reinterpret_cast<uint4*>(dst + (r0 + e) * 16) = v;
+            *reinterpret_cast<uint2*>(dst0 + (r0 + e) * 16) = make_uint2(pack_act2(ra[e].x, ra[e].y), pack_act2(ra[e].z, ra[e].w));
+            *reinterpret_cast<uint2*>(dst1 + (r0 + e) * 16) = make_uint2(pack_act2(rb[e].x, rb[e].y), pack_act2(rb[e].z, rb[e].w));
           }
         };
         if (active) load_rows(0);
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) cnn1d_fused_kernel(const __grid
         tmem_ld_32x32(tmem_base + ((uint32_t)(32 * qd) << 16) + kFuAcc3 + acc * 128 + blk * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) part = fmaf(fmaxf(v[c] + p.b3[blk * 32 + c], 0.0f), p.fcw[blk * 32 + c], part);
+        for (int c = 0; c < 32; ++c) part = fmaf(relu_nan(v[c] + p.b3[blk * 32 + c]), p.fcw[blk * 32 + c], part);
       }
       tc_fence_before();
       __syncwarp();

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) cnn1d_l1_fused_kernel(const __g
         if (lane == 0) mbar_arrive(&tempty[acc]);
         uint32_t pk[16];
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) pk[c >> 1] = pack_act2(fmaxf(v[c] + p.bias[c], 0.0f), fmaxf(v[c + 1] + p.bias[c + 1], 0.0f));
+        for (int c = 0; c < 32; c += 2) pk[c >> 1] = pack_act2(relu_nan(v[c] + p.bias[c]), relu_nan(v[c + 1] + p.bias[c + 1]));
         const int tp = 1 + 8 * tt + i;
         if (colvalid && tp <= kT) {
           uint16_t* dst = p.out + ((1 + n) * (long long)p.out_rs + tp) * 8;

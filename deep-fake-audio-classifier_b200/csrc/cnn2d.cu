@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x,
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
               for (int kw = 0; kw < 3; ++kw) a = fmaf(w.w[c * 9 + kh * 3 + kw], xin[kh + dt][kw + df], a);
-            acc += fmaxf(a, 0.0f);
+            acc += relu_nan(a);
           }
         r[e] = acc * (POOLF ? 0.25f : 0.5f);
       }
@@ -192,7 +192,7 @@ __global__ void cnn2d_conv2_simt_kernel(ActBuf act1, const uint16_t* __restrict_
       }
     }
   }
-  const float s = fmaxf(acc[0] + bias[co], 0.0f) + fmaxf(acc[1] + bias[co], 0.0f);
+  const float s = relu_nan(acc[0] + bias[co]) + relu_nan(acc[1] + bias[co]);
   const __half b = __float2half_rn(fminf(s, 65504.0f));
   act2.ptr[(co >> 3) * act2.plane_elems() + (gc * act2.RS + to + 1) * 8 + (co & 7)] = *reinterpret_cast<const uint16_t*>(&b);
 }
@@ -207,7 +207,7 @@ __global__ void cnn2d_conv3_simt_kernel(ActBuf act2, const uint16_t* __restrict_
   const long long n = pos / kF;
   const long long gc = n * kCols + f + 1;
   float s = 0.0f;
-  for (int tp = 1; tp <= 80; ++tp) s += fmaxf(conv_at<64, 128>(act2, wpack, gc, tp, co) + bias[co], 0.0f);
+  for (int tp = 1; tp <= 80; ++tp) s += relu_nan(conv_at<64, 128>(act2, wpack, gc, tp, co) + bias[co]);
   emb[idx] = s;  // idx == (n*180 + f)*128 + co
 }
 

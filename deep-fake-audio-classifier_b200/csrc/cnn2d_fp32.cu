@@ -92,15 +92,15 @@ __global__ void __launch_bounds__(128) conv3x3_fp32_kernel(const float* __restri
   for (int c = 0; c < 2; ++c) {
     if constexpr (POOL) {   // relu, then the (2,1) average (model.py:18,24)
       float4 o;
-      o.x = 0.5f * (fmaxf(accf[0][c][0], 0.f) + fmaxf(accf[1][c][0], 0.f));
-      o.y = 0.5f * (fmaxf(accf[0][c][1], 0.f) + fmaxf(accf[1][c][1], 0.f));
-      o.z = 0.5f * (fmaxf(accf[0][c][2], 0.f) + fmaxf(accf[1][c][2], 0.f));
-      o.w = 0.5f * (fmaxf(accf[0][c][3], 0.f) + fmaxf(accf[1][c][3], 0.f));
+      o.x = 0.5f * (relu_nan(accf[0][c][0]) + relu_nan(accf[1][c][0]));
+      o.y = 0.5f * (relu_nan(accf[0][c][1]) + relu_nan(accf[1][c][1]));
+      o.z = 0.5f * (relu_nan(accf[0][c][2]) + relu_nan(accf[1][c][2]));
+      o.w = 0.5f * (relu_nan(accf[0][c][3]) + relu_nan(accf[1][c][3]));
       *reinterpret_cast<float4*>(out + ((n * HP + j) * kF + f0 + c) * CO + co) = o;
     } else {
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
-        const float4 o = make_float4(fmaxf(accf[a][c][0], 0.f), fmaxf(accf[a][c][1], 0.f), fmaxf(accf[a][c][2], 0.f), fmaxf(accf[a][c][3], 0.f));
+        const float4 o = make_float4(relu_nan(accf[a][c][0]), relu_nan(accf[a][c][1]), relu_nan(accf[a][c][2]), relu_nan(accf[a][c][3]));
         *reinterpret_cast<float4*>(out + ((n * H + 2 * j + a) * kF + f0 + c) * CO + co) = o;
       }
     }

@@ -81,6 +81,14 @@ __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// ReLU that PROPAGATES NaN (FMNMX.NAN), like torch.relu on the reference's CPU path: fmaxf(NaN, 0) is 0, which would turn a NaN feature
+// into a finite score.  With this, a NaN anywhere in an utterance's features reaches its logit as NaN through every layer
+// (cvt.rn.satfinite keeps NaN as NaN, the MMAs propagate it); +-inf features are clamped to +-65504 by the input conversion.
+__device__ __forceinline__ float relu_nan(float x) {
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float act_bits_to_float(uint16_t b) {
   return __half2float(*reinterpret_cast<const __half*>(&b));
 }

@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
         uint32_t pk[8];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
-          const float o0 = fmaxf(av[c] + p.bias[16 * h + c], 0.0f) + fmaxf(bv[c] + p.bias[16 * h + c], 0.0f);
-          const float o1 = fmaxf(av[c + 1] + p.bias[16 * h + c + 1], 0.0f) + fmaxf(bv[c + 1] + p.bias[16 * h + c + 1], 0.0f);
+          const float o0 = relu_nan(av[c] + p.bias[16 * h + c]) + relu_nan(bv[c] + p.bias[16 * h + c]);
+          const float o1 = relu_nan(av[c + 1] + p.bias[16 * h + c + 1]) + relu_nan(bv[c + 1] + p.bias[16 * h + c + 1]);
           pk[c >> 1] = pack_act2(o0, o1);
         }
         // pooled step j = 4tb + k: parity k&1, row offset k>>1 within the lane's two rows of that parity plane

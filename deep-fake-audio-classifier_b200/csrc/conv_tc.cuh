@@ -336,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           // bias + ReLU on both time steps, sum = time pool (the pool's 1/2 or 1/4 is folded into weights and bias)
           float o[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = fmaxf(a[c] + bias[h * HC + c], 0.0f) + fmaxf(b[c] + bias[h * HC + c], 0.0f);
+          for (int c = 0; c < 32; ++c) o[c] = relu_nan(a[c] + bias[h * HC + c]) + relu_nan(b[c] + bias[h * HC + c]);
           const int row_out = 8 * tt + i + 1;  // pair index + 1 = padded output row
           if constexpr (Cfg::EPI == EPI_PAIR_POOL) {
             uint32_t pk[16];
@@ -387,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             tmem_ld_wait();
             if (8 * tt + i + 1 <= p.rows_valid) {  // rows beyond the valid range are padding (1D-CNN: 321 of 328)
 #pragma unroll
-              for (int c = 0; c < 32; ++c) sum[blk * 32 + c] += fmaxf(v[c] + bias[h * HC + blk * 32 + c], 0.0f);
+              for (int c = 0; c < 32; ++c) sum[blk * 32 + c] += relu_nan(v[c] + bias[h * HC + blk * 32 + c]);
             }
           }
           tc_fence_before();
@@ -449,7 +449,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * NG + h * 128 + blk * 32, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) tsum[blk * 4 + (k >> 3)] += fmaxf(v[k] + bc, 0.0f);
+            for (int k = 0; k < 32; ++k) tsum[blk * 4 + (k >> 3)] += relu_nan(v[k] + bc);
           }
           tc_fence_before();
           __syncwarp();
@@ -500,7 +500,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
             }
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k] + bc, 0.0f);
+            for (int k = 0; k < 32; ++k) v[k] = relu_nan(v[k] + bc);
 #pragma unroll
             for (int fpair = 0; fpair < 2; ++fpair) {
               const long long co = coloff[2 * blk + fpair];
@@ -535,7 +535,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           __syncwarp();
           if (lane == 0) acc_release<Cfg::CTA2>(&tempty[acc]);
 #pragma unroll
-          for (int c = 0; c < HC; ++c) v[c] = fmaxf(v[c] + bias[grp * COUT + h * HC + c], 0.0f);
+          for (int c = 0; c < HC; ++c) v[c] = relu_nan(v[c] + bias[grp * COUT + h * HC + c]);
 #pragma unroll
           for (int c = 0; c < Q1; ++c) {
             const float send = oddi ? v[c] : v[c + Q1];
@@ -589,8 +589,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               a0 = 0.5f * a0 * (1.0f + erff(a0 * 0.70710678118654752f));
               a1 = 0.5f * a1 * (1.0f + erff(a1 * 0.70710678118654752f));
             } else {
-              a0 = fmaxf(a0, 0.0f);
-              a1 = fmaxf(a1, 0.0f);
+              a0 = relu_nan(a0);
+              a1 = relu_nan(a1);
             }
             pk[c >> 1] = pack_act2(a0, a1);
           }
@@ -628,7 +628,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               float d[32];
 #pragma unroll
               for (int c = 0; c < 32; c += 2) {   // d3 rounded to fp16 like the stored layer (pack_act2), then widened again
-                const uint32_t pk = pack_act2(fmaxf(v[b * 32 + c] + bias[c], 0.0f), fmaxf(v[b * 32 + c + 1] + bias[c + 1], 0.0f));
+                const uint32_t pk = pack_act2(relu_nan(v[b * 32 + c] + bias[c]), relu_nan(v[b * 32 + c + 1] + bias[c + 1]));
                 const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&pk));
                 d[c] = f2.x;
                 d[c + 1] = f2.y;
@@ -727,8 +727,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             uint32_t p0[16], up[16];
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
-              p0[c >> 1] = pack_act2(fmaxf(v[c] + bs[sub][c], 0.0f), fmaxf(v[c + 1] + bs[sub][c + 1], 0.0f));
-              up[c >> 1] = pack_act2(fmaxf(v[32 + c] + bs[sub][c], 0.0f), fmaxf(v[33 + c] + bs[sub][c + 1], 0.0f));
+              p0[c >> 1] = pack_act2(relu_nan(v[c] + bs[sub][c]), relu_nan(v[c + 1] + bs[sub][c + 1]));
+              up[c >> 1] = pack_act2(relu_nan(v[32 + c] + bs[sub][c]), relu_nan(v[33 + c] + bs[sub][c + 1]));
             }
             uint16_t* cb = colbase[sub];
             if (i == 7 && colvalid && tp <= p.rows_valid) {   // the a = 1 half of the tile's last row: the next tile owns the other half
@@ -782,7 +782,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             uint32_t pk[CPT / 2];
 #pragma unroll
             for (int c = 0; c < CPT; c += 2)
-              pk[c >> 1] = pack_act2(fmaxf(v[s * CPT + c] + bias[c0 + c], 0.0f), fmaxf(v[s * CPT + c + 1] + bias[c0 + c + 1], 0.0f));
+              pk[c >> 1] = pack_act2(relu_nan(v[s * CPT + c] + bias[c0 + c]), relu_nan(v[s * CPT + c + 1] + bias[c0 + c + 1]));
             if (ok) {
               const int to = 2 * (tp - 1) + (qid >> 1), fo = 2 * (fp - 1) + (qid & 1);
               const long long gco = (long long)n * p.out_cols + fo + 1;

@@ -34,7 +34,7 @@ __global__ void conv1d_k3_kernel(const float* __restrict__ in, long long sn, lon
     const float* wk = w + (long long)k * CI * CO + co;
     for (int ci = 0; ci < CI; ++ci) acc = fmaf(src[ci * cs], wk[(long long)ci * CO], acc);
   }
-  out[idx] = fmaxf(acc, 0.0f);
+  out[idx] = relu_nan(acc);
 }
 
 // logits[n] = fcb + sum_c fcw[c] * mean_t h[n][t][c]; one block (128 threads = channels) per utterance
@@ -122,7 +122,7 @@ __global__ void cae_enc_kernel(const float* __restrict__ in, long long sn, long 
           }
         }
       }
-      pooled += fmaxf(acc, 0.0f);
+      pooled += relu_nan(acc);
     }
   out[idx] = pooled * 0.25f;
 }
@@ -146,7 +146,7 @@ __global__ void cae_dec_kernel(const float* __restrict__ in, int H, int W, int C
     const float* wk = w + (long long)((a * 2 + bb) * CI) * CO + co;
     for (int ci = 0; ci < CI; ++ci) acc = fmaf(src[ci], wk[(long long)ci * CO], acc);
   }
-  out[idx] = fmaxf(acc, 0.0f);
+  out[idx] = relu_nan(acc);
 }
 
 // final ConvTranspose2d(32,1,k2,s2) (no BN / activation), zero row 320, fused per-utterance MSE:

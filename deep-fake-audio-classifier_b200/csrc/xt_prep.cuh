@@ -43,9 +43,9 @@ __global__ void __launch_bounds__(256) xt_prep_transpose_kernel(const float* __r
       const int t = t0 + 8 * k;
       float a = v[k];
       if (mean != nullptr) a = (a - m) / sg;     // FeatureNormalizer.transform, before the zero padding
-      a = (f < kF) ? fmaxf(a, -65504.0f) : 0.0f;
-      const __half h = __float2half_rn(fminf(a, 65504.0f));
-      if (t < kT) tile[fl * kXpPitch + t + 1] = *reinterpret_cast<const uint16_t*>(&h);
+      a = (f < kF) ? a : 0.0f;
+      // one saturating convert: |a| > 65504 and +-inf -> +-65504, NaN stays NaN (fmaxf / fminf clamps would swallow it)
+      if (t < kT) tile[fl * kXpPitch + t + 1] = (uint16_t)(pack_act2(a, 0.0f) & 0xffffu);
     }
   }
   __syncthreads();

@@ -16,6 +16,10 @@
  *  - a dfs_model owns its folded/re-packed weights and its activation workspace; it is bound
  *    to one device and is not thread-safe (one handle per device per thread, like the
  *    reference's single-threaded host loop, SURVEY.md §8b "Threading").
+ *  - the metric calls (dfs_eer, dfs_eer_select, dfs_confusion, dfs_blend_f64, dfs_bce_with_logits) share one grow-only
+ *    scratch workspace per device; the library serialises them per device with a mutex held for the whole call.  dfs_blend_f64
+ *    and dfs_widen_f32_f64 return with their kernels still enqueued: issue the next metric call of that device on the SAME
+ *    stream, or synchronise the stream first.
  *  - there is NO CPU fallback: without a CUDA device every compute call fails with
  *    DFS_ERR_CUDA.
  */
@@ -142,7 +146,7 @@ int dfs_model_profile(dfs_model* m, double* ms_out, int64_t* launches_out, int n
  * (|v| > 65504 becomes +-65504 silently).  This scans the fp16 buffers the LAST pass (<= chunk utterances) of `m` left
  * behind -- feature image and every inter-layer activation -- and returns how many elements sit exactly at +-65504 and how
  * many are non-finite.  0 / 0 on real LFCC maps (range -61 ... +86, model_prediction_report.md:24-29); tests feed
- * heavy-tailed inputs and check it.  Synchronises `stream`.                                                          */
+ * heavy-tailed inputs and check it.  1D-CNN: needs option "fused" = 0 (the one-kernel path never stores its activations). Synchronises `stream`.                                                          */
 int dfs_model_saturation_count(dfs_model* m, int64_t* saturated_out, int64_t* nonfinite_out, void* stream);
 
 /* ---- scoring (device-resident features) --------------------------------------------- */

@@ -126,6 +126,8 @@ def _trained_case(tag, precision, structured):
     sd = factory(0, logit_scale=float(T[f"{tag}_scale"]), classifier_bias=float(T[f"{tag}_bias"]))
     assert syn.state_digest(sd) == str(T[f"{tag}_sha256"])
     sc = cls(sd, precision=precision)
+    if tag == "cnn1d":
+        sc.set_option("fused", 0)                                   # the census below needs the activations in HBM; the one-kernel path is gated in its own test
     n = structured.shape[0] if precision == "fp16" or tag == "cnn1d" else 512       # the fp32 CUDA-core 2D-CNN runs ~8 k utt/s
     x = structured[:n].cuda()
     logits = sc.score(x, apply_sigmoid=False).cpu().numpy()
@@ -198,8 +200,12 @@ def test_saturation_census_counts_clipped_values():
     x = torch.from_numpy(syn.features_structured(6, seed=77)).cuda()
     assert float(x.abs().max()) >= 60.0
     mean, std = syn.normalizer_stats(1)
-    for sc in (Cnn2dScorer(syn.cnn2d_state(0), max_chunk=8), Cnn1dScorer(syn.cnn1d_state(0), max_chunk=16),
-               CaeScorer(syn.cae_state(0), mean, std, max_chunk=8)):
+    c1 = Cnn1dScorer(syn.cnn1d_state(0), max_chunk=16)
+    c1.score(x)
+    with pytest.raises(RuntimeError, match="fused"):             # the one-kernel path keeps its activations on the SM
+        c1.saturation_count()
+    c1.set_option("fused", 0)
+    for sc in (Cnn2dScorer(syn.cnn2d_state(0), max_chunk=8), c1, CaeScorer(syn.cae_state(0), mean, std, max_chunk=8)):
         sc.score(x)
         assert sc.saturation_count() == (0, 0), type(sc).__name__
         sc.score(x * 1e4)
@@ -284,3 +290,23 @@ def test_ensemble_mean_of_more_than_eight_models_is_numpy_exact():
     for v, wi in zip(vecs, w):
         want = want + wi * v
     np.testing.assert_array_equal(D.blend(vecs, w, [0] * 19, 3.0), want / 3.0)
+
+
+def test_nan_features_give_nan_scores_like_the_reference():
+    """A NaN in an utterance's features reaches the reference's logit as NaN (torch's conv / relu / mean propagate it).  The
+    engine's ReLUs are NaN-propagating maxima and its fp16 converts keep NaN, so exactly that utterance scores NaN and its
+    neighbours in the pass keep their bits (fmaxf used to turn the NaN into a finite score)."""
+    x = torch.from_numpy(syn.features(9, seed=21)).cuda()
+    bad = x.clone()
+    bad[4, 100, 57] = float("nan")
+    mean, std = syn.normalizer_stats(1)
+    c1 = Cnn1dScorer(syn.cnn1d_state(0), max_chunk=16)
+    c1l = Cnn1dScorer(syn.cnn1d_state(0), max_chunk=16)
+    c1l.set_option("fused", 0)
+    for sc in (Cnn2dScorer(syn.cnn2d_state(0), max_chunk=16), c1, c1l, CaeScorer(syn.cae_state(0), mean, std, max_chunk=16)):
+        good = sc.score(x).cpu().numpy()
+        got = sc.score(bad).cpu().numpy()
+        assert np.isnan(got[4]), type(sc).__name__
+        keep = np.arange(9) != 4
+        assert np.isfinite(got[keep]).all()
+        np.testing.assert_array_equal(got[keep], good[keep])
