@@ -140,6 +140,22 @@ static std::vector<uint16_t> round_conv3x3_f16(const dfs_conv_bn& c, int co, int
   return q;
 }
 
+// conv1 / enc1 add their bias with the tensor core: appended to the Toeplitz weights are (i) the bias as a B operand
+// [K chunk 2][n 256][8]: K slot 0 = fp16(bias[n % 32]), slot 1 = the fp16 rounding residual, and (ii) the matching A operand
+// [K chunk 2][128 rows][8] whose every row is (1, 1, 0, ..., 0); one MMA of the two initialises an accumulator tile with the bias.
+static void append_bias_and_ones(std::vector<uint16_t>& pack, const float* bias32) {
+  const size_t at = pack.size();
+  pack.resize(at + (size_t)2 * 256 * 8 + (size_t)2 * 128 * 8, 0);
+  for (int n = 0; n < 256; ++n) {
+    const double b = (double)bias32[n % 32];
+    const uint16_t hi = f32_to_act_bits((float)b);
+    pack[at + (size_t)n * 8 + 0] = hi;
+    pack[at + (size_t)n * 8 + 1] = f32_to_act_bits((float)(b - act_bits_to_double(hi)));
+  }
+  const size_t ones = at + (size_t)2 * 256 * 8;
+  for (int r = 0; r < 128; ++r) pack[ones + (size_t)r * 8 + 0] = pack[ones + (size_t)r * 8 + 1] = 0x3C00;   // fp16 1.0
+}
+
 // BN fold in double: scale[co], shift[co] such that  y = scale*(conv_nobias) + shift
 static void bn_fold(const dfs_conv_bn& c, int co, std::vector<double>& scale, std::vector<double>& shift) {
   scale.assign(co, 1.0);
@@ -441,6 +457,7 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
             p1[img + at] = f32_to_act_bits((float)(wv - act_bits_to_double(p1[at])));
           }
     for (int c = 0; c < 32; ++c) m->b1h[c] = 0.5f * m->c1.b[c];
+    append_bias_and_ones(p1, m->b1h);
     if ((st = dev_upload(m, &m->w1pack, p1)) != DFS_OK) return fail(st);
     if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->xt), (size_t)conv1_xt_rows(m->chunk) * 16, true)) != DFS_OK) return fail(st);
   }
@@ -825,6 +842,7 @@ static int cae_tc_create(dfs_model* m, const dfs_cae_weights* w) {
             p1[(((size_t)kw * 2 + (o >> 3)) * 256 + nn) * 8 + (o & 7)] = f32_to_act_bits(0.25f * s->c1.w[c * 9 + kh * 3 + kw]);
           }
     for (int c = 0; c < 32; ++c) s->b1q[c] = 0.25f * s->c1.b[c];
+    append_bias_and_ones(p1, s->b1q);
     uint16_t* d = nullptr;
     DFS_PROPAGATE(dev_upload(m, &d, p1));
     s->w1pack = d;

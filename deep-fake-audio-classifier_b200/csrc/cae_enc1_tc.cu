@@ -14,7 +14,8 @@
 // of each output plane.  One bulk copy of 18 columns x 41 rows (11.8 KB) feeds the 5 tiles (tb 0..39) of a 16-column unit.
 // The 0.25 of the 2x2 average is folded into weights and bias (ReLU is positively homogeneous).  Output: e1 in the FT8P
 // layout enc2's PAIR GEMM reads (layout.cuh): pooled time step 4tb + k -> parity plane k & 1, row 2tb + (k >> 1) + 1.
-// Like conv1_tc the kernel is bound by the TMEM read-out of the fp32 accumulators (64 B/clk/SM), not by the MMAs.
+// Like conv1_tc the kernel is bound by its epilogue (a chain of dependent latencies), not by the MMAs; the bias is added by
+// the tensor core (a ones x bias MMA initialises every accumulator).
 #include "common.cuh"
 #include "kernels.h"
 #include "layout.cuh"
@@ -31,7 +32,9 @@ constexpr int kE1WinB = kE1WinRows * 16;                // 11808
 constexpr int kE1WinBAl = 12288;
 constexpr int kE1Stages = 4;
 constexpr int kE1TilesPerUnit = 5;                      // time blocks 0..39 in tiles of 8 (block 40 only feeds K chunk 1)
-constexpr int kE1WgtB = 3 * 256 * 16 * 2;               // 24576
+constexpr int kE1BiasOff = 3 * 256 * 16 * 2;            // 24576: bias as a B operand [chunk 2][256][8] (K slot 0 = fp16(bias), slot 1 = its residual)
+constexpr int kE1OnesOff = kE1BiasOff + 8192;           // the matching A operand [chunk 2][128][8]: every row = (1, 1, 0, ...)
+constexpr int kE1WgtB = kE1OnesOff + 4096;              // weights + bias image + ones tile
 constexpr int kE1EpiWarps = 16;
 constexpr int kE1Threads = (kE1EpiWarps + 3) * 32;      // 608
 constexpr int kE1BarOff = kE1WgtB + kE1Stages * kE1WinBAl;
@@ -75,8 +78,7 @@ __global__ void __launch_bounds__(256) cae_enc1_prep_kernel(const float* __restr
 
 struct Enc1TcParams {
   const uint16_t* xt;      // xT2 rows (16 B each)
-  const uint16_t* wpack;   // [kw][chunk 2][n 256][8] fp16 Toeplitz weights, 0.25 folded
-  float bias[32];          // 0.25 * folded bias
+  const uint16_t* wpack;   // [kw][chunk 2][n 256][8] fp16 Toeplitz weights, 0.25 folded | bias image | ones tile
   int n_units;             // 16-column units over the global column index n * 184 + f''
   int n_utts;
   uint16_t* out;           // e1, FT8P, 8 planes x (92 columns per utterance) x RS 82
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
     // ===================== producer =====================
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(wbar, kE1WgtB);
-      for (int off = 0; off < kE1WgtB; off += 8192) bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, 8192, wbar);
+      for (int off = 0; off < kE1WgtB; off += 4096) bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, 4096, wbar);
       uint32_t ws = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ws) {
         const int stage = ws % kE1Stages;
@@ -137,6 +139,9 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
       // A: K chunk 1 of a row is the next row (LBO = 16 B); the 16 core-matrix groups of a tile are 16 columns (SBO = 41 rows)
       const uint64_t a_desc0 = umma_smem_desc(smem_u32(win0), 16, kE1Blocks * 16);
       const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
+      // the bias enters through the tensor core: ones[128 x 16] * biasB[256 x 16]^T initialises the accumulator (fp16 value + residual)
+      const uint64_t ones_desc = umma_smem_desc(smem_u32(wsm + kE1OnesOff), 128 * 16, 128);
+      const uint32_t ones_lo = (uint32_t)ones_desc, ones_hi = (uint32_t)(ones_desc >> 32);
       mbar_wait(wbar, 0, 42);
       uint32_t ws = 0, it = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++ws) {
@@ -148,10 +153,10 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
           const int acc = it & 1;
           mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, 44);
           tc_fence_after();
+          umma_f16_lohi(tmem_base + acc * 256, ones_lo, ones_hi, b_lo0 + (uint32_t)(kE1BiasOff >> 4), b_hi, idesc, 0u);
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw)   // window column 0 is 16u - 1: tap kw starts kw columns in; tile tt starts at row 8 tt
-            umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kw * kE1Blocks + 8 * tt), a_hi, b_lo0 + (uint32_t)(kw * (8192 >> 4)), b_hi, idesc,
-                          kw != 0 ? 1u : 0u);
+            umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kw * kE1Blocks + 8 * tt), a_hi, b_lo0 + (uint32_t)(kw * (8192 >> 4)), b_hi, idesc, 1u);
           umma_commit(&tfull[acc]);
         }
         umma_commit(&empty[stage]);
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
           const float* bv = b[k & 1];
           float o[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) o[c] = relu_nan(av[c] + p.bias[16 * h + c]) + relu_nan(bv[c] + p.bias[16 * h + c]);
+          for (int c = 0; c < 16; ++c) o[c] = relu_nan(av[c]) + relu_nan(bv[c]);   // the bias is already in the accumulator
           float v[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -249,7 +254,7 @@ int launch_cae_enc1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n
   Enc1TcParams p{};
   p.xt = xt;
   p.wpack = wpack;
-  for (int i = 0; i < 32; ++i) p.bias[i] = bias_quarter[i];
+  (void)bias_quarter;   // rides in wpack's bias image
   p.n_units = (int)ceil_div64((long long)n_utts * kE1Cols, kE1UnitCols);
   p.n_utts = n_utts;
   p.out = out.ptr;

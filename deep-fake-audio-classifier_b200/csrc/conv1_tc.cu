@@ -30,7 +30,9 @@ constexpr int kC1WinB = kC1WinRows * 16;               // 3392
 constexpr int kC1WinBAl = 3456;
 constexpr int kC1Stages = 4;
 constexpr int kC1WgtImgB = 3 * 256 * 16 * 2;           // 24576: one image [kw][chunk 2][256][8]
-constexpr int kC1WgtB = 2 * kC1WgtImgB;                // value image + residual image (w = hi + lo)
+constexpr int kC1BiasOff = 2 * kC1WgtImgB;             // bias as a B operand [chunk 2][256][8]: K slot 0 = fp16(bias), slot 1 = its residual
+constexpr int kC1OnesOff = kC1BiasOff + 8192;          // the matching A operand [chunk 2][128][8]: every row = (1, 1, 0, ...)
+constexpr int kC1WgtB = kC1OnesOff + 4096;             // value image + residual image + bias image + ones tile
 constexpr int kC1EpiWarps = 16;
 constexpr int kC1Threads = (kC1EpiWarps + 3) * 32;     // 608
 constexpr int kC1StageWarpB = 2 * 128 * 16;              // epilogue staging per warp: 2 planes x 128 chunks x 16 B
@@ -75,8 +77,7 @@ __global__ void __launch_bounds__(256) conv1_prep_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------
 struct Conv1TcParams {
   const uint16_t* xt;      // xT rows (16 B each)
-  const uint16_t* wpack;   // [hi | lo][kw][chunk 2][n 256][8] fp16 Toeplitz weights: value and rounding residual
-  float bias[32];          // 0.5 * folded bias
+  const uint16_t* wpack;   // [hi | lo][kw][chunk 2][n 256][8] fp16 Toeplitz weights (value, rounding residual) | bias image | ones tile
   int n_tiles;
   int n_utts;
   uint16_t* out;           // act1, FT8, RS = 162
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
     // ===================== producer =====================
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(wbar, kC1WgtB);
-      for (int off = 0; off < kC1WgtB; off += 8192) bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, 8192, wbar);
+      for (int off = 0; off < kC1WgtB; off += 4096) bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, 4096, wbar);
       uint32_t ws = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ws) {
         const int stage = ws % kC1Stages;
@@ -135,6 +136,9 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
       const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
       const uint64_t a_desc0 = umma_smem_desc(smem_u32(win0), 16, 128);   // LBO = 16 B: K chunk 1 of row R is row R+1
       const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
+      // the bias enters through the tensor core: ones[128 x 16] * biasB[256 x 16]^T initialises the accumulator (2 of the 16 K slots used:
+      // fp16 value + residual), which takes 2 FADD per channel pair out of an epilogue that is the kernel's bottleneck
+      const uint32_t ones_lo = (uint32_t)umma_smem_desc(smem_u32(wsm + kC1OnesOff), 128 * 16, 128);
       mbar_wait(wbar, 0, 22);
       uint32_t ws = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ws) {
@@ -143,12 +147,13 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
         mbar_wait(&tempty[acc], ((ws >> 1) & 1) ^ 1, 24);
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (kC1WinBAl >> 4));
+        umma_f16_lohi(tmem_base + acc * 256, ones_lo, a_hi, b_lo0 + (uint32_t)(kC1BiasOff >> 4), b_hi, idesc, 0u);
 #pragma unroll
         for (int part = 0; part < 2; ++part) {   // weight value, then weight residual
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw)
             umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kw * kXtBlocks), a_hi,
-                          b_lo0 + (uint32_t)((part * kC1WgtImgB + kw * 8192) >> 4), b_hi, idesc, (part | kw) != 0 ? 1u : 0u);
+                          b_lo0 + (uint32_t)((part * kC1WgtImgB + kw * 8192) >> 4), b_hi, idesc, 1u);
         }
         umma_commit(&tfull[acc]);
         umma_commit(&empty[stage]);
@@ -204,8 +209,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
         uint32_t pk[8];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
-          const float o0 = relu_nan(av[c] + p.bias[16 * h + c]) + relu_nan(bv[c] + p.bias[16 * h + c]);
-          const float o1 = relu_nan(av[c + 1] + p.bias[16 * h + c + 1]) + relu_nan(bv[c + 1] + p.bias[16 * h + c + 1]);
+          const float o0 = relu_nan(av[c]) + relu_nan(bv[c]);                 // the bias is already in the accumulator
+          const float o1 = relu_nan(av[c + 1]) + relu_nan(bv[c + 1]);
           pk[c >> 1] = pack_act2(o0, o1);
         }
         // pooled step j = 4tb + k: parity k&1, row offset k>>1 within the lane's two rows of that parity plane
@@ -263,7 +268,7 @@ int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_ut
   Conv1TcParams p{};
   p.xt = xt;
   p.wpack = wpack;
-  for (int i = 0; i < 32; ++i) p.bias[i] = bias_half[i];
+  (void)bias_half;   // rides in wpack's bias image
   p.n_tiles = (int)ceil_div64((long long)n_utts * kCols * kXtBlocks, 128);
   p.n_utts = n_utts;
   p.out = out.ptr;
