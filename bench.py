@@ -612,8 +612,9 @@ def main():
 
     # ---- e2e: the same metric through the public host-buffer call (pinned host -> H2D -> kernels -> D2H) ----
     Pe = min(args.e2e_pool, P)
-    host_pool = torch.empty((Pe, 321, 180), dtype=torch.float32, pin_memory=True)   # allocated after set_device, by this rank
-    host_pool.copy_(pool[:Pe])
+    with D.hostmem.numa_local(local) as numa:                                       # pages next to this rank's GPU where the host has > 1 node
+        host_pool = torch.empty((Pe, 321, 180), dtype=torch.float32, pin_memory=True)   # allocated after set_device, by this rank
+        host_pool.copy_(pool[:Pe])
     lab_e = labels_global[:Pe]
     e2e_last = {}
 
@@ -694,6 +695,7 @@ def main():
                    "frac_of_device_resident": e2e_value / value,
                    "h2d_ceiling_note": f"bare pinned cudaMemcpyAsync of the same pool in 96 MB pieces, {world} rank(s) copying at once, no kernels: "
                                        "what this host can feed; the fp32 e2e number is bound by it, not by a kernel",
+                   "numa": dict(numa.applied, host_nodes=len(D.hostmem.host_nodes())),
                    "note": "dfs_score_host: pinned host features -> double-buffered H2D -> kernels -> D2H scores, + EER"},
            "e2e_f16_slab": {"value": e2e16_value, "unit": "utterances/s", "h2d_bytes_per_step": Pe * BYTES_PER_UTT // 2, "steps": e16_steps,
                             "scores_identical_to_fp32_slab": same16,

@@ -53,7 +53,13 @@ class FeatureTable:
 
 
 def _alloc(n, dtype=torch.float32):
-    return torch.empty((n, N_FEATS, T_FRAMES), dtype=dtype, pin_memory=torch.cuda.is_available())
+    """One slab for the whole table; pinned next to the current GPU's PCIe root where the host has several NUMA nodes
+    (dfs_b200.hostmem: the upload of this slab is what bounds the end-to-end rate)."""
+    if not torch.cuda.is_available():
+        return torch.empty((n, N_FEATS, T_FRAMES), dtype=dtype)
+    from dfs_b200 import hostmem
+    with hostmem.numa_local(torch.cuda.current_device()):
+        return torch.empty((n, N_FEATS, T_FRAMES), dtype=dtype, pin_memory=True)   # cudaHostAlloc populates the pages here
 
 
 def pack_features(rows, dtype=torch.float32) -> "torch.Tensor":

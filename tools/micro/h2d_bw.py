@@ -124,6 +124,96 @@ try:
 except OSError as e:
     if rank == 0:
         print("# sched_setaffinity not permitted:", e)
+
+# ---- NUMA placement: where the pinned pages live relative to the GPU's PCIe root ---------------------------------------
+from dfs_b200 import hostmem  # noqa: E402
+from dfs_b200.hostmem import MPOL_BIND, MPOL_DEFAULT, MPOL_INTERLEAVE, host_nodes, node_cpus, set_mempolicy  # noqa: E402
+
+node = hostmem.gpu_numa_node(local)
+try:
+    bdf = hostmem.gpu_pci_bdf(local)
+except Exception as e:  # noqa: BLE001
+    bdf = str(e)
+nodes = host_nodes()
+info = [None] * world
+if world > 1:
+    dist.all_gather_object(info, (rank, bdf, node))
+else:
+    info = [(rank, bdf, node)]
+if rank == 0:
+    print(f"# host NUMA nodes {nodes}; this process may run on cpus {sorted(os.sched_getaffinity(0))}")
+    for n_ in nodes:
+        print(f"#   node{n_} cpus {node_cpus(n_)[:4]}...({len(node_cpus(n_))})")
+    for r_, b_, n_ in info:
+        print(f"#   rank {r_} GPU {b_} numa_node {n_}")
+for name, mode, sel in (("mempolicy BIND to the GPU's node", MPOL_BIND, [node] if node >= 0 else []),
+                        ("mempolicy INTERLEAVE over all nodes", MPOL_INTERLEAVE, nodes)):
+    if not sel or len(nodes) < 2:
+        if rank == 0:
+            print(f"# {name}: skipped (nodes {nodes}, gpu node {node})")
+        continue
+    err = set_mempolicy(mode, sel)
+    errs = [None] * world
+    if world > 1:
+        dist.all_gather_object(errs, err)
+    else:
+        errs = [err]
+    if any(errs):
+        if rank == 0:
+            print(f"# {name}: set_mempolicy failed, errno {errs}")
+        set_mempolicy(MPOL_DEFAULT, [])
+        continue
+    local_cpus = [c for c in node_cpus(node) if c in cores] if mode == MPOL_BIND else []
+    if local_cpus:
+        os.sched_setaffinity(0, local_cpus)
+    c_ = D.pinned_empty((N_UTT * UTT // 4,), "float32")
+    c_[...] = 1.0
+    report(f"{name} (+ cpu affinity to {len(local_cpus)} local cores), cudaHostAlloc, 416-utterance pieces", measure(torch_view(c_), 416))
+    del c_
+    set_mempolicy(MPOL_DEFAULT, [])
+    os.sched_setaffinity(0, cores)
+
+with hostmem.numa_local(local) as nl:
+    e_ = D.pinned_empty((N_UTT * UTT // 4,), "float32")
+    e_[...] = 1.0
+applied = [None] * world
+if world > 1:
+    dist.all_gather_object(applied, nl.applied)
+else:
+    applied = [nl.applied]
+report("hostmem.numa_local(device) around pinned_empty + first touch (the product call)", measure(torch_view(e_), 416))
+if rank == 0:
+    print("#   applied per rank:", applied)
+del e_
+
+# ---- how the aggregate builds up: only the first k ranks copy, the others idle (same slab, default placement) ----------
+if world > 1:
+    d_ = D.pinned_empty((N_UTT * UTT // 4,), "float32")
+    d_[...] = 1.0
+    dv = torch_view(d_)
+    k = 1
+    while k <= world:
+        active = rank < k
+        piece = 416 * UTT // 4
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        reps = 12 if active else 0
+        for _ in range(reps):
+            for kk, i in enumerate(range(0, dv.numel(), piece)):
+                m = min(piece, dv.numel() - i)
+                dst[(kk & 1) * piece:(kk & 1) * piece + m].copy_(dv[i:i + m], non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1) if active else 0.0], dtype=torch.float64, device=dev)
+        per = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(per, ms)
+        rates = [dv.numel() * 4 * 12 / (float(p.item()) * 1e-3) / 1e9 for p in per[:k]]
+        results[f"first {k} rank(s) copying"] = rates
+        if rank == 0:
+            print(f"first {k} rank(s) copying, others idle: per-rank GB/s {[round(r_, 1) for r_ in rates]}  sum {sum(rates):.1f}", flush=True)
+        k *= 2
+    del d_, dv
 if rank == 0:
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
