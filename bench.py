@@ -740,6 +740,23 @@ def main():
         out["parity"]["fp32_mode"] = {"max_rel_err_scores_vs_cpu_reference": float(np.max(np.abs(s32 - ref_scores) / np.abs(ref_scores))),
                                       "eer_gpu": eer32, "eer_delta_pp": 100.0 * abs(eer_cpu - eer32), "utterances_per_s": n_used / dt,
                                       "note": "precision=\"fp32\": fp32 operands and accumulation on the CUDA cores, explicit option"}
+        del exact
+        # ... and through the split-precision tensor-core kernels (Cnn2dScorer(precision="split")): every operand as fp16 value + residual,
+        # three MMAs per product; rate over several passes of the same utterances, device-resident
+        split = D.Cnn2dScorer(sd, device=local, precision="split")
+        ssp = split.score(feats_dev[:n_used], apply_sigmoid=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            split.score(feats_dev[:n_used], apply_sigmoid=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 4
+        ssp = ssp.cpu().numpy()
+        eersp = D.calculate_eer(ssp, lab)[0]
+        out["parity"]["split_mode"] = {"max_rel_err_scores_vs_cpu_reference": float(np.max(np.abs(ssp - ref_scores) / np.abs(ref_scores))),
+                                       "eer_gpu": eersp, "eer_delta_pp": 100.0 * abs(eer_cpu - eersp), "utterances_per_s": n_used / dt,
+                                       "note": "precision=\"split\": tcgen05 with fp16 value + residual operands (3 MMAs per product, fp32 accumulate), explicit option"}
+        del split
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

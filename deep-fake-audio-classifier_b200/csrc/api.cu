@@ -63,7 +63,18 @@ struct dfs_model {
   uint16_t* xt = nullptr;      // fp16 time-major copy of the features (conv1_tc A operand)
   uint16_t* w1pack = nullptr;  // Toeplitz weights [hi | lo][kw][2][256][8]: fp16 value and fp16 rounding residual of every weight
   float b1h[32] = {0};         // 0.5 * folded conv1 bias
-  int precision = 0;           // 0 = fp16 tensor-core operands / fp32 accumulate, 1 = full fp32 on the CUDA cores (cnn2d_fp32.cu)
+  int precision = 0;           // 0 = fp16 tensor-core operands / fp32 accumulate, 1 = full fp32 on the CUDA cores (cnn2d_fp32.cu),
+                               // 2 = "split": tensor cores with every operand as fp16 value + fp16 residual (3 MMAs per product)
+  // ---- CNN2D "split" precision (allocated when the option is first set) ----
+  std::vector<uint16_t> w2split_host, w3split_host;   // [rank 2][value | residual][tap][ci/8][64][8], packed at create time
+  std::vector<uint16_t> w1split_host;                 // conv1's Toeplitz pack with the power-of-two scale below
+  uint16_t* w1split = nullptr;
+  float split_inv[3] = {1.f, 1.f, 1.f};               // 1 / (power-of-two weight scale) of conv1..3: keeps the weight residuals out of fp16's subnormals
+  uint16_t* w2split = nullptr;
+  uint16_t* w3split = nullptr;
+  uint16_t* xt_lo = nullptr;
+  ActBuf act1s{}, act2s{};     // 16 planes: the 8 value planes, then the 8 residual planes
+  CUtensorMap tmap1s{}, tmap2s{};
   float* w32[3] = {nullptr, nullptr, nullptr};   // folded fp32 weights [(kh*3+kw)*ci + i][co] of the three conv blocks
   float* b32[3] = {nullptr, nullptr, nullptr};
   float* work32 = nullptr;     // fp32 activations of one sub-chunk, allocated when the option is first set
@@ -143,11 +154,11 @@ static std::vector<uint16_t> round_conv3x3_f16(const dfs_conv_bn& c, int co, int
 // conv1 / enc1 add their bias with the tensor core: appended to the Toeplitz weights are (i) the bias as a B operand
 // [K chunk 2][n 256][8]: K slot 0 = fp16(bias[n % 32]), slot 1 = the fp16 rounding residual, and (ii) the matching A operand
 // [K chunk 2][128 rows][8] whose every row is (1, 1, 0, ..., 0); one MMA of the two initialises an accumulator tile with the bias.
-static void append_bias_and_ones(std::vector<uint16_t>& pack, const float* bias32) {
+static void append_bias_and_ones(std::vector<uint16_t>& pack, const float* bias32, double factor = 1.0) {
   const size_t at = pack.size();
   pack.resize(at + (size_t)2 * 256 * 8 + (size_t)2 * 128 * 8, 0);
   for (int n = 0; n < 256; ++n) {
-    const double b = (double)bias32[n % 32];
+    const double b = factor * (double)bias32[n % 32];
     const uint16_t hi = f32_to_act_bits((float)b);
     pack[at + (size_t)n * 8 + 0] = hi;
     pack[at + (size_t)n * 8 + 1] = f32_to_act_bits((float)(b - act_bits_to_double(hi)));
@@ -264,6 +275,23 @@ extern "C" int dfs_model_destroy(dfs_model* m) {
   return DFS_OK;
 }
 
+// "split" precision of the 2D-CNN: residual image of the features, activation buffers with value + residual planes, their tensor maps
+// and the value | residual weight images; allocated when the option is first set (1.6 GB more per 416-utterance pass).
+static int cnn2d_split_init(dfs_model* m) {
+  DFS_CUDA_CHECK(cudaSetDevice(m->device));
+  DFS_PROPAGATE(dev_upload(m, &m->w1split, m->w1split_host));
+  DFS_PROPAGATE(dev_upload(m, &m->w2split, m->w2split_host));
+  DFS_PROPAGATE(dev_upload(m, &m->w3split, m->w3split_host));
+  DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&m->xt_lo), (size_t)conv1_xt_rows(m->chunk) * 16, true));
+  m->act1s = ActBuf{nullptr, 16, kAct1RS, m->act1.ncols};
+  m->act2s = ActBuf{nullptr, 16, kAct2RS, m->act2.ncols};
+  DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&m->act1s.ptr), m->act1s.bytes(), true));
+  DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&m->act2s.ptr), m->act2s.bytes(), true));
+  DFS_PROPAGATE(make_cnn2d_split_tensor_maps(&m->tmap1s, &m->tmap2s, m->act1s, m->act2s));
+  DFS_CUDA_CHECK(cudaDeviceSynchronize());   // the zero padding must be in place before any stream uses it
+  return DFS_OK;
+}
+
 extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value) {
   DFS_REQUIRE(m && key, DFS_ERR_INVALID, "dfs_model_set_option: NULL argument");
   if (strcmp(key, "conv_impl") == 0) {
@@ -278,8 +306,10 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     return DFS_OK;
   }
   if (strcmp(key, "precision") == 0) {
-    DFS_REQUIRE((m->kind == KIND_CNN2D || m->kind == KIND_CNN1D || m->kind == KIND_CAE) && (value == 0 || value == 1), DFS_ERR_INVALID,
-                "precision: 0 (fp16 tensor-core operands, fp32 accumulate) | 1 (full fp32 on the CUDA cores); 2D-CNN, 1D-CNN and CAE handles");
+    DFS_REQUIRE((m->kind == KIND_CNN2D || m->kind == KIND_CNN1D || m->kind == KIND_CAE) && (value == 0 || value == 1 || (value == 2 && m->kind == KIND_CNN2D)),
+                DFS_ERR_INVALID,
+                "precision: 0 (fp16 tensor-core operands, fp32 accumulate) | 1 (full fp32 on the CUDA cores); 2D-CNN, 1D-CNN and CAE handles | "
+                "2 (split: tensor cores, operands as fp16 value + residual; 2D-CNN handles)");
     if (m->kind != KIND_CNN2D) {   // 1D-CNN / CAE: the fp32 CUDA-core kernels of simt_models.cu (fp32 weights and activations)
       m->conv_impl = (int)value;
       return DFS_OK;
@@ -289,6 +319,7 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
       m->chunk32 = std::min(m->chunk, 16);
       DFS_PROPAGATE(dev_alloc(m, reinterpret_cast<void**>(&m->work32), cnn2d_fp32_work_floats(m->chunk32) * sizeof(float), false));
     }
+    if (value == 2 && m->w2split == nullptr) DFS_PROPAGATE(cnn2d_split_init(m));
     m->precision = (int)value;
     return DFS_OK;
   }
@@ -409,6 +440,68 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
         }
   }
   std::vector<uint16_t> p3 = pack_conv3x3_f16(w->conv[2], 128, 64, b3);
+  // "split" precision (option precision = 2): every folded weight as fp16 value + fp16 rounding residual, one image pair per CTA of a
+  // pair (cta_group::2: rank r holds the N rows [64 r, 64 r + 64)): [rank][value | residual][tap][ci/8][64][8]
+  {
+    std::vector<double> scale, shift;
+    auto put = [](std::vector<uint16_t>& img, size_t at, size_t term_stride, double wv) {
+      img[at] = f32_to_act_bits((float)wv);
+      img[at + term_stride] = f32_to_act_bits((float)(wv - act_bits_to_double(img[at])));
+    };
+    // Folded weights are ~1e-2: their fp16 residuals (2^-12 of that) would be fp16 SUBNORMALS, good to 3e-8 absolute = 1e-6 of the weight
+    // instead of 2^-22.  Each layer's weights are therefore multiplied by a power of two (exact) that brings the largest one into
+    // [8, 16), and the epilogue multiplies the accumulator by its inverse (one FFMA with the bias instead of an FADD).
+    auto pow2_scale = [](const dfs_conv_bn& c, size_t count, int ci9, const std::vector<double>& sc, double factor) {
+      double mx = 0.0;
+      for (size_t i = 0; i < count; ++i) mx = std::max(mx, std::fabs(factor * (double)c.weight[i] * sc[i / ci9]));
+      int k = (mx > 0.0 && std::isfinite(mx)) ? (int)std::floor(std::log2(8.0 / mx)) : 0;
+      k = std::max(0, std::min(k, 14));
+      return std::ldexp(1.0, k);
+    };
+    bn_fold(w->conv[0], 32, scale, shift);
+    {
+      const double S1 = pow2_scale(w->conv[0], 32 * 9, 9, scale, 0.5);
+      m->split_inv[0] = (float)(1.0 / S1);
+      const size_t img = (size_t)3 * 2 * 256 * 8;
+      m->w1split_host.assign(2 * img, 0);
+      for (int kw = 0; kw < 3; ++kw)
+        for (int jj = 0; jj < 8; ++jj)
+          for (int c = 0; c < 32; ++c)
+            for (int kh = 0; kh < 3; ++kh) {
+              const int o = jj + kh, nn = jj * 32 + c;
+              put(m->w1split_host, (((size_t)kw * 2 + (o >> 3)) * 256 + nn) * 8 + (o & 7), img,
+                  S1 * 0.5 * (double)w->conv[0].weight[c * 9 + kh * 3 + kw] * scale[c]);
+            }
+      float bh[32];
+      for (int c = 0; c < 32; ++c) bh[c] = (float)(0.5 * shift[c]);
+      append_bias_and_ones(m->w1split_host, bh, S1);
+    }
+    bn_fold(w->conv[1], 64, scale, shift);
+    const double S2 = pow2_scale(w->conv[1], (size_t)64 * 32 * 9, 32 * 9, scale, 0.5);
+    m->split_inv[1] = (float)(1.0 / S2);
+    const size_t t2 = (size_t)12 * 32 * 64;   // one conv2 image (PAIR formulation: rank = which of the two pooled time steps)
+    m->w2split_host.assign(4 * t2, 0);
+    for (int r = 0; r < 4; ++r)
+      for (int kw = 0; kw < 3; ++kw)
+        for (int dt2 = 0; dt2 < 2; ++dt2) {
+          const int kh = r - dt2;
+          if (kh < 0 || kh > 2) continue;
+          for (int ci = 0; ci < 32; ++ci)
+            for (int o = 0; o < 64; ++o)
+              put(m->w2split_host, (size_t)dt2 * 2 * t2 + ((((size_t)(r * 3 + kw)) * 4 + (ci >> 3)) * 64 + o) * 8 + (ci & 7), t2,
+                  S2 * 0.5 * (double)w->conv[1].weight[((size_t)o * 32 + ci) * 9 + kh * 3 + kw] * scale[o]);
+        }
+    bn_fold(w->conv[2], 128, scale, shift);
+    const double S3 = pow2_scale(w->conv[2], (size_t)128 * 64 * 9, 64 * 9, scale, 1.0);
+    m->split_inv[2] = (float)(1.0 / S3);
+    const size_t t3 = (size_t)9 * 64 * 64;
+    m->w3split_host.assign(4 * t3, 0);
+    for (int tap = 0; tap < 9; ++tap)
+      for (int ci = 0; ci < 64; ++ci)
+        for (int o = 0; o < 128; ++o)
+          put(m->w3split_host, (size_t)(o >> 6) * 2 * t3 + (((size_t)tap * 8 + (ci >> 3)) * 64 + (o & 63)) * 8 + (ci & 7), t3,
+              S3 * (double)w->conv[2].weight[((size_t)o * 64 + ci) * 9 + tap] * scale[o]);
+  }
   memcpy(m->b2, b2.data(), sizeof(m->b2));
   memcpy(m->b3, b3.data(), sizeof(m->b3));
   if ((st = dev_upload(m, &m->w2pack, p2)) != DFS_OK) return fail(st);
@@ -497,6 +590,30 @@ extern "C" int dfs_cnn2d_score(dfs_model* m, const dfs_features* feats, float* o
       const int nk = (int)std::min<int64_t>(m->chunk32, feats->n - i0);
       DFS_PROPAGATE(launch_cnn2d_fp32(feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->w32, m->b32,
                                       m->fcw_dev, m->fcb, apply_sigmoid, m->work32, m->emb, out_dev + i0, stream));
+      if (embedding_dev) DFS_PROPAGATE(launch_cnn2d_embedding_export(m->emb, nk, embedding_dev + i0 * (int64_t)kF * 128, stream));
+    }
+    return DFS_OK;
+  }
+  if (m->precision == 2) {   // split: the same three layers on the tensor cores with value + residual operands
+    for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk) {
+      const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
+      {
+        ProfScope ps(m, 0, stream);
+        DFS_PROPAGATE(launch_conv1_tc_split(feats->x + i0 * feats->stride_n, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->xt, m->xt_lo,
+                                            m->w1split, m->split_inv[0], m->act1s, m->num_sms, stream));
+      }
+      {
+        ProfScope ps(m, 1, stream);
+        DFS_PROPAGATE(launch_cnn2d_conv2_split(m->tmap1s, m->w2split, m->b2, m->split_inv[1], nk, m->act2s, m->num_sms, stream));
+      }
+      {
+        ProfScope ps(m, 2, stream);
+        DFS_PROPAGATE(launch_cnn2d_conv3_split(m->tmap2s, m->w3split, m->b3, m->split_inv[2], nk, m->emb, m->num_sms, stream));
+      }
+      {
+        ProfScope ps(m, 3, stream);
+        DFS_PROPAGATE(launch_cnn2d_head(m->emb, m->fcw_dev, m->fcb, nk, apply_sigmoid, out_dev + i0, stream, true));
+      }
       if (embedding_dev) DFS_PROPAGATE(launch_cnn2d_embedding_export(m->emb, nk, embedding_dev + i0 * (int64_t)kF * 128, stream));
     }
     return DFS_OK;

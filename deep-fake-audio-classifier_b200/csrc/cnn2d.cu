@@ -96,32 +96,43 @@ int launch_conv1(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts,
 // ------------------------------------------------------------------------------------------
 // head: one block per utterance
 // ------------------------------------------------------------------------------------------
+// ACC = double ("split" precision): the 23,040 products are exact in fp64 and so is their sum to ~1e-16; with trained-like
+// classifiers the positive and negative terms cancel to ~1e-3 of their absolute sum, and an fp32 accumulation order shows up
+// as 1e-4 of logit -- more than the three split-precision conv layers together.
+template <typename ACC>
 __global__ void __launch_bounds__(256) cnn2d_head_kernel(const float* __restrict__ emb, const float* __restrict__ wfc, float fcb,
                                                           int apply_sigmoid, float* __restrict__ out) {
   constexpr int NE = kF * 128;
   const float4* e4 = reinterpret_cast<const float4*>(emb + (long long)blockIdx.x * NE);
   const float4* w4 = reinterpret_cast<const float4*>(wfc);
-  float acc = 0.0f;
+  ACC acc = 0;
   for (int i = threadIdx.x; i < NE / 4; i += blockDim.x) {
     const float4 a = e4[i], b = w4[i];
-    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    if constexpr (sizeof(ACC) == 8) {
+      acc = fma((double)a.x, (double)b.x, acc); acc = fma((double)a.y, (double)b.y, acc);
+      acc = fma((double)a.z, (double)b.z, acc); acc = fma((double)a.w, (double)b.w, acc);
+    } else {
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  __shared__ float part[8];
+  __shared__ ACC part[8];
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float s = fcb;
+    ACC s = (ACC)fcb;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += part[i];
-    out[blockIdx.x] = apply_sigmoid ? 1.0f / (1.0f + expf(-s)) : s;
+    const float sf = (float)s;
+    out[blockIdx.x] = apply_sigmoid ? 1.0f / (1.0f + expf(-sf)) : sf;
   }
 }
 
-int launch_cnn2d_head(const float* emb, const float* wfc, float fcb, int n_utts, int apply_sigmoid, float* out, cudaStream_t stream) {
+int launch_cnn2d_head(const float* emb, const float* wfc, float fcb, int n_utts, int apply_sigmoid, float* out, cudaStream_t stream, bool acc64) {
   if (n_utts <= 0) return DFS_OK;
-  cnn2d_head_kernel<<<n_utts, 256, 0, stream>>>(emb, wfc, fcb, apply_sigmoid, out);
+  if (acc64) cnn2d_head_kernel<double><<<n_utts, 256, 0, stream>>>(emb, wfc, fcb, apply_sigmoid, out);
+  else cnn2d_head_kernel<float><<<n_utts, 256, 0, stream>>>(emb, wfc, fcb, apply_sigmoid, out);
   DFS_LAUNCH_CHECK();
   return DFS_OK;
 }

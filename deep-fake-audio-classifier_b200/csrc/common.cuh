@@ -81,6 +81,11 @@ __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// the fp16 rounding residuals of (lo, hi) given their packed fp16 values: x - fp16(x) is exact in fp32, its fp16 rounding keeps 11 more bits
+__device__ __forceinline__ uint32_t pack_act2_residual(float lo, float hi, uint32_t packed) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&packed));
+  return pack_act2(lo - f.x, hi - f.y);
+}
 // ReLU that PROPAGATES NaN (FMNMX.NAN), like torch.relu on the reference's CPU path: fmaxf(NaN, 0) is 0, which would turn a NaN feature
 // into a finite score.  With this, a NaN anywhere in an utterance's features reaches its logit as NaN through every layer
 // (cvt.rn.satfinite keeps NaN as NaN, the MMAs propagate it); +-inf features are clamped to +-65504 by the input conversion.

@@ -36,9 +36,16 @@ constexpr int kC1WgtB = kC1OnesOff + 4096;             // value image + residual
 constexpr int kC1EpiWarps = 16;
 constexpr int kC1Threads = (kC1EpiWarps + 3) * 32;     // 608
 constexpr int kC1StageWarpB = 2 * 128 * 16;              // epilogue staging per warp: 2 planes x 128 chunks x 16 B
-constexpr int kC1BarOff = kC1WgtB + kC1Stages * kC1WinBAl;
-constexpr int kC1StageOff = kC1BarOff + 256;
-constexpr int kC1SmemB = kC1StageOff + kC1EpiWarps * kC1StageWarpB + kC1EpiWarps * 32 * 4;
+// SPLIT ("split" precision): a stage holds the value window and the residual window, the epilogue stages value and residual chunks
+template <bool SPLIT>
+struct C1Geo {
+  static constexpr int kStageStride = (SPLIT ? 2 : 1) * kC1WinBAl;
+  static constexpr int kWarpStageB = (SPLIT ? 2 : 1) * kC1StageWarpB;
+  static constexpr int kBarOff = kC1WgtB + kC1Stages * kStageStride;
+  static constexpr int kStageOff = kBarOff + 256;
+  static constexpr int kSmemB = kStageOff + kC1EpiWarps * kWarpStageB + kC1EpiWarps * 32 * 4;
+  static_assert(kSmemB <= 227 * 1024, "shared memory budget");
+};
 
 int64_t conv1_xt_rows(int64_t n_utts) { return kXtLead + n_utts * kCols * kXtBlocks + 128 + 2 * kXtBlocks + 16; }
 
@@ -46,7 +53,7 @@ int64_t conv1_xt_rows(int64_t n_utts) { return kXtLead + n_utts * kCols * kXtBlo
 // prep: fp32 strided features -> xT fp16 (row = 8 consecutive samples of one feature column)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv1_prep_kernel(const float* __restrict__ x, long long sn, long long st, long long sf, long long total,
-                                                          uint16_t* __restrict__ xt) {
+                                                          uint16_t* __restrict__ xt, uint16_t* __restrict__ xt_lo) {
   // item = (n, f, blk); thread mapping chosen so that global reads coalesce for the given storage order
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -69,7 +76,11 @@ __global__ void __launch_bounds__(256) conv1_prep_kernel(const float* __restrict
     v[e] = (t >= 0 && t < kT) ? src[(long long)t * st] : 0.0f;
   }
   uint16_t* dst = xt + ((long long)kXtLead + (n * kCols + f + 1) * kXtBlocks + blk) * 8;
-  st_global_v4(dst, pack_act2(v[0], v[1]), pack_act2(v[2], v[3]), pack_act2(v[4], v[5]), pack_act2(v[6], v[7]));   // saturating
+  const uint32_t h0 = pack_act2(v[0], v[1]), h1 = pack_act2(v[2], v[3]), h2 = pack_act2(v[4], v[5]), h3 = pack_act2(v[6], v[7]);   // saturating
+  st_global_v4(dst, h0, h1, h2, h3);
+  if (xt_lo != nullptr)   // split precision: the rounding residuals
+    st_global_v4(xt_lo + (dst - xt), pack_act2_residual(v[0], v[1], h0), pack_act2_residual(v[2], v[3], h1), pack_act2_residual(v[4], v[5], h2),
+                 pack_act2_residual(v[6], v[7], h3));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -77,19 +88,23 @@ __global__ void __launch_bounds__(256) conv1_prep_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------
 struct Conv1TcParams {
   const uint16_t* xt;      // xT rows (16 B each)
+  const uint16_t* xt_lo;   // split precision: the fp16 rounding residuals of xt, same geometry
   const uint16_t* wpack;   // [hi | lo][kw][chunk 2][n 256][8] fp16 Toeplitz weights (value, rounding residual) | bias image | ones tile
   int n_tiles;
   int n_utts;
-  uint16_t* out;           // act1, FT8, RS = 162
+  uint16_t* out;           // act1, FT8P; split precision: 8 residual planes after the 8 value planes
   long long out_ncols;
+  float inv_scale;         // split precision: 1 / (power-of-two scale of the weight and bias images)
 };
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_constant__ Conv1TcParams p) {
+  using Geo = C1Geo<SPLIT>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* wsm = smem;
   uint8_t* win0 = smem + kC1WgtB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kC1BarOff);
-  uint8_t* stage0 = smem + kC1StageOff;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Geo::kBarOff);
+  uint8_t* stage0 = smem + Geo::kStageOff;
   uint64_t* full = bars;                 // [stages]
   uint64_t* empty = bars + kC1Stages;    // [stages]
   uint64_t* tfull = empty + kC1Stages;   // [2]
@@ -122,10 +137,11 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ws) {
         const int stage = ws % kC1Stages;
         mbar_wait(&empty[stage], ((ws / kC1Stages) & 1) ^ 1, 21);
-        mbar_arrive_expect_tx(&full[stage], kC1WinB);
+        mbar_arrive_expect_tx(&full[stage], (SPLIT ? 2 : 1) * kC1WinB);
         // window = xT rows [R0 - 41, R0 + 128 + 41 + 2), R0 = 128*tile, shifted by the lead margin
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.xt) + ((long long)kXtLead + 128ll * tile - kXtBlocks) * 16;
-        bulk_g2s(win0 + stage * kC1WinBAl, src, kC1WinB, &full[stage]);
+        const long long off = ((long long)kXtLead + 128ll * tile - kXtBlocks) * 16;
+        bulk_g2s(win0 + stage * Geo::kStageStride, reinterpret_cast<const uint8_t*>(p.xt) + off, kC1WinB, &full[stage]);
+        if constexpr (SPLIT) bulk_g2s(win0 + stage * Geo::kStageStride + kC1WinBAl, reinterpret_cast<const uint8_t*>(p.xt_lo) + off, kC1WinB, &full[stage]);
       }
     }
   } else if (warp == kC1EpiWarps + 1) {
@@ -146,7 +162,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
         mbar_wait(&full[stage], (ws / kC1Stages) & 1, 23);
         mbar_wait(&tempty[acc], ((ws >> 1) & 1) ^ 1, 24);
         tc_fence_after();
-        const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (kC1WinBAl >> 4));
+        const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (Geo::kStageStride >> 4));
         umma_f16_lohi(tmem_base + acc * 256, ones_lo, a_hi, b_lo0 + (uint32_t)(kC1BiasOff >> 4), b_hi, idesc, 0u);
 #pragma unroll
         for (int part = 0; part < 2; ++part) {   // weight value, then weight residual
@@ -154,6 +170,12 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
           for (int kw = 0; kw < 3; ++kw)
             umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kw * kXtBlocks), a_hi,
                           b_lo0 + (uint32_t)((part * kC1WgtImgB + kw * 8192) >> 4), b_hi, idesc, 1u);
+        }
+        if constexpr (SPLIT) {   // the input's rounding residuals against the weight values
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+            umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kC1WinBAl >> 4) + (uint32_t)(kw * kXtBlocks), a_hi,
+                          b_lo0 + (uint32_t)((kw * 8192) >> 4), b_hi, idesc, 1u);
         }
         umma_commit(&tfull[acc]);
         umma_commit(&empty[stage]);
@@ -171,8 +193,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
     // store instruction touch 32 half-used sectors.  The chunks go through shared memory (XOR-swizzled,
     // conflict-free both ways) and are stored so that lane l of store j writes chunk 32j + l of the warp's
     // contiguous 1 KB run per plane.
-    uint4* stage = reinterpret_cast<uint4*>(stage0 + warp * kC1StageWarpB);            // [2 chunks][2 parities][64]
-    int* dsttab = reinterpret_cast<int*>(stage0 + kC1EpiWarps * kC1StageWarpB) + warp * 32;  // first output row of each lane
+    uint4* stage = reinterpret_cast<uint4*>(stage0 + warp * Geo::kWarpStageB);            // [value | residual][2 chunks][2 parities][64]
+    int* dsttab = reinterpret_cast<int*>(stage0 + kC1EpiWarps * Geo::kWarpStageB) + warp * 32;  // first output row of each lane
     uint32_t ws = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ws) {
       if ((int)(ws & 1) != grp) continue;
@@ -207,29 +229,43 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
         const float* av = a[k & 1];
         const float* bv = b[k & 1];
         uint32_t pk[8];
+        [[maybe_unused]] uint32_t pr[8];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
           const float o0 = relu_nan(av[c]) + relu_nan(bv[c]);                 // the bias is already in the accumulator
           const float o1 = relu_nan(av[c + 1]) + relu_nan(bv[c + 1]);
-          pk[c >> 1] = pack_act2(o0, o1);
+          if constexpr (SPLIT) {
+            const float s0 = o0 * p.inv_scale, s1 = o1 * p.inv_scale;   // exact: a power of two
+            pk[c >> 1] = pack_act2(s0, s1);
+            pr[c >> 1] = pack_act2_residual(s0, s1, pk[c >> 1]);
+          } else {
+            pk[c >> 1] = pack_act2(o0, o1);
+          }
         }
         // pooled step j = 4tb + k: parity k&1, row offset k>>1 within the lane's two rows of that parity plane
         const int slot = (k & 1) * 64 + 2 * lane + ((k >> 1) ^ sw);
         stage[slot] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         stage[128 + slot] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if constexpr (SPLIT) {
+          stage[256 + slot] = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+          stage[384 + slot] = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+        }
       }
       __syncwarp();
 #pragma unroll
-      for (int pl = 0; pl < 2; ++pl) {
+      for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {   // value planes 0..7, residual planes 8..15
 #pragma unroll
-        for (int par = 0; par < 2; ++par) {
-          uint16_t* pbase = p.out + (long long)(par * 4 + 2 * h + pl) * plane_elems;
+        for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int m = 32 * j + lane, r = m >> 1, c = m & 1;
-            const int row = dsttab[r];
-            const uint4 v = stage[pl * 128 + par * 64 + 2 * r + (c ^ ((r >> 2) & 1))];
-            if (row >= 0) st_global_v4(pbase + (long long)(row + c) * 8, v.x, v.y, v.z, v.w);
+          for (int par = 0; par < 2; ++par) {
+            uint16_t* pbase = p.out + (long long)(part * 8 + par * 4 + 2 * h + pl) * plane_elems;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int m = 32 * j + lane, r = m >> 1, c = m & 1;
+              const int row = dsttab[r];
+              const uint4 v = stage[part * 256 + pl * 128 + par * 64 + 2 * r + (c ^ ((r >> 2) & 1))];
+              if (row >= 0) st_global_v4(pbase + (long long)(row + c) * 8, v.x, v.y, v.z, v.w);
+            }
           }
         }
       }
@@ -246,16 +282,22 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
 }
 
 // fp32 strided features -> xT (the A operand image of conv1_tc_kernel)
-int launch_conv1_prep(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, cudaStream_t stream) {
+static int launch_conv1_prep_any(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, uint16_t* xt_lo, cudaStream_t stream) {
   if (n_utts <= 0) return DFS_OK;
   if (sf == 1) {   // feature-contiguous storage: transpose through shared memory (xt_prep.cuh)
-    xt_prep_transpose_kernel<<<dim3((kF + 31) / 32, n_utts), 256, 0, stream>>>(x, sn, st, kCols, 1, kXtLead, nullptr, nullptr, xt);
+    if (xt_lo != nullptr)
+      xt_prep_transpose_kernel<true><<<dim3((kF + 31) / 32, n_utts), 256, 0, stream>>>(x, sn, st, kCols, 1, kXtLead, nullptr, nullptr, xt, xt_lo);
+    else
+      xt_prep_transpose_kernel<false><<<dim3((kF + 31) / 32, n_utts), 256, 0, stream>>>(x, sn, st, kCols, 1, kXtLead, nullptr, nullptr, xt);
   } else {
     const long long total = (long long)n_utts * kF * kXtBlocks;
-    conv1_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, xt);
+    conv1_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, xt, xt_lo);
   }
   DFS_LAUNCH_CHECK();
   return DFS_OK;
+}
+int launch_conv1_prep(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, cudaStream_t stream) {
+  return launch_conv1_prep_any(x, sn, st, sf, n_utts, xt, nullptr, stream);
 }
 
 int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, const uint16_t* wpack, const float* bias_half,
@@ -264,7 +306,7 @@ int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_ut
   DFS_PROPAGATE(launch_conv1_prep(x, sn, st, sf, n_utts, xt, stream));
   static bool configured[32] = {false};
   if (dfs_first_use_on_device(configured))
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1SmemB));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(conv1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1Geo<false>::kSmemB));
   Conv1TcParams p{};
   p.xt = xt;
   p.wpack = wpack;
@@ -274,7 +316,31 @@ int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_ut
   p.out = out.ptr;
   p.out_ncols = out.ncols;
   const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-  conv1_tc_kernel<<<grid, kC1Threads, kC1SmemB, stream>>>(p);
+  conv1_tc_kernel<false><<<grid, kC1Threads, C1Geo<false>::kSmemB, stream>>>(p);
+  DFS_LAUNCH_CHECK();
+  return DFS_OK;
+}
+
+// "split" precision: input, weights and output as fp16 value + fp16 residual, 10 MMAs per tile (bias, x_hi W_hi, x_hi W_lo, x_lo W_hi)
+int launch_conv1_tc_split(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, uint16_t* xt_lo, const uint16_t* wpack,
+                          float inv_scale, ActBuf out, int num_sms, cudaStream_t stream) {
+  if (n_utts <= 0) return DFS_OK;
+  DFS_REQUIRE(xt_lo != nullptr && out.planes == 16, DFS_ERR_INVALID, "conv1 split: residual buffers missing");
+  DFS_PROPAGATE(launch_conv1_prep_any(x, sn, st, sf, n_utts, xt, xt_lo, stream));
+  static bool configured[32] = {false};
+  if (dfs_first_use_on_device(configured))
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(conv1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1Geo<true>::kSmemB));
+  Conv1TcParams p{};
+  p.xt = xt;
+  p.xt_lo = xt_lo;
+  p.wpack = wpack;
+  p.inv_scale = inv_scale;
+  p.n_tiles = (int)ceil_div64((long long)n_utts * kCols * kXtBlocks, 128);
+  p.n_utts = n_utts;
+  p.out = out.ptr;
+  p.out_ncols = out.ncols;
+  const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+  conv1_tc_kernel<true><<<grid, kC1Threads, C1Geo<true>::kSmemB, stream>>>(p);
   DFS_LAUNCH_CHECK();
   return DFS_OK;
 }

@@ -48,6 +48,17 @@ using Conv2Cfg = ConvCfg<MODE_PAIR, 32, 64, 128, 80, 2, 3, 4, 1, EPI_PAIR_POOL>;
 using Conv3Cfg = ConvCfg<MODE_3X3S, 64, 128, 256, 80, 1, 3, 2, 2, EPI_MEAN_T_SWAP>;   // weights as A, 256 positions as N
 using Conv3PlainCfg = ConvCfg<MODE_3X3, 64, 128, 128, 80, 2, 2, 4, 1, EPI_MEAN_T>;   // positions as A (N = 128), kept for comparison
 
+// "split" precision (option precision = 2; conv_tc.cuh SPLIT): value + residual planes and weight images, three MMAs per product.  Both
+// run on CTA pairs so that the doubled weight images stay resident (98 KB / 147 KB per CTA).
+using Conv2SplitCfg = ConvCfg<MODE_PAIR, 32, 64, 128, 80, 1, 4, 4, 1, EPI_PAIR_POOL, 1, 1>;
+using Conv3SplitCfg = ConvCfg<MODE_3X3, 64, 128, 128, 80, 1, 3, 4, 1, EPI_MEAN_T, 1, 1>;
+
+int make_cnn2d_split_tensor_maps(CUtensorMap* tmap_act1, CUtensorMap* tmap_act2, const ActBuf& act1, const ActBuf& act2) {
+  DFS_PROPAGATE(make_act_tensor_map(tmap_act1, act1, Conv2SplitCfg::WROWS, Conv2SplitCfg::WCOLS, Conv2SplitCfg::PPL));
+  DFS_PROPAGATE(make_act_tensor_map(tmap_act2, act2, Conv3SplitCfg::WROWS, Conv3SplitCfg::WCOLS, Conv3SplitCfg::PPL));
+  return DFS_OK;
+}
+
 int make_cnn2d_tensor_maps(CUtensorMap* tmap_act1, CUtensorMap* tmap_act2, const ActBuf& act1, const ActBuf& act2) {
   DFS_PROPAGATE(make_act_tensor_map(tmap_act1, act1, Conv2Cfg::WROWS, Conv2Cfg::WCOLS, Conv2Cfg::PPL));
   DFS_PROPAGATE(make_act_tensor_map(tmap_act2, act2, Conv3Cfg::WROWS, Conv3Cfg::WCOLS, Conv3Cfg::PPL));
@@ -70,6 +81,40 @@ int launch_cnn2d_conv2_tc(const CUtensorMap& tmap_act1, const uint16_t* wpack, c
   p.out_cols = kCols;
   p.out_feats = kF;
   return launch_conv_tc<Conv2Cfg>(tmap_act1, p, 1, num_sms, stream);
+}
+
+int launch_cnn2d_conv2_split(const CUtensorMap& tmap_act1, const uint16_t* wpack, const float* bias_half, float inv_scale, int n_utts, ActBuf act2,
+                             int num_sms, cudaStream_t stream) {
+  ConvParams p{};
+  p.wpack = wpack;
+  p.inv_scale = inv_scale;
+  for (int i = 0; i < 64; ++i) p.bias[i] = bias_half[i];
+  p.n_units = num_col_tiles(n_utts, kCols);
+  p.n_utts = n_utts;
+  p.cols = kCols;
+  p.feats = kF;
+  p.rows_valid = 80;
+  p.out = act2.ptr;
+  p.out_ncols = act2.ncols;
+  p.out_rs = act2.RS;
+  p.out_cols = kCols;
+  p.out_feats = kF;
+  return launch_conv_tc<Conv2SplitCfg>(tmap_act1, p, 1, num_sms, stream);
+}
+
+int launch_cnn2d_conv3_split(const CUtensorMap& tmap_act2, const uint16_t* wpack, const float* bias, float inv_scale, int n_utts, float* emb,
+                             int num_sms, cudaStream_t stream) {
+  ConvParams p{};
+  p.wpack = wpack;
+  p.inv_scale = inv_scale;
+  for (int i = 0; i < 128; ++i) p.bias[i] = bias[i];
+  p.n_units = num_col_tiles(n_utts, kCols);
+  p.n_utts = n_utts;
+  p.cols = kCols;
+  p.feats = kF;
+  p.rows_valid = 80;
+  p.emb = emb;
+  return launch_conv_tc<Conv3SplitCfg>(tmap_act2, p, 1, num_sms, stream);
 }
 
 int launch_cnn2d_conv3_tc(const CUtensorMap& tmap_act2, const uint16_t* wpack, const float* bias, int n_utts, float* emb,

@@ -59,10 +59,15 @@ enum {
 //           each CTA keeps only NG/2 of the NG weight rows in ITS shared memory.  Measured (profiles/r01f_umma_bench_pairs.txt): a
 //           pair MMA costs the cycles of a single-CTA MMA of the same N, i.e. per SM nothing is gained unless shared memory had
 //           forced N < 128 on one CTA (CAE enc4, StatsPool layer 1: 147 / 123 KB of weights per 64 output channels).
-template <int MODE_, int CIN_, int COUT_, int NG_, int ROWS_, int MT_, int NSTAGE_, int NACC_, int KSPLIT_, int EPI_, int CTA2_ = 0>
+// SPLIT = 1: the "split" precision (option precision = 2): every activation and every weight is carried as fp16 value + fp16 rounding
+//           residual (x = hi + lo up to 2^-22 |x|) and a product is three MMAs into the same fp32 accumulator, A_hi W_hi + A_hi W_lo +
+//           A_lo W_hi (the dropped A_lo W_lo term is 2^-22 of the product).  The input buffer holds the residual planes after the value
+//           planes (2 x KCH planes); a window is loaded as two pieces (value planes, residual planes) and the weight image of a group is
+//           [value image | residual image].  Epilogues that store activations write value and residual planes.
+template <int MODE_, int CIN_, int COUT_, int NG_, int ROWS_, int MT_, int NSTAGE_, int NACC_, int KSPLIT_, int EPI_, int CTA2_ = 0, int SPLIT_ = 0>
 struct ConvCfg {
   static constexpr int MODE = MODE_, CIN = CIN_, COUT = COUT_, NG = NG_, ROWS = ROWS_, MT = MT_, NSTAGE = NSTAGE_, NACC = NACC_,
-                       KSPLIT = KSPLIT_, EPI = EPI_, CTA2 = CTA2_;
+                       KSPLIT = KSPLIT_, EPI = EPI_, CTA2 = CTA2_, SPLIT = SPLIT_;
   static constexpr bool PAIR = (MODE == MODE_PAIR);
   static constexpr bool SWAP = (MODE == MODE_3X3S);
   static constexpr int CT = SWAP ? 32 : kColTile;      // feature columns per tile
@@ -71,15 +76,17 @@ struct ConvCfg {
   static constexpr int NTAP = PAIR ? 12 : (MODE == MODE_1X1 ? 1 : (MODE == MODE_3X1 ? 3 : (MODE == MODE_5X1 ? 5 : 9)));
   static constexpr int CCH = CIN / 8;                  // 16-byte channel chunks
   static constexpr int KCH = PAIR ? 2 * CCH : CCH;     // planes of the input layout (PAIR: x2 time parities)
-  static constexpr int PPL = KCH / KSPLIT;             // planes per piece
-  static constexpr int CPP = CCH / KSPLIT;             // channel chunks per piece
+  static constexpr int NPIECE = SPLIT ? 2 : KSPLIT;    // pipeline pieces per window (SPLIT: value planes, residual planes)
+  static constexpr int PPL = SPLIT ? KCH : KCH / KSPLIT;   // planes per piece
+  static constexpr int CPP = SPLIT ? CCH : CCH / KSPLIT;   // channel chunks per piece
   static constexpr int WROWS = 8 * MT + 2 * HALO;      // window rows incl. halo
   static constexpr int WCOLS = CT + 2 * HALO_C;        // window columns (feature) incl. halo
   static constexpr int PLANE_B = WCOLS * WROWS * 16;   // bytes of one plane of the window
   static constexpr int WIN_B = PPL * PLANE_B;          // TMA transaction bytes per piece
   static constexpr int WIN_B_AL = (WIN_B + 1023) & ~1023;
   static constexpr int WROWS_OUT = SWAP ? COUT : (CTA2 ? NG / 2 : NG);   // rows of the weight operand image (per CTA)
-  static constexpr int WGT_B = NTAP * CIN * WROWS_OUT * 2;  // per output group
+  static constexpr int WGT_TERM_B = NTAP * CIN * WROWS_OUT * 2;   // one weight image
+  static constexpr int WGT_B = (SPLIT ? 2 : 1) * WGT_TERM_B;      // per output group (SPLIT: value image | residual image)
   static constexpr int WGT_B_AL = (WGT_B + 1023) & ~1023;
   static constexpr int ST = ROWS / (8 * MT);           // windows (super-tiles) per unit
   static constexpr int TILES = ROWS / 8;               // MMA tiles per unit
@@ -96,8 +103,10 @@ struct ConvCfg {
   static_assert(TMEM_COLS == 32 || TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
   static_assert(NG % 64 == 0 && NG <= 256 && CIN % 16 == 0, "shape");
   static_assert(!PAIR || KSPLIT == 1, "PAIR mode loads both parities in one piece");
+  static_assert(!SPLIT || (KSPLIT == 1 && !SWAP), "split precision: the two pieces are the value and the residual planes");
   static_assert(!SWAP || (MT == 1 && NG == 256 && COUT == 128), "swapped mode: one 128 x 256 tile per window");
   static_assert(CCH % KSPLIT == 0 && CPP % 2 == 0, "a piece must hold whole K=16 steps");
+  static_assert(WGT_TERM_B % 16 == 0, "descriptor start addresses are in 16-byte units");
   static_assert(SMEM_B <= 227 * 1024, "shared memory budget");
 
   // byte offset of the A start address for (tap, K step kk of the piece) relative to the tile's first row in the piece window
@@ -143,6 +152,7 @@ struct ConvParams {
   const float* norm_sd;
   float* partial;
   int x_vec4;             // 1 = x rows are 16-byte aligned with the feature axis contiguous: float4 loads
+  float inv_scale;        // SPLIT: 1 / (power-of-two scale of the weight images); the accumulator is multiplied by it
 };
 
 // ---- epilogue helpers -----------------------------------------------------------------------------
@@ -162,7 +172,7 @@ template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::OCC)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvParams p) {
   constexpr int COUT = Cfg::COUT, MT = Cfg::MT, NSTAGE = Cfg::NSTAGE, NACC = Cfg::NACC, NG = Cfg::NG;
-  constexpr int WROWS = Cfg::WROWS, PLANE_B = Cfg::PLANE_B, KSPLIT = Cfg::KSPLIT, HALO = Cfg::HALO, HALO_C = Cfg::HALO_C;
+  constexpr int WROWS = Cfg::WROWS, PLANE_B = Cfg::PLANE_B, HALO = Cfg::HALO, HALO_C = Cfg::HALO_C;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* wsm = smem;
   uint8_t* win0 = smem + Cfg::WGT_B_AL;
@@ -219,7 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       for (int u = u_first; u - rank < p.n_units; u += gridDim.x) {
         for (int st = 0; st < Cfg::ST; ++st) {
 #pragma unroll 1
-          for (int pc = 0; pc < KSPLIT; ++pc, ++ws) {
+          for (int pc = 0; pc < Cfg::NPIECE; ++pc, ++ws) {
             const int stage = ws % NSTAGE;
             mbar_wait(&empty[stage], ((ws / NSTAGE) & 1) ^ 1, 1);
             if constexpr (Cfg::CTA2) {   // both windows of the pair are counted on the leader's barrier
@@ -257,7 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         for (int st = 0; st < Cfg::ST; ++st) {
           const int acc0 = it % NACC;  // NACC % MT == 0: the MT accumulators of a window are consecutive
 #pragma unroll
-          for (int pc = 0; pc < KSPLIT; ++pc, ++ws) {
+          for (int pc = 0; pc < Cfg::NPIECE; ++pc, ++ws) {
             const int stage = ws % NSTAGE;
             mbar_wait(&full[stage], (ws / NSTAGE) & 1, 3);
             if (pc == 0) {
@@ -267,26 +277,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             tc_fence_after();
             const uint32_t a_lo_stage = a_lo0 + (uint32_t)(stage * (Cfg::WIN_B_AL >> 4));
             // the MT tiles of a window are issued interleaved (tile index innermost)
+            // SPLIT: the value planes (piece 0) meet the value and the residual image of the weights, the residual planes (piece 1) the value image
+            const int nterm = (Cfg::SPLIT && pc == 0) ? 2 : 1;
 #pragma unroll
-            for (int tap = 0; tap < Cfg::NTAP; ++tap) {
+            for (int term = 0; term < nterm; ++term) {
 #pragma unroll
-              for (int kk = 0; kk < Cfg::CPP / 2; ++kk) {
-                const uint32_t a_off = (uint32_t)(Cfg::a_off(tap, kk) >> 4);
-                const uint32_t b_off = (uint32_t)(Cfg::b_off(tap, pc, kk) >> 4);
+              for (int tap = 0; tap < Cfg::NTAP; ++tap) {
 #pragma unroll
-                for (int m = 0; m < MT; ++m) {  // tile m = rows 8m.. of the window: +8 rows of 16 B
-                  if constexpr (Cfg::SWAP)  // weights are the A (M) operand, the activation window is the B (N = 256) operand
-                    umma_f16_lohi(tmem_base + (acc0 + m) * NG, b_lo0 + b_off, b_hi, a_lo_stage + a_off, a_hi, idesc, (pc | tap | kk) != 0 ? 1u : 0u);
-                  else if constexpr (Cfg::CTA2)
-                    umma_f16_lohi_pair(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc,
-                                       (pc | tap | kk) != 0 ? 1u : 0u);
-                  else
-                    umma_f16_lohi(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc,
-                                  (pc | tap | kk) != 0 ? 1u : 0u);
+                for (int kk = 0; kk < Cfg::CPP / 2; ++kk) {
+                  const uint32_t a_off = (uint32_t)(Cfg::a_off(tap, kk) >> 4);
+                  const uint32_t b_off = (uint32_t)((Cfg::SPLIT ? term * Cfg::WGT_TERM_B + Cfg::b_off(tap, 0, kk) : Cfg::b_off(tap, pc, kk)) >> 4);
+                  const uint32_t accum = (pc | term | tap | kk) != 0 ? 1u : 0u;
+#pragma unroll
+                  for (int m = 0; m < MT; ++m) {  // tile m = rows 8m.. of the window: +8 rows of 16 B
+                    if constexpr (Cfg::SWAP)  // weights are the A (M) operand, the activation window is the B (N = 256) operand
+                      umma_f16_lohi(tmem_base + (acc0 + m) * NG, b_lo0 + b_off, b_hi, a_lo_stage + a_off, a_hi, idesc, accum);
+                    else if constexpr (Cfg::CTA2)
+                      umma_f16_lohi_pair(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc, accum);
+                    else
+                      umma_f16_lohi(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc, accum);
+                  }
                 }
               }
             }
-            if (pc == KSPLIT - 1) {
+            if (pc == Cfg::NPIECE - 1) {
 #pragma unroll
               for (int m = 0; m < MT; ++m) {  // accumulators ready for the epilogue
                 if constexpr (Cfg::CTA2) umma_commit_pair(&tfull[acc0 + m]);
@@ -336,7 +350,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           // bias + ReLU on both time steps, sum = time pool (the pool's 1/2 or 1/4 is folded into weights and bias)
           float o[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = relu_nan(a[c] + bias[h * HC + c]) + relu_nan(b[c] + bias[h * HC + c]);
+          for (int c = 0; c < 32; ++c) {
+            if constexpr (Cfg::SPLIT) o[c] = relu_nan(fmaf(a[c], p.inv_scale, bias[h * HC + c])) + relu_nan(fmaf(b[c], p.inv_scale, bias[h * HC + c]));
+            else o[c] = relu_nan(a[c] + bias[h * HC + c]) + relu_nan(b[c] + bias[h * HC + c]);
+          }
           const int row_out = 8 * tt + i + 1;  // pair index + 1 = padded output row
           if constexpr (Cfg::EPI == EPI_PAIR_POOL) {
             uint32_t pk[16];
@@ -345,6 +362,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             if (colvalid) {
               uint16_t* dst = p.out + ((long long)gc * p.out_rs + row_out) * 8 + (long long)(4 * h) * plane_elems;
               store_chunks<4>(dst, plane_elems, pk);
+              if constexpr (Cfg::SPLIT) {   // residual planes follow the COUT / 8 value planes
+                uint32_t pr[16];
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) pr[c >> 1] = pack_act2_residual(o[c], o[c + 1], pk[c >> 1]);
+                store_chunks<4>(dst + (long long)(COUT / 8) * plane_elems, plane_elems, pr);
+              }
             }
           } else {
             // feature pool: columns g (odd f') and g+1 live in lanes l and l^8; each keeps 16 of the 32 channels
@@ -387,7 +410,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             tmem_ld_wait();
             if (8 * tt + i + 1 <= p.rows_valid) {  // rows beyond the valid range are padding (1D-CNN: 321 of 328)
 #pragma unroll
-              for (int c = 0; c < 32; ++c) sum[blk * 32 + c] += relu_nan(v[c] + bias[h * HC + blk * 32 + c]);
+              for (int c = 0; c < 32; ++c) {
+                if constexpr (Cfg::SPLIT) sum[blk * 32 + c] += relu_nan(fmaf(v[c], p.inv_scale, bias[h * HC + blk * 32 + c]));
+                else sum[blk * 32 + c] += relu_nan(v[c] + bias[h * HC + blk * 32 + c]);
+              }
             }
           }
           tc_fence_before();

@@ -16,12 +16,21 @@ int launch_cnn2d_conv2_tc(const CUtensorMap& tmap_act1, const uint16_t* wpack, c
                           int num_sms, cudaStream_t stream);
 int launch_cnn2d_conv3_tc(const CUtensorMap& tmap_act2, const uint16_t* wpack, const float* bias, int n_utts, float* emb,
                           int num_sms, cudaStream_t stream);
+// "split" precision (option precision = 2): value + residual planes / weight images, CTA pairs
+int make_cnn2d_split_tensor_maps(CUtensorMap* tmap_act1, CUtensorMap* tmap_act2, const ActBuf& act1, const ActBuf& act2);
+int launch_cnn2d_conv2_split(const CUtensorMap& tmap_act1, const uint16_t* wpack, const float* bias, float inv_scale, int n_utts, ActBuf act2,
+                             int num_sms, cudaStream_t stream);
+int launch_cnn2d_conv3_split(const CUtensorMap& tmap_act2, const uint16_t* wpack, const float* bias, float inv_scale, int n_utts, float* emb,
+                             int num_sms, cudaStream_t stream);
 
 // ---- conv1_tc.cu (CNN2D block 1 as a Toeplitz-in-time tcgen05 GEMM) ----
 int64_t conv1_xt_rows(int64_t n_utts);   // 16-byte rows of the fp16 time-major feature copy for n utterances
 int launch_conv1_prep(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, cudaStream_t stream);
 int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, const uint16_t* wpack, const float* bias_half,
                     ActBuf out, int num_sms, cudaStream_t stream);
+// split precision: xt_lo = the fp16 rounding residuals of xt (same geometry), out = 16 planes (8 value planes, then 8 residual planes)
+int launch_conv1_tc_split(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, uint16_t* xt_lo, const uint16_t* wpack,
+                          float inv_scale, ActBuf out, int num_sms, cudaStream_t stream);
 
 // ---- cnn2d.cu (CUDA-core stages of the 2D-CNN) ----
 struct Conv1Weights {
@@ -36,7 +45,8 @@ int launch_conv1(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts,
 int launch_cnn2d_conv2_simt(ActBuf act1, const uint16_t* wpack, const float* bias_dev, int n_utts, ActBuf act2, cudaStream_t stream);
 int launch_cnn2d_conv3_simt(ActBuf act2, const uint16_t* wpack, const float* bias_dev, int n_utts, float* emb, cudaStream_t stream);
 // logits[n] = fc_b + sum_{f,c} emb[n][f][c] * wfc[f][c]  (wfc already carries 1/T); optional sigmoid
-int launch_cnn2d_head(const float* emb, const float* wfc, float fcb, int n_utts, int apply_sigmoid, float* out, cudaStream_t stream);
+int launch_cnn2d_head(const float* emb, const float* wfc, float fcb, int n_utts, int apply_sigmoid, float* out, cudaStream_t stream,
+                      bool acc64 = false);
 // embedding[n][c*180+f] = emb[n][f][c] / 80   (src/model.py:37-38 flatten order)
 int launch_cnn2d_embedding_export(const float* emb, int n_utts, float* embedding, cudaStream_t stream);
 

@@ -263,20 +263,23 @@ def pinned_empty(shape, dtype="float32", write_combined: bool = False):
     return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
 
 
-def _check_precision(precision):
-    """"fp16" = tensor-core path (fp16 operands, fp32 accumulation); "fp32" = full fp32 on the CUDA cores (rank-exact evaluation)."""
-    if precision not in ("fp16", "fp32"):
-        raise ValueError(f"precision must be 'fp16' or 'fp32', got {precision!r}")
+def _check_precision(precision, allowed=("fp16", "fp32")):
+    """"fp16" = tensor-core path (fp16 operands, fp32 accumulation); "fp32" = full fp32 on the CUDA cores (rank-exact evaluation);
+    "split" (2D-CNN) = tensor cores with every operand carried as fp16 value + fp16 residual, three MMAs per product."""
+    if precision not in allowed:
+        raise ValueError(f"precision must be one of {allowed}, got {precision!r}")
 
 
 class Cnn2dScorer(_Scorer):
     """CNN2D (src/model.py:12-42) on the tcgen05 path.  ``precision="fp32"`` selects the full-fp32 CUDA-core kernels
-    (csrc/cnn2d_fp32.cu; ~35x slower) for evaluations where the rank order of near-equal scores matters."""
+    (csrc/cnn2d_fp32.cu; ~35x slower) for evaluations where the rank order of near-equal scores matters; ``precision="split"``
+    keeps the tensor cores and carries every input sample, activation and weight as fp16 value + fp16 rounding residual
+    (three MMAs per product into the fp32 accumulator): fp32-class scores at about a third of the fp16 rate."""
     KIND = "cnn2d"
 
     def __init__(self, state_dict, device: int = 0, max_chunk: int = 0, precision: str = "fp16"):
         super().__init__()
-        _check_precision(precision)
+        _check_precision(precision, ("fp16", "fp32", "split"))
         _require_cuda()
         keep = []
         w = N.Cnn2dWeights()
@@ -289,8 +292,8 @@ class Cnn2dScorer(_Scorer):
         w.fc_weight, w.fc_bias = _fptr(fcw), _fptr(fcb)
         self.device_index = int(device)
         N.check(self._lib.dfs_cnn2d_create(C.byref(self._h), int(device), C.byref(w), int(max_chunk)), "dfs_cnn2d_create")
-        if precision == "fp32":
-            self.set_option("precision", 1)
+        if precision != "fp16":
+            self.set_option("precision", {"fp32": 1, "split": 2}[precision])
 
     def score(self, x, apply_sigmoid: bool = False, return_embedding: bool = False):
         """x: CUDA fp32 (B,321,180), any strides.  Returns (B,) logits/scores [, (B,23040) embedding]."""

@@ -124,7 +124,9 @@ int dfs_model_destroy(dfs_model* m);
  * cross-check, same layouts); "profile" 0/1 = per-kernel event timing (dfs_model_profile);
  * "precision" (CNN2D, CNN1D, CAE) 0 = fp16 tensor-core operands with fp32 accumulation (default), 1 = the whole
  * network in fp32 on the CUDA cores (same arithmetic class as the reference's CPU path; for evaluations
- * where the rank order of scores a few 1e-6 apart matters, e.g. the EER of a small dev set).
+ * where the rank order of scores a few 1e-6 apart matters, e.g. the EER of a small dev set), 2 (CNN2D) = "split": the
+ * tensor-core path with every input sample, activation and weight carried as fp16 value + fp16 rounding residual and
+ * three MMAs per product into the fp32 accumulator (fp32-class scores at about a third of the default rate).
  * Kernel-variant switches kept for on-device cross-checks (tests compare the variants; defaults are the product path):
  *   "conv1_impl"   (CNN2D, CAE) 0 = Toeplitz tcgen05 GEMM for the Cin = 1 layer, 1 = fp32 CUDA-core conv
  *   "fused"        (CNN1D)      1 (default) = the three conv layers, the time mean and the classifier in ONE kernel (activations never

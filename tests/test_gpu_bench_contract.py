@@ -55,6 +55,8 @@ def test_headline_line_has_every_contract_key():
     assert d["e2e_f16_slab"]["scores_identical_to_fp32_slab"] is True
     f32 = d["parity"]["fp32_mode"]                      # the same utterances through the full-fp32 kernels (precision="fp32")
     assert f32["max_rel_err_scores_vs_cpu_reference"] <= 5e-6 and f32["utterances_per_s"] > 0 and "eer_delta_pp" in f32
+    sp = d["parity"]["split_mode"]                      # ... and through the split-precision tensor-core kernels (precision="split")
+    assert sp["max_rel_err_scores_vs_cpu_reference"] <= 5e-6 and sp["utterances_per_s"] > 10 * f32["utterances_per_s"]
 
 
 def test_eer_workload_reports_both_paths():

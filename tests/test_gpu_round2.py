@@ -128,7 +128,7 @@ def _trained_case(tag, precision, structured):
     sc = cls(sd, precision=precision)
     if tag == "cnn1d":
         sc.set_option("fused", 0)                                   # the census below needs the activations in HBM; the one-kernel path is gated in its own test
-    n = structured.shape[0] if precision == "fp16" or tag == "cnn1d" else 512       # the fp32 CUDA-core 2D-CNN runs ~8 k utt/s
+    n = structured.shape[0] if precision != "fp32" or tag == "cnn1d" else 512       # the fp32 CUDA-core 2D-CNN runs ~8 k utt/s
     x = structured[:n].cuda()
     logits = sc.score(x, apply_sigmoid=False).cpu().numpy()
     scores = sc.score(x, apply_sigmoid=True).cpu().numpy()
@@ -157,7 +157,8 @@ def _trained_case(tag, precision, structured):
 #   default (fp16 tensor-core operands): measured 3e-3 ... 9e-3, of which the fp16 rounding of the WEIGHTS is 70-90 %
 #   (tools/experiments/fp16_error_budget.py; it is the same error for every utterance, so it barely moves ranks: EER delta 0.00 pp).
 #   The gate below is what that path guarantees; the measured figures are written to gpurun_out/parity_round2.json.
-SIGMOID_REL = {"fp32": REL, "fp16": 1.5e-2}
+#   precision="split" (2D-CNN; tensor cores, every operand as fp16 value + residual, 3 MMAs per product): holds the 1e-3 like fp32.
+SIGMOID_REL = {"fp32": REL, "fp16": 1.5e-2, "split": REL}
 
 
 @pytest.mark.parametrize("tag", ["cnn2d", "cnn1d"])
@@ -174,6 +175,45 @@ def test_trained_like_regime_against_the_reference(tag, precision, structured):
     assert r["max_abs_logit_err"] <= SIGMOID_REL[precision], r
     assert abs(r["eer_dev"] - r["eer_ref"]) <= EER_ABS, r
     assert abs(r["eer_logits_dev"] - r["eer_logits_ref"]) <= EER_ABS, r
+
+
+def test_trained_like_regime_split_precision_on_the_tensor_cores(structured):
+    """VERDICT r01 missing #3: a tensor-core mode that holds the north_star tolerance where fp16 operands do not.  Same gates as the
+    fp32 mode on all 2,048 utterances, plus: the split logits agree with the fp32 CUDA-core mode to 2.5e-4 on the first 256."""
+    r = _trained_case("cnn2d", "split", structured)
+    assert r["max_rel_sigmoid_err_unsaturated"] <= SIGMOID_REL["split"], r
+    assert r["max_abs_logit_err"] <= SIGMOID_REL["split"], r
+    assert abs(r["eer_dev"] - r["eer_ref"]) <= EER_ABS and abs(r["eer_logits_dev"] - r["eer_logits_ref"]) <= EER_ABS, r
+    sd = syn.cnn2d_state(0, logit_scale=float(T["cnn2d_scale"]), classifier_bias=float(T["cnn2d_bias"]))
+    x = structured[:256].cuda()
+    ls = Cnn2dScorer(sd, precision="split").score(x).cpu().numpy()
+    l32 = Cnn2dScorer(sd, precision="fp32").score(x).cpu().numpy()
+    _record("trained_like/cnn2d/split_vs_fp32", dict(max_abs_logit_diff=float(np.max(np.abs(ls - l32)))))
+    assert np.max(np.abs(ls - l32)) <= 2.5e-4                       # measured 9e-5 (1e-6 of the raw logit times the calibrated classifier scale)
+
+
+def test_split_precision_small_batches_and_switching():
+    """Ragged passes (max_chunk 5 over 13 utterances), strided input (the reference's transposed view), and switching one handle
+    fp16 -> split -> fp16: the fp16 scores before and after are the same bits, the split scores match the float64 oracle to fp32 round-off."""
+    sd = syn.cnn2d_state(0)
+    x = syn.features(13, seed=77)
+    xd = torch.from_numpy(x).cuda()
+    sc = Cnn2dScorer(sd, max_chunk=5)
+    a = sc.score(xd).cpu().numpy()
+    sc.set_option("precision", 2)
+    s1 = sc.score(xd).cpu().numpy()
+    xt = torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 1))).cuda().transpose(1, 2)      # (B,180,321) storage viewed as (B,321,180)
+    s2 = sc.score(xt).cpu().numpy()
+    sc.set_option("precision", 0)
+    b = sc.score(xd).cpu().numpy()
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(s1, s2)
+    from oracle import models_np as onp
+    ref = onp.cnn2d_forward(sd, x)[:, 0]
+    _record("split/random_init", dict(max_rel_err_split=_rel(s1, ref), max_rel_err_fp16=_rel(a, ref)))
+    assert _rel(s1, ref) <= 2e-5
+    full = Cnn2dScorer(sd, precision="split").score(xd).cpu().numpy()                               # one pass of 13 instead of 5 + 5 + 3
+    np.testing.assert_array_equal(full, s1)
 
 
 def test_trained_like_scores_through_the_group_host_path(structured):
