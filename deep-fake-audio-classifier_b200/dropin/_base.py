@@ -21,9 +21,11 @@ if _PKG not in sys.path:
 
 class NativeBackedModule(nn.Module):
     # "fp16" (default): tensor-core path, fp16 operands / fp32 accumulation.  "fp32": the full-fp32 CUDA-core kernels, for evaluations
-    # where the rank order of near-equal scores matters.  Set it on the instance (or class) before the first CUDA forward, or export
-    # DFS_B200_PRECISION=fp32.
+    # where the rank order of near-equal scores matters.  "split": the 2D-CNN's accurate tensor-core mode (every operand as fp16 value +
+    # residual, ~0.4x the fp16 rate, fp32-class scores); the 1D-CNN and the CAE have no such mode and take their fp32 kernels for it
+    # (at least as accurate).  Set it on the instance (or class) before the first CUDA forward, or export DFS_B200_PRECISION.
     precision = None
+    HAS_SPLIT = False            # CNN2D overrides
 
     def __init__(self):
         super().__init__()
@@ -31,7 +33,8 @@ class NativeBackedModule(nn.Module):
         self._native_key = None
 
     def _precision(self):
-        return self.precision or os.environ.get("DFS_B200_PRECISION", "fp16")
+        p = self.precision or os.environ.get("DFS_B200_PRECISION", "fp16")
+        return "fp32" if (p == "split" and not self.HAS_SPLIT) else p
 
     def _make_scorer(self, state_dict, device_index):  # pragma: no cover - overridden
         raise NotImplementedError

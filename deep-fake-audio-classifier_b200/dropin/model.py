@@ -15,6 +15,8 @@ def _block(cin, cout, pool, dropout):
 
 
 class CNN2D(NativeBackedModule):
+    HAS_SPLIT = True             # precision = "split": the accurate tensor-core mode (dfs_b200.Cnn2dScorer)
+
     def __init__(self, in_features=180, base_channels=32, num_classes=1, dropout=0.2):
         super().__init__()
         c = base_channels

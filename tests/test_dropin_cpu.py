@@ -103,10 +103,28 @@ def test_precision_selection_on_the_dropin_classes(monkeypatch):
         net.precision = "fp32"
         assert net._weights_key(dev) + (net._precision(),) != k16
         assert not any("precision" in k for k in net.state_dict())
+        net.precision = "split"                                           # the 2D-CNN's accurate tensor-core mode; the others take fp32
+        assert net._precision() == ("split" if cls is m2.CNN2D else "fp32")
         monkeypatch.delenv("DFS_B200_PRECISION")
     from dfs_b200 import engine
     with pytest.raises(ValueError, match="precision must be"):
         engine._check_precision("bf16")
+    with pytest.raises(ValueError, match="precision must be"):
+        engine._check_precision("split")                                  # only where a scorer lists it (Cnn2dScorer)
+    engine._check_precision("split", ("fp16", "fp32", "split"))
+
+
+def test_hostmem_helpers():
+    """dfs_b200.hostmem: sysfs cpulist parsing, and numa_local() is a no-op context manager on hosts without a second node or
+    without a known GPU node (this container, and the KVM guests of the GPU pool: profiles/r02h_h2d_bw_n8.txt)."""
+    from dfs_b200 import hostmem as H
+    assert H.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11] and H.parse_cpulist("") == []
+    assert isinstance(H.host_nodes(), list)
+    import os as _os
+    before = _os.sched_getaffinity(0)
+    with H.numa_local(0) as ctx:
+        assert set(ctx.applied) == {"node", "mempolicy", "cpus"}
+    assert _os.sched_getaffinity(0) == before
 
 
 def test_host_slab_validates_dtype_device_and_layout():
