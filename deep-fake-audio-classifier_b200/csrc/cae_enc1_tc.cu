@@ -94,15 +94,15 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kE1BarOff);
   uint64_t* full = bars;                 // [stages]
   uint64_t* empty = bars + kE1Stages;    // [stages]
-  uint64_t* tfull = empty + kE1Stages;   // [2]
-  uint64_t* tempty = tfull + 2;          // [2]
-  uint64_t* wbar = tempty + 2;
+  uint64_t* tfull = empty + kE1Stages;   // [2 accumulators][2 halves]
+  uint64_t* tempty = tfull + 4;          // [2][2]
+  uint64_t* wbar = tempty + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == kE1EpiWarps && lane == 0) {
     for (int i = 0; i < kE1Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }   // [2 accumulators][2 halves], see conv1_tc.cu
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
   } else if (warp == kE1EpiWarps + 1) {
     // ===================== MMA issuer =====================
     if (elect_one_sync()) {   // not `lane == 0`: see conv_tc.cuh
-      constexpr uint32_t idesc = umma_idesc_f16(128, 256);
+      constexpr uint32_t idesc = umma_idesc_f16(128, 128);   // an accumulator is produced as two N = 128 halves (time offsets 0..3 | 4..7)
       const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 256 * 16, 128);
       const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
       // A: K chunk 1 of a row is the next row (LBO = 16 B); the 16 core-matrix groups of a tile are 16 columns (SBO = 41 rows)
@@ -151,13 +151,18 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
 #pragma unroll 1
         for (int tt = 0; tt < kE1TilesPerUnit; ++tt, ++it) {
           const int acc = it & 1;
-          mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, 44);
-          tc_fence_after();
-          umma_f16_lohi(tmem_base + acc * 256, ones_lo, ones_hi, b_lo0 + (uint32_t)(kE1BiasOff >> 4), b_hi, idesc, 0u);
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw)   // window column 0 is 16u - 1: tap kw starts kw columns in; tile tt starts at row 8 tt
-            umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kw * kE1Blocks + 8 * tt), a_hi, b_lo0 + (uint32_t)(kw * (8192 >> 4)), b_hi, idesc, 1u);
-          umma_commit(&tfull[acc]);
+          for (int hh = 0; hh < 2; ++hh) {
+            mbar_wait(&tempty[2 * acc + hh], ((it >> 1) & 1) ^ 1, 44);
+            tc_fence_after();
+            const uint32_t d = tmem_base + acc * 256 + hh * 128;
+            const uint32_t b_lo = b_lo0 + (uint32_t)(hh * 128);   // rows [128 hh, 128 hh + 128) of every B image
+            umma_f16_lohi(d, ones_lo, ones_hi, b_lo + (uint32_t)(kE1BiasOff >> 4), b_hi, idesc, 0u);
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)   // window column 0 is 16u - 1: tap kw starts kw columns in; tile tt starts at row 8 tt
+              umma_f16_lohi(d, a_lo + (uint32_t)(kw * kE1Blocks + 8 * tt), a_hi, b_lo + (uint32_t)(kw * (8192 >> 4)), b_hi, idesc, 1u);
+            umma_commit(&tfull[2 * acc + hh]);
+          }
         }
         umma_commit(&empty[stage]);
       }
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
         if ((int)(it & 1) != grp) continue;
         const int acc = grp;
         const int tb = 8 * tt + i;
-        mbar_wait(&tfull[acc], (it >> 1) & 1, 45);
+        mbar_wait(&tfull[2 * acc], (it >> 1) & 1, 45);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * h;
         uint32_t pk[4][4];
@@ -193,13 +198,18 @@ __global__ void __launch_bounds__(kE1Threads, 1) cae_enc1_tc_kernel(const __grid
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // pooled time step within the block: conv time offsets jj = 2k, 2k+1
           tmem_ld_wait();
+          if (k & 1) {  // all TMEM reads of this warp from half k >> 1 are done: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[2 * acc + (k >> 1)]);
+          }
+          if (k == 1) {
+            mbar_wait(&tfull[2 * acc + 1], (it >> 1) & 1, 46);
+            tc_fence_after();
+          }
           if (k < 3) {
             tmem_ld_32x16(taddr + (2 * k + 2) * 32, a[(k + 1) & 1]);
             tmem_ld_32x16(taddr + (2 * k + 3) * 32, b[(k + 1) & 1]);
-          } else {  // all TMEM reads of this warp are done: release the accumulator early
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
           }
           const float* av = a[k & 1];
           const float* bv = b[k & 1];

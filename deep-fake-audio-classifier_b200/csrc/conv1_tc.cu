@@ -107,15 +107,20 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
   uint8_t* stage0 = smem + Geo::kStageOff;
   uint64_t* full = bars;                 // [stages]
   uint64_t* empty = bars + kC1Stages;    // [stages]
-  uint64_t* tfull = empty + kC1Stages;   // [2]
-  uint64_t* tempty = tfull + 2;          // [2]
-  uint64_t* wbar = tempty + 2;
+  // An accumulator (256 TMEM columns = 8 time offsets x 32 channels) is produced and drained as two N = 128 HALVES with their own
+  // barriers: the MMAs of the next tile's first half start as soon as the epilogue has read this tile's first half, i.e. while it
+  // still works on the second one.  With whole-tile hand-over the 8 epilogue warps of a tile parity sat idle for the ~900 cycles of
+  // their tile's MMAs + two barrier round trips every time (ncu: 21 % of the stall samples on the accumulator-ready wait).  An
+  // N = 128 MMA costs half an N = 256 one (64 vs 128 cycles), so the tensor-pipe time is unchanged.
+  uint64_t* tfull = empty + kC1Stages;   // [2 accumulators][2 halves]
+  uint64_t* tempty = tfull + 4;          // [2][2]
+  uint64_t* wbar = tempty + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == kC1EpiWarps && lane == 0) {
     for (int i = 0; i < kC1Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
   } else if (warp == kC1EpiWarps + 1) {
     // ===================== MMA issuer =====================
     if (elect_one_sync()) {   // not `lane == 0`: see conv_tc.cuh
-      constexpr uint32_t idesc = umma_idesc_f16(128, 256);
+      constexpr uint32_t idesc = umma_idesc_f16(128, 128);
       const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), 256 * 16, 128);
       const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
       const uint64_t a_desc0 = umma_smem_desc(smem_u32(win0), 16, 128);   // LBO = 16 B: K chunk 1 of row R is row R+1
@@ -160,24 +165,27 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ws) {
         const int stage = ws % kC1Stages, acc = ws & 1;
         mbar_wait(&full[stage], (ws / kC1Stages) & 1, 23);
-        mbar_wait(&tempty[acc], ((ws >> 1) & 1) ^ 1, 24);
-        tc_fence_after();
         const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (Geo::kStageStride >> 4));
-        umma_f16_lohi(tmem_base + acc * 256, ones_lo, a_hi, b_lo0 + (uint32_t)(kC1BiasOff >> 4), b_hi, idesc, 0u);
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {   // weight value, then weight residual
+        for (int hh = 0; hh < 2; ++hh) {         // half hh = time offsets 4 hh .. 4 hh + 3 = rows [128 hh, 128 hh + 128) of every B image
+          mbar_wait(&tempty[2 * acc + hh], ((ws >> 1) & 1) ^ 1, 24);
+          tc_fence_after();
+          const uint32_t d = tmem_base + acc * 256 + hh * 128;
+          const uint32_t b_lo = b_lo0 + (uint32_t)(hh * 128);   // 128 rows of 16 B
+          umma_f16_lohi(d, ones_lo, a_hi, b_lo + (uint32_t)(kC1BiasOff >> 4), b_hi, idesc, 0u);
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw)
-            umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kw * kXtBlocks), a_hi,
-                          b_lo0 + (uint32_t)((part * kC1WgtImgB + kw * 8192) >> 4), b_hi, idesc, 1u);
+          for (int part = 0; part < 2; ++part) {   // weight value, then weight residual
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+              umma_f16_lohi(d, a_lo + (uint32_t)(kw * kXtBlocks), a_hi, b_lo + (uint32_t)((part * kC1WgtImgB + kw * 8192) >> 4), b_hi, idesc, 1u);
+          }
+          if constexpr (SPLIT) {   // the input's rounding residuals against the weight values
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+              umma_f16_lohi(d, a_lo + (uint32_t)(kC1WinBAl >> 4) + (uint32_t)(kw * kXtBlocks), a_hi, b_lo + (uint32_t)((kw * 8192) >> 4), b_hi, idesc, 1u);
+          }
+          umma_commit(&tfull[2 * acc + hh]);
         }
-        if constexpr (SPLIT) {   // the input's rounding residuals against the weight values
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw)
-            umma_f16_lohi(tmem_base + acc * 256, a_lo + (uint32_t)(kC1WinBAl >> 4) + (uint32_t)(kw * kXtBlocks), a_hi,
-                          b_lo0 + (uint32_t)((kw * 8192) >> 4), b_hi, idesc, 1u);
-        }
-        umma_commit(&tfull[acc]);
         umma_commit(&empty[stage]);
       }
     }
@@ -199,14 +207,16 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ws) {
       if ((int)(ws & 1) != grp) continue;
       const int acc = grp;
-      const long long R = 128ll * tile + 32 * q + lane;
-      const long long gcx = R / kXtBlocks;
+      // 32-bit index arithmetic (a pass is < 2^31 / (182 * 82) utterances, checked by the launcher): the 64-bit divisions by 41 and 182
+      // were ~50 instructions per tile and thread
+      const uint32_t R = 128u * (uint32_t)tile + 32u * q + lane;
+      const uint32_t gcx = R / (uint32_t)kXtBlocks;
       const int tb = (int)(R - gcx * kXtBlocks);
-      const long long n = gcx / kCols;
+      const uint32_t n = gcx / (uint32_t)kCols;
       const int fp = (int)(gcx - n * kCols);
-      const bool valid = (tb < 40) && (fp >= 1) && (fp <= kF) && (n < p.n_utts);
+      const bool valid = (tb < 40) && (fp >= 1) && (fp <= kF) && ((int)n < p.n_utts);
       dsttab[lane] = valid ? (int)(gcx * kAct1RS + 2 * tb + 1) : -1;
-      mbar_wait(&tfull[acc], (ws >> 1) & 1, 25);
+      mbar_wait(&tfull[2 * acc], (ws >> 1) & 1, 25);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + 16 * h;
       const int sw = (lane >> 2) & 1;
@@ -218,13 +228,18 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_tc_kernel(const __grid_co
 #pragma unroll
       for (int k = 0; k < 4; ++k) {  // pooled row within the block: conv time offsets jj = 2k, 2k+1
         tmem_ld_wait();
+        if (k & 1) {  // all TMEM reads of this warp from half k >> 1 are done: hand it back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[2 * acc + (k >> 1)]);
+        }
+        if (k == 1) {
+          mbar_wait(&tfull[2 * acc + 1], (ws >> 1) & 1, 26);
+          tc_fence_after();
+        }
         if (k < 3) {
           tmem_ld_32x16(taddr + (2 * k + 2) * 32, a[(k + 1) & 1]);
           tmem_ld_32x16(taddr + (2 * k + 3) * 32, b[(k + 1) & 1]);
-        } else {  // all TMEM reads of this warp are done: release the accumulator early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
         }
         const float* av = a[k & 1];
         const float* bv = b[k & 1];
@@ -303,6 +318,7 @@ int launch_conv1_prep(const float* x, int64_t sn, int64_t st, int64_t sf, int n_
 int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, const uint16_t* wpack, const float* bias_half,
                     ActBuf out, int num_sms, cudaStream_t stream) {
   if (n_utts <= 0) return DFS_OK;
+  DFS_REQUIRE(n_utts <= 100000, DFS_ERR_INVALID, "conv1: at most 100,000 utterances per pass (32-bit row indices)");
   DFS_PROPAGATE(launch_conv1_prep(x, sn, st, sf, n_utts, xt, stream));
   static bool configured[32] = {false};
   if (dfs_first_use_on_device(configured))
@@ -326,6 +342,7 @@ int launch_conv1_tc_split(const float* x, int64_t sn, int64_t st, int64_t sf, in
                           float inv_scale, ActBuf out, int num_sms, cudaStream_t stream) {
   if (n_utts <= 0) return DFS_OK;
   DFS_REQUIRE(xt_lo != nullptr && out.planes == 16, DFS_ERR_INVALID, "conv1 split: residual buffers missing");
+  DFS_REQUIRE(n_utts <= 100000, DFS_ERR_INVALID, "conv1: at most 100,000 utterances per pass (32-bit row indices)");
   DFS_PROPAGATE(launch_conv1_prep_any(x, sn, st, sf, n_utts, xt, xt_lo, stream));
   static bool configured[32] = {false};
   if (dfs_first_use_on_device(configured))

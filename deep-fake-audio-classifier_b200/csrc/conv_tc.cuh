@@ -254,6 +254,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       }
     } else if (elect_one_sync()) {   // elect_one_sync(), not `lane == 0`: under a lane test the compiler cannot tell that a single thread is active and wraps EVERY tcgen05.mma / TMA issue in an ELECT + BRA.U.ANY serialisation loop (measured: ~100 instead of 64 cycles per N = 128 MMA)
       constexpr uint32_t idesc = umma_idesc_f16(Cfg::CTA2 ? 256 : 128, NG);
+      [[maybe_unused]] constexpr uint32_t idesc_half = umma_idesc_f16(128, COUT < 16 ? 16 : COUT);   // PAIR: N = COUT for the half-width taps
       // descriptor = (low word: start address >> 4 | LBO >> 4 << 16, high word: SBO >> 4 | version); taps and
       // K steps only move the start address, i.e. add a compile-time constant to the low word
       const uint64_t b_desc0 = umma_smem_desc(smem_u32(wsm), Cfg::WROWS_OUT * 16, 128);
@@ -282,12 +283,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
             for (int term = 0; term < nterm; ++term) {
 #pragma unroll
-              for (int tap = 0; tap < Cfg::NTAP; ++tap) {
+              for (int tq = 0; tq < Cfg::NTAP; ++tq) {
+                // PAIR on a single CTA: the taps of input time step r = 0 reach only the first output of the pair (columns [0, COUT)) and
+                // those of r = 3 only the second one (columns [COUT, 2 COUT)) -- the other half of their weight rows is zeros.  They are
+                // issued as N = COUT MMAs into that half of the accumulator (48 instead of 64 cycles each, none of the zero MACs), after
+                // the full-width taps r = 1, 2 so that the first MMA of a tile initialises all columns.
+                constexpr bool HALF_TAPS = Cfg::PAIR && !Cfg::CTA2 && !Cfg::SPLIT;
+                const int tap = HALF_TAPS ? (tq < 6 ? tq + 3 : (tq < 9 ? tq - 6 : tq)) : tq;
+                const bool half = HALF_TAPS && (tap < 3 || tap >= 9);
+                const uint32_t half_col = (HALF_TAPS && tap >= 9) ? (uint32_t)COUT : 0u;   // accumulator column = weight row offset of the r = 3 taps
 #pragma unroll
                 for (int kk = 0; kk < Cfg::CPP / 2; ++kk) {
                   const uint32_t a_off = (uint32_t)(Cfg::a_off(tap, kk) >> 4);
-                  const uint32_t b_off = (uint32_t)((Cfg::SPLIT ? term * Cfg::WGT_TERM_B + Cfg::b_off(tap, 0, kk) : Cfg::b_off(tap, pc, kk)) >> 4);
-                  const uint32_t accum = (pc | term | tap | kk) != 0 ? 1u : 0u;
+                  const uint32_t b_off = (uint32_t)((Cfg::SPLIT ? term * Cfg::WGT_TERM_B + Cfg::b_off(tap, 0, kk) : Cfg::b_off(tap, pc, kk)) >> 4) + half_col;
+                  const uint32_t accum = (pc | term | tq | kk) != 0 ? 1u : 0u;
 #pragma unroll
                   for (int m = 0; m < MT; ++m) {  // tile m = rows 8m.. of the window: +8 rows of 16 B
                     if constexpr (Cfg::SWAP)  // weights are the A (M) operand, the activation window is the B (N = 256) operand
@@ -295,7 +304,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                     else if constexpr (Cfg::CTA2)
                       umma_f16_lohi_pair(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc, accum);
                     else
-                      umma_f16_lohi(tmem_base + (acc0 + m) * NG, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi, idesc, accum);
+                      umma_f16_lohi(tmem_base + (acc0 + m) * NG + half_col, a_lo_stage + (uint32_t)(m * 8) + a_off, a_hi, b_lo0 + b_off, b_hi,
+                                    half ? idesc_half : idesc, accum);
                   }
                 }
               }
