@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libdfs_b200.so")
 OUT_PROBES = os.path.join(HERE, "lib", "libdfs_b200_probes.so")   # bring-up probes + micro-benchmarks (tests / tools only)
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "conv_tc.cu", "conv1_tc.cu", "cae_tc.cu", "cae_enc1_tc.cu", "cnn1d_tc.cu", "cnn1d_l1_fused.cu", "cnn1d_fused.cu", "cnn2d.cu", "cnn2d_fp32.cu", "simt_models.cu", "eer.cu", "synth.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv1_tc.cu", "conv12_fused.cu", "cae_tc.cu", "cae_enc1_tc.cu", "cnn1d_tc.cu", "cnn1d_l1_fused.cu", "cnn1d_fused.cu", "cnn2d.cu", "cnn2d_fp32.cu", "simt_models.cu", "eer.cu", "synth.cu"]
 PROBE_SOURCES = ["probe.cu", "conv_tc.cu"]   # probe.cu uses conv_tc.cu's tensor-map helper
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",

@@ -60,6 +60,9 @@ struct dfs_model {
   float* emb = nullptr;
   CUtensorMap tmap1{}, tmap2{};
   int conv1_impl = 0;          // 0 = tensor-core Toeplitz GEMM, 1 = CUDA-core cross-check
+  int conv12_fused = 1;        // 1 (default) = conv1 + conv2 in one kernel (conv12_fused.cu), act1 never written; 0 = separate kernels
+  uint16_t* w1pack_fused = nullptr;  // conv1's Toeplitz weights as two 16-channel passes [pass][value | residual][kw][2][128][8]
+  uint16_t* w2pack_fused = nullptr;  // conv2's PAIR weights without the zero halves of the r = 0 / r = 3 taps
   uint16_t* xt = nullptr;      // fp16 time-major copy of the features (conv1_tc A operand)
   uint16_t* w1pack = nullptr;  // Toeplitz weights [hi | lo][kw][2][256][8]: fp16 value and fp16 rounding residual of every weight
   float b1h[32] = {0};         // 0.5 * folded conv1 bias
@@ -323,6 +326,11 @@ extern "C" int dfs_model_set_option(dfs_model* m, const char* key, int64_t value
     m->precision = (int)value;
     return DFS_OK;
   }
+  if (strcmp(key, "conv12_fused") == 0) {
+    DFS_REQUIRE(m->kind == KIND_CNN2D && (value == 0 || value == 1), DFS_ERR_INVALID, "conv12_fused is a CNN2D option (0 | 1)");
+    m->conv12_fused = (int)value;
+    return DFS_OK;
+  }
   if (strcmp(key, "final_fused") == 0) {
     DFS_REQUIRE(m->cae != nullptr && (value == 0 || value == 1), DFS_ERR_INVALID, "final_fused is a CAE option (0 | 1)");
     m->cae->final_fused = (int)value;
@@ -505,6 +513,21 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
   memcpy(m->b2, b2.data(), sizeof(m->b2));
   memcpy(m->b3, b3.data(), sizeof(m->b3));
   if ((st = dev_upload(m, &m->w2pack, p2)) != DFS_OK) return fail(st);
+  {
+    // conv12_fused.cu's image of the same conv2 weights: the taps of r = 1, 2 with all 128 rows, then the taps of r = 0 with their 64
+    // non-zero rows (outputs dt = 0) and those of r = 3 with theirs (dt = 1): [6][4][128][8] | [3][4][64][8] | [3][4][64][8]
+    std::vector<uint16_t> p2f((size_t)(6 * 4 * 128 + 2 * 3 * 4 * 64) * 8, 0);
+    for (int t = 0; t < 6; ++t)
+      for (size_t i = 0; i < (size_t)4 * 128 * 8; ++i) p2f[(size_t)t * 4 * 128 * 8 + i] = p2[(size_t)(t + 3) * 4 * 128 * 8 + i];
+    const size_t half0 = (size_t)6 * 4 * 128 * 8;
+    for (int blk = 0; blk < 2; ++blk)        // r = 0 (rows 0..63), r = 3 (rows 64..127)
+      for (int kw = 0; kw < 3; ++kw)
+        for (int ch = 0; ch < 4; ++ch)
+          for (int o = 0; o < 64; ++o)
+            for (int e = 0; e < 8; ++e)
+              p2f[half0 + ((((size_t)blk * 3 + kw) * 4 + ch) * 64 + o) * 8 + e] = p2[((((size_t)(blk * 9 + kw)) * 4 + ch) * 128 + blk * 64 + o) * 8 + e];
+    if ((st = dev_upload(m, &m->w2pack_fused, p2f)) != DFS_OK) return fail(st);
+  }
   if ((st = dev_upload(m, &m->w3pack, p3)) != DFS_OK) return fail(st);
   if ((st = dev_upload(m, &m->b2_dev, b2)) != DFS_OK) return fail(st);
   if ((st = dev_upload(m, &m->b3_dev, b3)) != DFS_OK) return fail(st);
@@ -550,6 +573,22 @@ extern "C" int dfs_cnn2d_create(dfs_model** out, int device, const dfs_cnn2d_wei
             p1[img + at] = f32_to_act_bits((float)(wv - act_bits_to_double(p1[at])));
           }
     for (int c = 0; c < 32; ++c) m->b1h[c] = 0.5f * m->c1.b[c];
+    // the same weights for conv12_fused.cu, which runs conv1 as two N = 128 passes of 16 output channels each (its accumulator gets
+    // 128 TMEM columns): [pass][value | residual][kw][K chunk][n' = (c' / 8) * 64 + jj * 8 + c' % 8][8], channel c = 16*pass + c' (an epilogue
+    // warp reads 8 channels x 8 time offsets = 64 CONTIGUOUS accumulator columns with two 32-column loads)
+    {
+      std::vector<uint16_t> p1f((size_t)2 * 2 * 3 * 2 * 128 * 8, 0);
+      for (int ps = 0; ps < 2; ++ps)
+        for (int part = 0; part < 2; ++part)
+          for (int kw = 0; kw < 3; ++kw)
+            for (int ch = 0; ch < 2; ++ch)
+              for (int jj = 0; jj < 8; ++jj)
+                for (int cp = 0; cp < 16; ++cp)
+                  for (int e = 0; e < 8; ++e)
+                    p1f[((((((size_t)ps * 2 + part) * 3 + kw) * 2 + ch) * 128) + (cp >> 3) * 64 + jj * 8 + (cp & 7)) * 8 + e] =
+                        p1[part * img + (((size_t)kw * 2 + ch) * 256 + jj * 32 + 16 * ps + cp) * 8 + e];
+      if ((st = dev_upload(m, &m->w1pack_fused, p1f)) != DFS_OK) return fail(st);
+    }
     append_bias_and_ones(p1, m->b1h);
     if ((st = dev_upload(m, &m->w1pack, p1)) != DFS_OK) return fail(st);
     if ((st = dev_alloc(m, reinterpret_cast<void**>(&m->xt), (size_t)conv1_xt_rows(m->chunk) * 16, true)) != DFS_OK) return fail(st);
@@ -621,7 +660,18 @@ extern "C" int dfs_cnn2d_score(dfs_model* m, const dfs_features* feats, float* o
   for (int64_t i0 = 0; i0 < feats->n; i0 += m->chunk) {
     const int nk = (int)std::min<int64_t>(m->chunk, feats->n - i0);
     const float* x = feats->x + i0 * feats->stride_n;
-    {
+    const bool fused12 = m->conv12_fused && m->conv_impl == 0 && m->conv1_impl == 0;
+    if (fused12) {
+      {
+        ProfScope ps(m, 0, stream);
+        DFS_PROPAGATE(launch_conv1_prep(x, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->xt, stream));
+      }
+      {
+        ProfScope ps(m, 1, stream);
+        DFS_PROPAGATE(launch_cnn2d_conv12_fused(m->xt, m->w1pack_fused, m->b1h, m->w2pack_fused, m->b2, nk, m->act2, m->num_sms, stream));
+      }
+    }
+    if (!fused12) {
       ProfScope ps(m, 0, stream);
       if (m->conv1_impl == 0)
         DFS_PROPAGATE(launch_conv1_tc(x, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->xt, m->w1pack, m->b1h, m->act1, m->num_sms,
@@ -629,7 +679,7 @@ extern "C" int dfs_cnn2d_score(dfs_model* m, const dfs_features* feats, float* o
       else
         DFS_PROPAGATE(launch_conv1(x, feats->stride_n, feats->stride_t, feats->stride_f, nk, m->c1, nullptr, nullptr, false, m->act1, stream));
     }
-    {
+    if (!fused12) {
       ProfScope ps(m, 1, stream);
       if (m->conv_impl == 0) DFS_PROPAGATE(launch_cnn2d_conv2_tc(m->tmap1, m->w2pack, m->b2, nk, m->act2, m->num_sms, stream));
       else DFS_PROPAGATE(launch_cnn2d_conv2_simt(m->act1, m->w2pack, m->b2_dev, nk, m->act2, stream));

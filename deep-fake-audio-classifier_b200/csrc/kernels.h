@@ -26,6 +26,9 @@ int launch_cnn2d_conv3_split(const CUtensorMap& tmap_act2, const uint16_t* wpack
 // ---- conv1_tc.cu (CNN2D block 1 as a Toeplitz-in-time tcgen05 GEMM) ----
 int64_t conv1_xt_rows(int64_t n_utts);   // 16-byte rows of the fp16 time-major feature copy for n utterances
 int launch_conv1_prep(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, cudaStream_t stream);
+// conv12_fused.cu: conv1 + conv2 in one kernel (act1 stays in shared memory); weight images: see Conv12Params
+int launch_cnn2d_conv12_fused(const uint16_t* xt, const uint16_t* w1pack, const float* b1_half, const uint16_t* w2pack, const float* b2_half, int n_utts,
+                              ActBuf act2, int num_sms, cudaStream_t stream);
 int launch_conv1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n_utts, uint16_t* xt, const uint16_t* wpack, const float* bias_half,
                     ActBuf out, int num_sms, cudaStream_t stream);
 // split precision: xt_lo = the fp16 rounding residuals of xt (same geometry), out = 16 planes (8 value planes, then 8 residual planes)

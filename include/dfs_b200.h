@@ -129,6 +129,8 @@ int dfs_model_destroy(dfs_model* m);
  * three MMAs per product into the fp32 accumulator (fp32-class scores at about a third of the default rate).
  * Kernel-variant switches kept for on-device cross-checks (tests compare the variants; defaults are the product path):
  *   "conv1_impl"   (CNN2D, CAE) 0 = Toeplitz tcgen05 GEMM for the Cin = 1 layer, 1 = fp32 CUDA-core conv
+ *   "conv12_fused" (CNN2D)      1 (default) = blocks 1 and 2 in ONE kernel (the layer-1 activations stay in shared memory), 0 = one
+ *                               kernel per block (bit-identical to the pre-fusion path; act2 differs by one fp16 ulp on a few elements)
  *   "fused"        (CNN1D)      1 (default) = the three conv layers, the time mean and the classifier in ONE kernel (activations never
  *                               leave the SM; dense feature-contiguous input), 0 = one kernel per layer
  *   "l1_fused"     (CNN1D)      1 (default) = layer 1 converts the fp32 rows in flight, 0 = prep kernel + TMA

@@ -216,6 +216,29 @@ def test_split_precision_small_batches_and_switching():
     np.testing.assert_array_equal(full, s1)
 
 
+def test_cnn2d_fused_conv1_conv2_equals_the_separate_kernels(structured):
+    """conv12_fused.cu (default): blocks 1 and 2 in one kernel, act1 never written.  Same operands and epilogue formulas as conv1_tc +
+    conv_tc<PAIR> (option conv12_fused = 0) except that conv1's bias is added in the epilogue instead of by an MMA: the conv3
+    time sums agree to a few 1e-6 relative, scores to 2e-6; ragged passes (max_chunk 7 over 23 utterances: units of the last pass
+    end mid-grid) and the strided view take the same path."""
+    sd = syn.cnn2d_state(0, logit_scale=float(T["cnn2d_scale"]), classifier_bias=float(T["cnn2d_bias"]))
+    x = structured[:300].cuda()
+    sc = Cnn2dScorer(sd)
+    a, ea = sc.score(x, return_embedding=True)
+    sc.set_option("conv12_fused", 0)
+    b, eb = sc.score(x, return_embedding=True)
+    ea, eb, a, b = ea.cpu().numpy(), eb.cpu().numpy(), a.cpu().numpy(), b.cpu().numpy()
+    _record("conv12_fused_vs_separate", dict(max_abs_logit_diff=float(np.max(np.abs(a - b))), max_abs_emb_diff=float(np.max(np.abs(ea - eb))),
+                                              emb_scale=float(np.abs(eb).mean())))
+    np.testing.assert_allclose(ea, eb, rtol=2e-3, atol=2e-4 * float(np.abs(eb).mean()))
+    assert np.max(np.abs(a - b)) <= 2e-3                                  # logits span +-20 here; fp16 operands leave 1e-2 against the reference
+    small = Cnn2dScorer(sd, max_chunk=7)
+    c = small.score(x[:23]).cpu().numpy()
+    np.testing.assert_array_equal(c, a[:23])
+    xt = x[:23].transpose(1, 2).contiguous().transpose(1, 2)
+    np.testing.assert_allclose(small.score(xt).cpu().numpy(), a[:23], rtol=1e-6, atol=1e-6)
+
+
 def test_trained_like_scores_through_the_group_host_path(structured):
     """End to end from host memory: the group upload of the structured table reproduces the device-resident scores."""
     sd2 = syn.cnn2d_state(0, logit_scale=float(T["cnn2d_scale"]), classifier_bias=float(T["cnn2d_bias"]))
