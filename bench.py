@@ -673,9 +673,10 @@ def main():
                 "traffic_note": "DRAM bytes per launch (ncu); the tensor-bound kernel's algorithmic operand is the fp16 act2 read, 1.91 MB/utterance",
                 "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)",
                 "flops_per_launch": CONV3_FLOP_PER_UTT * utt_per_launch, "avg_launch_ms": conv3_ms,
-                "kernel_ms_share": {k: v / max(sum(share_ms), 1e-9) for k, v in zip(("conv1", "conv2", "conv3", "head"), share_ms)},
-                "kernel_ms_share_note": "from one fully profiled step before the timed region; conv3's launches are timed inside it",
-                "conv2_tflops": CONV2_FLOP_PER_UTT * P / (share_ms[1] * 1e-3) / 1e12 if share_ms[1] > 0 else None,
+                "kernel_ms_share": {k: v / max(sum(share_ms), 1e-9) for k, v in zip(("xt_prep", "conv12_fused", "conv3", "head"), share_ms)},
+                "kernel_ms_share_note": "from one fully profiled step before the timed region; conv3's launches are timed inside it; conv12_fused = blocks 1 + 2 "
+                                        "of the 2D-CNN in one kernel (kernel ids 0..3 of dfs_model_profile)",
+                "conv12_fused_tflops": (CONV2_FLOP_PER_UTT + 2 * 9 * 32 * 321 * 180) * P / (share_ms[1] * 1e-3) / 1e12 if share_ms[1] > 0 else None,
                 "whole_path_tflops": whole, "whole_path_frac_of_sustained_peak": whole / pk["tflops_sustained"],
                 "whole_path_frac_of_burst_peak": whole / pk["tflops_burst"], "whole_path_frac_of_nominal_peak": whole / NOMINAL_TFLOPS}
 
