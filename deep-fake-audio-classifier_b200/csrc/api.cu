@@ -1290,9 +1290,23 @@ extern "C" int dfs_model_saturation_count(dfs_model* m, int64_t* saturated_out, 
   DFS_CUDA_CHECK(cudaSetDevice(m->device));
   std::vector<std::pair<const void*, size_t>> bufs;   // (pointer, bytes), all 16-byte multiples
   if (m->kind == KIND_CNN2D) {
+    // what the last pass materialised in fp16: the feature image always; act1 only with separate kernels (the fused blocks 1 + 2 keep it
+    // in shared memory -- a clipped act1 element shows in act2 only through the convolution); split precision: the value planes
+    // (the first half of each buffer; residual planes are differences, never near the range limit); fp32 precision: nothing is fp16
+    if (m->precision == 1) {
+      *saturated_out = 0;
+      *nonfinite_out = 0;
+      return DFS_OK;
+    }
     bufs.push_back({m->xt, (size_t)conv1_xt_rows(m->chunk) * 16});
-    bufs.push_back({m->act1.ptr, (size_t)m->act1.bytes()});
-    bufs.push_back({m->act2.ptr, (size_t)m->act2.bytes()});
+    if (m->precision == 2) {
+      bufs.push_back({m->act1s.ptr, (size_t)m->act1s.bytes() / 2});
+      bufs.push_back({m->act2s.ptr, (size_t)m->act2s.bytes() / 2});
+    } else {
+      const bool fused12 = m->conv12_fused && m->conv_impl == 0 && m->conv1_impl == 0;
+      if (!fused12) bufs.push_back({m->act1.ptr, (size_t)m->act1.bytes()});
+      bufs.push_back({m->act2.ptr, (size_t)m->act2.bytes()});
+    }
   } else if (m->kind == KIND_CNN1D) {
     DFS_REQUIRE(m->c1d->fused == 0, DFS_ERR_UNSUPPORTED,
                 "dfs_model_saturation_count: the one-kernel 1D-CNN keeps its activations on the SM; set option \"fused\" = 0 and score again");

@@ -150,7 +150,10 @@ int dfs_model_profile(dfs_model* m, double* ms_out, int64_t* launches_out, int n
  * (|v| > 65504 becomes +-65504 silently).  This scans the fp16 buffers the LAST pass (<= chunk utterances) of `m` left
  * behind -- feature image and every inter-layer activation -- and returns how many elements sit exactly at +-65504 and how
  * many are non-finite.  0 / 0 on real LFCC maps (range -61 ... +86, model_prediction_report.md:24-29); tests feed
- * heavy-tailed inputs and check it.  1D-CNN: needs option "fused" = 0 (the one-kernel path never stores its activations). Synchronises `stream`.                                                          */
+ * heavy-tailed inputs and check it.  1D-CNN: needs option "fused" = 0 (the one-kernel path never stores its activations).
+ * 2D-CNN: with the fused blocks 1 + 2 (default) the layer-1 activations stay in shared memory and are not part of the census
+ * (set "conv12_fused" = 0 to include them); precision "split" counts the value planes, precision "fp32" returns 0 / 0.
+ * Synchronises `stream`.                                                                                                   */
 int dfs_model_saturation_count(dfs_model* m, int64_t* saturated_out, int64_t* nonfinite_out, void* stream);
 
 /* ---- scoring (device-resident features) --------------------------------------------- */

@@ -274,6 +274,21 @@ def test_saturation_census_counts_clipped_values():
         sc.score(x * 1e4)
         sat, nonfin = sc.saturation_count()
         assert sat > 0 and nonfin == 0, (type(sc).__name__, sat, nonfin)
+    # 2D-CNN by mode: separate kernels materialise act1 as well (more clipped elements than the fused default sees), the split
+    # precision counts its value planes, the fp32 precision stores nothing in fp16
+    c2 = Cnn2dScorer(syn.cnn2d_state(0), max_chunk=8)
+    c2.score(x * 1e4)
+    fused_sat = c2.saturation_count()[0]
+    c2.set_option("conv12_fused", 0)
+    c2.score(x * 1e4)
+    assert c2.saturation_count()[0] > fused_sat > 0
+    c2.set_option("precision", 2)
+    c2.score(x)
+    assert c2.saturation_count() == (0, 0)
+    c2.score(x * 1e4)
+    assert c2.saturation_count()[0] > 0
+    c2.set_option("precision", 1)
+    assert c2.saturation_count() == (0, 0)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
