@@ -1,9 +1,9 @@
 // conv12_fused.cu -- CNN2D blocks 1 and 2 in ONE kernel: the layer-1 activations never reach HBM.
 //   Conv2d(1,32,3,p1)+BN+ReLU+AvgPool(2,1)  ->  Conv2d(32,64,3,p1)+BN+ReLU+AvgPool(2,1)      /root/reference/src/model.py:15-25
 //
-// Why: conv1_tc.cu writes 1.84 MB of act1 per utterance and is bound by the device's pure-write rate (765 MB per 416-utterance pass at
-// the 3.3 TB/s a memset reaches = 232 us; measured with its stores switched off it takes half the time), and conv2 reads those bytes
-// back.  Here conv1 is a producer stage of conv2's pipeline and the kernel is bound by its MMAs:
+// Why: conv1_tc.cu writes 1.84 MB of act1 per utterance (765 MB per 416-utterance pass, which its epilogue warps get out at about half of
+// what the write path takes: measured with its stores switched off the kernel needs half the time) and conv2 reads those bytes back.  Here
+// conv1 is a producer stage of conv2's pipeline and the kernel is bound by its MMAs / the shared-memory port:
 //
 //   unit    = 14 output feature columns of one utterance (182 padded columns = 13 units: a unit never straddles utterances).
 //             Its act1 window is 16 columns wide and therefore comes from ONE conv1 tile of 16 columns x 8 time blocks
