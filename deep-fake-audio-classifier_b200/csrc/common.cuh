@@ -151,22 +151,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
-// The same bounded wait for warps that can afford ~100 ns of wake-up latency: between two tests the warp SLEEPS instead of re-issuing
-// try_wait.  A spinning warp takes issue slots from the working warps of its scheduler: with 23 producer warps polling for the stage of the
-// one-kernel 1D-CNN the four epilogue warps ran 7x slower than their instruction count (cycle counters, profiles/r02t).
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, int tag = 0, unsigned ns = 100) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0 = global_timer_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(ns);
-    if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > DFS_WAIT_LIMIT_NS) {
-      printf("dfs_b200: mbarrier wait timeout (tag %d, block %d, thread %d, parity %u)\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-
 // ---- bulk / tensor copies (TMA) ---------------------------------------------------------
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
