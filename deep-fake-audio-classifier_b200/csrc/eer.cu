@@ -93,9 +93,13 @@ __device__ __forceinline__ uint32_t warp_peers8(uint32_t d, bool ok) {
   uint32_t peers = __ballot_sync(0xffffffffu, ok);
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
-    const bool bit = (d >> b) & 1u;
-    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-    peers &= bit ? bal : ~bal;
+    // bal = lanes whose bit b is set; m = 0 if mine is set, ~0 if not: peers &= (mine set ? bal : ~bal).  Written with the predicate kept
+    // in the asm block so that ptxas moves the digit's bits into predicates with one R2P and spends VOTE + predicated NOT + AND per bit
+    // (29 instructions per 32 keys; the C++ forms `bit ? bal : ~bal` and `~(bal ^ -bit)` compile to 51)
+    uint32_t bal, m;
+    asm volatile("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %2, %3;\n setp.ne.b32 p, t, 0;\n vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+                 " selp.b32 %1, 0, 0xffffffff, p;\n}" : "=r"(bal), "=r"(m) : "r"(d), "r"(1u << b));
+    peers &= bal ^ m;
   }
   return peers;
 }
@@ -357,6 +361,383 @@ __global__ void __launch_bounds__(kSortThreads, 4) radix_downsweep_kernel(const 
   }
 }
 
+// ---- the same LSD sort as ONE scatter kernel per pass ("onesweep") ------------------------------------------------------------
+// What the super-tile form above costs at 100 M keys (profiles/r02v): every CTA owns 256 private output streams, so ~600 resident CTAs
+// write 150 k streams in 64-byte pieces -- partial 32-byte sectors that leave the L2 before the same CTA's next tile completes them
+// (ECC DRAM: read-modify-write, +40 % traffic) and no DRAM page locality -- plus a counting pass per digit (0.17 ms each).
+// Here the tiles are handed out in INPUT ORDER (atomic ticket), so all resident CTAs work on one window of consecutive tiles and their
+// runs of a digit are adjacent in the output and written within microseconds of each other; a tile's global offset per digit comes from a
+// decoupled look-back over the tiles before it (status word = 2 flag bits + 30-bit count, hence n < 2^30; a ticket holder is always a
+// running CTA, so the chain cannot dead-lock; the first wave resolves in ~sqrt(#resident) steps, then the chain is 1-2 tiles deep).
+// No counting pass: the global histogram of the NEXT pass's digit is taken by the same kernel from the ballots it already issues
+// (per-warp counters kept across the CTA's tiles, 256 atomics per CTA at the end); the first pass's histogram comes from the prep
+// kernel.  Tile = 512 threads x 16 keys = 8,192 (128-byte runs per digit); 2 CTAs per SM.
+constexpr uint32_t kOsAgg = 1u << 30, kOsIncl = 1u << 31, kOsMask = kOsAgg - 1u;
+template <typename K, int T> struct OsCfg {
+  static constexpr int I = sizeof(K) == 4 ? 16 : 8;   // keys per thread
+  static constexpr int TILE = T * I;
+  static constexpr int W = T / 32;
+  static constexpr int CTAS = 1024 / T;               // per SM: 64 registers per thread
+  static constexpr size_t SMEM = (sizeof(K) + 4) * (size_t)TILE;
+};
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// exclusive scan of one value per thread over the first 256 threads of the block (8 warps); `wsum` = 8 words of shared memory.
+// Called by ALL threads of the block (it contains a barrier); threads >= 256 pass 0 and ignore the result.
+__device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t* wsum) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31 && w < 8) wsum[w] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+#pragma unroll
+  for (int ww = 0; ww < 8; ++ww) woff += (ww < w) ? wsum[ww] : 0u;
+  return woff + incl - v;
+}
+
+// HIST: how the next pass's histogram is taken -- 0: not here (radix_hist_kernel runs before each pass), 1: one shared-memory atomic per key
+// (a warp whose 32 keys share the digit adds 32 at once), 2: ballot peers + per-warp counters (no atomics, ~45 more instructions per 32 keys).
+// T: threads per CTA (512: tiles of 8,192 fp32 keys, 2 CTAs per SM; 256: 4,096 keys, 4 CTAs per SM).
+template <typename K, int HIST, int T>
+__global__ void __launch_bounds__(T, 1024 / T) radix_onesweep_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ pin, K* __restrict__ kout,
+                                                                     uint32_t* __restrict__ pout, uint32_t n /* < 2^30 */, int shift, int next_shift,
+                                                                     const uint32_t* __restrict__ hist_cur, uint32_t* __restrict__ hist_next,
+                                                                     uint32_t* __restrict__ status /*[tiles][256]*/, unsigned int* __restrict__ ticket) {
+  constexpr int I = OsCfg<K, T>::I, TILE = OsCfg<K, T>::TILE, W = OsCfg<K, T>::W;
+  __shared__ uint32_t cnt[W][256];          // per-warp counts of the current digit -> exclusive prefix over the warps
+  __shared__ uint32_t nxt[HIST == 2 ? W : 1][256];   // counts of the next pass's digit (per warp for HIST = 2), kept over all tiles of this CTA
+  __shared__ uint32_t digit_start[256];     // tile-local offset of each digit's run in the staging buffer
+  __shared__ uint32_t gbase[256];           // global position of each digit's run of this tile - its offset in the staging buffer
+  __shared__ uint32_t bbase[256];           // bucket bases: exclusive prefix of the global histogram
+  __shared__ uint32_t wsum[8];
+  __shared__ uint32_t s_tile[2];
+  extern __shared__ __align__(16) uint8_t dyn[];
+  K* skeys = reinterpret_cast<K*>(dyn);
+  uint32_t* spay = reinterpret_cast<uint32_t*>(dyn + sizeof(K) * TILE);
+
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t tiles = (n + TILE - 1) / TILE;
+  const int mine0 = w * (32 * I) + lane;    // this thread's keys of a tile: mine0 + 32 i
+
+  for (int i = tid; i < (HIST == 2 ? W : 1) * 256; i += T) (&nxt[0][0])[i] = 0u;
+  for (int i = tid; i < W * 256; i += T) (&cnt[0][0])[i] = 0u;
+  {
+    const uint32_t tot = tid < 256 ? hist_cur[tid] : 0u;
+    const uint32_t ex = block_excl_scan256(tot, wsum);
+    if (tid < 256) bbase[tid] = ex;
+  }
+  if (tid == 0) s_tile[0] = atomicAdd(ticket, 1u);
+  __syncthreads();
+
+  // the keys of a tile are loaded while the tile before it is still looked back and written out (the registers are free from the
+  // staging scatter on), so their DRAM latency is off the critical path; the payloads are prefetched into the L2 at the same point
+  K key[I];
+  {
+    const uint32_t t0 = s_tile[0];
+    if (t0 < tiles) {
+      const uint32_t base = t0 * TILE;
+      const int valid = (int)((n - base) < TILE ? (n - base) : TILE);
+#pragma unroll
+      for (int i = 0; i < I; ++i) key[i] = (mine0 + 32 * i < valid) ? kin[base + mine0 + 32 * i] : ~(K)0;
+    }
+  }
+  int buf = 0;
+  while (true) {
+    const uint32_t tile = s_tile[buf];
+    if (tile >= tiles) break;
+    if (tid == 0) s_tile[buf ^ 1] = atomicAdd(ticket, 1u);   // the ticket after this one
+    const uint32_t base = tile * TILE;
+    const int valid = (int)((n - base) < TILE ? (n - base) : TILE);   // padding keys ~0: digit 255, ranked after every valid key, never written
+
+    uint32_t rnk2[I / 2];   // ranks inside the warp's digit count (< 512) as 16-bit halves: the kernel must fit 64 registers
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+      const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
+      const uint32_t peers = warp_peers8(d, true);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader) {
+        old = cnt[w][d];
+        cnt[w][d] = old + __popc(peers);
+      }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      const uint32_t r = old + __popc(peers & lt_mask);
+      rnk2[i >> 1] = (i & 1) ? (rnk2[i >> 1] | (r << 16)) : r;
+      if (HIST != 0 && next_shift >= 0) {   // block-uniform
+        const bool ok = (mine0 + 32 * i) < valid;
+        const uint32_t d2 = (uint32_t)(key[i] >> next_shift) & 0xffu;
+        if constexpr (HIST == 2) {
+          const uint32_t p2 = warp_peers8(d2, ok);
+          if (ok && lane == __ffs(p2) - 1) nxt[w][d2] += __popc(p2);
+        } else {
+          const uint32_t d0 = __shfl_sync(0xffffffffu, d2, 0);
+          if (__all_sync(0xffffffffu, ok && d2 == d0)) {   // tied scores: one atomic for the warp instead of a 32-way conflict
+            if (lane == 0) atomicAdd(&nxt[0][d0], 32u);
+          } else if (ok) {
+            atomicAdd(&nxt[0][d2], 1u);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d < 256 owns digit d: prefix over the warps, this tile's count published for the tiles after it, tile-local run offsets
+    uint32_t tot = 0, count_d = 0;
+    if (tid < 256) {
+#pragma unroll
+      for (int ww = 0; ww < W; ++ww) {
+        const uint32_t c = cnt[ww][tid];
+        cnt[ww][tid] = tot;
+        tot += c;
+      }
+      count_d = tot - ((tid == 255) ? (uint32_t)(TILE - valid) : 0u);
+      st_relaxed_u32(status + (size_t)tile * 256 + tid, (tile == 0 ? kOsIncl : kOsAgg) | count_d);
+    }
+    {
+      const uint32_t ex = block_excl_scan256(tot, wsum);
+      if (tid < 256) digit_start[tid] = ex;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+      const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
+      const uint32_t pos = digit_start[d] + cnt[w][d] + ((i & 1) ? (rnk2[i >> 1] >> 16) : (rnk2[i >> 1] & 0xffffu));
+      const uint32_t sw = pos ^ ((pos >> 5) & 31u);   // staging slot: see the write-out loop
+      skeys[sw] = key[i];
+      spay[sw] = (mine0 + 32 * i < valid) ? pin[base + mine0 + 32 * i] : 0u;
+    }
+
+    // next tile: keys into the registers, payloads into the L2
+    {
+      const uint32_t nt = s_tile[buf ^ 1];   // written before the first barrier of this iteration
+      if (nt < tiles) {
+        const uint32_t nb = nt * TILE;
+        const int nvalid = (int)((n - nb) < TILE ? (n - nb) : TILE);
+#pragma unroll
+        for (int i = 0; i < I; ++i) key[i] = (mine0 + 32 * i < nvalid) ? kin[nb + mine0 + 32 * i] : ~(K)0;
+        constexpr int PJ = TILE * 4 / 32 / T;   // 32-byte sectors of payloads per thread
+#pragma unroll
+        for (int j = 0; j < PJ; ++j) {
+          const uint32_t e = (uint32_t)(PJ * tid + j) * 8;
+          if ((int)e < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(pin + nb + e) : "memory");
+        }
+      }
+    }
+
+    // decoupled look-back, after the staging so that the tiles before this one have had time to publish
+    if (tid < 256) {
+      uint32_t excl = 0;
+      if (tile > 0) {
+        const uint32_t* sp = status + (size_t)(tile - 1) * 256 + tid;
+        while (true) {
+          uint32_t v = ld_relaxed_u32(sp);
+          while ((v >> 30) == 0u) {
+            __nanosleep(40);
+            v = ld_relaxed_u32(sp);
+          }
+          excl += v & kOsMask;
+          if (v & kOsIncl) break;
+          sp -= 256;
+        }
+        st_relaxed_u32(status + (size_t)tile * 256 + tid, kOsIncl | (excl + count_d));
+      }
+      gbase[tid] = bbase[tid] + excl - digit_start[tid];   // + staging position = global position
+    }
+    __syncthreads();
+
+    for (int i = tid; i < W * 256; i += T) (&cnt[0][0])[i] = 0u;   // for the next tile (its ranking starts after the barrier below)
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+      const int pos = tid + i * T;
+      if (pos < valid) {
+        // staging slots are XOR-swizzled by their 32-slot group: a warp still reads 32 consecutive words here, while the scatter
+        // above no longer piles up on two banks when every digit holds the same number of keys (runs starting at multiples of 16:
+        // the arithmetic-progression scores of synthetic.tie_free_scores made its first pass 16-way bank-conflicted)
+        const uint32_t sw = (uint32_t)pos ^ (((uint32_t)pos >> 5) & 31u);
+        const K k = skeys[sw];
+        const uint32_t d = (uint32_t)(k >> shift) & 0xffu;
+        const uint32_t dst = gbase[d] + (uint32_t)pos;
+        kout[dst] = k;
+        pout[dst] = spay[sw];
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  if (HIST != 0 && next_shift >= 0 && tid < 256) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int ww = 0; ww < (HIST == 2 ? W : 1); ++ww) s += nxt[ww][tid];
+    if (s) atomicAdd(hist_next + tid, s);
+  }
+}
+
+// ---- global histogram of one key byte: thread-private byte counters in a bank-conflict-free layout ------------------------
+// The [digit][thread] byte table of radix_upsweep_kernel puts a warp's 32 increments on ~random banks (3.4 wavefronts per LDS.U8 and
+// per STS.U8: the kernel runs at the shared-memory port, 0.17 ms per 100 M keys).  Here thread t owns WORD t of each of 64 rows; row g
+// packs its counters of the digits 4 g .. 4 g + 3 as the four bytes of that word, so every access of a warp hits bank = lane: one
+// wavefront per instruction.  A thread adds at most 252 keys between two flushes; a flush sums each row's bytes with dp4a (thread
+// (g, q) takes the quarter row q, skewed by its lane so that the 32 lanes again read 32 different banks) and clears the table.
+constexpr int kPrivBytes = 64 * 256 * 4;
+
+__device__ __forceinline__ void priv_count(uint32_t* tab, uint32_t d) {
+  uint32_t* w = tab + (d >> 2) * 256 + threadIdx.x;
+  *w += 1u << ((d & 3u) * 8u);
+}
+// called by all 256 threads between two barriers; tot[k] of the threads with (tid & 3) == 0 belongs to digit 4 (tid >> 2) + k
+__device__ __forceinline__ void priv_flush(uint32_t* tab, uint32_t (&tot)[4]) {
+  const int lane = threadIdx.x & 31;
+  uint32_t* row = tab + (threadIdx.x >> 2) * 256 + (threadIdx.x & 3) * 64;
+  uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 8
+  for (int j = 0; j < 64; ++j) {
+    const int jj = (j + lane) & 63;
+    const uint32_t w = row[jj];
+    row[jj] = 0u;
+    s0 = __dp4a(w, 0x00000001u, s0);
+    s1 = __dp4a(w, 0x00000100u, s1);
+    s2 = __dp4a(w, 0x00010000u, s2);
+    s3 = __dp4a(w, 0x01000000u, s3);
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+  }
+  tot[0] += s0; tot[1] += s1; tot[2] += s2; tot[3] += s3;
+}
+__device__ __forceinline__ void priv_publish(const uint32_t (&tot)[4], uint32_t* __restrict__ hist) {
+  if ((threadIdx.x & 3) == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (tot[k]) atomicAdd(hist + (threadIdx.x >> 2) * 4 + k, tot[k]);
+  }
+}
+
+// used when the prep kernel's histogram of byte 0 is not the first pass's (byte 0 constant over all keys) and, in histogram mode 0,
+// before every later pass
+template <typename K>
+__global__ void __launch_bounds__(256) radix_hist_kernel(const K* __restrict__ kin, long long n, int shift, uint32_t* __restrict__ hist) {
+  extern __shared__ __align__(16) uint32_t tab[];   // [64][256]
+  constexpr int V = VecOf<K>::V, U = 4;              // U 16-byte loads in flight per thread (the workspace keys are 256-byte aligned)
+  for (int i = threadIdx.x; i < 64 * 256; i += 256) tab[i] = 0u;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * (256 * V * U);
+  const long long iters = (n + stride - 1) / stride;
+  uint32_t tot[4] = {0u, 0u, 0u, 0u};
+  int since = 0;
+  for (long long it = 0; it < iters; ++it) {
+    const long long b = it * stride + (long long)blockIdx.x * (256 * V * U) + (long long)threadIdx.x * V;
+    K k[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = b + (long long)u * 256 * V;
+      if (i + V <= n) {
+        load_vec<K, V>(kin + i, k[u]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) k[u][e] = i + e < n ? kin[i + e] : (K)0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = b + (long long)u * 256 * V;
+#pragma unroll
+      for (int e = 0; e < V; ++e)
+        if (i + e < n) priv_count(tab, (uint32_t)(k[u][e] >> shift) & 0xffu);
+    }
+    since += U * V;
+    if (since + U * V > 255 || it == iters - 1) {   // block-uniform
+      __syncthreads();
+      priv_flush(tab, tot);
+      __syncthreads();
+      since = 0;
+    }
+  }
+  priv_publish(tot, hist);
+}
+
+// sort_prep_kernel + the global histogram of key byte 0 in the same read of the scores
+template <typename K>
+__global__ void __launch_bounds__(256) sort_prep_hist_kernel(const typename ScoreOf<K>::type* __restrict__ scores, const uint8_t* __restrict__ labels,
+                                                              long long n, K* __restrict__ keys, uint32_t* __restrict__ pay, SortHeader* __restrict__ hdr,
+                                                              uint32_t* __restrict__ hist0) {
+  typedef typename ScoreOf<K>::type S;
+  extern __shared__ __align__(16) uint32_t tab[];   // [64][256]
+  for (int i = threadIdx.x; i < 64 * 256; i += 256) tab[i] = 0u;
+  __syncthreads();
+  constexpr int U = 8;   // scores and labels in flight per thread (scalar loads: the caller's pointers need no alignment)
+  const long long stride = (long long)gridDim.x * (256 * U);
+  const long long iters = (n + stride - 1) / stride;
+  uint32_t ones = 0;
+  uint32_t tot[4] = {0u, 0u, 0u, 0u};
+  K kand = ~(K)0, kor = 0;
+  int since = 0;
+  for (long long it = 0; it < iters; ++it) {
+    const long long b = it * stride + (long long)blockIdx.x * (256 * U) + threadIdx.x;
+    S s[U];
+    uint8_t lb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = b + u * 256;
+      s[u] = i < n ? scores[i] : (S)0;
+      lb[u] = i < n ? labels[i] : (uint8_t)0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = b + u * 256;
+      if (i < n) {
+        const K k = to_key(s[u]);
+        const uint32_t lab = lb[u] != 0;
+        keys[i] = k;
+        pay[i] = (uint32_t)i | (lab << 31);
+        ones += lab;
+        kand &= k;
+        kor |= k;
+        priv_count(tab, (uint32_t)k & 0xffu);
+      }
+    }
+    since += U;
+    if (since + U > 255 || it == iters - 1) {   // block-uniform
+      __syncthreads();
+      priv_flush(tab, tot);
+      __syncthreads();
+      since = 0;
+    }
+  }
+  priv_publish(tot, hist0);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    ones += __shfl_xor_sync(0xffffffffu, ones, o);
+    kand &= (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)kand, o);
+    kor |= (K)__shfl_xor_sync(0xffffffffu, (unsigned long long)kor, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (ones) atomicAdd(&hdr->ones, (unsigned long long)ones);
+    atomicAnd(&hdr->key_and, (unsigned long long)kand);
+    atomicOr(&hdr->key_or, (unsigned long long)kor);
+  }
+}
+
 // ---- FAR/FRR sweep ----------------------------------------------------------------------
 struct SweepBest {
   double diff;
@@ -384,31 +765,47 @@ __global__ void __launch_bounds__(256) sweep_count_kernel(const uint32_t* __rest
   }
 }
 
-// single-block exclusive scan of the per-tile bonafide counts (<= ~260k tiles at n = 2^30)
+// single-block exclusive scan of the per-tile bonafide counts (<= ~260k tiles at n = 2^30).  The counts of 16 chunks of 1,024 tiles are
+// loaded together before the dependent chain of block scans starts (the first version paid one L2 round trip per chunk: 36 us at 100 M).
 __global__ void __launch_bounds__(1024) sweep_scan_kernel(const uint32_t* __restrict__ block_ones, long long nb,
                                                            unsigned long long* __restrict__ block_excl) {
-  __shared__ unsigned long long wsum[32];
-  __shared__ unsigned long long carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
+  __shared__ unsigned long long wsum[2][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (long long start = 0; start < nb; start += 1024) {
-    const long long i = start + threadIdx.x;
-    const unsigned long long v = i < nb ? block_ones[i] : 0ull;
-    unsigned long long incl = v;
+  unsigned long long carry = 0;   // kept identically by every thread
+  int par = 0;
+  for (long long start0 = 0; start0 < nb; start0 += 16 * 1024) {
+    uint32_t v[16];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
+    for (int c = 0; c < 16; ++c) {
+      const long long i = start0 + c * 1024 + threadIdx.x;
+      v[c] = i < nb ? block_ones[i] : 0u;
     }
-    if (lane == 31) wsum[w] = incl;
-    __syncthreads();
-    unsigned long long woff = 0;
-    for (int ww = 0; ww < w; ++ww) woff += wsum[ww];
-    if (i < nb) block_excl[i] = carry + woff + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += woff + incl;
-    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const long long start = start0 + c * 1024;
+      if (start >= nb) break;   // block-uniform
+      const long long i = start + threadIdx.x;
+      unsigned long long incl = v[c];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (lane == 31) wsum[par][w] = incl;
+      __syncthreads();
+      const unsigned long long mine = wsum[par][lane];   // warp totals, one per lane
+      unsigned long long winc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += up;
+      }
+      const unsigned long long total = __shfl_sync(0xffffffffu, winc, 31);
+      const unsigned long long woff = __shfl_sync(0xffffffffu, winc - mine, w);
+      if (i < nb) block_excl[i] = carry + woff + incl - v[c];
+      carry += total;
+      par ^= 1;   // the next chunk writes the other half of wsum: one barrier per chunk
+    }
   }
 }
 
@@ -421,7 +818,8 @@ __device__ __forceinline__ bool better(double d, long long i, double bd, long lo
 // counts); every other tile returns at once without reading its payloads or doing fp64 divisions.
 __global__ void __launch_bounds__(256) sweep_min_kernel(const uint32_t* __restrict__ pay, long long n, long long n_bona, long long n_spoof,
                                                          const unsigned long long* __restrict__ block_excl, const uint32_t* __restrict__ block_ones,
-                                                         SweepBest* __restrict__ block_best, long long k_base, long long c1_base) {
+                                                         SweepBest* __restrict__ block_best, long long k_base, long long c1_base, int single) {
+  // single != 0: exactly one tile holds the crossing (the curve runs from +1 at k = 0 to -1 at k = n); it alone writes block_best[0]
   {
     const long long t0 = (long long)blockIdx.x * kSortTile;
     const long long len = (n - t0) < kSortTile ? (n - t0) : kSortTile;
@@ -430,7 +828,7 @@ __global__ void __launch_bounds__(256) sweep_min_kernel(const uint32_t* __restri
     const double ds = __dsub_rn(__ddiv_rn((double)(n_spoof - (ks - c1s)), (double)n_spoof), __ddiv_rn((double)c1s, (double)n_bona));
     const double de = __dsub_rn(__ddiv_rn((double)(n_spoof - (ke - c1e)), (double)n_spoof), __ddiv_rn((double)c1e, (double)n_bona));
     if (!(ds >= 0.0 && de < 0.0)) {   // block-uniform
-      if (threadIdx.x == 0) block_best[blockIdx.x] = SweepBest{1.0e300, 0x7fffffffffffffffll, 0};
+      if (threadIdx.x == 0 && !single) block_best[blockIdx.x] = SweepBest{1.0e300, 0x7fffffffffffffffll, 0};
       return;
     }
   }
@@ -505,7 +903,7 @@ __global__ void __launch_bounds__(256) sweep_min_kernel(const uint32_t* __restri
     SweepBest b = part[0];
     for (int i = 1; i < 8; ++i)
       if (better(part[i].diff, part[i].idx, b.diff, b.idx)) b = part[i];
-    block_best[blockIdx.x] = b;
+    block_best[single ? 0 : blockIdx.x] = b;
   }
 }
 
@@ -585,6 +983,32 @@ static int get_workspace(size_t bytes, void** out) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// one radix pass of the one-sweep form: status words cleared, kernel launched on as many CTAs as are resident at once
+template <typename K, int HIST, int T>
+static int onesweep_launch(const K* kin, const uint32_t* pin, K* kout, uint32_t* pout, int64_t n, int shift, int next_shift, const uint32_t* hist_cur,
+                           uint32_t* hist_next, uint32_t* status, unsigned int* ticket, int num_sms, cudaStream_t stream) {
+  typedef OsCfg<K, T> Cfg;
+  static bool configured[32] = {false};
+  if (dfs_first_use_on_device(configured))
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_onesweep_kernel<K, HIST, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  int ctas = 0;
+  DFS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, radix_onesweep_kernel<K, HIST, T>, T, Cfg::SMEM));
+  DFS_REQUIRE(ctas >= 1, DFS_ERR_CUDA, "dfs_eer: the one-sweep kernel does not fit on this device");
+  const long long tiles = ceil_div64(n, Cfg::TILE);
+  DFS_CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t)tiles * 256 * 4, stream));
+  radix_onesweep_kernel<K, HIST, T><<<(unsigned)std::min<long long>(tiles, (long long)num_sms * ctas), T, Cfg::SMEM, stream>>>(
+      kin, pin, kout, pout, (uint32_t)n, shift, next_shift, hist_cur, hist_next, status, ticket);
+  DFS_LAUNCH_CHECK();
+  return DFS_OK;
+}
+template <typename K, typename... A>
+static int onesweep_pass(int hmode, bool small_tiles, A... a) {
+  if (small_tiles) return hmode == 0 ? onesweep_launch<K, 0, 256>(a...) : hmode == 1 ? onesweep_launch<K, 1, 256>(a...) : onesweep_launch<K, 2, 256>(a...);
+  return hmode == 0 ? onesweep_launch<K, 0, 512>(a...) : hmode == 1 ? onesweep_launch<K, 1, 512>(a...) : onesweep_launch<K, 2, 512>(a...);
+}
+
+int g_sort_onesweep = 1;   // dfs_set_global_option("eer_sort_onesweep"): 0 = count / scan / scatter over super-tiles (cross-check), 1..3 = one-sweep on 512-thread tiles, histogram mode 0..2, 4..6 = on 256-thread tiles
+
 template <typename K>
 static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_eer_result* result_host, uint32_t* perm, void* sorted,
                     cudaStream_t stream) {
@@ -599,6 +1023,10 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   const long long supers = ceil_div64(n, kSuperKeys);
   const size_t o_counts = carve((size_t)supers * 256 * 4);
   const size_t o_hist = carve(3 * 256 * 4);   // bucket bases of the current pass | per-digit totals | completion counter of the scan
+  // one-sweep form: global histogram of every key byte [8][256] + one tile ticket per pass [8] (zeroed together), look-back status words
+  const long long os_tiles = ceil_div64(n, OsCfg<K, 256>::TILE);   // the smaller of the two tile sizes
+  const size_t o_oshist = carve((8 * 256 + 8) * 4);
+  const size_t o_status = carve((size_t)os_tiles * 256 * 4);
   const size_t o_small = carve(256);      // SortHeader
   const size_t o_bones = carve((size_t)tiles * 4), o_bexcl = carve((size_t)tiles * 8), o_bbest = carve((size_t)tiles * sizeof(SweepBest));
   const size_t o_res = carve(sizeof(dfs_eer_result));
@@ -615,25 +1043,21 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   SweepBest* bbest = reinterpret_cast<SweepBest*>(b8 + o_bbest);
   dfs_eer_result* res_dev = reinterpret_cast<dfs_eer_result*>(b8 + o_res);
 
-  SortHeader h0{0ull, ~0ull, 0ull};
-  DFS_CUDA_CHECK(cudaMemcpyAsync(hdr, &h0, sizeof(h0), cudaMemcpyHostToDevice, stream));
+  uint32_t* oshist = reinterpret_cast<uint32_t*>(b8 + o_oshist);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(oshist + 8 * 256);
+  uint32_t* status = reinterpret_cast<uint32_t*>(b8 + o_status);
+  const bool onesweep = g_sort_onesweep != 0;
+
+  // SortHeader{ones = 0, key_and = ~0, key_or = 0} by memsets: no host buffer to keep alive, no synchronisation before the first kernel
+  DFS_CUDA_CHECK(cudaMemsetAsync(hdr, 0, sizeof(SortHeader), stream));
+  DFS_CUDA_CHECK(cudaMemsetAsync(&hdr->key_and, 0xff, sizeof(unsigned long long), stream));
   DFS_CUDA_CHECK(cudaMemsetAsync(hist + 512, 0, 4, stream));   // completion counter of radix_scan_kernel (the workspace is shared and grow-only)
-  DFS_CUDA_CHECK(cudaStreamSynchronize(stream));  // h0 is a stack buffer
   int num_sms = 148;
   {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const unsigned prep_grid = (unsigned)std::min<long long>(ceil_div64(n, 256), (long long)num_sms * 8);
-  sort_prep_kernel<K><<<prep_grid, 256, 0, stream>>>(static_cast<const S*>(scores), labels, n, keys[0], pay[0], hdr);
-  DFS_LAUNCH_CHECK();
-  // the label count and the key AND/OR decide the host control flow (single-class early-out; skipped passes)
-  SortHeader small_host;
-  DFS_CUDA_CHECK(cudaMemcpyAsync(&small_host, hdr, sizeof(small_host), cudaMemcpyDeviceToHost, stream));
-  DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
-  const long long n_bona = (long long)small_host.ones, n_spoof = n - n_bona;
-
   static bool configured[32] = {false};
   const size_t dyn_smem = (sizeof(K) + 4) * kSortTile;
   if (dfs_first_use_on_device(configured)) {
@@ -641,9 +1065,49 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
     DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kSortTile));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_upsweep_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kCntStride));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_upsweep_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kCntStride));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_hist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_hist_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(sort_prep_hist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(sort_prep_hist_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
   }
+  const unsigned hist_grid = (unsigned)std::min<long long>(ceil_div64(n, 2048), (long long)num_sms * 3);   // 3 CTAs of 64 KB per SM
+  if (onesweep) {
+    DFS_CUDA_CHECK(cudaMemsetAsync(oshist, 0, (8 * 256 + 8) * 4, stream));
+    sort_prep_hist_kernel<K><<<hist_grid, 256, kPrivBytes, stream>>>(static_cast<const S*>(scores), labels, n, keys[0], pay[0], hdr, oshist);
+  } else {
+    const unsigned prep_grid = (unsigned)std::min<long long>(ceil_div64(n, 256), (long long)num_sms * 8);
+    sort_prep_kernel<K><<<prep_grid, 256, 0, stream>>>(static_cast<const S*>(scores), labels, n, keys[0], pay[0], hdr);
+  }
+  DFS_LAUNCH_CHECK();
+  // the label count and the key AND/OR decide the host control flow (single-class early-out; skipped passes)
+  SortHeader small_host;
+  DFS_CUDA_CHECK(cudaMemcpyAsync(&small_host, hdr, sizeof(small_host), cudaMemcpyDeviceToHost, stream));
+  DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
+  const long long n_bona = (long long)small_host.ones, n_spoof = n - n_bona;
+
   int cur = 0;
-  for (int ps = 0; ps < PASSES; ++ps) {
+  if (onesweep) {
+    int pass_list[8], np = 0;
+    for (int ps = 0; ps < PASSES; ++ps)
+      if ((((small_host.key_and ^ small_host.key_or) >> (8 * ps)) & 0xffull) != 0) pass_list[np++] = ps;   // other bytes: identity passes
+    if (np > 0 && pass_list[0] != 0) {   // the prep kernel counted byte 0; the first pass sorts another one
+      radix_hist_kernel<K><<<hist_grid, 256, kPrivBytes, stream>>>(keys[0], n, 8 * pass_list[0], oshist + 256 * pass_list[0]);
+      DFS_LAUNCH_CHECK();
+    }
+    const int hmode = (g_sort_onesweep - 1) % 3;   // 0: histogram kernel before each pass, 1: shared-memory atomics in the scatter kernel, 2: ballots
+    const bool small_tiles = g_sort_onesweep >= 4;
+    for (int ip = 0; ip < np; ++ip) {
+      const int ps = pass_list[ip], nx = ip + 1 < np ? pass_list[ip + 1] : -1;
+      if (hmode == 0 && ip > 0) {
+        radix_hist_kernel<K><<<hist_grid, 256, kPrivBytes, stream>>>(keys[cur], n, 8 * ps, oshist + 256 * ps);
+        DFS_LAUNCH_CHECK();
+      }
+      DFS_PROPAGATE(onesweep_pass<K>(hmode, small_tiles, keys[cur], pay[cur], keys[cur ^ 1], pay[cur ^ 1], n, 8 * ps, nx < 0 ? -1 : 8 * nx, oshist + 256 * ps,
+                                     oshist + 256 * (nx < 0 ? 0 : nx), status, tickets + ps, num_sms, stream));
+      cur ^= 1;
+    }
+  }
+  for (int ps = 0; ps < PASSES && !onesweep; ++ps) {
     if ((((small_host.key_and ^ small_host.key_or) >> (8 * ps)) & 0xffull) == 0) continue;  // every key shares this digit: identity pass
     radix_upsweep_kernel<K><<<(unsigned)supers, 256, 256 * kCntStride, stream>>>(keys[cur], n, 8 * ps, counts);
     DFS_LAUNCH_CHECK();
@@ -672,9 +1136,9 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   DFS_LAUNCH_CHECK();
   sweep_scan_kernel<<<1, 1024, 0, stream>>>(bones, tiles, bexcl);
   DFS_LAUNCH_CHECK();
-  sweep_min_kernel<<<(unsigned)tiles, 256, 0, stream>>>(pay[cur], n, n_bona, n_spoof, bexcl, bones, bbest, 0, 0);
+  sweep_min_kernel<<<(unsigned)tiles, 256, 0, stream>>>(pay[cur], n, n_bona, n_spoof, bexcl, bones, bbest, 0, 0, /*single=*/1);
   DFS_LAUNCH_CHECK();
-  sweep_final_kernel<K><<<1, 256, 0, stream>>>(bbest, tiles, keys[cur], n, n_bona, n_spoof, res_dev);
+  sweep_final_kernel<K><<<1, 256, 0, stream>>>(bbest, 1, keys[cur], n, n_bona, n_spoof, res_dev);
   DFS_LAUNCH_CHECK();
   DFS_CUDA_CHECK(cudaMemcpyAsync(result_host, res_dev, sizeof(dfs_eer_result), cudaMemcpyDeviceToHost, stream));
   DFS_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1310,7 +1774,7 @@ static int eer_select_impl(const void* scores_v, const uint8_t* labels, int64_t 
     sweep_scan_kernel<<<1, 1024, 0, stream>>>(bones, tiles_m, bexcl);
     DFS_LAUNCH_CHECK();
     sweep_min_kernel<<<(unsigned)tiles_m, 256, 0, stream>>>(gpay, m, (long long)host.n_bona, (long long)host.n_spoof, bexcl, bones, bbest, start,
-                                                           (long long)host.c1_below);
+                                                           (long long)host.c1_below, /*single=*/0);
     DFS_LAUNCH_CHECK();
     select_reduce_best_kernel<<<1, 256, 0, stream>>>(bbest, tiles_m, sc.state);
     DFS_LAUNCH_CHECK();

@@ -211,3 +211,61 @@ def test_eer_select_tma_ring_matches_direct_loads():
                 assert out[0] == out[1] == (d["eer"], d["threshold"], d["eer_idx"], d["n_bonafide"]), (dtype, n)
     finally:
         D._native.set_global_option("eer_select_tma", 1)
+
+
+def _sort_forms_agree(s, l, tag):
+    """dfs_eer under every form of the radix passes: identical permutation, sorted scores and result."""
+    out = []
+    try:
+        for form in (0, 1, 2, 3, 4, 5, 6):
+            D._native.set_global_option("eer_sort_onesweep", form)
+            d = D.eer_details(s, l, want_perm=True, want_sorted=True)
+            out.append(d)
+    finally:
+        D._native.set_global_option("eer_sort_onesweep", 1)
+    base = out[0]
+    for form, d in enumerate(out[1:], start=1):
+        assert torch.equal(d["perm"], base["perm"]), (tag, form)
+        assert torch.equal(d["sorted"].view(torch.uint8), base["sorted"].view(torch.uint8)), (tag, form)   # bytes: NaN == NaN
+        assert (d["eer"], d["threshold"], d["eer_idx"], d["n_bonafide"]) == \
+               (base["eer"], base["threshold"], base["eer_idx"], base["n_bonafide"]) or np.isnan(d["threshold"]), (tag, form)
+    return base
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_eer_sort_one_sweep_matches_super_tile_form_and_oracle(dtype):
+    """The one-sweep passes (ticketed tiles + decoupled look-back; histogram by a kernel of its own, by shared-memory atomics or by
+    ballots) against the count / scan / scatter form and the stable oracle: sizes around the tile (8,192 fp32 / 4,096 fp64 keys),
+    many tiles (a long look-back chain), ties, NaN, a constant low key byte (the first pass is not byte 0) and negative scores."""
+    rng = np.random.default_rng(77)
+    tile = 8192 if dtype == np.float32 else 4096
+    for n in (1, 2, 31, tile - 1, tile, tile + 1, 5 * tile + 3, 1_000_003, 600 * tile + 17):
+        s = (rng.standard_normal(n) * 3).astype(dtype)
+        l = (rng.random(n) < 0.4).astype(np.uint8)
+        if n >= 2:
+            l[0], l[1] = 0, 1
+        base = _sort_forms_agree(torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda(), ("normal", n))
+        if n <= 1_000_003:
+            o = oeer.eer_details(s, l, kind="stable")
+            assert np.array_equal(base["perm"].cpu().numpy().astype(np.int64), o["perm"]), n
+            assert (base["eer"], base["threshold"], base["eer_idx"]) == (o["eer"], o["threshold"], o["eer_idx"]), n
+    n = 300_001
+    l = (rng.random(n) < 0.5).astype(np.uint8)
+    # heavy ties (17 levels), NaN scattered in, -0.0 / +0.0
+    s = rng.integers(0, 17, n).astype(dtype) / 16
+    s[::1001] = np.nan
+    s[5::997] = -0.0
+    base = _sort_forms_agree(torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda(), "ties+nan")
+    o = oeer.eer_details(s, l, kind="stable")
+    assert np.array_equal(base["perm"].cpu().numpy().astype(np.int64), o["perm"])
+    # low mantissa byte constant: the prep kernel's histogram of byte 0 is not the first pass's
+    bits = np.dtype(dtype).itemsize * 8
+    u = (rng.standard_normal(n) * 2).astype(dtype).view(np.uint32 if bits == 32 else np.uint64)
+    s = (u & ~np.array(0xff, dtype=u.dtype)).view(dtype)
+    base = _sort_forms_agree(torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda(), "byte0 constant")
+    o = oeer.eer_details(s, l, kind="stable")
+    assert np.array_equal(base["perm"].cpu().numpy().astype(np.int64), o["perm"])
+    # one value only: every pass is the identity
+    s = np.full(n, 0.25, dtype=dtype)
+    base = _sort_forms_agree(torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda(), "constant")
+    assert np.array_equal(base["perm"].cpu().numpy(), np.arange(n))

@@ -9,6 +9,8 @@ import dfs_b200 as D  # noqa: E402
 from dfs_b200 import synthetic as syn  # noqa: E402
 
 n = int(os.environ.get("EER_N", 20_000_000))
+if "EER_FORM" in os.environ:   # dfs_set_global_option("eer_sort_onesweep"): 0 = super-tile passes, 1..3 = one-sweep passes
+    D._native.set_global_option("eer_sort_onesweep", int(os.environ["EER_FORM"]))
 sc, lab = syn.tie_free_scores(n, seed=6)
 s, l = torch.from_numpy(sc).cuda(), torch.from_numpy(lab).cuda()
 for _ in range(2):
