@@ -408,20 +408,29 @@ __device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t* wsu
   return woff + incl - v;
 }
 
-// HIST: how the next pass's histogram is taken -- 0: not here (radix_hist_kernel runs before each pass), 1: one shared-memory atomic per key
-// (a warp whose 32 keys share the digit adds 32 at once), 2: ballot peers + per-warp counters (no atomics, ~45 more instructions per 32 keys).
+// Schedule of a CTA: the look-back of a tile sits behind the RANKING OF THE CTA'S NEXT TILE -- stage tile t, rank tile t' (publishing its
+// aggregate), then look back for t and write it out.  A tile's aggregate is thus public ~0.8 of a tile time before the tiles after it
+// ask for it (with the look-back right after a tile's own staging, ncu showed 35 % of the warp samples spinning in it: ~12 hops and
+// ~40 polls per tile), at no cost in shared memory: the per-warp counter rows are private to their warp between barriers, and the key
+// registers of t are free once staged (the keys of t' are loaded item by item behind the staging stores).
+// HIST: how the next pass's histogram is taken -- 0: not here (radix_hist_kernel runs before each pass), 1: one shared-memory atomic per key,
+// 2: ballot peers + per-warp counters (no atomics, ~45 more instructions per 32 keys).
 // T: threads per CTA (512: tiles of 8,192 fp32 keys, 2 CTAs per SM; 256: 4,096 keys, 4 CTAs per SM).
+// (A first pass that reads the scores and labels itself, with a header-and-histogram-only kernel before it, was measured and dropped:
+// 0.27 + 0.84 ms against 0.26 + 0.55 ms for the image-writing prep kernel and a plain first pass.)
 template <typename K, int HIST, int T>
 __global__ void __launch_bounds__(T, 1024 / T) radix_onesweep_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ pin, K* __restrict__ kout,
                                                                      uint32_t* __restrict__ pout, uint32_t n /* < 2^30 */, int shift, int next_shift,
                                                                      const uint32_t* __restrict__ hist_cur, uint32_t* __restrict__ hist_next,
                                                                      uint32_t* __restrict__ status /*[tiles][256]*/, unsigned int* __restrict__ ticket) {
+  auto load_key = [&](uint32_t idx) -> K { return kin[idx]; };
+  auto load_pay = [&](uint32_t idx) -> uint32_t { return pin[idx]; };
   constexpr int I = OsCfg<K, T>::I, TILE = OsCfg<K, T>::TILE, W = OsCfg<K, T>::W;
-  __shared__ uint32_t cnt[W][256];          // per-warp counts of the current digit -> exclusive prefix over the warps
-  __shared__ uint32_t nxt[HIST == 2 ? W : 1][256];   // counts of the next pass's digit (per warp for HIST = 2), kept over all tiles of this CTA
-  __shared__ uint32_t digit_start[256];     // tile-local offset of each digit's run in the staging buffer
-  __shared__ uint32_t gbase[256];           // global position of each digit's run of this tile - its offset in the staging buffer
-  __shared__ uint32_t bbase[256];           // bucket bases: exclusive prefix of the global histogram
+  __shared__ uint32_t cnt[W][256];
+  __shared__ uint32_t nxt[HIST == 2 ? W : 1][256];
+  __shared__ uint32_t digit_start[256];
+  __shared__ uint32_t gbase[256];
+  __shared__ uint32_t bbase[256];
   __shared__ uint32_t wsum[8];
   __shared__ uint32_t s_tile[2];
   extern __shared__ __align__(16) uint8_t dyn[];
@@ -431,7 +440,13 @@ __global__ void __launch_bounds__(T, 1024 / T) radix_onesweep_kernel(const K* __
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t tiles = (n + TILE - 1) / TILE;
-  const int mine0 = w * (32 * I) + lane;    // this thread's keys of a tile: mine0 + 32 i
+  const int mine0 = w * (32 * I) + lane;
+  // key byte -> digit with one PRMT (selector 0x444b: byte b, zero-extended) instead of shift + mask; 64-bit keys pick their half first
+  const uint32_t sel = 0x4440u | (((uint32_t)shift & 31u) >> 3), sel2 = 0x4440u | (((uint32_t)next_shift & 31u) >> 3);
+  auto digit = [&](K k2, uint32_t selector, int sh) -> uint32_t {
+    const uint32_t word = sizeof(K) == 8 ? (uint32_t)((unsigned long long)k2 >> (sh & 32)) : (uint32_t)k2;
+    return __byte_perm(word, 0u, selector);
+  };
 
   for (int i = tid; i < (HIST == 2 ? W : 1) * 256; i += T) (&nxt[0][0])[i] = 0u;
   for (int i = tid; i < W * 256; i += T) (&cnt[0][0])[i] = 0u;
@@ -440,33 +455,19 @@ __global__ void __launch_bounds__(T, 1024 / T) radix_onesweep_kernel(const K* __
     const uint32_t ex = block_excl_scan256(tot, wsum);
     if (tid < 256) bbase[tid] = ex;
   }
-  if (tid == 0) s_tile[0] = atomicAdd(ticket, 1u);
+  if (tid == 0) {
+    s_tile[0] = atomicAdd(ticket, 1u);
+    s_tile[1] = atomicAdd(ticket, 1u);
+  }
   __syncthreads();
 
-  // the keys of a tile are loaded while the tile before it is still looked back and written out (the registers are free from the
-  // staging scatter on), so their DRAM latency is off the critical path; the payloads are prefetched into the L2 at the same point
   K key[I];
-  {
-    const uint32_t t0 = s_tile[0];
-    if (t0 < tiles) {
-      const uint32_t base = t0 * TILE;
-      const int valid = (int)((n - base) < TILE ? (n - base) : TILE);
-#pragma unroll
-      for (int i = 0; i < I; ++i) key[i] = (mine0 + 32 * i < valid) ? kin[base + mine0 + 32 * i] : ~(K)0;
-    }
-  }
-  int buf = 0;
-  while (true) {
-    const uint32_t tile = s_tile[buf];
-    if (tile >= tiles) break;
-    if (tid == 0) s_tile[buf ^ 1] = atomicAdd(ticket, 1u);   // the ticket after this one
-    const uint32_t base = tile * TILE;
-    const int valid = (int)((n - base) < TILE ? (n - base) : TILE);   // padding keys ~0: digit 255, ranked after every valid key, never written
-
-    uint32_t rnk2[I / 2];   // ranks inside the warp's digit count (< 512) as 16-bit halves: the kernel must fit 64 registers
+  uint32_t rnk2[I / 2];
+  // ranks of key[] within this warp's digit counts (cnt row w, zero on entry); next pass's histogram on the way
+  auto rank_tile = [&](int valid) {
 #pragma unroll
     for (int i = 0; i < I; ++i) {
-      const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
+      const uint32_t d = digit(key[i], sel, shift);
       const uint32_t peers = warp_peers8(d, true);
       const int leader = __ffs(peers) - 1;
       uint32_t old = 0;
@@ -479,106 +480,140 @@ __global__ void __launch_bounds__(T, 1024 / T) radix_onesweep_kernel(const K* __
       rnk2[i >> 1] = (i & 1) ? (rnk2[i >> 1] | (r << 16)) : r;
       if (HIST != 0 && next_shift >= 0) {   // block-uniform
         const bool ok = (mine0 + 32 * i) < valid;
-        const uint32_t d2 = (uint32_t)(key[i] >> next_shift) & 0xffu;
+        const uint32_t d2 = digit(key[i], sel2, next_shift);
         if constexpr (HIST == 2) {
           const uint32_t p2 = warp_peers8(d2, ok);
           if (ok && lane == __ffs(p2) - 1) nxt[w][d2] += __popc(p2);
         } else {
-          const uint32_t d0 = __shfl_sync(0xffffffffu, d2, 0);
-          if (__all_sync(0xffffffffu, ok && d2 == d0)) {   // tied scores: one atomic for the warp instead of a 32-way conflict
-            if (lane == 0) atomicAdd(&nxt[0][d0], 32u);
-          } else if (ok) {
-            atomicAdd(&nxt[0][d2], 1u);
-          }
+          if (ok) atomicAdd(&nxt[0][d2], 1u);
         }
       }
       __syncwarp();
     }
-    __syncthreads();
-
-    // thread d < 256 owns digit d: prefix over the warps, this tile's count published for the tiles after it, tile-local run offsets
-    uint32_t tot = 0, count_d = 0;
-    if (tid < 256) {
+  };
+  // thread d < 256: exclusive prefix of digit d over the warps (left in cnt), the tile's count published; returns the padded total
+  auto publish_tile = [&](uint32_t tile, int valid, uint32_t& count_d) -> uint32_t {
+    uint32_t tot = 0;
 #pragma unroll
-      for (int ww = 0; ww < W; ++ww) {
-        const uint32_t c = cnt[ww][tid];
-        cnt[ww][tid] = tot;
-        tot += c;
-      }
-      count_d = tot - ((tid == 255) ? (uint32_t)(TILE - valid) : 0u);
-      st_relaxed_u32(status + (size_t)tile * 256 + tid, (tile == 0 ? kOsIncl : kOsAgg) | count_d);
+    for (int ww = 0; ww < W; ++ww) {
+      const uint32_t c = cnt[ww][tid];
+      cnt[ww][tid] = tot;
+      tot += c;
     }
+    count_d = tot - ((tid == 255) ? (uint32_t)(TILE - valid) : 0u);
+    st_relaxed_u32(status + (size_t)tile * 256 + tid, (tile == 0 ? kOsIncl : kOsAgg) | count_d);
+    return tot;
+  };
+
+  uint32_t tile = s_tile[0];
+  uint32_t count_d = 0;
+  if (tile < tiles) {   // block-uniform
     {
+      const uint32_t base = tile * TILE;
+      const int valid = (int)((n - base) < TILE ? (n - base) : TILE);
+#pragma unroll
+      for (int i = 0; i < I; ++i) key[i] = (mine0 + 32 * i < valid) ? load_key(base + mine0 + 32 * i) : ~(K)0;
+      rank_tile(valid);
+      __syncthreads();
+      uint32_t tot = 0;
+      if (tid < 256) tot = publish_tile(tile, valid, count_d);
       const uint32_t ex = block_excl_scan256(tot, wsum);
       if (tid < 256) digit_start[tid] = ex;
+      __syncthreads();
     }
-    __syncthreads();
+    int buf = 0;
+    while (true) {
+      // here: key / rnk2 / cnt / digit_start / count_d belong to `tile`, whose aggregate is public
+      const uint32_t ntile = s_tile[buf ^ 1];
+      const bool has_next = ntile < tiles;
+      const uint32_t base = tile * TILE, nbase = ntile * TILE;
+      const int valid = (int)((n - base) < TILE ? (n - base) : TILE);
+      const int nvalid = has_next ? (int)((n - nbase) < TILE ? (n - nbase) : TILE) : 0;
+      if (tid == 0) s_tile[buf] = has_next ? atomicAdd(ticket, 1u) : 0xffffffffu;   // the ticket after ntile (slot of `tile`: read a loop ago)
 
+      // stage `tile`; each key register is refilled with the next tile's key as soon as it is stored
 #pragma unroll
-    for (int i = 0; i < I; ++i) {
-      const uint32_t d = (uint32_t)(key[i] >> shift) & 0xffu;
-      const uint32_t pos = digit_start[d] + cnt[w][d] + ((i & 1) ? (rnk2[i >> 1] >> 16) : (rnk2[i >> 1] & 0xffffu));
-      const uint32_t sw = pos ^ ((pos >> 5) & 31u);   // staging slot: see the write-out loop
-      skeys[sw] = key[i];
-      spay[sw] = (mine0 + 32 * i < valid) ? pin[base + mine0 + 32 * i] : 0u;
-    }
-
-    // next tile: keys into the registers, payloads into the L2
-    {
-      const uint32_t nt = s_tile[buf ^ 1];   // written before the first barrier of this iteration
-      if (nt < tiles) {
-        const uint32_t nb = nt * TILE;
-        const int nvalid = (int)((n - nb) < TILE ? (n - nb) : TILE);
-#pragma unroll
-        for (int i = 0; i < I; ++i) key[i] = (mine0 + 32 * i < nvalid) ? kin[nb + mine0 + 32 * i] : ~(K)0;
-        constexpr int PJ = TILE * 4 / 32 / T;   // 32-byte sectors of payloads per thread
+      for (int i = 0; i < I; ++i) {
+        const uint32_t d = digit(key[i], sel, shift);
+        const uint32_t pos = digit_start[d] + cnt[w][d] + ((i & 1) ? (rnk2[i >> 1] >> 16) : (rnk2[i >> 1] & 0xffffu));
+        const uint32_t sw = pos ^ ((pos >> 5) & 31u);
+        skeys[sw] = key[i];
+        spay[sw] = (mine0 + 32 * i < valid) ? load_pay(base + mine0 + 32 * i) : 0u;
+        if (has_next) key[i] = (mine0 + 32 * i < nvalid) ? load_key(nbase + mine0 + 32 * i) : ~(K)0;
+      }
+      if (has_next) {   // the next tile's payloads into the L2
+        constexpr int PJ = TILE * 4 / 32 / T;
 #pragma unroll
         for (int j = 0; j < PJ; ++j) {
           const uint32_t e = (uint32_t)(PJ * tid + j) * 8;
-          if ((int)e < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(pin + nb + e) : "memory");
+          if ((int)e < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(pin + nbase + e) : "memory");
         }
       }
-    }
-
-    // decoupled look-back, after the staging so that the tiles before this one have had time to publish
-    if (tid < 256) {
-      uint32_t excl = 0;
-      if (tile > 0) {
-        const uint32_t* sp = status + (size_t)(tile - 1) * 256 + tid;
-        while (true) {
-          uint32_t v = ld_relaxed_u32(sp);
-          while ((v >> 30) == 0u) {
-            __nanosleep(40);
-            v = ld_relaxed_u32(sp);
-          }
-          excl += v & kOsMask;
-          if (v & kOsIncl) break;
-          sp -= 256;
-        }
-        st_relaxed_u32(status + (size_t)tile * 256 + tid, kOsIncl | (excl + count_d));
-      }
-      gbase[tid] = bbase[tid] + excl - digit_start[tid];   // + staging position = global position
-    }
-    __syncthreads();
-
-    for (int i = tid; i < W * 256; i += T) (&cnt[0][0])[i] = 0u;   // for the next tile (its ranking starts after the barrier below)
+      __syncwarp();
 #pragma unroll
-    for (int i = 0; i < I; ++i) {
-      const int pos = tid + i * T;
-      if (pos < valid) {
-        // staging slots are XOR-swizzled by their 32-slot group: a warp still reads 32 consecutive words here, while the scatter
-        // above no longer piles up on two banks when every digit holds the same number of keys (runs starting at multiples of 16:
-        // the arithmetic-progression scores of synthetic.tie_free_scores made its first pass 16-way bank-conflicted)
-        const uint32_t sw = (uint32_t)pos ^ (((uint32_t)pos >> 5) & 31u);
-        const K k = skeys[sw];
-        const uint32_t d = (uint32_t)(k >> shift) & 0xffu;
-        const uint32_t dst = gbase[d] + (uint32_t)pos;
-        kout[dst] = k;
-        pout[dst] = spay[sw];
+      for (int j = 0; j < 8; ++j) cnt[w][lane + 32 * j] = 0u;   // this warp's row: nobody else touches it before the next barrier
+      __syncwarp();
+      if (has_next) rank_tile(nvalid);
+      __syncthreads();   // `tile` staged, `ntile` ranked
+
+      uint32_t tot = 0, ncount = 0;
+      if (tid < 256) {
+        if (has_next) tot = publish_tile(ntile, nvalid, ncount);
+        uint32_t excl = 0;
+        if (tile > 0) {
+          const uint32_t* sp = status + (size_t)(tile - 1) * 256 + tid;
+          while (true) {
+            uint32_t v = ld_relaxed_u32(sp);
+            while ((v >> 30) == 0u) {
+              __nanosleep(40);
+              v = ld_relaxed_u32(sp);
+            }
+            excl += v & kOsMask;
+            if (v & kOsIncl) break;
+            sp -= 256;
+          }
+          st_relaxed_u32(status + (size_t)tile * 256 + tid, kOsIncl | (excl + count_d));
+        }
+        gbase[tid] = bbase[tid] + excl - digit_start[tid];
       }
+      {
+        const uint32_t ex = block_excl_scan256(tot, wsum);   // barrier inside: every thread of the first 256 has read its digit_start
+        if (tid < 256) digit_start[tid] = ex;
+      }
+      __syncthreads();   // gbase of `tile`, digit_start of `ntile`
+
+      if (valid == TILE) {   // block-uniform; all but the last tile: no bounds predicates, the swizzled slot from G precomputed lane offsets
+        constexpr int G = 32 / W;   // (pos >> 5) & 31 = (w + i W) & 31 takes G values
+        uint32_t lx[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) lx[j] = 32u * w + ((uint32_t)lane ^ ((uint32_t)(w + j * W) & 31u));
+#pragma unroll
+        for (int i = 0; i < I; ++i) {
+          const uint32_t sw = lx[i % G] + (uint32_t)(i * T);
+          const K k = skeys[sw];
+          const uint32_t dst = gbase[digit(k, sel, shift)] + (uint32_t)(tid + i * T);
+          kout[dst] = k;
+          pout[dst] = spay[sw];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < I; ++i) {
+          const int pos = tid + i * T;
+          if (pos < valid) {
+            const uint32_t sw = (uint32_t)pos ^ (((uint32_t)pos >> 5) & 31u);
+            const K k = skeys[sw];
+            const uint32_t dst = gbase[digit(k, sel, shift)] + (uint32_t)pos;
+            kout[dst] = k;
+            pout[dst] = spay[sw];
+          }
+        }
+      }
+      __syncthreads();   // staging buffer free
+      if (!has_next) break;
+      tile = ntile;
+      count_d = ncount;
+      buf ^= 1;
     }
-    __syncthreads();
-    buf ^= 1;
   }
 
   if (HIST != 0 && next_shift >= 0 && tid < 256) {
@@ -767,10 +802,15 @@ __global__ void __launch_bounds__(256) sweep_count_kernel(const uint32_t* __rest
 
 // single-block exclusive scan of the per-tile bonafide counts (<= ~260k tiles at n = 2^30).  The counts of 16 chunks of 1,024 tiles are
 // loaded together before the dependent chain of block scans starts (the first version paid one L2 round trip per chunk: 36 us at 100 M).
+// cross_tile != nullptr (full sweep: curve points 0 .. n): the tile whose first curve point is >= 0 and whose last one is < 0 is recorded
+// (the test of sweep_min_kernel, same fp64 operations; FAR - FRR does not increase along the curve), so that the arg-min kernel runs as ONE CTA instead of one early-exiting CTA per tile.
 __global__ void __launch_bounds__(1024) sweep_scan_kernel(const uint32_t* __restrict__ block_ones, long long nb,
-                                                           unsigned long long* __restrict__ block_excl) {
+                                                           unsigned long long* __restrict__ block_excl, long long n, long long n_bona,
+                                                           long long n_spoof, int* __restrict__ cross_tile) {
   __shared__ unsigned long long wsum[2][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (cross_tile != nullptr && threadIdx.x == 0) *cross_tile = 0x7fffffff;
+  __syncthreads();
   unsigned long long carry = 0;   // kept identically by every thread
   int par = 0;
   for (long long start0 = 0; start0 < nb; start0 += 16 * 1024) {
@@ -802,7 +842,16 @@ __global__ void __launch_bounds__(1024) sweep_scan_kernel(const uint32_t* __rest
       }
       const unsigned long long total = __shfl_sync(0xffffffffu, winc, 31);
       const unsigned long long woff = __shfl_sync(0xffffffffu, winc - mine, w);
-      if (i < nb) block_excl[i] = carry + woff + incl - v[c];
+      if (i < nb) {
+        const unsigned long long ex = carry + woff + incl - v[c];
+        block_excl[i] = ex;
+        if (cross_tile != nullptr) {   // a tile's first point is the last point of the tile before it (+1 at k = 0): the first tile ending below 0
+          const long long ks = i * kSortTile, len = (n - ks) < kSortTile ? (n - ks) : kSortTile;
+          const long long ke = ks + len, c1e = (long long)ex + (long long)v[c];
+          const double de = __dsub_rn(__ddiv_rn((double)(n_spoof - (ke - c1e)), (double)n_spoof), __ddiv_rn((double)c1e, (double)n_bona));
+          if (de < 0.0) atomicMin(cross_tile, (int)i);
+        }
+      }
       carry += total;
       par ^= 1;   // the next chunk writes the other half of wsum: one barrier per chunk
     }
@@ -818,22 +867,25 @@ __device__ __forceinline__ bool better(double d, long long i, double bd, long lo
 // counts); every other tile returns at once without reading its payloads or doing fp64 divisions.
 __global__ void __launch_bounds__(256) sweep_min_kernel(const uint32_t* __restrict__ pay, long long n, long long n_bona, long long n_spoof,
                                                          const unsigned long long* __restrict__ block_excl, const uint32_t* __restrict__ block_ones,
-                                                         SweepBest* __restrict__ block_best, long long k_base, long long c1_base, int single) {
+                                                         SweepBest* __restrict__ block_best, long long k_base, long long c1_base, int single,
+                                                         const int* __restrict__ cross_tile) {
+  // cross_tile (with single): the tile that holds the crossing, found by sweep_scan_kernel -- one CTA is launched instead of one per tile
+  const long long bx = cross_tile ? (long long)*cross_tile : (long long)blockIdx.x;
   // single != 0: exactly one tile holds the crossing (the curve runs from +1 at k = 0 to -1 at k = n); it alone writes block_best[0]
   {
-    const long long t0 = (long long)blockIdx.x * kSortTile;
+    const long long t0 = bx * kSortTile;
     const long long len = (n - t0) < kSortTile ? (n - t0) : kSortTile;
-    const long long ks = k_base + t0, c1s = c1_base + (long long)block_excl[blockIdx.x];
-    const long long ke = ks + len, c1e = c1s + (long long)block_ones[blockIdx.x];
+    const long long ks = k_base + t0, c1s = c1_base + (long long)block_excl[bx];
+    const long long ke = ks + len, c1e = c1s + (long long)block_ones[bx];
     const double ds = __dsub_rn(__ddiv_rn((double)(n_spoof - (ks - c1s)), (double)n_spoof), __ddiv_rn((double)c1s, (double)n_bona));
     const double de = __dsub_rn(__ddiv_rn((double)(n_spoof - (ke - c1e)), (double)n_spoof), __ddiv_rn((double)c1e, (double)n_bona));
     if (!(ds >= 0.0 && de < 0.0)) {   // block-uniform
-      if (threadIdx.x == 0 && !single) block_best[blockIdx.x] = SweepBest{1.0e300, 0x7fffffffffffffffll, 0};
+      if (threadIdx.x == 0 && !single) block_best[bx] = SweepBest{1.0e300, 0x7fffffffffffffffll, 0};
       return;
     }
   }
   // blocked arrangement: thread t owns sorted positions base + 16 t .. + 15
-  const long long base = (long long)blockIdx.x * kSortTile + (long long)threadIdx.x * kSortItems;
+  const long long base = bx * kSortTile + (long long)threadIdx.x * kSortItems;
   uint32_t lab[kSortItems];
   uint32_t ones = 0;
   if (base + kSortItems <= n) {
@@ -863,13 +915,13 @@ __global__ void __launch_bounds__(256) sweep_min_kernel(const uint32_t* __restri
   uint32_t woff = 0;
 #pragma unroll
   for (int ww = 0; ww < 8; ++ww) woff += (ww < w) ? wsum[ww] : 0u;
-  long long c1 = c1_base + (long long)block_excl[blockIdx.x] + woff + incl - ones;
+  long long c1 = c1_base + (long long)block_excl[bx] + woff + incl - ones;
 
   const double dspoof = (double)n_spoof, dbona = (double)n_bona;
   double bd = 1.0e300;
   long long bi = 0x7fffffffffffffffll, bc1 = 0;
   if (threadIdx.x == 0) {  // the point just before this tile's first score (k = 0 for the first tile: FAR = 1, FRR = 0)
-    const long long ks = k_base + (long long)blockIdx.x * kSortTile;
+    const long long ks = k_base + bx * kSortTile;
     const double far0 = __ddiv_rn((double)(n_spoof - (ks - c1)), dspoof);
     const double frr0 = __ddiv_rn((double)c1, dbona);
     bd = fabs(__dsub_rn(far0, frr0));
@@ -903,7 +955,7 @@ __global__ void __launch_bounds__(256) sweep_min_kernel(const uint32_t* __restri
     SweepBest b = part[0];
     for (int i = 1; i < 8; ++i)
       if (better(part[i].diff, part[i].idx, b.diff, b.idx)) b = part[i];
-    block_best[single ? 0 : blockIdx.x] = b;
+    block_best[single ? 0 : bx] = b;
   }
 }
 
@@ -988,26 +1040,33 @@ template <typename K, int HIST, int T>
 static int onesweep_launch(const K* kin, const uint32_t* pin, K* kout, uint32_t* pout, int64_t n, int shift, int next_shift, const uint32_t* hist_cur,
                            uint32_t* hist_next, uint32_t* status, unsigned int* ticket, int num_sms, cudaStream_t stream) {
   typedef OsCfg<K, T> Cfg;
+  auto kern = radix_onesweep_kernel<K, HIST, T>;
   static bool configured[32] = {false};
-  if (dfs_first_use_on_device(configured))
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_onesweep_kernel<K, HIST, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  if (dfs_first_use_on_device(configured)) DFS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   int ctas = 0;
-  DFS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, radix_onesweep_kernel<K, HIST, T>, T, Cfg::SMEM));
+  DFS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, T, Cfg::SMEM));
   DFS_REQUIRE(ctas >= 1, DFS_ERR_CUDA, "dfs_eer: the one-sweep kernel does not fit on this device");
   const long long tiles = ceil_div64(n, Cfg::TILE);
   DFS_CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t)tiles * 256 * 4, stream));
-  radix_onesweep_kernel<K, HIST, T><<<(unsigned)std::min<long long>(tiles, (long long)num_sms * ctas), T, Cfg::SMEM, stream>>>(
+  kern<<<(unsigned)std::min<long long>(tiles, (long long)num_sms * ctas), T, Cfg::SMEM, stream>>>(
       kin, pin, kout, pout, (uint32_t)n, shift, next_shift, hist_cur, hist_next, status, ticket);
   DFS_LAUNCH_CHECK();
   return DFS_OK;
 }
+// dfs_set_global_option("eer_sort_onesweep"): form of dfs_eer's radix passes
+//   0 = count / scan / scatter kernels over per-CTA super-tiles (round 1; cross-check)
+//   1 = one-sweep, 512-thread tiles, next pass's histogram by shared-memory atomics in the scatter kernel (default)
+//   2 = as 1 on 256-thread tiles      3 = as 1, histogram by a kernel of its own before each pass      4 = as 1, histogram by ballots
+int g_sort_onesweep = 1;
 template <typename K, typename... A>
-static int onesweep_pass(int hmode, bool small_tiles, A... a) {
-  if (small_tiles) return hmode == 0 ? onesweep_launch<K, 0, 256>(a...) : hmode == 1 ? onesweep_launch<K, 1, 256>(a...) : onesweep_launch<K, 2, 256>(a...);
-  return hmode == 0 ? onesweep_launch<K, 0, 512>(a...) : hmode == 1 ? onesweep_launch<K, 1, 512>(a...) : onesweep_launch<K, 2, 512>(a...);
+static int onesweep_pass(int form, A... a) {
+  switch (form) {
+    case 2: return onesweep_launch<K, 1, 256>(a...);
+    case 3: return onesweep_launch<K, 0, 512>(a...);
+    case 4: return onesweep_launch<K, 2, 512>(a...);
+    default: return onesweep_launch<K, 1, 512>(a...);
+  }
 }
-
-int g_sort_onesweep = 1;   // dfs_set_global_option("eer_sort_onesweep"): 0 = count / scan / scatter over super-tiles (cross-check), 1..3 = one-sweep on 512-thread tiles, histogram mode 0..2, 4..6 = on 256-thread tiles
 
 template <typename K>
 static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_eer_result* result_host, uint32_t* perm, void* sorted,
@@ -1061,14 +1120,10 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   static bool configured[32] = {false};
   const size_t dyn_smem = (sizeof(K) + 4) * kSortTile;
   if (dfs_first_use_on_device(configured)) {
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kSortTile));
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kSortTile));
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_upsweep_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kCntStride));
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_upsweep_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kCntStride));
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_hist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_hist_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(sort_prep_hist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(sort_prep_hist_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_upsweep_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kCntStride));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_hist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(sort_prep_hist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
   }
   const unsigned hist_grid = (unsigned)std::min<long long>(ceil_div64(n, 2048), (long long)num_sms * 3);   // 3 CTAs of 64 KB per SM
   if (onesweep) {
@@ -1090,20 +1145,19 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
     int pass_list[8], np = 0;
     for (int ps = 0; ps < PASSES; ++ps)
       if ((((small_host.key_and ^ small_host.key_or) >> (8 * ps)) & 0xffull) != 0) pass_list[np++] = ps;   // other bytes: identity passes
+    const bool hist_kernel = g_sort_onesweep == 3;
     if (np > 0 && pass_list[0] != 0) {   // the prep kernel counted byte 0; the first pass sorts another one
       radix_hist_kernel<K><<<hist_grid, 256, kPrivBytes, stream>>>(keys[0], n, 8 * pass_list[0], oshist + 256 * pass_list[0]);
       DFS_LAUNCH_CHECK();
     }
-    const int hmode = (g_sort_onesweep - 1) % 3;   // 0: histogram kernel before each pass, 1: shared-memory atomics in the scatter kernel, 2: ballots
-    const bool small_tiles = g_sort_onesweep >= 4;
     for (int ip = 0; ip < np; ++ip) {
       const int ps = pass_list[ip], nx = ip + 1 < np ? pass_list[ip + 1] : -1;
-      if (hmode == 0 && ip > 0) {
+      if (hist_kernel && ip > 0) {
         radix_hist_kernel<K><<<hist_grid, 256, kPrivBytes, stream>>>(keys[cur], n, 8 * ps, oshist + 256 * ps);
         DFS_LAUNCH_CHECK();
       }
-      DFS_PROPAGATE(onesweep_pass<K>(hmode, small_tiles, keys[cur], pay[cur], keys[cur ^ 1], pay[cur ^ 1], n, 8 * ps, nx < 0 ? -1 : 8 * nx, oshist + 256 * ps,
-                                     oshist + 256 * (nx < 0 ? 0 : nx), status, tickets + ps, num_sms, stream));
+      DFS_PROPAGATE(onesweep_pass<K>(g_sort_onesweep, (const K*)keys[cur], (const uint32_t*)pay[cur], keys[cur ^ 1], pay[cur ^ 1], n, 8 * ps, nx < 0 ? -1 : 8 * nx,
+                                     oshist + 256 * ps, oshist + 256 * (nx < 0 ? 0 : nx), status, tickets + ps, num_sms, stream));
       cur ^= 1;
     }
   }
@@ -1134,9 +1188,10 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
   }
   sweep_count_kernel<<<(unsigned)tiles, 256, 0, stream>>>(pay[cur], n, bones);
   DFS_LAUNCH_CHECK();
-  sweep_scan_kernel<<<1, 1024, 0, stream>>>(bones, tiles, bexcl);
+  int* cross = reinterpret_cast<int*>(tickets);   // the pass tickets are spent
+  sweep_scan_kernel<<<1, 1024, 0, stream>>>(bones, tiles, bexcl, n, n_bona, n_spoof, cross);
   DFS_LAUNCH_CHECK();
-  sweep_min_kernel<<<(unsigned)tiles, 256, 0, stream>>>(pay[cur], n, n_bona, n_spoof, bexcl, bones, bbest, 0, 0, /*single=*/1);
+  sweep_min_kernel<<<1, 256, 0, stream>>>(pay[cur], n, n_bona, n_spoof, bexcl, bones, bbest, 0, 0, /*single=*/1, cross);
   DFS_LAUNCH_CHECK();
   sweep_final_kernel<K><<<1, 256, 0, stream>>>(bbest, 1, keys[cur], n, n_bona, n_spoof, res_dev);
   DFS_LAUNCH_CHECK();
@@ -1765,16 +1820,16 @@ static int eer_select_impl(const void* scores_v, const uint8_t* labels, int64_t 
     SweepBest* bbest = reinterpret_cast<SweepBest*>(b8 + o_bbest);
     group_count_kernel<K><<<(unsigned)tiles_n, 256, 0, stream>>>(scores, n, sc.state, tcnt);
     DFS_LAUNCH_CHECK();
-    sweep_scan_kernel<<<1, 1024, 0, stream>>>(tcnt, tiles_n, texcl);
+    sweep_scan_kernel<<<1, 1024, 0, stream>>>(tcnt, tiles_n, texcl, 0, 0, 0, nullptr);
     DFS_LAUNCH_CHECK();
     group_write_kernel<K><<<(unsigned)tiles_n, 256, 0, stream>>>(scores, labels, n, sc.state, texcl, gpay);
     DFS_LAUNCH_CHECK();
     sweep_count_kernel<<<(unsigned)tiles_m, 256, 0, stream>>>(gpay, m, bones);
     DFS_LAUNCH_CHECK();
-    sweep_scan_kernel<<<1, 1024, 0, stream>>>(bones, tiles_m, bexcl);
+    sweep_scan_kernel<<<1, 1024, 0, stream>>>(bones, tiles_m, bexcl, 0, 0, 0, nullptr);
     DFS_LAUNCH_CHECK();
     sweep_min_kernel<<<(unsigned)tiles_m, 256, 0, stream>>>(gpay, m, (long long)host.n_bona, (long long)host.n_spoof, bexcl, bones, bbest, start,
-                                                           (long long)host.c1_below, /*single=*/0);
+                                                           (long long)host.c1_below, /*single=*/0, nullptr);
     DFS_LAUNCH_CHECK();
     select_reduce_best_kernel<<<1, 256, 0, stream>>>(bbest, tiles_m, sc.state);
     DFS_LAUNCH_CHECK();

@@ -252,10 +252,10 @@ int dfs_eer_select(const void* scores_dev, int key_bytes, const uint8_t* labels_
 /* Library-wide switches for cross-checks (tests only; defaults are the product path):
  *   "eer_select_tma" 1 (default) = cp.async.bulk-fed histogram kernel, 0 = direct vector loads.
  *   "eer_sort_onesweep" (default 1): form of dfs_eer's radix passes.  0 = count / scan / scatter kernels over per-CTA
- *                       super-tiles; 1..6 = one scatter kernel per pass (tiles ticketed in input order, decoupled look-back)
- *                       on tiles of 512 threads (1..3) or 256 threads (4..6), the next pass's histogram taken by a kernel of
- *                       its own (1, 4), by shared-memory atomics in the scatter kernel (2, 5) or by its ballots (3, 6).
- *                       All are stable LSD sorts: identical permutation.                                              */
+ *                       super-tiles (round 1); 1 = one scatter kernel per pass (tiles ticketed in input order, decoupled
+ *                       look-back, next pass's histogram by shared-memory atomics in the same kernel), 512-thread tiles;
+ *                       2 = the same on 256-thread tiles; 3 = histogram by a kernel of its own before each pass;
+ *                       4 = histogram by ballots.  All are stable LSD sorts: identical permutation.                   */
 int dfs_set_global_option(const char* key, int64_t value);
 /* confusion_at_threshold (scripts/evaluation.py:42-56): out4_host = {tp, fp, tn, fn}. */
 int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,

@@ -1,6 +1,5 @@
 """Time dfs_eer (sort path) at 100 M scores under every form of the radix passes (dfs_set_global_option "eer_sort_onesweep"):
-0 = count / scan / scatter over super-tiles, 1..3 = one-sweep with the next pass's histogram taken by a kernel of its own / by
-shared-memory atomics / by ballots.  Prints ms per call (CUDA events, after warm-up) per input distribution and checks that every form
+0 = count / scan / scatter over super-tiles, 1..4 = the one-sweep forms listed in include/dfs_b200.h.  Prints ms per call (CUDA events, after warm-up) per input distribution and checks that every form
 returns the same permutation.  Usage: python tools/eer_forms.py [n] [forms...]"""
 import os
 import sys
@@ -14,7 +13,7 @@ from dfs_b200 import synthetic as syn  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
-    forms = [int(a) for a in sys.argv[2:]] or [0, 1, 2, 3, 4, 5, 6]
+    forms = [int(a) for a in sys.argv[2:]] or [0, 1, 2, 3, 4]
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev)
     g.manual_seed(1234)
