@@ -476,7 +476,7 @@ def leg_eer(ctx, side_D, seconds, n, method="sort"):
     main_, other = first[method], first["select" if method == "sort" else "sort"]
     gbs = 13.0 * main_["scores_per_s"] / 1e9
     roof = _hbm_roof(ctx, gbs, "13 B/score algorithmic (SURVEY.md 8d: read 4 B score + 1 B label, write 4 B sorted score + 4 B permutation); "
-                               "implementation traffic: sort = 13 B prep + (4 B count + 16 B scatter) per varying key byte + 8 B sweep; "
+                               "implementation traffic: sort = 13 B prep + 16 B scatter per varying key byte (one kernel per pass: ticketed tiles, decoupled look-back) + 4 B sweep; "
                                "select = 5 B/score per varying key byte")
     return {"metric": "EER sweep (device radix sort + FAR/FRR crossing) on tie-free fp32 scores (BASELINE configs[4])",
             "value": main_["scores_per_s"], "unit": "scores/s", "ms_per_step": main_["ms_per_step"], "steps": main_["steps"], "n_scores": n,

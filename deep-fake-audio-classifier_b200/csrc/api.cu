@@ -1556,7 +1556,7 @@ extern "C" int dfs_set_global_option(const char* key, int64_t value) {
     return DFS_OK;
   }
   if (strcmp(key, "eer_sort_onesweep") == 0) {
-    DFS_REQUIRE(value >= 0 && value <= 4, DFS_ERR_INVALID, "dfs_set_global_option: eer_sort_onesweep must be 0..4");
+    DFS_REQUIRE(value >= 0 && value <= 5, DFS_ERR_INVALID, "dfs_set_global_option: eer_sort_onesweep must be 0..5");
     dfs::g_sort_onesweep = (int)value;
     return DFS_OK;
   }

@@ -3,11 +3,11 @@
 //   confusion_at_threshold   /root/reference/scripts/evaluation.py:42-56
 //   normalise_01 + blend     /root/reference/src/predict_hybrid.py:81-85,149-151, src/ensemble.py:121
 //
-// EER = stable LSD radix sort (8-bit digits, per pass: count -> scan -> stable scatter, key =
-// order-preserving integer image of the fp32/fp64 score, payload = original index | label<<31)
-// followed by a prefix-count FAR/FRR sweep in IEEE fp64 and a (value, lowest index) arg-min.
-// All kernels are HBM-bound streaming kernels: 16-byte vector accesses where the layout allows,
-// one super-tile of 16 x 4096 keys per CTA; no kernel waits on another CTA.
+// EER = stable LSD radix sort (8-bit digits, key = order-preserving integer image of the fp32/fp64
+// score, payload = original index | label<<31) followed by a prefix-count FAR/FRR sweep in IEEE fp64
+// and a (value, lowest index) arg-min.  A radix pass is ONE scatter kernel (radix_onesweep_kernel:
+// tiles ticketed in input order, decoupled look-back, the next pass's histogram taken on the way);
+// round 1's count -> scan -> scatter kernels over per-CTA super-tiles stay as a cross-check form.
 #include <algorithm>
 
 #include "common.cuh"
@@ -416,15 +416,20 @@ __device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t* wsu
 // HIST: how the next pass's histogram is taken -- 0: not here (radix_hist_kernel runs before each pass), 1: one shared-memory atomic per key,
 // 2: ballot peers + per-warp counters (no atomics, ~45 more instructions per 32 keys).
 // T: threads per CTA (512: tiles of 8,192 fp32 keys, 2 CTAs per SM; 256: 4,096 keys, 4 CTAs per SM).
-// (A first pass that reads the scores and labels itself, with a header-and-histogram-only kernel before it, was measured and dropped:
-// 0.27 + 0.84 ms against 0.26 + 0.55 ms for the image-writing prep kernel and a plain first pass.)
-template <typename K, int HIST, int T>
+// FIRST: the pass reads the caller's scores and labels instead of a key / payload image (key = to_key(score), payload = index | label << 31),
+// so no such image is written and read back before the first pass (8 + 8 B per score).  The score bits are converted to keys when the
+// ranking starts, not where they are loaded: converting in the load loop made every load wait for its data (0.84 ms per pass).
+template <typename K, int HIST, int T, bool FIRST>
 __global__ void __launch_bounds__(T, 1024 / T) radix_onesweep_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ pin, K* __restrict__ kout,
                                                                      uint32_t* __restrict__ pout, uint32_t n /* < 2^30 */, int shift, int next_shift,
                                                                      const uint32_t* __restrict__ hist_cur, uint32_t* __restrict__ hist_next,
                                                                      uint32_t* __restrict__ status /*[tiles][256]*/, unsigned int* __restrict__ ticket) {
-  auto load_key = [&](uint32_t idx) -> K { return kin[idx]; };
-  auto load_pay = [&](uint32_t idx) -> uint32_t { return pin[idx]; };
+  typedef typename ScoreOf<K>::type S;
+  auto load_key = [&](uint32_t idx) -> K { return kin[idx]; };   // FIRST: kin = the scores' bits
+  auto load_pay = [&](uint32_t idx) -> uint32_t {
+    if constexpr (FIRST) return idx | ((uint32_t)(reinterpret_cast<const uint8_t*>(pin)[idx] != 0) << 31);   // pin = the labels
+    else return pin[idx];
+  };
   constexpr int I = OsCfg<K, T>::I, TILE = OsCfg<K, T>::TILE, W = OsCfg<K, T>::W;
   __shared__ uint32_t cnt[W][256];
   __shared__ uint32_t nxt[HIST == 2 ? W : 1][256];
@@ -465,6 +470,15 @@ __global__ void __launch_bounds__(T, 1024 / T) radix_onesweep_kernel(const K* __
   uint32_t rnk2[I / 2];
   // ranks of key[] within this warp's digit counts (cnt row w, zero on entry); next pass's histogram on the way
   auto rank_tile = [&](int valid) {
+    if constexpr (FIRST) {
+#pragma unroll
+      for (int i = 0; i < I; ++i)
+        if (mine0 + 32 * i < valid) {
+          S sc;
+          memcpy(&sc, &key[i], sizeof(K));
+          key[i] = to_key(sc);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < I; ++i) {
       const uint32_t d = digit(key[i], sel, shift);
@@ -541,12 +555,16 @@ __global__ void __launch_bounds__(T, 1024 / T) radix_onesweep_kernel(const K* __
         spay[sw] = (mine0 + 32 * i < valid) ? load_pay(base + mine0 + 32 * i) : 0u;
         if (has_next) key[i] = (mine0 + 32 * i < nvalid) ? load_key(nbase + mine0 + 32 * i) : ~(K)0;
       }
-      if (has_next) {   // the next tile's payloads into the L2
-        constexpr int PJ = TILE * 4 / 32 / T;
+      if (has_next) {   // the next tile's payloads (labels) into the L2
+        if constexpr (FIRST) {
+          if (tid < TILE / 32 && tid * 32 < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(pin) + nbase + tid * 32) : "memory");
+        } else {
+          constexpr int PJ = TILE * 4 / 32 / T;
 #pragma unroll
-        for (int j = 0; j < PJ; ++j) {
-          const uint32_t e = (uint32_t)(PJ * tid + j) * 8;
-          if ((int)e < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(pin + nbase + e) : "memory");
+          for (int j = 0; j < PJ; ++j) {
+            const uint32_t e = (uint32_t)(PJ * tid + j) * 8;
+            if ((int)e < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(pin + nbase + e) : "memory");
+          }
         }
       }
       __syncwarp();
@@ -711,8 +729,9 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const K* __restrict__ k
   priv_publish(tot, hist);
 }
 
-// sort_prep_kernel + the global histogram of key byte 0 in the same read of the scores
-template <typename K>
+// sort_prep_kernel + the global histogram of key byte 0 in the same read of the scores; WRITE = false: header and histogram only (the
+// first radix pass then reads the scores itself)
+template <typename K, bool WRITE>
 __global__ void __launch_bounds__(256) sort_prep_hist_kernel(const typename ScoreOf<K>::type* __restrict__ scores, const uint8_t* __restrict__ labels,
                                                               long long n, K* __restrict__ keys, uint32_t* __restrict__ pay, SortHeader* __restrict__ hdr,
                                                               uint32_t* __restrict__ hist0) {
@@ -720,7 +739,7 @@ __global__ void __launch_bounds__(256) sort_prep_hist_kernel(const typename Scor
   extern __shared__ __align__(16) uint32_t tab[];   // [64][256]
   for (int i = threadIdx.x; i < 64 * 256; i += 256) tab[i] = 0u;
   __syncthreads();
-  constexpr int U = 8;   // scores and labels in flight per thread (scalar loads: the caller's pointers need no alignment)
+  constexpr int U = WRITE ? 8 : 16;   // scores and labels in flight per thread (scalar loads: the caller's pointers need no alignment)
   const long long stride = (long long)gridDim.x * (256 * U);
   const long long iters = (n + stride - 1) / stride;
   uint32_t ones = 0;
@@ -743,8 +762,10 @@ __global__ void __launch_bounds__(256) sort_prep_hist_kernel(const typename Scor
       if (i < n) {
         const K k = to_key(s[u]);
         const uint32_t lab = lb[u] != 0;
-        keys[i] = k;
-        pay[i] = (uint32_t)i | (lab << 31);
+        if constexpr (WRITE) {
+          keys[i] = k;
+          pay[i] = (uint32_t)i | (lab << 31);
+        }
         ones += lab;
         kand &= k;
         kor |= k;
@@ -1036,11 +1057,11 @@ static int get_workspace(size_t bytes, void** out) {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // one radix pass of the one-sweep form: status words cleared, kernel launched on as many CTAs as are resident at once
-template <typename K, int HIST, int T>
+template <typename K, int HIST, int T, bool FIRST>
 static int onesweep_launch(const K* kin, const uint32_t* pin, K* kout, uint32_t* pout, int64_t n, int shift, int next_shift, const uint32_t* hist_cur,
                            uint32_t* hist_next, uint32_t* status, unsigned int* ticket, int num_sms, cudaStream_t stream) {
   typedef OsCfg<K, T> Cfg;
-  auto kern = radix_onesweep_kernel<K, HIST, T>;
+  auto kern = radix_onesweep_kernel<K, HIST, T, FIRST>;
   static bool configured[32] = {false};
   if (dfs_first_use_on_device(configured)) DFS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   int ctas = 0;
@@ -1057,14 +1078,15 @@ static int onesweep_launch(const K* kin, const uint32_t* pin, K* kout, uint32_t*
 //   0 = count / scan / scatter kernels over per-CTA super-tiles (round 1; cross-check)
 //   1 = one-sweep, 512-thread tiles, next pass's histogram by shared-memory atomics in the scatter kernel (default)
 //   2 = as 1 on 256-thread tiles      3 = as 1, histogram by a kernel of its own before each pass      4 = as 1, histogram by ballots
+//   5 = as 1, the first pass reads the scores and labels itself (no key / payload image written before it)
 int g_sort_onesweep = 1;
 template <typename K, typename... A>
 static int onesweep_pass(int form, A... a) {
   switch (form) {
-    case 2: return onesweep_launch<K, 1, 256>(a...);
-    case 3: return onesweep_launch<K, 0, 512>(a...);
-    case 4: return onesweep_launch<K, 2, 512>(a...);
-    default: return onesweep_launch<K, 1, 512>(a...);
+    case 2: return onesweep_launch<K, 1, 256, false>(a...);
+    case 3: return onesweep_launch<K, 0, 512, false>(a...);
+    case 4: return onesweep_launch<K, 2, 512, false>(a...);
+    default: return onesweep_launch<K, 1, 512, false>(a...);
   }
 }
 
@@ -1123,12 +1145,17 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
     DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_downsweep_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_upsweep_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kCntStride));
     DFS_CUDA_CHECK(cudaFuncSetAttribute(radix_hist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
-    DFS_CUDA_CHECK(cudaFuncSetAttribute(sort_prep_hist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(sort_prep_hist_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
+    DFS_CUDA_CHECK(cudaFuncSetAttribute(sort_prep_hist_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrivBytes));
   }
+  const bool fused_first = g_sort_onesweep == 5;
   const unsigned hist_grid = (unsigned)std::min<long long>(ceil_div64(n, 2048), (long long)num_sms * 3);   // 3 CTAs of 64 KB per SM
   if (onesweep) {
     DFS_CUDA_CHECK(cudaMemsetAsync(oshist, 0, (8 * 256 + 8) * 4, stream));
-    sort_prep_hist_kernel<K><<<hist_grid, 256, kPrivBytes, stream>>>(static_cast<const S*>(scores), labels, n, keys[0], pay[0], hdr, oshist);
+    if (fused_first)
+      sort_prep_hist_kernel<K, false><<<hist_grid, 256, kPrivBytes, stream>>>(static_cast<const S*>(scores), labels, n, nullptr, nullptr, hdr, oshist);
+    else
+      sort_prep_hist_kernel<K, true><<<hist_grid, 256, kPrivBytes, stream>>>(static_cast<const S*>(scores), labels, n, keys[0], pay[0], hdr, oshist);
   } else {
     const unsigned prep_grid = (unsigned)std::min<long long>(ceil_div64(n, 256), (long long)num_sms * 8);
     sort_prep_kernel<K><<<prep_grid, 256, 0, stream>>>(static_cast<const S*>(scores), labels, n, keys[0], pay[0], hdr);
@@ -1146,6 +1173,15 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
     for (int ps = 0; ps < PASSES; ++ps)
       if ((((small_host.key_and ^ small_host.key_or) >> (8 * ps)) & 0xffull) != 0) pass_list[np++] = ps;   // other bytes: identity passes
     const bool hist_kernel = g_sort_onesweep == 3;
+    // the first pass can read the scores itself when it sorts byte 0 (whose histogram the header kernel took); otherwise (byte 0 constant
+    // over all scores, or every score equal) the key / payload image is written after all and the passes start from it
+    bool image = !fused_first;
+    if (fused_first && (np == 0 || pass_list[0] != 0)) {
+      const unsigned prep_grid = (unsigned)std::min<long long>(ceil_div64(n, 256), (long long)num_sms * 8);
+      sort_prep_kernel<K><<<prep_grid, 256, 0, stream>>>(static_cast<const S*>(scores), labels, n, keys[0], pay[0], hdr);   // hdr: counted twice, not read again
+      DFS_LAUNCH_CHECK();
+      image = true;
+    }
     if (np > 0 && pass_list[0] != 0) {   // the prep kernel counted byte 0; the first pass sorts another one
       radix_hist_kernel<K><<<hist_grid, 256, kPrivBytes, stream>>>(keys[0], n, 8 * pass_list[0], oshist + 256 * pass_list[0]);
       DFS_LAUNCH_CHECK();
@@ -1155,6 +1191,13 @@ static int eer_impl(const void* scores, const uint8_t* labels, int64_t n, dfs_ee
       if (hist_kernel && ip > 0) {
         radix_hist_kernel<K><<<hist_grid, 256, kPrivBytes, stream>>>(keys[cur], n, 8 * ps, oshist + 256 * ps);
         DFS_LAUNCH_CHECK();
+      }
+      if (ip == 0 && !image) {   // scores -> buffer 0
+        DFS_PROPAGATE((onesweep_launch<K, 1, 512, true>(static_cast<const K*>(scores), reinterpret_cast<const uint32_t*>(labels), keys[0], pay[0], n, 8 * ps,
+                                                        nx < 0 ? -1 : 8 * nx, oshist + 256 * ps, oshist + 256 * (nx < 0 ? 0 : nx), status, tickets + ps, num_sms,
+                                                        stream)));
+        cur = 0;
+        continue;
       }
       DFS_PROPAGATE(onesweep_pass<K>(g_sort_onesweep, (const K*)keys[cur], (const uint32_t*)pay[cur], keys[cur ^ 1], pay[cur ^ 1], n, 8 * ps, nx < 0 ? -1 : 8 * nx,
                                      oshist + 256 * ps, oshist + 256 * (nx < 0 ? 0 : nx), status, tickets + ps, num_sms, stream));

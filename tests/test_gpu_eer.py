@@ -217,7 +217,7 @@ def _sort_forms_agree(s, l, tag):
     """dfs_eer under every form of the radix passes: identical permutation, sorted scores and result."""
     out = []
     try:
-        for form in (0, 1, 2, 3, 4):
+        for form in (0, 1, 2, 3, 4, 5):
             D._native.set_global_option("eer_sort_onesweep", form)
             d = D.eer_details(s, l, want_perm=True, want_sorted=True)
             out.append(d)

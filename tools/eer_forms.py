@@ -13,7 +13,7 @@ from dfs_b200 import synthetic as syn  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
-    forms = [int(a) for a in sys.argv[2:]] or [0, 1, 2, 3, 4]
+    forms = [int(a) for a in sys.argv[2:]] or [0, 1, 2, 3, 4, 5]
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev)
     g.manual_seed(1234)
