@@ -46,12 +46,15 @@ def _require_cuda():
     return torch
 
 
-def _features_struct(x):
-    """torch CUDA fp32 tensor (B, 321, 180) with arbitrary strides -> dfs_features."""
+def _features_struct(x, device_index=None):
+    """torch CUDA fp32 tensor (B, 321, 180) with arbitrary strides -> dfs_features.  ``device_index``: the scorer's device; a
+    tensor on another GPU raises (the kernels would otherwise read the weights of one device from a stream of another)."""
     if x.dim() != 3 or x.shape[1] != T_FRAMES or x.shape[2] != N_FEATS:
         raise ValueError(f"expected features of shape (B, {T_FRAMES}, {N_FEATS}), got {tuple(x.shape)}")
     if not x.is_cuda:
         raise RuntimeError("dfs_b200 scoring takes CUDA tensors (no CPU fallback); use score_host() for host buffers")
+    if device_index is not None and x.device.index != device_index:
+        raise RuntimeError(f"features live on {x.device} but the scorer was created on cuda:{device_index}")
     if x.dtype != _require_cuda().float32:
         x = x.float()
     sn, st, sf = x.stride()
@@ -298,7 +301,7 @@ class Cnn2dScorer(_Scorer):
     def score(self, x, apply_sigmoid: bool = False, return_embedding: bool = False):
         """x: CUDA fp32 (B,321,180), any strides.  Returns (B,) logits/scores [, (B,23040) embedding]."""
         torch = _require_cuda()
-        f, x = _features_struct(x)
+        f, x = _features_struct(x, self.device_index)
         out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         emb = torch.empty((x.shape[0], 128 * N_FEATS), dtype=torch.float32, device=x.device) if return_embedding else None
         with torch.cuda.device(x.device):
@@ -332,7 +335,7 @@ class Cnn1dScorer(_Scorer):
 
     def score(self, x, apply_sigmoid: bool = False):
         torch = _require_cuda()
-        f, x = _features_struct(x)
+        f, x = _features_struct(x, self.device_index)
         out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             N.check(self._lib.dfs_cnn1d_score(self._h, C.byref(f), C.c_void_p(out.data_ptr()), int(bool(apply_sigmoid)),
@@ -364,7 +367,7 @@ class DlqScorer(_Scorer):
         """x: CUDA fp32 (B,321,180) view (any strides; the reference's (B,180,T) batch is ``x.transpose(1, 2)``); lengths:
         optional (B,) valid frame counts.  Returns (B,) logits / sigmoid scores."""
         torch = _require_cuda()
-        f, x = _features_struct(x)
+        f, x = _features_struct(x, self.device_index)
         out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         lp = None
         if lengths is not None:
@@ -414,7 +417,7 @@ class CaeScorer(_Scorer):
         torch = _require_cuda()
         if apply_normalizer is None:
             apply_normalizer = self.has_normalizer
-        f, x = _features_struct(x)
+        f, x = _features_struct(x, self.device_index)
         out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             N.check(self._lib.dfs_cae_score(self._h, C.byref(f), int(bool(apply_normalizer)), C.c_void_p(out.data_ptr()),
@@ -424,7 +427,7 @@ class CaeScorer(_Scorer):
     def forward(self, x):
         """Compat path of ConvAutoencoder.forward: (recon (B,321,180), latent (B,256,20,11)); x already normalised."""
         torch = _require_cuda()
-        f, x = _features_struct(x)
+        f, x = _features_struct(x, self.device_index)
         recon = torch.empty((x.shape[0], T_FRAMES, N_FEATS), dtype=torch.float32, device=x.device)
         latent = torch.empty((x.shape[0], 256, 20, 11), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
@@ -439,7 +442,7 @@ class CaeScorer(_Scorer):
         torch = _require_cuda()
         if apply_normalizer is None:
             apply_normalizer = self.has_normalizer
-        f, x = _features_struct(x)
+        f, x = _features_struct(x, self.device_index)
         h, w, c = self.LAYER_SHAPES[layer]
         out = torch.empty((x.shape[0], h, w, c), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):

@@ -18,6 +18,10 @@ GPU box, so the tests only ever read the .npz files written here.  What is pinne
                    +-20 on 2,048 heterogeneous utterances (dfs_b200.synthetic.features_structured, heavy tails to -61 / +86);
                    reference logits, sigmoids, labels and the reference's own EER on them.
 * dlq.npz       -- reference DeepfakeDetector (src/dlqueen_model.py) logits on seeded weights, full-length and ragged batches.
+* hybrid_wide.npz -- the reference's OWN hybrid scoring functions (src/predict_hybrid.py: get_supervised_scores, get_cae_scores,
+                   normalise_01, the alpha blend of main()) on the first 1,024 structured utterances, stored the way the reference
+                   stores them ((180,321) rows in a DataFrame), with the calibrated 2D-CNN of trained.npz and the CAE + normaliser
+                   of models.npz; the reference's calculate_eer on the supervised, CAE and hybrid columns.
 """
 import importlib.util
 import json
@@ -156,6 +160,49 @@ def make_trained():
     np.savez_compressed(os.path.join(HERE, "trained.npz"), **out)
 
 
+def make_hybrid_wide():
+    """The hybrid path end to end through the reference's unmodified functions (src/predict_hybrid.py:52-85, 142-151)."""
+    import pandas as pd
+    import predict_hybrid as ph                                       # the unmodified module
+    from dataset_cae import FeatureNormalizer
+    from model import CNN2D
+    from model_cae import ConvAutoencoder
+    ev = _load_ref_eval()
+    torch.set_num_threads(os.cpu_count() or 8)
+    tr = np.load(os.path.join(HERE, "trained.npz"))
+    n, seed, alpha = 1024, int(tr["seed"]), 0.8
+    x_np = syn.features_structured(n, seed=seed)
+    assert syn.state_digest([x_np[:64]]) == str(tr["features_sha256_first64"])
+    # features.pkl rows are (180, 321) tensors (src/predict_hybrid.py:46-47 transposes them back)
+    df = pd.DataFrame({"uttid": [f"utt_{i:05d}" for i in range(n)],
+                       "features": [torch.from_numpy(np.ascontiguousarray(x_np[i].T)) for i in range(n)]})
+    sd2 = syn.cnn2d_state(0, logit_scale=float(tr["cnn2d_scale"]), classifier_bias=float(tr["cnn2d_bias"]))
+    assert syn.state_digest(sd2) == str(tr["cnn2d_sha256"])
+    sup = CNN2D(in_features=180, dropout=0.2)
+    sup.load_state_dict(_to_torch(sd2))
+    sdc = syn.cae_state(0)
+    mean, std = syn.normalizer_stats(1)
+    cae = ConvAutoencoder()
+    cae.load_state_dict(_to_torch(sdc))
+    norm = FeatureNormalizer()
+    norm.mean, norm.std = torch.from_numpy(mean), torch.from_numpy(std)
+    sup_scores = ph.get_supervised_scores(sup, df, "cpu", batch_size=32)
+    cae_mse = ph.get_cae_scores(cae, df, norm, "cpu", batch_size=32)
+    sup_norm = ph.normalise_01(sup_scores)                            # predict_hybrid.py:148-150, verbatim semantics
+    cae_norm = ph.normalise_01(cae_mse)
+    hybrid = alpha * sup_norm + (1 - alpha) * cae_norm
+    lab = tr["cnn2d_labels"][:n]
+    out = dict(n=n, seed=seed, alpha=alpha, cae_sha256=syn.state_digest(sdc), cae_norm_sha256=syn.state_digest([mean, std]),
+               sup_scores=sup_scores, cae_mse=cae_mse, sup_norm=sup_norm, cae_norm=cae_norm, hybrid=hybrid, labels=lab,
+               eer_thr_sup=np.array(ev.calculate_eer(sup_scores, lab), dtype=np.float64),
+               eer_thr_cae=np.array(ev.calculate_eer(cae_norm, lab), dtype=np.float64),
+               eer_thr_hybrid=np.array(ev.calculate_eer(hybrid, lab), dtype=np.float64))
+    assert np.array_equal(sup_scores.astype(np.float32), tr["cnn2d_sigmoid"][:n])   # same reference, two call paths
+    np.savez_compressed(os.path.join(HERE, "hybrid_wide.npz"), **out)
+    print("hybrid_wide.npz: cae_mse", cae_mse.min(), cae_mse.max(), "EER sup / cae / hybrid", out["eer_thr_sup"], out["eer_thr_cae"],
+          out["eer_thr_hybrid"])
+
+
 def make_eer():
     ev = _load_ref_eval()
     cases = {}
@@ -267,3 +314,5 @@ if __name__ == "__main__":
         make_dlq()
     if "trained" in which:
         make_trained()
+    if "hybrid_wide" in which:
+        make_hybrid_wide()

@@ -121,3 +121,27 @@ def test_prediction_format_facts():
     assert facts["columns"] == ["uttid", "predictions"]
     assert facts["dtypes"] == {"uttid": "object", "predictions": "float64"}
     assert facts["index_type"] == "RangeIndex"
+
+
+def test_hybrid_path_oracle_matches_the_reference_functions():
+    """hybrid_wide.npz holds what the unmodified src/predict_hybrid.py functions return on 1,024 structured utterances.  The
+    oracle's blend / min-max / EER reproduce the reference's columns bit for bit; its CAE and 2D-CNN loops reproduce the first
+    utterances' scores to fp32 round-off (the whole table would take minutes on the CPU)."""
+    import torch
+    from oracle import models_torch as ot
+    H = np.load(os.path.join(GOLDEN, "hybrid_wide.npz"))
+    T = np.load(os.path.join(GOLDEN, "trained.npz"))
+    alpha, lab = float(H["alpha"]), H["labels"]
+    assert np.array_equal(oeer.normalise_01(H["cae_mse"]), H["cae_norm"])
+    assert np.array_equal(oeer.normalise_01(H["sup_scores"]), H["sup_norm"])
+    assert np.array_equal(oeer.hybrid_blend(H["sup_scores"], H["cae_mse"], alpha), H["hybrid"])
+    for col, key in (("sup_scores", "eer_thr_sup"), ("cae_norm", "eer_thr_cae"), ("hybrid", "eer_thr_hybrid")):
+        assert oeer.calculate_eer(H[col], lab) == tuple(H[key])
+    k = 8
+    x = torch.from_numpy(syn.features_structured(k, seed=int(H["seed"])))
+    mean, std = (torch.from_numpy(a) for a in syn.normalizer_stats(1))
+    mse = ot.reference_loop_cae(syn.cae_state(0), x, mean, std)
+    np.testing.assert_allclose(mse, H["cae_mse"][:k], rtol=1e-5)
+    sd2 = syn.cnn2d_state(0, logit_scale=float(T["cnn2d_scale"]), classifier_bias=float(T["cnn2d_bias"]))
+    sup = ot.reference_loop_supervised(ot.cnn2d_forward, sd2, x)
+    np.testing.assert_allclose(sup, H["sup_scores"][:k], rtol=1e-4, atol=1e-7)
