@@ -1548,7 +1548,7 @@ extern "C" int dfs_bce_with_logits(const float* logits_dev, const float* labels_
   DFS_METRIC_LOCK();
   return bce_with_logits_device(logits_dev, labels_dev, n, mean_host, static_cast<cudaStream_t>(stream));
 }
-namespace dfs { extern int g_select_use_tma; extern int g_sort_onesweep; }
+namespace dfs { extern int g_select_use_tma; extern int g_sort_onesweep; extern int g_sort_overlap; }
 extern "C" int dfs_set_global_option(const char* key, int64_t value) {
   DFS_REQUIRE(key != nullptr, DFS_ERR_INVALID, "dfs_set_global_option: key is NULL");
   if (strcmp(key, "eer_select_tma") == 0) {
@@ -1558,6 +1558,10 @@ extern "C" int dfs_set_global_option(const char* key, int64_t value) {
   if (strcmp(key, "eer_sort_onesweep") == 0) {
     DFS_REQUIRE(value >= 0 && value <= 5, DFS_ERR_INVALID, "dfs_set_global_option: eer_sort_onesweep must be 0..5");
     dfs::g_sort_onesweep = (int)value;
+    return DFS_OK;
+  }
+  if (strcmp(key, "eer_sort_overlap") == 0) {
+    dfs::g_sort_overlap = value != 0;
     return DFS_OK;
   }
   dfs_set_error("dfs_set_global_option: unknown key '%s'", key);

@@ -255,7 +255,11 @@ int dfs_eer_select(const void* scores_dev, int key_bytes, const uint8_t* labels_
  *                       super-tiles (round 1); 1 = one scatter kernel per pass (tiles ticketed in input order, decoupled
  *                       look-back, next pass's histogram by shared-memory atomics in the same kernel), 512-thread tiles;
  *                       2 = the same on 256-thread tiles; 3 = histogram by a kernel of its own before each pass;
- *                       4 = histogram by ballots.  All are stable LSD sorts: identical permutation.                   */
+ *                       4 = histogram by ballots; 5 = the first pass reads the scores and labels itself.  All are stable
+ *                       LSD sorts: identical permutation.
+ *   "eer_sort_overlap" (default 1; fp32 scores, one-sweep forms 1 / 2 / 4): the pass over key byte 0 is launched before the
+ *                       host has read back the label count and the key AND / OR (copied on a side stream), instead of
+ *                       after that round trip; 0 = read back first.  Same result either way.                           */
 int dfs_set_global_option(const char* key, int64_t value);
 /* confusion_at_threshold (scripts/evaluation.py:42-56): out4_host = {tp, fp, tn, fn}. */
 int dfs_confusion(const void* scores_dev, int key_bytes, const uint8_t* labels_dev, int64_t n, double threshold,

@@ -214,15 +214,18 @@ def test_eer_select_tma_ring_matches_direct_loads():
 
 
 def _sort_forms_agree(s, l, tag):
-    """dfs_eer under every form of the radix passes: identical permutation, sorted scores and result."""
+    """dfs_eer under every form of the radix passes (and with / without the speculative first pass, "eer_sort_overlap"): identical
+    permutation, sorted scores and result."""
     out = []
     try:
-        for form in (0, 1, 2, 3, 4, 5):
+        for form, overlap in ((0, 1), (1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (1, 0), (2, 0), (4, 0)):
             D._native.set_global_option("eer_sort_onesweep", form)
+            D._native.set_global_option("eer_sort_overlap", overlap)
             d = D.eer_details(s, l, want_perm=True, want_sorted=True)
             out.append(d)
     finally:
         D._native.set_global_option("eer_sort_onesweep", 1)
+        D._native.set_global_option("eer_sort_overlap", 1)
     base = out[0]
     for form, d in enumerate(out[1:], start=1):
         assert torch.equal(d["perm"], base["perm"]), (tag, form)

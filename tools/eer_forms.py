@@ -13,7 +13,7 @@ from dfs_b200 import synthetic as syn  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
-    forms = [int(a) for a in sys.argv[2:]] or [0, 1, 2, 3, 4, 5]
+    forms = sys.argv[2:] or ["0", "1", "2", "3", "4", "5", "1n"]      # "1n": form 1 without the speculative first pass
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev)
     g.manual_seed(1234)
@@ -25,7 +25,8 @@ def main():
     for name, (s, l) in inputs.items():
         ref = None
         for form in forms:
-            D._native.set_global_option("eer_sort_onesweep", form)
+            D._native.set_global_option("eer_sort_onesweep", int(form.rstrip("n")))
+            D._native.set_global_option("eer_sort_overlap", 0 if form.endswith("n") else 1)
             d = D.eer_details(s, l, want_perm=True)
             if ref is None:
                 ref = d
@@ -43,6 +44,7 @@ def main():
             print(f"{name:8s} n={n} form={form} sort_ms={e0.elapsed_time(e1) / reps:.3f} same_perm_as_form_{forms[0]}={same}", flush=True)
         ref = None
     D._native.set_global_option("eer_sort_onesweep", 1)
+    D._native.set_global_option("eer_sort_overlap", 1)
 
 
 if __name__ == "__main__":
