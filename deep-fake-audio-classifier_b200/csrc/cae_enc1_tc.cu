@@ -252,7 +252,10 @@ int launch_cae_enc1_tc(const float* x, int64_t sn, int64_t st, int64_t sf, int n
                        const uint16_t* wpack, const float* bias_quarter, ActBuf out, int out_cols, int num_sms, cudaStream_t stream) {
   if (n_utts <= 0) return DFS_OK;
   if (sf == 1) {   // feature-contiguous storage: transpose through shared memory (xt_prep.cuh)
-    xt_prep_transpose_kernel<false><<<dim3((kF + 31) / 32, n_utts), 256, 0, stream>>>(x, sn, st, kE1Cols, 2, kE1Lead, norm_mean, norm_std, xt);
+    if (norm_mean != nullptr)
+      xt_prep_transpose_kernel<false, true><<<dim3((kF + 31) / 32, n_utts), 256, 0, stream>>>(x, sn, st, kE1Cols, 2, kE1Lead, norm_mean, norm_std, xt);
+    else
+      xt_prep_transpose_kernel<false, false><<<dim3((kF + 31) / 32, n_utts), 256, 0, stream>>>(x, sn, st, kE1Cols, 2, kE1Lead, nullptr, nullptr, xt);
   } else {
     const long long total = (long long)n_utts * kF * kE1Blocks;
     cae_enc1_prep_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(x, sn, st, sf, total, norm_mean, norm_std, xt);

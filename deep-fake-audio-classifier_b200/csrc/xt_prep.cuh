@@ -14,7 +14,13 @@ namespace {
 constexpr int kXpPitch = 338;   // halfs per staged column: s = t + 1 in [0, 328), +10 pad (odd word pitch)
 
 // SPLIT: also writes xt_lo, the fp16 rounding residual of every sample (x = hi + lo up to 2^-22 |x|; "split" precision)
-template <bool SPLIT = false>
+// NORM: FeatureNormalizer.transform (mean / sd per feature) before the conversion.
+// The first version spent ~50 instructions per sample (64-bit index products, two bounds predicates and a divergence region per sample;
+// ncu: 76 % of the issue slots, DRAM at 33 %).  Here a thread walks its 40 rows (t = ty, ty + 8, ... ty + 312) with one pointer
+// increment per row, the shared-memory offsets are immediates, and the only predicates left are the block-uniform column bound of the
+// last column block and row 320 (row group 0 only).  Same samples, same conversions, same bits.
+static_assert(kT == 321, "row schedule below: 5 rounds of 8 rows per row group + row 320");
+template <bool SPLIT = false, bool NORM = false>
 __global__ void __launch_bounds__(256) xt_prep_transpose_kernel(const float* __restrict__ x, long long sn, long long st, int cols, int col_pad,
                                                                  int lead_rows, const float* __restrict__ mean, const float* __restrict__ sd,
                                                                  uint16_t* __restrict__ xt, uint16_t* __restrict__ xt_lo = nullptr) {
@@ -33,39 +39,40 @@ __global__ void __launch_bounds__(256) xt_prep_transpose_kernel(const float* __r
       if constexpr (SPLIT) tile[kLo + threadIdx.x * kXpPitch + s] = 0;
     }
   }
+  const bool colok = f < kF;   // false only in the last column block (columns 180 .. 191 are padding)
   float m = 0.0f, sg = 1.0f;
-  if (mean != nullptr && f < kF) { m = mean[f]; sg = sd[f]; }
-  const float* src = x + (long long)n * sn + f;
-  // 8 independent row loads in flight per thread (the plain loop issued one load, waited, converted, stored: ncu showed the
-  // kernel at 15 % of the DRAM rate with every warp parked on the long scoreboard)
-  for (int t0 = ty; t0 < kT; t0 += 64) {
+  if (NORM && colok) { m = mean[f]; sg = sd[f]; }
+  // one sample: normalise (FeatureNormalizer.transform, before the zero padding), one saturating convert -- |a| > 65504 and +-inf ->
+  // +-65504, NaN stays NaN (fmaxf / fminf clamps would swallow it) -- and the transposed 2-byte store
+  auto put = [&](float a, uint16_t* dst) {
+    if constexpr (NORM) a = (a - m) / sg;   // padding columns: (0 - 0) / 1 = 0
+    const uint32_t hi = pack_act2(a, 0.0f);
+    dst[0] = (uint16_t)(hi & 0xffffu);
+    if constexpr (SPLIT) dst[kLo] = (uint16_t)(pack_act2_residual(a, 0.0f, hi) & 0xffffu);
+  };
+  const float* p = x + (long long)n * sn + (long long)ty * st + f;   // dereferenced only where colok
+  const long long step = 8 * st;
+  uint16_t* trow = tile + fl * kXpPitch + ty + 1;
+#pragma unroll 1
+  for (int r = 0; r < 5; ++r) {   // 8 independent row loads in flight per thread
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int t = t0 + 8 * k;
-      v[k] = (f < kF && t < kT) ? __ldg(src + (long long)t * st) : 0.0f;
+      v[k] = colok ? __ldg(p) : 0.0f;
+      p += step;
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int t = t0 + 8 * k;
-      float a = v[k];
-      if (mean != nullptr) a = (a - m) / sg;     // FeatureNormalizer.transform, before the zero padding
-      a = (f < kF) ? a : 0.0f;
-      // one saturating convert: |a| > 65504 and +-inf -> +-65504, NaN stays NaN (fmaxf / fminf clamps would swallow it)
-      if (t < kT) {
-        const uint32_t hi = pack_act2(a, 0.0f);
-        tile[fl * kXpPitch + t + 1] = (uint16_t)(hi & 0xffffu);
-        if constexpr (SPLIT) tile[kLo + fl * kXpPitch + t + 1] = (uint16_t)(pack_act2_residual(a, 0.0f, hi) & 0xffffu);
-      }
-    }
+    for (int k = 0; k < 8; ++k) put(v[k], trow + 8 * k);
+    trow += 64;
   }
+  if (ty == 0) put(colok ? __ldg(p) : 0.0f, trow);   // row 320: p and trow have advanced 40 rows
   __syncthreads();
   const int nf = (kF - f0) < 32 ? (kF - f0) : 32;
   for (int item = threadIdx.x; item < nf * 41; item += 256) {
     const int c = item / 41, tb = item - c * 41;
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(tile + c * kXpPitch + 8 * tb);
+    const uint32_t* p4 = reinterpret_cast<const uint32_t*>(tile + c * kXpPitch + 8 * tb);
     uint16_t* dst = xt + ((long long)lead_rows + ((long long)n * cols + f0 + c + col_pad) * 41 + tb) * 8;
-    st_global_v4(dst, p[0], p[1], p[2], p[3]);
+    st_global_v4(dst, p4[0], p4[1], p4[2], p4[3]);
     if constexpr (SPLIT) {
       const uint32_t* pl = reinterpret_cast<const uint32_t*>(tile + kLo + c * kXpPitch + 8 * tb);
       st_global_v4(xt_lo + (dst - xt), pl[0], pl[1], pl[2], pl[3]);
