@@ -67,3 +67,13 @@ def test_every_option_key_is_documented_in_the_header():
         keys |= set(re.findall(r'strcmp\(key, "([a-z0-9_]+)"\)', text))
     header = open(os.path.join(root, "include", "dfs_b200.h")).read()
     assert keys and all(f'"{k}"' in header for k in keys), sorted(k for k in keys if f'"{k}"' not in header)
+
+
+def test_global_options_validate_their_arguments_without_gpu():
+    """dfs_set_global_option touches no device: keys and ranges are checked on the host."""
+    lib = N.load()
+    assert lib.dfs_set_global_option(b"eer_sort_overlap", 0) == 0 and lib.dfs_set_global_option(b"eer_sort_overlap", 1) == 0
+    assert lib.dfs_set_global_option(b"eer_sort_onesweep", 6) == -1 and b"eer_sort_onesweep" in lib.dfs_last_error()
+    assert lib.dfs_set_global_option(b"eer_sort_onesweep", 1) == 0
+    assert lib.dfs_set_global_option(b"no_such_switch", 1) == -1 and b"unknown key" in lib.dfs_last_error()
+    assert lib.dfs_set_global_option(None, 1) == -1
